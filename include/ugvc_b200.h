@@ -1,0 +1,185 @@
+/*
+ * ugvc_b200.h -- C ABI of the B200-native filter_variants_pipeline hot path.
+ *
+ * The reference (Ultimagen/VariantCalling, 100 % Python) has no FFI for this
+ * path; its boundary is the CLI, the model pickle and the Python functions
+ * below.  Each entry point here replaces the native work behind one of them and
+ * is what a ctypes / cgo / JNI stub binds.  All pointers
+ * are plain host or device pointers; no torch / C++ types cross the boundary.
+ *
+ * Reference interfaces replaced (paths under ugbio_utils/src/):
+ *   get_vcf_df            core/ugbio_core/vcfbed/vcftools.py:16-217      -> K0 + K1 (line index, field parse)
+ *   transformer.transform filtering/ugbio_filtering/transformers.py:144-369
+ *                         (called at variant_filtering_utils.py:116-121)   -> K2 (feature assembly)
+ *   model.predict_proba   filtering/ugbio_filtering/variant_filtering_utils.py:123-124
+ *   score math + decision filtering/ugbio_filtering/filter_variants_pipeline.py:170-195
+ *                         core/ugbio_core/math_utils.py:28-44              -> K3 (inference + phred/qual/FILTER)
+ *   record writer         filtering/ugbio_filtering/filter_variants_pipeline.py:188-228
+ *                         (+ htslib BGZF / `bcftools index -t` at :115,:231) -> ugvc_bgzf_* / ugvc_splice_*
+ *
+ * Conventions: every function returns 0 on success or a negative UGVC_E_* code;
+ * ugvc_last_error() gives the message.  The caller owns all host buffers; the
+ * context owns device memory and streams.  One context per GPU; a context is
+ * not thread-safe, different contexts are independent.
+ */
+#ifndef UGVC_B200_H
+#define UGVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UGVC_OK 0
+#define UGVC_E_CUDA (-1)      /* CUDA runtime error (no device, launch failure, ...) */
+#define UGVC_E_ARG (-2)       /* bad argument / capacity exceeded */
+#define UGVC_E_PLAN (-3)      /* malformed or unsupported plan blob */
+#define UGVC_E_DATA (-4)      /* the reference would raise on this input (null feature, unknown category, ...) */
+#define UGVC_E_IO (-5)        /* file / BGZF error */
+#define UGVC_E_STATE (-6)     /* call order (no plan loaded, nothing submitted, ...) */
+
+typedef struct ugvc_ctx ugvc_ctx;
+
+/* Per-record writer support emitted by K1 (16 bytes, one 128-bit store).
+ * Offsets are relative to the start of the record's line; 0xFFFF = saturated
+ * (line longer than 64 KiB: the host re-scans that line). */
+typedef struct ugvc_recinfo {
+    int32_t pos;          /* 1-based POS */
+    uint16_t qual_off;    /* offset of the QUAL column */
+    uint16_t filter_off;  /* offset of the FILTER column */
+    uint16_t info_off;    /* offset of the INFO column */
+    uint16_t format_off;  /* offset one past the tab after INFO (== line length + 1 when there is no FORMAT column) */
+    uint32_t flags;       /* bit0: an allele equals GGC or CCG (blacklist_cg_insertions, blacklist.py:85-101) */
+} ugvc_recinfo;
+
+/* Counters of one batch / one run (what the single NCCL all-reduce sums). */
+typedef struct ugvc_counts {
+    int64_t n_records;
+    int64_t n_low_score;  /* records with quals <= threshold (filter_variants_pipeline.py:192) */
+    int64_t n_pass;       /* n_records - n_low_score */
+    int64_t n_cg;         /* records flagged by the CG-insertion rule */
+} ugvc_counts;
+
+/* ---- lifetime ---------------------------------------------------------- */
+int ugvc_init(int device, ugvc_ctx** out);
+void ugvc_free(ugvc_ctx* ctx);
+const char* ugvc_last_error(const ugvc_ctx* ctx); /* ctx may be NULL: error of a failed ugvc_init */
+int ugvc_version(void);
+
+/* Load the compiled plan: tag table built from the VCF header (Number/Type per
+ * INFO/FORMAT tag, replaces pysam's typed decode at vcftools.py:63-89), the
+ * fitted transformer lowered to slot/feature ops (transformers.py:221-344) and
+ * the model (sklearn LR / GB / RF natively, xgboost via its JSON dump;
+ * variant_filtering_utils.py:70-89).  Layout: variantcalling_b200/csrc/plan.h. */
+int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes);
+int ugvc_plan_info(const ugvc_ctx* ctx, int32_t* n_features, int32_t* n_classes, int32_t* n_slots);
+
+/* Size the context's device workspace: n_pipeline independent batch lanes, each
+ * for up to max_bytes of VCF text and max_records records. */
+int ugvc_reserve(ugvc_ctx* ctx, size_t max_bytes, size_t max_records, int n_pipeline);
+
+/* ---- the hot path: host buffers in, host buffers out -------------------- */
+/* One batch of whole VCF data lines (no header lines; must end with '\n').
+ * Copies the text to the device, runs K0..K3, copies results back, blocks.
+ * out_low_score[i] = 1 iff quals[i] <= threshold; out_probs is N x n_classes
+ * fp32 row-major; out_qual is the fp64 TREE_SCORE; out_recinfo may be NULL. */
+int ugvc_filter_batch(ugvc_ctx* ctx, const uint8_t* vcf_text, size_t n_bytes, double threshold,
+                      uint8_t* out_low_score, float* out_probs, double* out_qual,
+                      ugvc_recinfo* out_recinfo, int64_t* out_line_start,
+                      size_t capacity_records, int64_t* out_n_records);
+
+/* Pipelined form of the same call: submit on lane `lane` (0 <= lane <
+ * n_pipeline), collect later; copies and kernels of different lanes overlap. */
+int ugvc_submit_batch(ugvc_ctx* ctx, int lane, const uint8_t* vcf_text, size_t n_bytes, double threshold);
+int ugvc_collect_batch(ugvc_ctx* ctx, int lane, uint8_t* out_low_score, float* out_probs, double* out_qual,
+                       ugvc_recinfo* out_recinfo, int64_t* out_line_start,
+                       size_t capacity_records, int64_t* out_n_records);
+
+/* ---- the hot path: device-resident text (bench `value`, multi-GPU shards) - */
+/* d_* are device pointers sized for capacity_records (d_recinfo / d_line_start
+ * may be NULL -> context scratch).  Runs on `stream` (a cudaStream_t, NULL =
+ * the context's lane-0 stream) without any host synchronisation; the record
+ * count lands in *d_n_records (device int64). */
+int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n_bytes, double threshold,
+                       uint8_t* d_low_score, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
+                       int64_t* d_line_start, size_t capacity_records, int64_t* d_n_records, void* stream);
+
+/* Blocking: waits for `stream` and surfaces a data error (UGVC_E_DATA) of the last
+ * ugvc_filter_device call. */
+int ugvc_device_status(ugvc_ctx* ctx, void* stream);
+
+/* Pinned host memory for the host-buffer API (full-rate PCIe copies). */
+int ugvc_host_alloc(void** out, size_t n_bytes);
+int ugvc_host_free(void* p);
+
+/* Counters accumulated since the last reset (device-side, summed over batches). */
+int ugvc_counts_reset(ugvc_ctx* ctx);
+int ugvc_counts_get(ugvc_ctx* ctx, ugvc_counts* out);
+/* Device address of the int64[4] counter block {n_records, n_low_score, n_pass,
+ * n_cg}: this is the buffer the one NCCL all-reduce of the path sums in place
+ * (the host passes it to torch.distributed / ncclAllReduce). */
+int ugvc_counts_device_ptr(ugvc_ctx* ctx, int64_t** d_counts);
+
+/* ---- introspection for the parity tests --------------------------------- */
+/* Raw slot columns (K1 output, n_slots x n_records fp32 bit patterns) and the
+ * feature matrix (K2 output, n_features x n_records fp32, column-major) of the
+ * last batch on `lane`. */
+int ugvc_debug_raw(ugvc_ctx* ctx, int lane, uint32_t* out, size_t capacity_words);
+int ugvc_debug_features(ugvc_ctx* ctx, int lane, float* out, size_t capacity_floats);
+/* Error detail of the last UGVC_E_DATA: record index within the batch, feature
+ * column (or -1) and a reason code. */
+int ugvc_last_data_error(const ugvc_ctx* ctx, int64_t* record, int32_t* column, int32_t* reason);
+
+/* Number of kernel launches issued by this context since ugvc_init. */
+int64_t ugvc_launch_count(const ugvc_ctx* ctx);
+/* Device-side duration (ms) of each kernel stage of the last ugvc_filter_device /
+ * submit on lane 0 when stage timing is enabled: out[0..3] = K0,K1,K2,K3. */
+int ugvc_enable_stage_timing(ugvc_ctx* ctx, int on);
+int ugvc_stage_ms(ugvc_ctx* ctx, float out_ms[4]);
+
+/* ---- synthetic input (bench / tests) ------------------------------------ */
+/* Generate `n_records` synthetic single-sample VCF data lines (SURVEY.md 8d
+ * schema, n_custom custom annotations) for global record indices
+ * [first_record, first_record + n_records) of a job of total_records, straight
+ * into device memory.  Returns bytes written in *out_bytes. */
+int ugvc_synth_device(ugvc_ctx* ctx, uint64_t seed, int64_t first_record, int64_t n_records,
+                      int64_t total_records, int n_custom, uint8_t* d_text, size_t capacity_bytes,
+                      size_t* out_bytes, void* stream);
+/* The matching header text (host). Returns its length, or negative on error. */
+int64_t ugvc_synth_header(int n_custom, char* out, size_t capacity);
+
+/* ---- container formats either side of the path (host, multi-threaded) ---- */
+/* Inflate a whole BGZF file (or a virtual-offset range) into `out`; returns
+ * bytes produced in *out_bytes.  Replaces htslib's reader behind
+ * pysam.VariantFile (filter_variants_pipeline.py:106,117). */
+int ugvc_bgzf_inflate_file(const char* path, uint64_t voff_begin, uint64_t voff_end, uint8_t* out,
+                           size_t capacity, size_t* out_bytes, int n_threads);
+int64_t ugvc_bgzf_uncompressed_size(const char* path);
+/* Append `n_bytes` as BGZF blocks to `path` (mode 'w' truncates, 'a' appends;
+ * write_eof != 0 adds the 28-byte EOF block).  Every block but the last holds
+ * 0xff00 bytes of input; out_block_csize (may be NULL) receives the compressed
+ * size of each block so the caller can build the tabix index that the reference
+ * obtains from `bcftools index -t` (filter_variants_pipeline.py:231).  Replaces
+ * htslib's writer (filter_variants_pipeline.py:115,228). */
+int ugvc_bgzf_deflate_to_file(const char* path, const char* mode, const uint8_t* data, size_t n_bytes,
+                              int level, int write_eof, int n_threads, uint64_t* out_compressed_bytes,
+                              uint32_t* out_block_csize, size_t block_capacity, size_t* out_n_blocks);
+/* Build the edited output text of a batch: for each record copy the original
+ * line with FILTER rewritten (PASS removed / LOW_SCORE appended / empty -> PASS)
+ * and TREE_SCORE (and optionally QUAL, BLACKLST) spliced in, exactly the rules of
+ * filter_variants_pipeline.py:188-228.  blacklist_text/blacklist_off (may be
+ * NULL) give an optional per-record BLACKLST value; out_line_start (may be
+ * NULL, n_records + 1 entries) receives the offset of every output line.
+ * Returns bytes written. */
+int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_start, const ugvc_recinfo* recinfo,
+                            const uint8_t* low_score, const double* qual, int64_t n_records,
+                            int overwrite_qual, int with_model, const char* blacklist_text,
+                            const int64_t* blacklist_off, uint8_t* out, size_t capacity,
+                            int64_t* out_line_start, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UGVC_B200_H */

@@ -96,8 +96,18 @@ def validate_data(data) -> None:
             assert pd.isna(arr[:, c]).sum() == 0, f"Data matrix contains null in column {c}"  # noqa: S101
 
 
+def harness_float_columns(df: pd.DataFrame) -> pd.DataFrame:
+    """Harness shim for scikit-learn >= 1.6 (the reference pins 1.5.x): SimpleImputer now
+    refuses to transform an int64 column when it was fitted on the same column as float64
+    (a contig without any missing DP has an int column, the training frame had NaNs).  Integer
+    columns are presented as float64 at both fit and transform; values are unchanged."""
+    ints = [c for c in df.columns if pd.api.types.is_integer_dtype(df[c].dtype)]
+    return df.astype({c: np.float64 for c in ints}) if ints else df
+
+
 def transform_features(df: pd.DataFrame, transformer) -> pd.DataFrame:
     """Chunked ``transformer.transform``.  variant_filtering_utils.py:116-122."""
+    df = harness_float_columns(df)
     bounds = np.concatenate((np.arange(0, df.shape[0], MAX_CHUNK_SIZE, dtype=int), [df.shape[0]]))
     with pd.option_context("future.infer_string", False):
         parts = [transformer.transform(df.iloc[bounds[i]: bounds[i + 1]]) for i in range(len(bounds) - 1)]

@@ -1,0 +1,526 @@
+// capi.cu -- C ABI (include/ugvc_b200.h) over the kernels: context, plan upload,
+// batch lanes (stream + device workspace), host-buffer and device-resident entry points.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+#define UGVC_VERSION 100
+#define TEXT_SLACK 64
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    uint8_t* d_text = nullptr;
+    LaneBuffers b{};
+    unsigned long long* d_err = nullptr;
+    int64_t* h_n = nullptr;              // pinned
+    unsigned long long* h_err = nullptr; // pinned
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t n_bytes = 0;
+    bool submitted = false;
+    int64_t last_n = 0;
+};
+
+struct ugvc_ctx {
+    int device = 0;
+    int sm_count = 148;
+    std::string err;
+    bool has_plan = false;
+    DevPlan plan{};
+    uint8_t* d_plan = nullptr;
+    uint8_t* d_htab = nullptr;
+    std::vector<Lane> lanes;
+    size_t cap_bytes = 0, cap_records = 0;
+    long long* d_counts = nullptr;
+    int64_t launches = 0;
+    bool timing = false;
+    float stage_ms[4] = {0, 0, 0, 0};
+    int64_t err_record = -1;
+    int32_t err_column = -1, err_reason = 0;
+};
+
+static std::string g_init_error;
+
+static int fail(ugvc_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    else g_init_error = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(ctx, UGVC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+extern "C" int ugvc_version(void) { return UGVC_VERSION; }
+
+extern "C" const char* ugvc_last_error(const ugvc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+extern "C" int ugvc_init(int device, ugvc_ctx** out) {
+    ugvc_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, UGVC_E_ARG, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, UGVC_E_CUDA,
+                    std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                        "); this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, UGVC_E_ARG, "device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, UGVC_E_CUDA, cudaGetErrorString(e));
+    ctx = new ugvc_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CU(cudaMalloc(&ctx->d_counts, 4 * sizeof(long long)));
+    CU(cudaMemset(ctx->d_counts, 0, 4 * sizeof(long long)));
+    *out = ctx;
+    return UGVC_OK;
+}
+
+static void free_lane(Lane& l) {
+    if (l.stream) cudaStreamSynchronize(l.stream);
+    cudaFree(l.d_text);
+    cudaFree(l.b.chunk_first);
+    cudaFree(l.b.line_start);
+    cudaFree(l.b.n_records);
+    cudaFree(l.b.raw);
+    cudaFree(l.b.recinfo);
+    cudaFree(l.b.feats);
+    cudaFree(l.b.low_score);
+    cudaFree(l.b.probs);
+    cudaFree(l.b.qual);
+    cudaFree(l.d_err);
+    if (l.h_n) cudaFreeHost(l.h_n);
+    if (l.h_err) cudaFreeHost(l.h_err);
+    for (auto& ev : l.ev)
+        if (ev) cudaEventDestroy(ev);
+    if (l.stream) cudaStreamDestroy(l.stream);
+    l = Lane();
+}
+
+extern "C" void ugvc_free(ugvc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& l : ctx->lanes) free_lane(l);
+    cudaFree(ctx->d_plan);
+    cudaFree(ctx->d_htab);
+    cudaFree(ctx->d_counts);
+    delete ctx;
+}
+
+static size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
+
+extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
+    if (!ctx || !blob) return fail(ctx, UGVC_E_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    if (n_bytes < sizeof(PlanHeader)) return fail(ctx, UGVC_E_PLAN, "plan blob too small");
+    PlanHeader h;
+    memcpy(&h, blob, sizeof(h));
+    if (h.magic != UGVC_PLAN_MAGIC) return fail(ctx, UGVC_E_PLAN, "bad plan magic");
+    if (h.version != UGVC_PLAN_VERSION) return fail(ctx, UGVC_E_PLAN, "plan version mismatch");
+    if (h.n_tags > UGVC_MAX_TAGS || h.n_slots > UGVC_MAX_SLOTS || h.n_features > UGVC_MAX_FEATURES ||
+        h.n_checks > 64 || h.n_classes < 2 || h.n_classes > UGVC_MAX_CLASSES || h.n_outputs < 1 || h.n_outputs > UGVC_MAX_CLASSES)
+        return fail(ctx, UGVC_E_PLAN, "plan dimensions out of range");
+    size_t off = align8(sizeof(PlanHeader));
+    const size_t o_tags = off;
+    off = align8(off + (size_t)h.n_tags * sizeof(PlanTag));
+    const size_t o_slots = off;
+    off = align8(off + (size_t)h.n_slots * sizeof(PlanSlot));
+    const size_t o_dicts = off;
+    off = align8(off + (size_t)h.n_dicts * sizeof(PlanDict));
+    const size_t o_strings = off;
+    off = align8(off + (size_t)h.n_dict_strings * sizeof(PlanString));
+    const size_t o_feats = off;
+    off = align8(off + (size_t)h.n_features * sizeof(PlanFeature));
+    const size_t o_checks = off;
+    off = align8(off + (size_t)h.n_checks * sizeof(PlanCheck));
+    size_t o_coef = 0, o_icpt = 0, o_root = 0, o_tout = 0, o_nodes = 0, o_leaves = 0;
+    if (h.model_kind == MODEL_LOGISTIC) {
+        o_coef = off;
+        off = align8(off + (size_t)h.n_outputs * h.n_features * sizeof(double));
+        o_icpt = off;
+        off = align8(off + (size_t)h.n_outputs * sizeof(double));
+    } else if (h.model_kind >= MODEL_GB_SKLEARN && h.model_kind <= MODEL_XGB) {
+        o_root = off;
+        off = align8(off + (size_t)(h.n_trees + 1) * sizeof(uint32_t));
+        o_tout = off;
+        off = align8(off + (size_t)h.n_trees);
+        o_nodes = off;
+        off = align8(off + (size_t)h.n_nodes * sizeof(PlanNode));
+        o_leaves = off;
+        off = align8(off + (size_t)h.n_leaf_rows * h.leaf_width * sizeof(double));
+    } else {
+        return fail(ctx, UGVC_E_PLAN, "unsupported model kind");
+    }
+    if (off > n_bytes) return fail(ctx, UGVC_E_PLAN, "plan blob truncated");
+    const uint8_t* hb = static_cast<const uint8_t*>(blob);
+    // validate slot / feature references and build the tag hash table
+    const PlanTag* tags = reinterpret_cast<const PlanTag*>(hb + o_tags);
+    const PlanSlot* slots = reinterpret_cast<const PlanSlot*>(hb + o_slots);
+    const PlanFeature* feats = reinterpret_cast<const PlanFeature*>(hb + o_feats);
+    uint8_t htab[256];
+    memset(htab, 0xFF, sizeof(htab));
+    for (uint32_t t = 0; t < h.n_tags; ++t) {
+        if (tags[t].len == 0 || tags[t].len > UGVC_NAME_MAX) return fail(ctx, UGVC_E_PLAN, "bad tag name length");
+        if ((uint32_t)tags[t].first_slot + tags[t].n_slots > h.n_slots) return fail(ctx, UGVC_E_PLAN, "tag slots out of range");
+        unsigned hash = 2166136261u;
+        for (int i = 0; i < tags[t].len; ++i) hash = (hash ^ (uint8_t)tags[t].name[i]) * 16777619u;
+        unsigned idx = (hash ^ (hash >> 8) ^ (hash >> 16)) & 255u;
+        while (htab[idx] != 0xFF) idx = (idx + 1) & 255u;
+        htab[idx] = (uint8_t)t;
+    }
+    uint32_t first_fixed = h.n_slots;
+    for (uint32_t s = 0; s < h.n_slots; ++s) {
+        if (slots[s].tag == TAG_FIXED) {
+            if (first_fixed == h.n_slots) first_fixed = s;
+        } else {
+            if (first_fixed != h.n_slots) return fail(ctx, UGVC_E_PLAN, "fixed slots must come last");
+            if (slots[s].tag >= h.n_tags) return fail(ctx, UGVC_E_PLAN, "slot tag out of range");
+            if (slots[s].reducer == RED_DICT && slots[s].dict >= h.n_dicts) return fail(ctx, UGVC_E_PLAN, "slot dict out of range");
+        }
+    }
+    for (uint32_t f = 0; f < h.n_features; ++f)
+        if (feats[f].slot >= h.n_slots) return fail(ctx, UGVC_E_PLAN, "feature slot out of range");
+    {
+        const PlanCheck* checks = reinterpret_cast<const PlanCheck*>(hb + o_checks);
+        for (uint32_t c = 0; c < h.n_checks; ++c)
+            if (checks[c].slot >= h.n_slots) return fail(ctx, UGVC_E_PLAN, "check slot out of range");
+    }
+    if (h.model_kind != MODEL_LOGISTIC) {
+        const uint32_t* root = reinterpret_cast<const uint32_t*>(hb + o_root);
+        const PlanNode* nodes = reinterpret_cast<const PlanNode*>(hb + o_nodes);
+        const uint8_t* tout = hb + o_tout;
+        for (uint32_t t = 0; t < h.n_trees; ++t) {
+            if (root[t] > root[t + 1] || root[t + 1] > h.n_nodes) return fail(ctx, UGVC_E_PLAN, "tree roots not monotone");
+            if (tout[t] >= h.n_outputs) return fail(ctx, UGVC_E_PLAN, "tree output out of range");
+            const uint32_t n = root[t + 1] - root[t];
+            for (uint32_t i = 0; i < n; ++i) {
+                const PlanNode& nd = nodes[root[t] + i];
+                if (nd.feature >= 0) {
+                    if ((uint32_t)nd.feature >= h.n_features || nd.right >= n || i + 1 >= n)
+                        return fail(ctx, UGVC_E_PLAN, "tree node out of range");
+                } else {
+                    int32_t leaf;
+                    memcpy(&leaf, &nd.value, 4);
+                    if (leaf < 0 || (uint32_t)leaf >= h.n_leaf_rows) return fail(ctx, UGVC_E_PLAN, "leaf row out of range");
+                }
+            }
+        }
+    }
+    cudaFree(ctx->d_plan);
+    cudaFree(ctx->d_htab);
+    ctx->d_plan = nullptr;
+    ctx->d_htab = nullptr;
+    CU(cudaMalloc(&ctx->d_plan, off));
+    CU(cudaMemcpy(ctx->d_plan, blob, off, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_htab, 256));
+    CU(cudaMemcpy(ctx->d_htab, htab, 256, cudaMemcpyHostToDevice));
+    DevPlan& p = ctx->plan;
+    p.h = h;
+    const uint8_t* d = ctx->d_plan;
+    p.tags = reinterpret_cast<const PlanTag*>(d + o_tags);
+    p.slots = reinterpret_cast<const PlanSlot*>(d + o_slots);
+    p.dicts = reinterpret_cast<const PlanDict*>(d + o_dicts);
+    p.strings = reinterpret_cast<const PlanString*>(d + o_strings);
+    p.feats = reinterpret_cast<const PlanFeature*>(d + o_feats);
+    p.checks = reinterpret_cast<const PlanCheck*>(d + o_checks);
+    p.coef = reinterpret_cast<const double*>(d + o_coef);
+    p.intercept = reinterpret_cast<const double*>(d + o_icpt);
+    p.tree_root = reinterpret_cast<const uint32_t*>(d + o_root);
+    p.tree_out = d + o_tout;
+    p.nodes = reinterpret_cast<const PlanNode*>(d + o_nodes);
+    p.leaves = reinterpret_cast<const double*>(d + o_leaves);
+    p.htab = ctx->d_htab;
+    p.first_fixed_slot = first_fixed;
+    if (k1_smem_bytes(p) > 227 * 1024 || k3_smem_bytes(p) > 227 * 1024)
+        return fail(ctx, UGVC_E_PLAN, "plan needs more shared memory than one sm_100 CTA has");
+    CU(kernels_configure(p));
+    ctx->has_plan = true;
+    // a new plan changes the slot/feature counts: lanes must be re-reserved
+    for (auto& l : ctx->lanes) free_lane(l);
+    ctx->lanes.clear();
+    ctx->cap_bytes = ctx->cap_records = 0;
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_plan_info(const ugvc_ctx* ctx, int32_t* n_features, int32_t* n_classes, int32_t* n_slots) {
+    if (!ctx || !ctx->has_plan) return UGVC_E_STATE;
+    if (n_features) *n_features = (int32_t)ctx->plan.h.n_features;
+    if (n_classes) *n_classes = (int32_t)ctx->plan.h.n_classes;
+    if (n_slots) *n_slots = (int32_t)ctx->plan.h.n_slots;
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_reserve(ugvc_ctx* ctx, size_t max_bytes, size_t max_records, int n_pipeline) {
+    if (!ctx) return UGVC_E_ARG;
+    if (!ctx->has_plan) return fail(ctx, UGVC_E_STATE, "ugvc_reserve: load a plan first");
+    if (n_pipeline < 1 || n_pipeline > 8 || max_bytes == 0 || max_records == 0)
+        return fail(ctx, UGVC_E_ARG, "ugvc_reserve: bad sizes");
+    CU(cudaSetDevice(ctx->device));
+    for (auto& l : ctx->lanes) free_lane(l);
+    ctx->lanes.clear();
+    max_records = (max_records + 127) & ~(size_t)127;  // rows stay 512-byte aligned
+    ctx->cap_bytes = max_bytes;
+    ctx->cap_records = max_records;
+    ctx->lanes.resize(n_pipeline);
+    const size_t n_chunks = (max_bytes + K0_CHUNK_BYTES - 1) / K0_CHUNK_BYTES + 1;
+    const DevPlan& p = ctx->plan;
+    for (auto& l : ctx->lanes) {
+        CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&l.d_text, max_bytes + TEXT_SLACK));
+        l.b.cap_bytes = max_bytes;
+        l.b.cap_records = max_records;
+        CU(cudaMalloc(&l.b.chunk_first, n_chunks * sizeof(uint32_t)));
+        CU(cudaMalloc(&l.b.line_start, (max_records + 1) * sizeof(int64_t)));
+        CU(cudaMalloc(&l.b.n_records, sizeof(int64_t)));
+        CU(cudaMalloc(&l.b.raw, (size_t)p.h.n_slots * max_records * sizeof(uint32_t)));
+        CU(cudaMalloc(&l.b.recinfo, max_records * sizeof(ugvc_recinfo)));
+        CU(cudaMalloc(&l.b.feats, (size_t)p.h.n_features * max_records * sizeof(float)));
+        CU(cudaMalloc(&l.b.low_score, max_records));
+        CU(cudaMalloc(&l.b.probs, max_records * p.h.n_classes * sizeof(float)));
+        CU(cudaMalloc(&l.b.qual, max_records * sizeof(double)));
+        CU(cudaMalloc(&l.d_err, sizeof(unsigned long long)));
+        CU(cudaHostAlloc(&l.h_n, sizeof(int64_t), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&l.h_err, sizeof(unsigned long long), cudaHostAllocDefault));
+        for (auto& ev : l.ev) CU(cudaEventCreate(&ev));
+    }
+    return UGVC_OK;
+}
+
+// enqueue K0..K3 for text already on the device
+static int enqueue_kernels(ugvc_ctx* ctx, Lane& l, const uint8_t* d_text, size_t n_bytes, double threshold,
+                           uint8_t* d_low, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
+                           int64_t* d_line_start, size_t line_cap, int64_t* d_n_records, cudaStream_t st) {
+    const DevPlan& p = ctx->plan;
+    const bool timing = ctx->timing;
+    CU(cudaMemsetAsync(l.d_err, 0xFF, sizeof(unsigned long long), st));
+    if (timing) CU(cudaEventRecord(l.ev[0], st));
+    launch_k0(d_text, n_bytes, l.b.chunk_first, d_line_start, line_cap, d_n_records, l.d_err, ctx->sm_count, st);
+    if (timing) CU(cudaEventRecord(l.ev[1], st));
+    launch_k1(p, d_text, d_line_start, d_n_records, l.b.raw, l.b.cap_records, d_recinfo, l.d_err, ctx->d_counts,
+              ctx->sm_count, st);
+    if (timing) CU(cudaEventRecord(l.ev[2], st));
+    launch_k2(p, l.b.raw, l.b.cap_records, d_n_records, l.b.feats, l.d_err, ctx->sm_count, st);
+    if (timing) CU(cudaEventRecord(l.ev[3], st));
+    launch_k3(p, l.b.feats, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual, ctx->d_counts,
+              ctx->sm_count, st);
+    if (timing) CU(cudaEventRecord(l.ev[4], st));
+    ctx->launches += 6;
+    CU(cudaGetLastError());
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_submit_batch(ugvc_ctx* ctx, int lane, const uint8_t* vcf_text, size_t n_bytes, double threshold) {
+    if (!ctx) return UGVC_E_ARG;
+    if (!ctx->has_plan || ctx->lanes.empty()) return fail(ctx, UGVC_E_STATE, "submit: load a plan and reserve first");
+    if (lane < 0 || lane >= (int)ctx->lanes.size()) return fail(ctx, UGVC_E_ARG, "submit: lane out of range");
+    if (n_bytes > ctx->cap_bytes) return fail(ctx, UGVC_E_ARG, "submit: batch larger than the reserved max_bytes");
+    if (n_bytes && (!vcf_text || vcf_text[n_bytes - 1] != '\n'))
+        return fail(ctx, UGVC_E_ARG, "submit: the batch must be whole lines ending with a newline");
+    CU(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[lane];
+    if (l.submitted) return fail(ctx, UGVC_E_STATE, "submit: lane already has a batch in flight");
+    if (n_bytes) CU(cudaMemcpyAsync(l.d_text, vcf_text, n_bytes, cudaMemcpyHostToDevice, l.stream));
+    CU(cudaMemsetAsync(l.d_text + n_bytes, '\n', TEXT_SLACK, l.stream));
+    int rc = enqueue_kernels(ctx, l, l.d_text, n_bytes, threshold, l.b.low_score, l.b.probs, l.b.qual, l.b.recinfo,
+                             l.b.line_start, l.b.cap_records, l.b.n_records, l.stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(l.h_n, l.b.n_records, sizeof(int64_t), cudaMemcpyDeviceToHost, l.stream));
+    CU(cudaMemcpyAsync(l.h_err, l.d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
+    l.n_bytes = n_bytes;
+    l.submitted = true;
+    return UGVC_OK;
+}
+
+static int decode_error(ugvc_ctx* ctx, unsigned long long e) {
+    if (e == UGVC_NO_ERROR) return UGVC_OK;
+    ctx->err_record = (int64_t)(e >> 24);
+    const int col = (int)((e >> 8) & 0xFFFF);
+    ctx->err_column = col == 0xFFFF ? -1 : col;
+    ctx->err_reason = (int32_t)(e & 0xFF);
+    static const char* names[] = {"none",
+                                  "null feature value (the reference's _validate_data asserts)",
+                                  "value the reference transformer raises on (unknown category / ragged or absent tuple)",
+                                  "more elements than the fitted width / more records than reserved",
+                                  "numeric literal outside the exact-parse range",
+                                  "malformed line (fewer than 8 columns or batch not newline-terminated)"};
+    char buf[256];
+    snprintf(buf, sizeof(buf), "data error at record %lld, feature column %d: %s", (long long)ctx->err_record,
+             ctx->err_column, names[ctx->err_reason < 6 ? ctx->err_reason : 0]);
+    ctx->err = buf;
+    return UGVC_E_DATA;
+}
+
+extern "C" int ugvc_collect_batch(ugvc_ctx* ctx, int lane, uint8_t* out_low_score, float* out_probs, double* out_qual,
+                                  ugvc_recinfo* out_recinfo, int64_t* out_line_start, size_t capacity_records,
+                                  int64_t* out_n_records) {
+    if (!ctx) return UGVC_E_ARG;
+    if (lane < 0 || lane >= (int)ctx->lanes.size()) return fail(ctx, UGVC_E_ARG, "collect: lane out of range");
+    Lane& l = ctx->lanes[lane];
+    if (!l.submitted) return fail(ctx, UGVC_E_STATE, "collect: nothing submitted on this lane");
+    CU(cudaSetDevice(ctx->device));
+    l.submitted = false;
+    CU(cudaStreamSynchronize(l.stream));
+    const int64_t n = *l.h_n;
+    l.last_n = n;
+    if (out_n_records) *out_n_records = n;
+    if (ctx->timing) {
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ctx->stage_ms[i], l.ev[i], l.ev[i + 1]);
+    }
+    const int rc = decode_error(ctx, *l.h_err);
+    if (rc) return rc;
+    if ((size_t)n > capacity_records) return fail(ctx, UGVC_E_ARG, "collect: output capacity smaller than the record count");
+    const int K = ctx->plan.h.n_classes;
+    if (n > 0) {
+        if (out_low_score) CU(cudaMemcpyAsync(out_low_score, l.b.low_score, (size_t)n, cudaMemcpyDeviceToHost, l.stream));
+        if (out_probs) CU(cudaMemcpyAsync(out_probs, l.b.probs, (size_t)n * K * sizeof(float), cudaMemcpyDeviceToHost, l.stream));
+        if (out_qual) CU(cudaMemcpyAsync(out_qual, l.b.qual, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, l.stream));
+        if (out_recinfo) CU(cudaMemcpyAsync(out_recinfo, l.b.recinfo, (size_t)n * sizeof(ugvc_recinfo), cudaMemcpyDeviceToHost, l.stream));
+    }
+    if (out_line_start) CU(cudaMemcpyAsync(out_line_start, l.b.line_start, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, l.stream));
+    CU(cudaStreamSynchronize(l.stream));
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_filter_batch(ugvc_ctx* ctx, const uint8_t* vcf_text, size_t n_bytes, double threshold,
+                                 uint8_t* out_low_score, float* out_probs, double* out_qual,
+                                 ugvc_recinfo* out_recinfo, int64_t* out_line_start, size_t capacity_records,
+                                 int64_t* out_n_records) {
+    int rc = ugvc_submit_batch(ctx, 0, vcf_text, n_bytes, threshold);
+    if (rc) return rc;
+    return ugvc_collect_batch(ctx, 0, out_low_score, out_probs, out_qual, out_recinfo, out_line_start,
+                              capacity_records, out_n_records);
+}
+
+extern "C" int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n_bytes, double threshold,
+                                  uint8_t* d_low_score, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
+                                  int64_t* d_line_start, size_t capacity_records, int64_t* d_n_records, void* stream) {
+    if (!ctx) return UGVC_E_ARG;
+    if (!ctx->has_plan || ctx->lanes.empty()) return fail(ctx, UGVC_E_STATE, "filter_device: load a plan and reserve first");
+    if (n_bytes > ctx->cap_bytes) return fail(ctx, UGVC_E_ARG, "filter_device: batch larger than the reserved max_bytes");
+    if (!d_text || !d_low_score || !d_probs || !d_qual) return fail(ctx, UGVC_E_ARG, "filter_device: null device pointer");
+    CU(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[0];
+    if (capacity_records == 0 || capacity_records > l.b.cap_records)
+        return fail(ctx, UGVC_E_ARG, "filter_device: capacity_records must be in (0, reserved max_records]");
+    const size_t line_cap = capacity_records;
+    if (!d_line_start) d_line_start = l.b.line_start;
+    if (!d_recinfo) d_recinfo = l.b.recinfo;
+    if (!d_n_records) d_n_records = l.b.n_records;
+    cudaStream_t st = stream ? (cudaStream_t)stream : l.stream;
+    return enqueue_kernels(ctx, l, d_text, n_bytes, threshold, d_low_score, d_probs, d_qual, d_recinfo, d_line_start,
+                           line_cap, d_n_records, st);
+}
+
+extern "C" int ugvc_device_status(ugvc_ctx* ctx, void* stream) {
+    // blocking: surfaces data errors of the last ugvc_filter_device call
+    if (!ctx || ctx->lanes.empty()) return UGVC_E_STATE;
+    CU(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : l.stream;
+    CU(cudaStreamSynchronize(st));
+    unsigned long long e;
+    CU(cudaMemcpy(&e, l.d_err, sizeof(e), cudaMemcpyDeviceToHost));
+    if (ctx->timing)
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ctx->stage_ms[i], l.ev[i], l.ev[i + 1]);
+    return decode_error(ctx, e);
+}
+
+extern "C" int ugvc_counts_reset(ugvc_ctx* ctx) {
+    if (!ctx) return UGVC_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(ctx->d_counts, 0, 4 * sizeof(long long)));
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_counts_get(ugvc_ctx* ctx, ugvc_counts* out) {
+    if (!ctx || !out) return UGVC_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    long long c[4];
+    CU(cudaMemcpy(c, ctx->d_counts, sizeof(c), cudaMemcpyDeviceToHost));
+    out->n_records = c[0];
+    out->n_low_score = c[1];
+    out->n_pass = c[2];
+    out->n_cg = c[3];
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_counts_device_ptr(ugvc_ctx* ctx, int64_t** d_counts) {
+    if (!ctx || !d_counts) return UGVC_E_ARG;
+    *d_counts = reinterpret_cast<int64_t*>(ctx->d_counts);
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_debug_raw(ugvc_ctx* ctx, int lane, uint32_t* out, size_t capacity_words) {
+    if (!ctx || lane < 0 || lane >= (int)ctx->lanes.size()) return UGVC_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[lane];
+    const size_t n = (size_t)l.last_n, S = ctx->plan.h.n_slots;
+    if (capacity_words < n * S) return fail(ctx, UGVC_E_ARG, "debug_raw: capacity too small");
+    CU(cudaStreamSynchronize(l.stream));
+    if (n) CU(cudaMemcpy2D(out, n * 4, l.b.raw, l.b.cap_records * 4, n * 4, S, cudaMemcpyDeviceToHost));
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_debug_features(ugvc_ctx* ctx, int lane, float* out, size_t capacity_floats) {
+    if (!ctx || lane < 0 || lane >= (int)ctx->lanes.size()) return UGVC_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[lane];
+    const size_t n = (size_t)l.last_n, F = ctx->plan.h.n_features;
+    if (capacity_floats < n * F) return fail(ctx, UGVC_E_ARG, "debug_features: capacity too small");
+    CU(cudaStreamSynchronize(l.stream));
+    if (n) CU(cudaMemcpy2D(out, n * 4, l.b.feats, l.b.cap_records * 4, n * 4, F, cudaMemcpyDeviceToHost));
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_last_data_error(const ugvc_ctx* ctx, int64_t* record, int32_t* column, int32_t* reason) {
+    if (!ctx) return UGVC_E_ARG;
+    if (record) *record = ctx->err_record;
+    if (column) *column = ctx->err_column;
+    if (reason) *reason = ctx->err_reason;
+    return UGVC_OK;
+}
+
+extern "C" int64_t ugvc_launch_count(const ugvc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ugvc_enable_stage_timing(ugvc_ctx* ctx, int on) {
+    if (!ctx) return UGVC_E_ARG;
+    ctx->timing = on != 0;
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_stage_ms(ugvc_ctx* ctx, float out_ms[4]) {
+    if (!ctx || !out_ms) return UGVC_E_ARG;
+    for (int i = 0; i < 4; ++i) out_ms[i] = ctx->stage_ms[i];
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_host_alloc(void** out, size_t n_bytes) {
+    // pinned host memory for the host-buffer API (H2D/D2H at full PCIe rate)
+    ugvc_ctx* ctx = nullptr;
+    if (!out) return UGVC_E_ARG;
+    CU(cudaHostAlloc(out, n_bytes, cudaHostAllocDefault));
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_host_free(void* p) {
+    ugvc_ctx* ctx = nullptr;
+    CU(cudaFreeHost(p));
+    return UGVC_OK;
+}
+
+// used by synth_kernel.cu
+int ugvc_ctx_device(const ugvc_ctx* ctx) { return ctx->device; }
+int ugvc_ctx_sm_count(const ugvc_ctx* ctx) { return ctx->sm_count; }
+void ugvc_ctx_count_launches(ugvc_ctx* ctx, int n) { ctx->launches += n; }
+cudaStream_t ugvc_ctx_default_stream(ugvc_ctx* ctx) { return ctx->lanes.empty() ? nullptr : ctx->lanes[0].stream; }
+int ugvc_ctx_fail(ugvc_ctx* ctx, int code, const char* msg) { return fail(ctx, code, msg); }

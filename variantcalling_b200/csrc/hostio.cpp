@@ -1,0 +1,476 @@
+// hostio.cpp -- host side of the container formats around the hot path.
+//
+// The reference reads and writes bgzip'ed VCF through htslib (pysam.VariantFile at
+// filter_variants_pipeline.py:106,115) and re-serialises every record in Python
+// (filter_variants_pipeline.py:188-228).  Here: multi-threaded BGZF inflate/deflate over
+// zlib, and a record splicer that rewrites FILTER / QUAL / INFO in the original line bytes
+// following the same rules.  Plain C++17 + pthreads, no CUDA.
+#include <stdio.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ugvc_b200.h"
+
+namespace {
+
+struct Block {
+    uint64_t coff;   // file offset of the block
+    uint32_t csize;  // whole block size
+    uint32_t isize;  // uncompressed size
+    uint64_t uoff;   // uncompressed offset of the block start
+};
+
+bool read_all(FILE* f, uint64_t off, void* dst, size_t n) {
+    if (fseeko(f, (off_t)off, SEEK_SET) != 0) return false;
+    return fread(dst, 1, n, f) == n;
+}
+
+// Parse one BGZF block header at p (>= 18 bytes available); returns total block size or 0.
+uint32_t bgzf_block_size(const uint8_t* p, size_t avail) {
+    if (avail < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
+    const uint32_t xlen = p[10] | (p[11] << 8);
+    if (avail < 12 + xlen) return 0;
+    const uint8_t* x = p + 12;
+    const uint8_t* xe = x + xlen;
+    while (x + 4 <= xe) {
+        const uint32_t slen = x[2] | (x[3] << 8);
+        if (x[0] == 'B' && x[1] == 'C' && slen == 2 && x + 6 <= xe) return (uint32_t)(x[4] | (x[5] << 8)) + 1;
+        x += 4 + slen;
+    }
+    return 0;
+}
+
+int scan_blocks(FILE* f, uint64_t file_size, uint64_t begin, uint64_t end, std::vector<Block>& blocks) {
+    uint64_t off = begin, uoff = 0;
+    uint8_t hdr[18 + 256];
+    while (off < end && off < file_size) {
+        const size_t want = (size_t)std::min<uint64_t>(sizeof(hdr), file_size - off);
+        if (!read_all(f, off, hdr, want)) return UGVC_E_IO;
+        const uint32_t bs = bgzf_block_size(hdr, want);
+        if (bs < 26 || off + bs > file_size) return UGVC_E_IO;
+        uint8_t tail[4];
+        if (!read_all(f, off + bs - 4, tail, 4)) return UGVC_E_IO;
+        const uint32_t isize = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
+        blocks.push_back({off, bs, isize, uoff});
+        uoff += isize;
+        off += bs;
+    }
+    return UGVC_OK;
+}
+
+bool inflate_block(const uint8_t* src, uint32_t csize, uint8_t* dst, uint32_t isize) {
+    const uint32_t xlen = src[10] | (src[11] << 8);
+    const uint32_t hdr = 12 + xlen;
+    if (csize < hdr + 8) return false;
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<Bytef*>(src + hdr);
+    zs.avail_in = csize - hdr - 8;
+    zs.next_out = dst;
+    zs.avail_out = isize;
+    const int rc = inflate(&zs, Z_FINISH);
+    const bool ok = (rc == Z_STREAM_END) && zs.total_out == isize;
+    inflateEnd(&zs);
+    return ok;
+}
+
+int clamp_threads(int n) {
+    if (n <= 0) n = (int)std::thread::hardware_concurrency();
+    if (n < 1) n = 1;
+    if (n > 128) n = 128;
+    return n;
+}
+
+const uint8_t BGZF_EOF[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43,
+                              0x02, 0,    0x1b, 0,    0x03, 0, 0, 0, 0, 0, 0, 0,    0,    0};
+constexpr size_t BGZF_BLOCK_DATA = 0xff00;
+
+}  // namespace
+
+extern "C" int64_t ugvc_bgzf_uncompressed_size(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return UGVC_E_IO;
+    fseeko(f, 0, SEEK_END);
+    const uint64_t fs = (uint64_t)ftello(f);
+    std::vector<Block> blocks;
+    const int rc = scan_blocks(f, fs, 0, fs, blocks);
+    fclose(f);
+    if (rc) return rc;
+    return blocks.empty() ? 0 : (int64_t)(blocks.back().uoff + blocks.back().isize);
+}
+
+extern "C" int ugvc_bgzf_inflate_file(const char* path, uint64_t voff_begin, uint64_t voff_end, uint8_t* out,
+                                      size_t capacity, size_t* out_bytes, int n_threads) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return UGVC_E_IO;
+    fseeko(f, 0, SEEK_END);
+    const uint64_t fs = (uint64_t)ftello(f);
+    const uint64_t cb = voff_begin >> 16, ub = voff_begin & 0xffff;
+    const bool to_eof = (voff_end == 0 || voff_end == ~0ull);
+    const uint64_t ce = to_eof ? fs : (voff_end >> 16), ue = to_eof ? 0 : (voff_end & 0xffff);
+    std::vector<Block> blocks;
+    // blocks in [cb, ce) plus the block at ce when it is only partly wanted
+    int rc = scan_blocks(f, fs, cb, ue ? ce + 1 : ce, blocks);
+    if (rc) {
+        fclose(f);
+        return rc;
+    }
+    if (blocks.empty()) {
+        fclose(f);
+        if (out_bytes) *out_bytes = 0;
+        return UGVC_OK;
+    }
+    const uint64_t total_u = blocks.back().uoff + blocks.back().isize;
+    uint64_t last_cut = 0;  // bytes to drop from the tail of the last block
+    if (ue && blocks.back().coff == ce) {
+        if (ue > blocks.back().isize) {
+            fclose(f);
+            return UGVC_E_IO;
+        }
+        last_cut = blocks.back().isize - ue;
+    }
+    if (ub > blocks.front().isize || ub + last_cut > total_u) {
+        fclose(f);
+        return UGVC_E_IO;
+    }
+    const uint64_t produced = total_u - ub - last_cut;
+    if (out_bytes) *out_bytes = (size_t)produced;
+    if (produced > capacity) {
+        fclose(f);
+        return UGVC_E_ARG;
+    }
+    // read the compressed range once
+    const uint64_t c0 = blocks.front().coff, c1 = blocks.back().coff + blocks.back().csize;
+    std::vector<uint8_t> comp((size_t)(c1 - c0));
+    const bool ok_read = read_all(f, c0, comp.data(), comp.size());
+    fclose(f);
+    if (!ok_read) return UGVC_E_IO;
+    n_threads = clamp_threads(n_threads);
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    auto work = [&]() {
+        std::vector<uint8_t> tmp;
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= blocks.size() || failed.load()) break;
+            const Block& b = blocks[i];
+            if (b.isize == 0) continue;
+            const uint8_t* src = comp.data() + (b.coff - c0);
+            const bool first = (i == 0 && ub > 0), last = (i + 1 == blocks.size() && last_cut > 0);
+            if (!first && !last) {
+                if (!inflate_block(src, b.csize, out + (b.uoff - ub), b.isize)) failed = 1;
+            } else {
+                tmp.resize(b.isize);
+                if (!inflate_block(src, b.csize, tmp.data(), b.isize)) {
+                    failed = 1;
+                    continue;
+                }
+                const uint64_t s = first ? ub : 0, e = b.isize - (last ? last_cut : 0);
+                if (e > s) memcpy(out + (b.uoff + s - ub), tmp.data() + s, (size_t)(e - s));
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    return failed.load() ? UGVC_E_IO : UGVC_OK;
+}
+
+extern "C" int ugvc_bgzf_deflate_to_file(const char* path, const char* mode, const uint8_t* data, size_t n_bytes,
+                                         int level, int write_eof, int n_threads, uint64_t* out_compressed_bytes,
+                                         uint32_t* out_block_csize, size_t block_capacity, size_t* out_n_blocks) {
+    const size_t n_blocks = (n_bytes + BGZF_BLOCK_DATA - 1) / BGZF_BLOCK_DATA;
+    if (out_n_blocks) *out_n_blocks = n_blocks;
+    if (out_block_csize && block_capacity < n_blocks) return UGVC_E_ARG;
+    std::vector<std::vector<uint8_t>> outb(n_blocks);
+    n_threads = clamp_threads(n_threads);
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    if (level < 0 || level > 9) level = 6;
+    auto work = [&]() {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
+            failed = 1;
+            return;
+        }
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n_blocks) break;
+            const size_t off = i * BGZF_BLOCK_DATA;
+            const size_t len = std::min(BGZF_BLOCK_DATA, n_bytes - off);
+            std::vector<uint8_t>& o = outb[i];
+            o.resize(18 + deflateBound(&zs, (uLong)len) + 8);
+            deflateReset(&zs);
+            zs.next_in = const_cast<Bytef*>(data + off);
+            zs.avail_in = (uInt)len;
+            zs.next_out = o.data() + 18;
+            zs.avail_out = (uInt)(o.size() - 18 - 8);
+            if (deflate(&zs, Z_FINISH) != Z_STREAM_END || 18 + zs.total_out + 8 > 65536) {
+                // incompressible: store
+                deflateEnd(&zs);
+                z_stream z0;
+                memset(&z0, 0, sizeof(z0));
+                deflateInit2(&z0, 0, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+                z0.next_in = const_cast<Bytef*>(data + off);
+                z0.avail_in = (uInt)len;
+                z0.next_out = o.data() + 18;
+                z0.avail_out = (uInt)(o.size() - 18 - 8);
+                const int rc0 = deflate(&z0, Z_FINISH);
+                zs.total_out = z0.total_out;
+                deflateEnd(&z0);
+                deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+                if (rc0 != Z_STREAM_END || 18 + zs.total_out + 8 > 65536) {
+                    failed = 1;
+                    break;
+                }
+            }
+            const uint32_t clen = (uint32_t)zs.total_out;
+            const uint32_t bsize = 18 + clen + 8;
+            static const uint8_t H[12] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0};
+            memcpy(o.data(), H, 12);
+            o[12] = 'B';
+            o[13] = 'C';
+            o[14] = 2;
+            o[15] = 0;
+            o[16] = (uint8_t)((bsize - 1) & 0xff);
+            o[17] = (uint8_t)((bsize - 1) >> 8);
+            const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), data + off, (uInt)len);
+            uint8_t* t = o.data() + 18 + clen;
+            t[0] = crc & 0xff; t[1] = (crc >> 8) & 0xff; t[2] = (crc >> 16) & 0xff; t[3] = (crc >> 24) & 0xff;
+            t[4] = len & 0xff; t[5] = (len >> 8) & 0xff; t[6] = (len >> 16) & 0xff; t[7] = (len >> 24) & 0xff;
+            o.resize(bsize);
+        }
+        deflateEnd(&zs);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    if (failed.load()) return UGVC_E_IO;
+    FILE* f = fopen(path, (mode && mode[0] == 'a') ? "ab" : "wb");
+    if (!f) return UGVC_E_IO;
+    uint64_t total = 0;
+    for (size_t i = 0; i < n_blocks; ++i) {
+        if (fwrite(outb[i].data(), 1, outb[i].size(), f) != outb[i].size()) {
+            fclose(f);
+            return UGVC_E_IO;
+        }
+        if (out_block_csize) out_block_csize[i] = (uint32_t)outb[i].size();
+        total += outb[i].size();
+    }
+    if (write_eof) {
+        if (fwrite(BGZF_EOF, 1, 28, f) != 28) {
+            fclose(f);
+            return UGVC_E_IO;
+        }
+        total += 28;
+    }
+    if (fclose(f) != 0) return UGVC_E_IO;
+    if (out_compressed_bytes) *out_compressed_bytes = total;
+    return UGVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// record splicer: filter_variants_pipeline.py:188-228 on the original line bytes
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct Piece {
+    const uint8_t* p;
+    size_t n;
+};
+
+inline bool piece_is(const Piece& a, const char* s) {
+    const size_t n = strlen(s);
+    return a.n == n && memcmp(a.p, s, n) == 0;
+}
+
+// htslib prints INFO/QUAL floats (float32) with %g semantics
+int format_g(double q, char* buf, size_t cap) { return snprintf(buf, cap, "%g", (double)(float)q); }
+
+void splice_one(const uint8_t* line, size_t len, const ugvc_recinfo& ri, bool with_model, bool low, double qual,
+                bool overwrite_qual, const char* bl, size_t bl_len, std::string& out) {
+    size_t off[4] = {ri.qual_off, ri.filter_off, ri.info_off, ri.format_off};
+    if (ri.qual_off == 0xFFFF || ri.filter_off == 0xFFFF || ri.info_off == 0xFFFF || ri.format_off == 0xFFFF) {
+        // long line: recount the tabs
+        size_t tabs = 0, k = 0;
+        for (size_t i = 0; i < len && k < 4; ++i)
+            if (line[i] == '\t') {
+                ++tabs;
+                if (tabs >= 5) off[k++] = i + 1;
+            }
+        while (k < 4) off[k++] = len + 1;
+    }
+    const size_t q0 = off[0], f0 = off[1], i0 = off[2], x0 = off[3];  // x0: one past the tab after INFO
+    if (!(q0 <= f0 && f0 <= i0 && i0 <= x0 && x0 <= len + 1) || q0 == 0) {
+        out.append(reinterpret_cast<const char*>(line), len);  // malformed: pass through
+        out.push_back('\n');
+        return;
+    }
+    char num[48];
+    // columns 1-5 incl. trailing tab
+    out.append(reinterpret_cast<const char*>(line), q0);
+    // QUAL
+    if (with_model && overwrite_qual) out.append(num, (size_t)format_g(qual, num, sizeof(num)));
+    else out.append(reinterpret_cast<const char*>(line + q0), f0 - 1 - q0);
+    out.push_back('\t');
+    // FILTER
+    {
+        const uint8_t* fp = line + f0;
+        const size_t fl = i0 - 1 - f0;
+        size_t written = 0;
+        bool has_low = false;
+        if (!(fl == 1 && fp[0] == '.')) {
+            size_t s = 0;
+            for (size_t e = 0; e <= fl; ++e) {
+                if (e == fl || fp[e] == ';') {
+                    Piece k{fp + s, e - s};
+                    const bool drop = k.n == 0 || (with_model && low && piece_is(k, "PASS"));
+                    if (!drop) {
+                        if (written) out.push_back(';');
+                        out.append(reinterpret_cast<const char*>(k.p), k.n);
+                        ++written;
+                        has_low |= piece_is(k, "LOW_SCORE");
+                    }
+                    s = e + 1;
+                }
+            }
+        }
+        if (with_model && low && !has_low) {
+            if (written) out.push_back(';');
+            out.append("LOW_SCORE");
+            ++written;
+        }
+        if (!written) out.append("PASS");
+    }
+    out.push_back('\t');
+    // INFO
+    {
+        const uint8_t* ip = line + i0;
+        const size_t il = x0 - 1 - i0;
+        size_t written = 0;
+        bool done_score = !with_model, done_bl = (bl_len == 0);
+        std::string score;
+        if (with_model) {
+            score = "TREE_SCORE=";
+            score.append(num, (size_t)format_g(qual, num, sizeof(num)));
+        }
+        std::string blv;
+        if (bl_len) {
+            // ';'-joined blacklist annotations, PASS entries dropped (filter_variants_pipeline.py:217-224)
+            size_t s = 0;
+            for (size_t e = 0; e <= bl_len; ++e)
+                if (e == bl_len || bl[e] == ';') {
+                    if (e > s && !(e - s == 4 && memcmp(bl + s, "PASS", 4) == 0)) {
+                        blv += blv.empty() ? "BLACKLST=" : ",";
+                        blv.append(bl + s, e - s);
+                    }
+                    s = e + 1;
+                }
+            if (blv.empty()) done_bl = true;
+        }
+        if (!(il == 1 && ip[0] == '.')) {
+            size_t s = 0;
+            for (size_t e = 0; e <= il; ++e) {
+                if (e == il || ip[e] == ';') {
+                    Piece k{ip + s, e - s};
+                    if (k.n) {
+                        if (written) out.push_back(';');
+                        if (!done_score && k.n >= 11 && memcmp(k.p, "TREE_SCORE=", 11) == 0) {
+                            out += score;
+                            done_score = true;
+                        } else if (!done_bl && k.n >= 9 && memcmp(k.p, "BLACKLST=", 9) == 0) {
+                            out += blv;
+                            done_bl = true;
+                        } else
+                            out.append(reinterpret_cast<const char*>(k.p), k.n);
+                        ++written;
+                    }
+                    s = e + 1;
+                }
+            }
+        }
+        if (!done_score) {
+            if (written) out.push_back(';');
+            out += score;
+            ++written;
+        }
+        if (!done_bl) {
+            if (written) out.push_back(';');
+            out += blv;
+            ++written;
+        }
+        if (!written) out.push_back('.');
+    }
+    // FORMAT + samples (with the tab before them), untouched
+    if (x0 <= len) {
+        out.push_back('\t');
+        out.append(reinterpret_cast<const char*>(line + x0), len - x0);
+    }
+    out.push_back('\n');
+}
+
+}  // namespace
+
+extern "C" int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_start, const ugvc_recinfo* recinfo,
+                                       const uint8_t* low_score, const double* qual, int64_t n_records,
+                                       int overwrite_qual, int with_model, const char* blacklist_text,
+                                       const int64_t* blacklist_off, uint8_t* out, size_t capacity,
+                                       int64_t* out_line_start, int n_threads) {
+    if (!text || !line_start || !recinfo || n_records < 0) return UGVC_E_ARG;
+    if (with_model && (!low_score || !qual)) return UGVC_E_ARG;
+    n_threads = clamp_threads(n_threads);
+    if ((int64_t)n_threads > n_records / 4096 + 1) n_threads = (int)(n_records / 4096 + 1);
+    std::vector<std::string> parts(n_threads);
+    std::vector<std::vector<int64_t>> lens(n_threads);
+    auto work = [&](int t) {
+        const int64_t lo = n_records * t / n_threads, hi = n_records * (t + 1) / n_threads;
+        std::string& o = parts[t];
+        o.reserve((size_t)((line_start[hi] - line_start[lo]) + (hi - lo) * 40));
+        if (out_line_start) lens[t].reserve((size_t)(hi - lo));
+        for (int64_t i = lo; i < hi; ++i) {
+            const size_t before = o.size();
+            const uint8_t* line = text + line_start[i];
+            const size_t len = (size_t)(line_start[i + 1] - line_start[i] - 1);
+            const char* bl = nullptr;
+            size_t bl_len = 0;
+            if (blacklist_text && blacklist_off) {
+                bl = blacklist_text + blacklist_off[i];
+                bl_len = (size_t)(blacklist_off[i + 1] - blacklist_off[i]);
+            }
+            splice_one(line, len, recinfo[i], with_model != 0, with_model && low_score[i] != 0,
+                       with_model ? qual[i] : 0.0, overwrite_qual != 0, bl, bl_len, o);
+            if (out_line_start) lens[t].push_back((int64_t)(o.size() - before));
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    size_t total = 0;
+    for (auto& p : parts) total += p.size();
+    if (total > capacity) return UGVC_E_ARG;
+    size_t off = 0;
+    int64_t rec = 0;
+    for (int t = 0; t < n_threads; ++t) {
+        memcpy(out + off, parts[t].data(), parts[t].size());
+        if (out_line_start) {
+            int64_t o2 = (int64_t)off;
+            for (int64_t l : lens[t]) {
+                out_line_start[rec++] = o2;
+                o2 += l;
+            }
+        }
+        off += parts[t].size();
+    }
+    if (out_line_start) out_line_start[n_records] = (int64_t)total;
+    return (int64_t)total;
+}

@@ -1,0 +1,67 @@
+// kernels.cuh -- device-side plan view and kernel launch prototypes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ugvc_b200.h"
+#include "plan.h"
+
+// Device view of a loaded plan (passed to kernels by value).
+struct DevPlan {
+    PlanHeader h;
+    const PlanTag* tags;
+    const PlanSlot* slots;
+    const PlanDict* dicts;
+    const PlanString* strings;
+    const PlanFeature* feats;
+    const PlanCheck* checks;
+    const double* coef;
+    const double* intercept;
+    const uint32_t* tree_root;
+    const uint8_t* tree_out;
+    const PlanNode* nodes;
+    const double* leaves;
+    const uint8_t* htab;       // 256-entry open-addressing table: tag index or 0xFF
+    uint32_t first_fixed_slot; // slots [first_fixed_slot, n_slots) are TAG_FIXED
+};
+
+// Error word: smaller is earlier.  (record << 24) | (column << 8) | reason
+#define UGVC_NO_ERROR 0xFFFFFFFFFFFFFFFFull
+__host__ __device__ inline unsigned long long ugvc_pack_error(long long rec, int col, int reason) {
+    return ((unsigned long long)rec << 24) | ((unsigned long long)(col & 0xFFFF) << 8) | (unsigned)(reason & 0xFF);
+}
+
+struct LaneBuffers {
+    // sizes
+    size_t cap_bytes, cap_records;
+    // K0
+    uint32_t* chunk_first;     // per 4 KiB chunk: records before it
+    int64_t* line_start;       // [cap_records + 1]
+    int64_t* n_records;        // device scalar
+    // K1
+    uint32_t* raw;             // [n_slots][cap_records]
+    ugvc_recinfo* recinfo;     // [cap_records]
+    // K2
+    float* feats;              // [n_features][cap_records]
+    // K3
+    uint8_t* low_score;        // [cap_records]
+    float* probs;              // [cap_records][n_classes]
+    double* qual;              // [cap_records]
+};
+
+#define K0_CHUNK_BYTES 4096
+
+void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* chunk_first, int64_t* line_start,
+               size_t cap_records, int64_t* d_n_records, unsigned long long* d_err, int sm_count,
+               cudaStream_t st);
+void launch_k1(const DevPlan& plan, const uint8_t* d_text, const int64_t* line_start, const int64_t* d_n_records,
+               uint32_t* raw, size_t row_stride, ugvc_recinfo* recinfo, unsigned long long* d_err,
+               long long* d_counts, int sm_count, cudaStream_t st);
+void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, const int64_t* d_n_records, float* feats,
+               unsigned long long* d_err, int sm_count, cudaStream_t st);
+void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const int64_t* d_n_records,
+               double threshold, uint8_t* low_score, float* probs, double* qual, long long* d_counts,
+               int sm_count, cudaStream_t st);
+size_t k1_smem_bytes(const DevPlan& plan);
+size_t k3_smem_bytes(const DevPlan& plan);
+cudaError_t kernels_configure(const DevPlan& plan);

@@ -1,0 +1,283 @@
+"""ctypes binding of ``libugvc_b200.so`` (C ABI: ``include/ugvc_b200.h``).
+
+There is no CPU fallback: importing the library needs the built shared object,
+and creating a :class:`Context` needs a CUDA device -- both fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libugvc_b200.so")
+
+UGVC_OK, UGVC_E_CUDA, UGVC_E_ARG, UGVC_E_PLAN, UGVC_E_DATA, UGVC_E_IO, UGVC_E_STATE = 0, -1, -2, -3, -4, -5, -6
+
+
+class UgvcError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[ugvc {code}] {message}")
+        self.code = code
+        self.message = message
+
+
+class UgvcDataError(UgvcError, AssertionError):
+    """The reference pipeline would raise on this input (null feature, unknown
+    category, ragged tuple ...); mirrors ``_validate_data``'s AssertionError."""
+
+
+RECINFO_DTYPE = np.dtype([("pos", "<i4"), ("qual_off", "<u2"), ("filter_off", "<u2"), ("info_off", "<u2"),
+                          ("format_off", "<u2"), ("flags", "<u4")])
+
+
+class Counts(C.Structure):
+    _fields_ = [("n_records", C.c_int64), ("n_low_score", C.c_int64), ("n_pass", C.c_int64), ("n_cg", C.c_int64)]
+
+
+_vp, _sz, _i64p = C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); every symbol declared in include/ugvc_b200.h
+SIGNATURES = {
+    "ugvc_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "ugvc_free": (None, [_vp]),
+    "ugvc_last_error": (C.c_char_p, [_vp]),
+    "ugvc_version": (C.c_int, []),
+    "ugvc_load_plan": (C.c_int, [_vp, _vp, _sz]),
+    "ugvc_plan_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ugvc_reserve": (C.c_int, [_vp, _sz, _sz, C.c_int]),
+    "ugvc_filter_batch": (C.c_int, [_vp, _vp, _sz, C.c_double, _vp, _vp, _vp, _vp, _vp, _sz, _i64p]),
+    "ugvc_submit_batch": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_double]),
+    "ugvc_collect_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _i64p]),
+    "ugvc_filter_device": (C.c_int, [_vp, _vp, _sz, C.c_double, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ugvc_device_status": (C.c_int, [_vp, _vp]),
+    "ugvc_host_alloc": (C.c_int, [C.POINTER(_vp), _sz]),
+    "ugvc_host_free": (C.c_int, [_vp]),
+    "ugvc_counts_reset": (C.c_int, [_vp]),
+    "ugvc_counts_get": (C.c_int, [_vp, C.POINTER(Counts)]),
+    "ugvc_counts_device_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "ugvc_debug_raw": (C.c_int, [_vp, C.c_int, _vp, _sz]),
+    "ugvc_debug_features": (C.c_int, [_vp, C.c_int, _vp, _sz]),
+    "ugvc_last_data_error": (C.c_int, [_vp, _i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ugvc_launch_count": (C.c_int64, [_vp]),
+    "ugvc_enable_stage_timing": (C.c_int, [_vp, C.c_int]),
+    "ugvc_stage_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "ugvc_synth_device": (C.c_int, [_vp, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp, _sz,
+                                    C.POINTER(_sz), _vp]),
+    "ugvc_synth_header": (C.c_int64, [C.c_int, C.c_char_p, _sz]),
+    "ugvc_bgzf_inflate_file": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, _vp, _sz, C.POINTER(_sz), C.c_int]),
+    "ugvc_bgzf_uncompressed_size": (C.c_int64, [C.c_char_p]),
+    "ugvc_bgzf_deflate_to_file": (C.c_int, [C.c_char_p, C.c_char_p, _vp, _sz, C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(C.c_uint64), _vp, _sz, C.POINTER(_sz)]),
+    "ugvc_splice_records": (C.c_int64, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp,
+                                        _sz, _vp, C.c_int]),
+}
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the shared library (once).  Raises if it was not built."""
+    global _lib  # noqa: PLW0603
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"(make -C variantcalling_b200/csrc).  There is no CPU fallback for the hot path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    raise TypeError(type(a))
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a numpy uint8 array."""
+
+    def __init__(self, n_bytes: int):
+        lib = load_library()
+        p = C.c_void_p()
+        rc = lib.ugvc_host_alloc(C.byref(p), max(1, n_bytes))
+        if rc:
+            raise UgvcError(rc, lib.ugvc_last_error(None).decode())
+        self._p = p
+        self.nbytes = n_bytes
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(1, n_bytes),))
+
+    @property
+    def ptr(self) -> int:
+        return self._p.value
+
+    def free(self):
+        if self._p:
+            self.array = None
+            load_library().ugvc_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:  # noqa: BLE001, S110
+            pass
+
+
+class Context:
+    """One GPU context (one per process/GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.ugvc_init(device, C.byref(h))
+        if rc:
+            raise UgvcError(rc, self.lib.ugvc_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self.n_features = self.n_classes = self.n_slots = 0
+        self.cap_bytes = self.cap_records = 0
+
+    def _check(self, rc: int):
+        if rc == UGVC_OK:
+            return
+        msg = self.lib.ugvc_last_error(self.h).decode()
+        if rc == UGVC_E_DATA:
+            raise UgvcDataError(rc, msg)
+        raise UgvcError(rc, msg)
+
+    def close(self):
+        if self.h:
+            self.lib.ugvc_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001, S110
+            pass
+
+    # ---- setup
+    def load_plan(self, blob: bytes):
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        self._check(self.lib.ugvc_load_plan(self.h, _ptr(buf), buf.size))
+        f, k, s = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self.lib.ugvc_plan_info(self.h, C.byref(f), C.byref(k), C.byref(s)))
+        self.n_features, self.n_classes, self.n_slots = f.value, k.value, s.value
+
+    def reserve(self, max_bytes: int, max_records: int, n_pipeline: int = 1):
+        self._check(self.lib.ugvc_reserve(self.h, max_bytes, max_records, n_pipeline))
+        self.cap_bytes, self.cap_records = max_bytes, (max_records + 127) // 128 * 128
+
+    # ---- host-buffer hot path
+    def alloc_outputs(self, n_max: int, want_recinfo: bool = True) -> dict:
+        out = {"low_score": np.empty(n_max, np.uint8), "probs": np.empty((n_max, self.n_classes), np.float32),
+               "qual": np.empty(n_max, np.float64)}
+        if want_recinfo:
+            out["recinfo"] = np.empty(n_max, RECINFO_DTYPE)
+            out["line_start"] = np.empty(n_max + 1, np.int64)
+        return out
+
+    @staticmethod
+    def trim_outputs(out: dict, n: int) -> dict:
+        res = {k: (v[: n + 1] if k == "line_start" else v[:n]) for k, v in out.items()}
+        res["n_records"] = n
+        return res
+
+    def filter_batch(self, text, threshold: float = 30.0, want_recinfo: bool = True) -> dict:
+        """One batch of VCF data lines (bytes / uint8 array) -> dict of numpy results."""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else text
+        n_max = max(1, int(np.count_nonzero(buf == 10)))  # noqa: PLR2004
+        out = self.alloc_outputs(n_max, want_recinfo)
+        n = C.c_int64()
+        rc = self.lib.ugvc_filter_batch(self.h, _ptr(buf), buf.size, threshold, _ptr(out["low_score"]),
+                                        _ptr(out["probs"]), _ptr(out["qual"]), _ptr(out.get("recinfo")),
+                                        _ptr(out.get("line_start")), n_max, C.byref(n))
+        self._check(rc)
+        return self.trim_outputs(out, n.value)
+
+    def submit(self, lane: int, text_ptr, n_bytes: int, threshold: float = 30.0):
+        self._check(self.lib.ugvc_submit_batch(self.h, lane, _ptr(text_ptr), n_bytes, threshold))
+
+    def collect(self, lane: int, out: dict, capacity: int) -> int:
+        n = C.c_int64()
+        self._check(self.lib.ugvc_collect_batch(self.h, lane, _ptr(out.get("low_score")), _ptr(out.get("probs")),
+                                                _ptr(out.get("qual")), _ptr(out.get("recinfo")),
+                                                _ptr(out.get("line_start")), capacity, C.byref(n)))
+        return n.value
+
+    # ---- device-resident hot path (pointers are ints, e.g. torch.Tensor.data_ptr())
+    def filter_device(self, d_text: int, n_bytes: int, threshold: float, d_low: int, d_probs: int, d_qual: int,
+                      capacity: int, d_n_records: int = 0, stream: int = 0, d_recinfo: int = 0,
+                      d_line_start: int = 0):
+        self._check(self.lib.ugvc_filter_device(self.h, d_text, n_bytes, threshold, d_low, d_probs, d_qual,
+                                                d_recinfo or None, d_line_start or None, capacity,
+                                                d_n_records or None, stream or None))
+
+    def device_status(self, stream: int = 0):
+        self._check(self.lib.ugvc_device_status(self.h, stream or None))
+
+    def synth_device(self, seed: int, first: int, n: int, total: int, n_custom: int, d_text: int, capacity: int,
+                     stream: int = 0) -> int:
+        nb = C.c_size_t()
+        self._check(self.lib.ugvc_synth_device(self.h, seed, first, n, total, n_custom, d_text, capacity,
+                                               C.byref(nb), stream or None))
+        return nb.value
+
+    # ---- counters / introspection
+    def counts_reset(self):
+        self._check(self.lib.ugvc_counts_reset(self.h))
+
+    def counts(self) -> dict:
+        c = Counts()
+        self._check(self.lib.ugvc_counts_get(self.h, C.byref(c)))
+        return {"n_records": c.n_records, "n_low_score": c.n_low_score, "n_pass": c.n_pass, "n_cg": c.n_cg}
+
+    def counts_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.ugvc_counts_device_ptr(self.h, C.byref(p)))
+        return p.value
+
+    def debug_features(self, n: int, lane: int = 0) -> np.ndarray:
+        out = np.empty((self.n_features, max(1, n)), np.float32)
+        self._check(self.lib.ugvc_debug_features(self.h, lane, _ptr(out), out.size))
+        return out[:, :n]
+
+    def debug_raw(self, n: int, lane: int = 0) -> np.ndarray:
+        out = np.empty((self.n_slots, max(1, n)), np.uint32)
+        self._check(self.lib.ugvc_debug_raw(self.h, lane, _ptr(out), out.size))
+        return out[:, :n]
+
+    def last_data_error(self) -> tuple[int, int, int]:
+        r, c, k = C.c_int64(), C.c_int32(), C.c_int32()
+        self.lib.ugvc_last_data_error(self.h, C.byref(r), C.byref(c), C.byref(k))
+        return r.value, c.value, k.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.ugvc_launch_count(self.h))
+
+    def enable_stage_timing(self, on: bool = True):
+        self._check(self.lib.ugvc_enable_stage_timing(self.h, int(on)))
+
+    def stage_ms(self) -> list[float]:
+        arr = (C.c_float * 4)()
+        self._check(self.lib.ugvc_stage_ms(self.h, arr))
+        return list(arr)
+
+
+def synth_header(n_custom: int) -> str:
+    lib = load_library()
+    n = lib.ugvc_synth_header(n_custom, None, 0)
+    buf = C.create_string_buffer(int(n))
+    lib.ugvc_synth_header(n_custom, buf, n)
+    return buf.raw.decode()
