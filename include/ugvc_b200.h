@@ -134,10 +134,11 @@ int ugvc_last_data_error(const ugvc_ctx* ctx, int64_t* record, int32_t* column, 
 
 /* Number of kernel launches issued by this context since ugvc_init. */
 int64_t ugvc_launch_count(const ugvc_ctx* ctx);
-/* Device-side duration (ms) of each kernel stage of the last ugvc_filter_device /
- * submit on lane 0 when stage timing is enabled: out[0..3] = K0,K1,K2,K3. */
+/* Stage timing: while enabled every enqueue brackets K0,K1,K2,K3 with CUDA events on
+ * the launching stream; ugvc_stage_ms blocks and returns the summed device time (ms) of
+ * each stage over all enqueues since ugvc_enable_stage_timing(ctx, 1), and their count. */
 int ugvc_enable_stage_timing(ugvc_ctx* ctx, int on);
-int ugvc_stage_ms(ugvc_ctx* ctx, float out_ms[4]);
+int ugvc_stage_ms(ugvc_ctx* ctx, float out_ms[4], int64_t* out_n_calls);
 
 /* ---- synthetic input (bench / tests) ------------------------------------ */
 /* Generate `n_records` synthetic single-sample VCF data lines (SURVEY.md 8d

@@ -19,7 +19,8 @@ struct Lane {
     unsigned long long* d_err = nullptr;
     int64_t* h_n = nullptr;              // pinned
     unsigned long long* h_err = nullptr; // pinned
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pool;  // 5 events per timed enqueue
+    size_t ev_used = 0;
     size_t n_bytes = 0;
     bool submitted = false;
     int64_t last_n = 0;
@@ -99,7 +100,7 @@ static void free_lane(Lane& l) {
     cudaFree(l.d_err);
     if (l.h_n) cudaFreeHost(l.h_n);
     if (l.h_err) cudaFreeHost(l.h_err);
-    for (auto& ev : l.ev)
+    for (auto& ev : l.ev_pool)
         if (ev) cudaEventDestroy(ev);
     if (l.stream) cudaStreamDestroy(l.stream);
     l = Lane();
@@ -289,7 +290,6 @@ extern "C" int ugvc_reserve(ugvc_ctx* ctx, size_t max_bytes, size_t max_records,
         CU(cudaMalloc(&l.d_err, sizeof(unsigned long long)));
         CU(cudaHostAlloc(&l.h_n, sizeof(int64_t), cudaHostAllocDefault));
         CU(cudaHostAlloc(&l.h_err, sizeof(unsigned long long), cudaHostAllocDefault));
-        for (auto& ev : l.ev) CU(cudaEventCreate(&ev));
     }
     return UGVC_OK;
 }
@@ -300,18 +300,28 @@ static int enqueue_kernels(ugvc_ctx* ctx, Lane& l, const uint8_t* d_text, size_t
                            int64_t* d_line_start, size_t line_cap, int64_t* d_n_records, cudaStream_t st) {
     const DevPlan& p = ctx->plan;
     const bool timing = ctx->timing;
+    cudaEvent_t* ev = nullptr;
+    if (timing) {
+        if (l.ev_used + 5 > l.ev_pool.size()) {
+            const size_t old = l.ev_pool.size();
+            l.ev_pool.resize(old + 5 * 64, nullptr);
+            for (size_t i = old; i < l.ev_pool.size(); ++i) CU(cudaEventCreate(&l.ev_pool[i]));
+        }
+        ev = &l.ev_pool[l.ev_used];
+        l.ev_used += 5;
+    }
     CU(cudaMemsetAsync(l.d_err, 0xFF, sizeof(unsigned long long), st));
-    if (timing) CU(cudaEventRecord(l.ev[0], st));
+    if (timing) CU(cudaEventRecord(ev[0], st));
     launch_k0(d_text, n_bytes, l.b.chunk_first, d_line_start, line_cap, d_n_records, l.d_err, ctx->sm_count, st);
-    if (timing) CU(cudaEventRecord(l.ev[1], st));
+    if (timing) CU(cudaEventRecord(ev[1], st));
     launch_k1(p, d_text, d_line_start, d_n_records, l.b.raw, l.b.cap_records, d_recinfo, l.d_err, ctx->d_counts,
               ctx->sm_count, st);
-    if (timing) CU(cudaEventRecord(l.ev[2], st));
+    if (timing) CU(cudaEventRecord(ev[2], st));
     launch_k2(p, l.b.raw, l.b.cap_records, d_n_records, l.b.feats, l.d_err, ctx->sm_count, st);
-    if (timing) CU(cudaEventRecord(l.ev[3], st));
+    if (timing) CU(cudaEventRecord(ev[3], st));
     launch_k3(p, l.b.feats, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual, ctx->d_counts,
               ctx->sm_count, st);
-    if (timing) CU(cudaEventRecord(l.ev[4], st));
+    if (timing) CU(cudaEventRecord(ev[4], st));
     ctx->launches += 6;
     CU(cudaGetLastError());
     return UGVC_OK;
@@ -371,9 +381,6 @@ extern "C" int ugvc_collect_batch(ugvc_ctx* ctx, int lane, uint8_t* out_low_scor
     const int64_t n = *l.h_n;
     l.last_n = n;
     if (out_n_records) *out_n_records = n;
-    if (ctx->timing) {
-        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ctx->stage_ms[i], l.ev[i], l.ev[i + 1]);
-    }
     const int rc = decode_error(ctx, *l.h_err);
     if (rc) return rc;
     if ((size_t)n > capacity_records) return fail(ctx, UGVC_E_ARG, "collect: output capacity smaller than the record count");
@@ -428,8 +435,6 @@ extern "C" int ugvc_device_status(ugvc_ctx* ctx, void* stream) {
     CU(cudaStreamSynchronize(st));
     unsigned long long e;
     CU(cudaMemcpy(&e, l.d_err, sizeof(e), cudaMemcpyDeviceToHost));
-    if (ctx->timing)
-        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ctx->stage_ms[i], l.ev[i], l.ev[i + 1]);
     return decode_error(ctx, e);
 }
 
@@ -495,12 +500,30 @@ extern "C" int64_t ugvc_launch_count(const ugvc_ctx* ctx) { return ctx ? ctx->la
 extern "C" int ugvc_enable_stage_timing(ugvc_ctx* ctx, int on) {
     if (!ctx) return UGVC_E_ARG;
     ctx->timing = on != 0;
+    for (auto& l : ctx->lanes) l.ev_used = 0;  // (re)start accumulation
     return UGVC_OK;
 }
 
-extern "C" int ugvc_stage_ms(ugvc_ctx* ctx, float out_ms[4]) {
+extern "C" int ugvc_stage_ms(ugvc_ctx* ctx, float out_ms[4], int64_t* out_n_calls) {
+    // Sum of the device-side durations of K0..K3 over every enqueue since
+    // ugvc_enable_stage_timing(ctx, 1); blocks until those enqueues finished.
     if (!ctx || !out_ms) return UGVC_E_ARG;
-    for (int i = 0; i < 4; ++i) out_ms[i] = ctx->stage_ms[i];
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    double sum[4] = {0, 0, 0, 0};
+    int64_t calls = 0;
+    for (auto& l : ctx->lanes) {
+        for (size_t i = 0; i + 5 <= l.ev_used; i += 5) {
+            for (int k = 0; k < 4; ++k) {
+                float ms = 0.f;
+                CU(cudaEventElapsedTime(&ms, l.ev_pool[i + k], l.ev_pool[i + k + 1]));
+                sum[k] += ms;
+            }
+            ++calls;
+        }
+    }
+    for (int k = 0; k < 4; ++k) out_ms[k] = (float)sum[k];
+    if (out_n_calls) *out_n_calls = calls;
     return UGVC_OK;
 }
 

@@ -62,7 +62,7 @@ SIGNATURES = {
     "ugvc_last_data_error": (C.c_int, [_vp, _i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ugvc_launch_count": (C.c_int64, [_vp]),
     "ugvc_enable_stage_timing": (C.c_int, [_vp, C.c_int]),
-    "ugvc_stage_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "ugvc_stage_ms": (C.c_int, [_vp, C.POINTER(C.c_float), _i64p]),
     "ugvc_synth_device": (C.c_int, [_vp, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp, _sz,
                                     C.POINTER(_sz), _vp]),
     "ugvc_synth_header": (C.c_int64, [C.c_int, C.c_char_p, _sz]),
@@ -269,10 +269,12 @@ class Context:
     def enable_stage_timing(self, on: bool = True):
         self._check(self.lib.ugvc_enable_stage_timing(self.h, int(on)))
 
-    def stage_ms(self) -> list[float]:
+    def stage_ms(self) -> tuple[list[float], int]:
+        """(summed ms of K0..K3, number of enqueues) since stage timing was enabled."""
         arr = (C.c_float * 4)()
-        self._check(self.lib.ugvc_stage_ms(self.h, arr))
-        return list(arr)
+        n = C.c_int64()
+        self._check(self.lib.ugvc_stage_ms(self.h, arr, C.byref(n)))
+        return list(arr), n.value
 
 
 def synth_header(n_custom: int) -> str:
