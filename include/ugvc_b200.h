@@ -51,7 +51,8 @@ typedef struct ugvc_recinfo {
     uint16_t filter_off;  /* offset of the FILTER column */
     uint16_t info_off;    /* offset of the INFO column */
     uint16_t format_off;  /* offset one past the tab after INFO (== line length + 1 when there is no FORMAT column) */
-    uint32_t flags;       /* bit0: an allele equals GGC or CCG (blacklist_cg_insertions, blacklist.py:85-101) */
+    uint32_t flags;       /* bit0: an allele equals GGC or CCG (blacklist_cg_insertions, blacklist.py:85-101);
+                             bits 8..31: length of REF (saturating), for the tabix index of the output */
 } ugvc_recinfo;
 
 /* Counters of one batch / one run (what the single NCCL all-reduce sums). */
@@ -170,15 +171,16 @@ int ugvc_bgzf_deflate_to_file(const char* path, const char* mode, const uint8_t*
 /* Build the edited output text of a batch: for each record copy the original
  * line with FILTER rewritten (PASS removed / LOW_SCORE appended / empty -> PASS)
  * and TREE_SCORE (and optionally QUAL, BLACKLST) spliced in, exactly the rules of
- * filter_variants_pipeline.py:188-228.  blacklist_text/blacklist_off (may be
- * NULL) give an optional per-record BLACKLST value; out_line_start (may be
+ * filter_variants_pipeline.py:188-228.  blacklist_code (may be NULL) selects,
+ * per record, one ';'-joined annotation string of blacklist_table (string c is
+ * bytes [table_off[c], table_off[c+1])) as the BLACKLST value; out_line_start (may be
  * NULL, n_records + 1 entries) receives the offset of every output line.
  * Returns bytes written. */
 int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_start, const ugvc_recinfo* recinfo,
                             const uint8_t* low_score, const double* qual, int64_t n_records,
-                            int overwrite_qual, int with_model, const char* blacklist_text,
-                            const int64_t* blacklist_off, uint8_t* out, size_t capacity,
-                            int64_t* out_line_start, int n_threads);
+                            int overwrite_qual, int with_model, const int32_t* blacklist_code,
+                            const char* blacklist_table, const int64_t* blacklist_table_off,
+                            uint8_t* out, size_t capacity, int64_t* out_line_start, int n_threads);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,53 @@
+"""CPU: the C-ABI library loads, exports every symbol include/ugvc_b200.h declares, and the
+product path fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from variantcalling_b200 import lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ugvc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ugvc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    L = lib.load_library()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ugvc_b200.h but not exported"
+        assert n in lib.SIGNATURES, f"{n} has no ctypes signature in variantcalling_b200/lib.py"
+    assert L.ugvc_version() >= 100
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "variantcalling_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{fn} imports the oracle"
+    for fn in ("ugvc/__main__.py",):
+        assert "oracle" not in open(os.path.join(ROOT, fn)).read()
+
+
+def test_no_cuda_device_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(lib.UgvcError) as ei:
+        lib.Context(0)
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_synth_header_host_call():
+    h = lib.synth_header(40)
+    assert h.startswith("##fileformat=VCFv4.2") and h.rstrip().endswith("SAMPLE1")
+    assert h.count("##INFO=<ID=ANN") == 35 and "##contig=<ID=chrY" in h

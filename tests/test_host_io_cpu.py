@@ -1,0 +1,102 @@
+"""CPU: BGZF / tabix containers and the record splicer (host C++) against Python's gzip and the
+oracle's writer rules (filter_variants_pipeline.py:188-228)."""
+import ctypes as C
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_pipeline as R
+from oracle.vcf_reader import OracleVariantFile
+from variantcalling_b200 import bgzf_io, lib, synth
+
+
+@pytest.fixture(scope="module")
+def small(tmp_path_factory):
+    d = tmp_path_factory.mktemp("io")
+    spec = synth.SynthSpec(n_records=3000, n_custom=3, seed=11)
+    header, lines, _ = synth.generate(spec)
+    path = str(d / "in.vcf.gz")
+    bgzf_io.write_vcf_gz(path, header, lines, n_threads=4)
+    return dict(path=path, header=header, lines=lines)
+
+
+def test_bgzf_roundtrip_and_eof_block(small):
+    raw = open(small["path"], "rb").read()
+    assert raw[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    text = gzip.open(small["path"]).read().decode()
+    assert text == "\n".join(small["header"]) + "\n" + "\n".join(small["lines"]) + "\n"
+    assert bgzf_io.uncompressed_size(small["path"]) == len(text)
+    assert bgzf_io.inflate(small["path"], n_threads=3).tobytes().decode() == text
+    assert bgzf_io.read_header_text(small["path"]) == "\n".join(small["header"]) + "\n"
+
+
+def test_tabix_ranges_select_exactly_each_contig(small):
+    idx = bgzf_io.read_tbi(small["path"] + ".tbi")
+    by_contig = {}
+    for ln in small["lines"]:
+        by_contig.setdefault(ln.split("\t", 1)[0], []).append(ln)
+    assert list(idx) == list(by_contig)
+    for c, (vb, ve) in idx.items():
+        got = bgzf_io.inflate(small["path"], vb, ve, n_threads=2).tobytes().decode().split("\n")[:-1]
+        assert got == by_contig[c]
+
+
+def test_reg2bin_known_values():
+    b = np.array([0, 16383, 16384, 0, 1 << 28], dtype=np.int64)
+    e = np.array([1, 16384, 16385, 1 << 29, (1 << 28) + 5], dtype=np.int64)
+    assert list(bgzf_io.reg2bin(b, e)) == [4681, 4681, 4682, 0, 4681 + (1 << 14)]
+
+
+def _recinfo_for(lines):
+    ri = np.zeros(len(lines), dtype=lib.RECINFO_DTYPE)
+    for i, ln in enumerate(lines):
+        cols = ln.split("\t")
+        start = lambda k: len("\t".join(cols[:k])) + 1  # noqa: E731
+        ri[i] = (int(cols[1]), start(5), start(6), start(7), start(8), (len(cols[3]) << 8))
+    return ri
+
+
+@pytest.mark.parametrize("overwrite_qual", [False, True])
+def test_splicer_matches_oracle_writer(overwrite_qual):
+    hdr = ["##fileformat=VCFv4.2", "##contig=<ID=c1,length=100>",
+           "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS"]
+    lines = ["c1\t1\t.\tA\tC\t5.5\tPASS\tX=1\tGT\t0/1", "c1\t2\t.\tA\tC\t.\tq10\t.\tGT\t1/1",
+             "c1\t3\trs\tAT\tA\t7\t.\tTREE_SCORE=1;Y=2\tGT:DP\t0/1:3", "c1\t4\t.\tG\tGGC\t8\tq10;PASS\tBLACKLST=old;Z\tGT\t0/0",
+             "c1\t5\t.\tG\tT\t9\tLOW_SCORE\tA=1", "c1\t6\t.\tG\tT\t9\t.\tA=1"]
+    quals = np.array([12.5, 30.0, 45.123456789, 0.0, 29.999999, 1e-7])
+    low = (quals <= 30.0).astype(np.uint8)
+    bl_strings = [b"PASS;PASS", b"CG_NON_HMER_INDEL;PASS", b"PASS;COHORT_FP", b"CG_NON_HMER_INDEL;COHORT_FP"]
+    codes = np.array([0, 2, 0, 3, 1, 0], dtype=np.int32)
+    text = ("\n".join(lines) + "\n").encode()
+    buf = np.frombuffer(text, dtype=np.uint8)
+    ls = np.concatenate(([0], np.cumsum([len(l) + 1 for l in lines]))).astype(np.int64)
+    ri = _recinfo_for(lines)
+    table = np.frombuffer(b"".join(bl_strings), dtype=np.uint8)
+    off = np.concatenate(([0], np.cumsum([len(s) for s in bl_strings]))).astype(np.int64)
+    out = np.empty(len(text) + 1024, dtype=np.uint8)
+    out_ls = np.empty(len(lines) + 1, dtype=np.int64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    n = lib.load_library().ugvc_splice_records(p(buf), p(ls), p(ri), p(low), p(quals), len(lines), int(overwrite_qual),
+                                               1, p(codes), p(table), p(off), p(out), out.size, p(out_ls), 2)
+    assert n > 0
+    got = out[:n].tobytes().decode().split("\n")[:-1]
+    vf = OracleVariantFile(("\n".join(hdr) + "\n" + "\n".join(lines) + "\n").encode())
+    want = [R.write_record(rec, float(quals[i]), 30.0, overwrite_qual=overwrite_qual,
+                           blacklist_value=bl_strings[codes[i]].decode())[0] for i, rec in enumerate(vf)]
+    assert got == want
+    assert [out[out_ls[i]:out_ls[i + 1] - 1].tobytes().decode() for i in range(len(lines))] == want
+
+
+def test_splicer_without_model_only_fills_pass():
+    lines = ["c1\t1\t.\tA\tC\t5\t.\tX=1", "c1\t2\t.\tA\tC\t5\tq10\t."]
+    text = ("\n".join(lines) + "\n").encode()
+    buf = np.frombuffer(text, dtype=np.uint8)
+    ls = np.concatenate(([0], np.cumsum([len(l) + 1 for l in lines]))).astype(np.int64)
+    ri = _recinfo_for(lines)
+    out = np.empty(256, dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    n = lib.load_library().ugvc_splice_records(p(buf), p(ls), p(ri), None, None, 2, 0, 0, None, None, None, p(out),
+                                               out.size, None, 1)
+    assert out[:n].tobytes().decode() == "c1\t1\t.\tA\tC\t5\tPASS\tX=1\nc1\t2\t.\tA\tC\t5\tq10\t.\n"

@@ -1,0 +1,86 @@
+"""CPU: lowering of fitted transformers / models to the plan blob."""
+import struct
+
+import numpy as np
+import pytest
+
+from tests import util
+from variantcalling_b200 import model_compiler as MC
+from variantcalling_b200.vcf_header import VcfHeader
+
+
+@pytest.fixture(scope="module")
+def ds():
+    d = util.make_dataset(n_records=1200, n_custom=5)
+    d["df"], d["tr"], d["x"] = util.fit_transformer(d)
+    return d
+
+
+@pytest.mark.parametrize("kind,model_kind", [("lr", MC.MODEL_LOGISTIC), ("gb_small", MC.MODEL_GB_SKLEARN),
+                                             ("rf", MC.MODEL_RF_SKLEARN)])
+def test_plan_layout(ds, kind, model_kind):
+    model = util.fit_model(kind, ds["x"], ds["labels"])
+    plan = MC.compile_plan(VcfHeader(ds["header_text"]), ds["tr"], model, ds["customs"])
+    hdr = struct.unpack_from("<16I4d", plan.blob, 0)
+    assert hdr[0] == MC.PLAN_MAGIC and hdr[1] == MC.PLAN_VERSION
+    assert hdr[4] == plan.n_features == ds["x"].shape[1] == 46
+    assert hdr[7] == model_kind and hdr[8] == 2
+    assert len(plan.blob) % 8 == 0
+    # stock single_sample layout of SURVEY.md appendix A
+    assert plan.feature_names[:7] == ["ad_0", "ad_1", "gt", "gq", "pl_0", "pl_1", "pl_2"]
+    assert plan.feature_names[21] == "qual" and plan.feature_names[41:] == ["lcr", "map_unique", "long_hmer",
+                                                                             "ug_hcr", "exome"]
+
+
+def test_threshold_floor_preserves_le_on_float32():
+    rng = np.random.default_rng(0)
+    t = rng.normal(size=20000) * 10.0 ** rng.integers(-3, 4, size=20000)
+    f = MC._f32_floor(t)
+    assert np.all(f.astype(np.float64) <= t)
+    up = np.nextafter(f, np.float32(np.inf))
+    assert np.all(up.astype(np.float64) > t)
+    x = rng.normal(size=20000).astype(np.float32) * 10
+    assert np.array_equal(x.astype(np.float64) <= t, x <= f)
+
+
+def test_missing_header_tag_is_a_plan_error(ds):
+    model = util.fit_model("lr", ds["x"], ds["labels"])
+    hdr = "\n".join(l for l in ds["header"] if "ID=X_GCC" not in l) + "\n"
+    with pytest.raises(MC.PlanError, match="x_gcc"):
+        MC.compile_plan(VcfHeader(hdr), ds["tr"], model, ds["customs"])
+
+
+def test_wrong_feature_count_is_a_plan_error(ds):
+    from sklearn.linear_model import LogisticRegression
+
+    model = LogisticRegression(max_iter=50).fit(ds["x"][:, :10], ds["labels"])
+    with pytest.raises(MC.PlanError, match="features"):
+        MC.compile_plan(VcfHeader(ds["header_text"]), ds["tr"], model, ds["customs"])
+
+
+def test_unfitted_transformer_rejected(ds):
+    from variantcalling_b200 import transformers as T
+    from variantcalling_b200.tprep_constants import VcfType
+
+    with pytest.raises(MC.PlanError, match="not fitted"):
+        MC.compile_plan(VcfHeader(ds["header_text"]), T.get_transformer(VcfType.SINGLE_SAMPLE), None)
+
+
+def test_xgboost_json_lowering():
+    """A hand-written xgboost JSON dump (2 stumps, binary:logistic) lowers to MODEL_XGB."""
+    def tree(feat, cond, lv, rv):
+        return {"left_children": [1, -1, -1], "right_children": [2, -1, -1], "split_indices": [feat, 0, 0],
+                "split_conditions": [cond, lv, rv], "default_left": [0, 0, 0], "base_weights": [0, lv, rv]}
+    doc = {"learner": {"objective": {"name": "binary:logistic"},
+                       "learner_model_param": {"base_score": "5E-1", "num_class": "0", "num_feature": "3"},
+                       "gradient_booster": {"name": "gbtree", "model": {"trees": [tree(0, 0.5, -0.1, 0.2),
+                                                                                   tree(2, 1.5, 0.3, -0.4)],
+                                                                        "tree_info": [0, 0]}}}}
+    m = MC._lower_xgboost_json(doc, 3)
+    assert m["kind"] == MC.MODEL_XGB and m["cmp"] == MC.CMP_LT and m["n_trees"] == 2 and m["n_nodes"] == 6
+    assert m["init"][0] == 0.0 and m["n_outputs"] == 1 and m["n_classes"] == 2
+
+
+def test_no_model_plan():
+    p = MC.compile_plan_no_model("##fileformat=VCFv4.2\n#CHROM\tPOS\n")
+    assert p.n_features == 0 and len(p.blob) == 96

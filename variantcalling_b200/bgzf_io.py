@@ -1,0 +1,265 @@
+"""BGZF / tabix containers around the hot path (host side).
+
+The reference gets these from htslib: ``pysam.VariantFile`` reads and writes the
+bgzip'ed VCF (``filter_variants_pipeline.py:106,115``) and ``bcftools index -t``
+writes the ``.tbi`` (``:231``).  Neither is in this image, so the byte formats are
+implemented here: block (de)compression is the multi-threaded C++ in
+``csrc/hostio.cpp`` (zlib), the tabix index is built/parsed with NumPy.
+
+Formats: BGZF = gzip members of <= 64 KiB with a ``BC`` extra field (SAM spec 4.1);
+tabix index (``.tbi``) per the tabix format note: magic ``TBI\\1``, per-reference
+binning index (``reg2bin``, 5 levels over 2^29) plus a 16 kb linear index of
+virtual file offsets ``coffset << 16 | uoffset``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import struct
+
+import numpy as np
+
+from variantcalling_b200 import lib as _lib
+
+BGZF_BLOCK_DATA = 0xFF00
+TBI_SHIFT, TBI_LEVELS = 14, 5
+
+
+def _check(rc: int, what: str):
+    if rc:
+        raise OSError(f"{what} failed (ugvc code {rc})")
+
+
+# --------------------------------------------------------------------------- BGZF
+def uncompressed_size(path: str) -> int:
+    n = _lib.load_library().ugvc_bgzf_uncompressed_size(path.encode())
+    if n < 0:
+        raise OSError(f"{path}: not a readable BGZF file (ugvc code {n})")
+    return int(n)
+
+
+def inflate(path: str, voff_begin: int = 0, voff_end: int = 0, capacity: int | None = None, n_threads: int = 0,
+            out: np.ndarray | None = None) -> np.ndarray:
+    """Inflate [voff_begin, voff_end) (0,0 = whole file) into a uint8 array."""
+    L = _lib.load_library()
+    if out is None:
+        if capacity is None:
+            capacity = uncompressed_size(path) if voff_end == 0 and voff_begin == 0 else None
+        if capacity is None:
+            # a virtual-offset range: bounded by the compressed span * worst ratio is unknown, so
+            # size from the block table (cheap header scan)
+            capacity = uncompressed_size(path)
+        out = np.empty(capacity + 64, dtype=np.uint8)
+    n = C.c_size_t()
+    rc = L.ugvc_bgzf_inflate_file(path.encode(), voff_begin, voff_end, out.ctypes.data_as(C.c_void_p), out.size,
+                                  C.byref(n), n_threads)
+    _check(rc, f"inflate {path}")
+    return out[: n.value]
+
+
+class BgzfWriter:
+    """Append-only BGZF writer that remembers every block's compressed size, so
+    virtual offsets of written bytes can be computed for the tabix index."""
+
+    def __init__(self, path: str, level: int = 6, n_threads: int = 0):
+        self.path, self.level, self.n_threads = path, level, n_threads
+        self.coffset = 0                 # compressed bytes written so far
+        self.uoffset = 0                 # uncompressed bytes written so far
+        self._started = False
+        # piecewise map uncompressed offset -> (block coffset, block uoffset)
+        self.block_u: list[np.ndarray] = []
+        self.block_c: list[np.ndarray] = []
+
+    def write(self, data: np.ndarray | bytes, last: bool = False):
+        buf = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data
+        L = _lib.load_library()
+        n_blocks = (buf.size + BGZF_BLOCK_DATA - 1) // BGZF_BLOCK_DATA
+        csz = np.zeros(max(1, n_blocks), dtype=np.uint32)
+        total, nb = C.c_uint64(), C.c_size_t()
+        rc = L.ugvc_bgzf_deflate_to_file(self.path.encode(), b"a" if self._started else b"w",
+                                         buf.ctypes.data_as(C.c_void_p) if buf.size else None, buf.size, self.level,
+                                         1 if last else 0, self.n_threads, C.byref(total),
+                                         csz.ctypes.data_as(C.c_void_p), csz.size, C.byref(nb))
+        _check(rc, f"deflate to {self.path}")
+        self._started = True
+        if n_blocks:
+            cs = csz[:n_blocks].astype(np.int64)
+            c_start = self.coffset + np.concatenate(([0], np.cumsum(cs)[:-1]))
+            u_start = self.uoffset + np.arange(n_blocks, dtype=np.int64) * BGZF_BLOCK_DATA
+            self.block_c.append(c_start)
+            self.block_u.append(u_start)
+        self.coffset += int(total.value)
+        self.uoffset += int(buf.size)
+
+    def close(self):
+        if not self._started:
+            self.write(np.zeros(0, np.uint8), last=True)
+        else:
+            L = _lib.load_library()
+            total = C.c_uint64()
+            rc = L.ugvc_bgzf_deflate_to_file(self.path.encode(), b"a", None, 0, self.level, 1, 1, C.byref(total),
+                                             None, 0, None)
+            _check(rc, f"close {self.path}")
+            self.coffset += int(total.value)
+
+    def virtual_offsets(self, uoffsets: np.ndarray) -> np.ndarray:
+        """Virtual file offsets of uncompressed stream offsets (of bytes already written)."""
+        if not self.block_u:
+            return np.zeros_like(uoffsets, dtype=np.uint64)
+        bu = np.concatenate(self.block_u)
+        bc = np.concatenate(self.block_c)
+        idx = np.searchsorted(bu, uoffsets, side="right") - 1
+        return (bc[idx].astype(np.uint64) << np.uint64(16)) | (uoffsets - bu[idx]).astype(np.uint64)
+
+
+def read_header_text(path: str) -> str:
+    """Header lines of a bgzip'ed / plain VCF (reads only as far as needed)."""
+    with open(path, "rb") as fh:
+        gz = fh.read(2) == b"\x1f\x8b"
+    opener = gzip.open if gz else open
+    lines = []
+    with opener(path, "rb") as fh:
+        for raw in fh:
+            if not raw.startswith(b"#"):
+                break
+            lines.append(raw.decode())
+    return "".join(lines)
+
+
+# --------------------------------------------------------------------------- tabix
+def reg2bin(beg: np.ndarray, end: np.ndarray) -> np.ndarray:
+    """UCSC binning (tabix spec): beg 0-based inclusive, end exclusive; vectorised."""
+    end = end - 1
+    out = np.zeros(beg.shape, dtype=np.int64)
+    done = np.zeros(beg.shape, dtype=bool)
+    for shift, offset in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        same = ((beg >> shift) == (end >> shift)) & ~done
+        out[same] = offset + (beg[same] >> shift)
+        done |= same
+    return out
+
+
+def build_tbi(contig_names: list[str], contig_of: np.ndarray, beg: np.ndarray, end: np.ndarray,
+              voff_start: np.ndarray, voff_end: np.ndarray) -> bytes:
+    """Uncompressed ``.tbi`` payload for records sorted by (contig block, position).
+
+    contig_of[i] indexes contig_names; beg/end are 0-based half-open; voff_* are the
+    virtual offsets of each record's first byte and one past its last byte.
+    """
+    names = b"".join(n.encode() + b"\0" for n in contig_names)
+    out = [b"TBI\x01", struct.pack("<8i", len(contig_names), 2, 1, 2, 0, ord("#"), 0, len(names)), names]
+    for ci in range(len(contig_names)):
+        sel = np.flatnonzero(contig_of == ci)
+        if sel.size == 0:
+            out.append(struct.pack("<i", 0))
+            out.append(struct.pack("<i", 0))
+            continue
+        b, e = beg[sel].astype(np.int64), end[sel].astype(np.int64)
+        vs, ve = voff_start[sel].astype(np.uint64), voff_end[sel].astype(np.uint64)
+        bins = reg2bin(b, np.maximum(e, b + 1))
+        # chunks: runs of consecutive records with the same bin
+        change = np.flatnonzero(np.concatenate(([True], bins[1:] != bins[:-1])))
+        run_bin = bins[change]
+        run_beg = vs[change]
+        run_end = ve[np.concatenate((change[1:] - 1, [bins.size - 1]))]
+        order = np.argsort(run_bin, kind="stable")
+        run_bin, run_beg, run_end = run_bin[order], run_beg[order], run_end[order]
+        uniq, first = np.unique(run_bin, return_index=True)
+        counts = np.diff(np.concatenate((first, [run_bin.size])))
+        out.append(struct.pack("<i", uniq.size))
+        for k, bn in enumerate(uniq):
+            lo, n = first[k], counts[k]
+            out.append(struct.pack("<Ii", int(bn), int(n)))
+            pairs = np.empty(2 * n, dtype="<u8")
+            pairs[0::2] = run_beg[lo:lo + n]
+            pairs[1::2] = run_end[lo:lo + n]
+            out.append(pairs.tobytes())
+        # linear index: smallest virtual offset of any record overlapping each 16 kb window
+        n_win = int((np.maximum(e, b + 1).max() - 1) >> TBI_SHIFT) + 1
+        lin = np.full(n_win, np.iinfo(np.uint64).max, dtype=np.uint64)
+        w0 = b >> TBI_SHIFT
+        w1 = (np.maximum(e, b + 1) - 1) >> TBI_SHIFT
+        np.minimum.at(lin, w0, vs)
+        span = np.flatnonzero(w1 > w0)
+        for i in span:  # records crossing window borders are rare (long REF alleles)
+            lin[w0[i] + 1: w1[i] + 1] = np.minimum(lin[w0[i] + 1: w1[i] + 1], vs[i])
+        # empty windows inherit the next filled offset (htslib convention: previous value)
+        filled = lin != np.iinfo(np.uint64).max
+        if not filled[0]:
+            lin[0] = vs[0]
+            filled[0] = True
+        idx = np.maximum.accumulate(np.where(filled, np.arange(n_win), 0))
+        lin = lin[idx]
+        out.append(struct.pack("<i", n_win))
+        out.append(lin.astype("<u8").tobytes())
+    return b"".join(out)
+
+
+def write_tbi(path: str, payload: bytes):
+    w = BgzfWriter(path, level=6, n_threads=1)
+    w.write(payload, last=True)
+
+
+def read_tbi(path: str) -> dict:
+    """{contig: (min chunk begin voff, max chunk end voff)} in file order, from a ``.tbi``."""
+    with gzip.open(path, "rb") as fh:
+        data = fh.read()
+    if data[:4] != b"TBI\x01":
+        raise OSError(f"{path}: not a tabix index")
+    n_ref, _fmt, _cs, _cb, _ce, _meta, _skip, l_nm = struct.unpack_from("<8i", data, 4)
+    p = 36
+    names = data[p:p + l_nm].split(b"\0")[:n_ref]
+    p += l_nm
+    out = {}
+    for r in range(n_ref):
+        (n_bin,) = struct.unpack_from("<i", data, p)
+        p += 4
+        lo, hi = None, None
+        for _ in range(n_bin):
+            bn, n_chunk = struct.unpack_from("<Ii", data, p)
+            p += 8
+            ch = np.frombuffer(data, dtype="<u8", count=2 * n_chunk, offset=p)
+            p += 16 * n_chunk
+            if bn == 37450 or n_chunk == 0:  # noqa: PLR2004  (htslib pseudo-bin: metadata)
+                continue
+            b, e = int(ch[0::2].min()), int(ch[1::2].max())
+            lo = b if lo is None else min(lo, b)
+            hi = e if hi is None else max(hi, e)
+        (n_intv,) = struct.unpack_from("<i", data, p)
+        p += 4 + 8 * n_intv
+        if lo is not None:
+            out[names[r].decode()] = (lo, hi)
+    return out
+
+
+def write_vcf_gz(path: str, header_lines: list[str], record_lines: list[str], n_threads: int = 0):
+    """Write a bgzip'ed VCF plus its ``.tbi`` from text lines (tests / fixtures)."""
+    hdr = ("\n".join(header_lines) + "\n").encode()
+    body = ("\n".join(record_lines) + ("\n" if record_lines else "")).encode()
+    w = BgzfWriter(path, n_threads=n_threads)
+    w.write(hdr)
+    w.write(body)
+    w.close()
+    if not record_lines:
+        write_tbi(path + ".tbi", build_tbi([], np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64),
+                                           np.zeros(0, np.uint64), np.zeros(0, np.uint64)))
+        return
+    names: list[str] = []
+    contig_of, beg, end = [], [], []
+    for ln in record_lines:
+        c, pos, _id, ref, _rest = ln.split("\t", 4)
+        if not names or names[-1] != c:
+            if c in names:
+                raise ValueError("records of a contig must be contiguous")
+            names.append(c)
+        contig_of.append(len(names) - 1)
+        beg.append(int(pos) - 1)
+        end.append(int(pos) - 1 + len(ref))
+    lens = np.array([len(ln.encode()) + 1 for ln in record_lines], dtype=np.int64)
+    u_start = len(hdr) + np.concatenate(([0], np.cumsum(lens)[:-1]))
+    u_end = u_start + lens
+    vs = w.virtual_offsets(u_start)
+    # the end of the last record of a block is the start of the next block: htslib reports
+    # one-past-the-end the same way, and readers only need end >= true end
+    ve = w.virtual_offsets(np.minimum(u_end, w.uoffset - 1)) + np.uint64(1)
+    write_tbi(path + ".tbi", build_tbi(names, np.array(contig_of), np.array(beg), np.array(end), vs, ve))

@@ -157,6 +157,8 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
         off = align8(off + (size_t)h.n_nodes * sizeof(PlanNode));
         o_leaves = off;
         off = align8(off + (size_t)h.n_leaf_rows * h.leaf_width * sizeof(double));
+    } else if (h.model_kind == MODEL_NONE) {
+        if (h.n_features != 0) return fail(ctx, UGVC_E_PLAN, "a plan without a model cannot have features");
     } else {
         return fail(ctx, UGVC_E_PLAN, "unsupported model kind");
     }
@@ -194,7 +196,7 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
         for (uint32_t c = 0; c < h.n_checks; ++c)
             if (checks[c].slot >= h.n_slots) return fail(ctx, UGVC_E_PLAN, "check slot out of range");
     }
-    if (h.model_kind != MODEL_LOGISTIC) {
+    if (h.model_kind != MODEL_LOGISTIC && h.model_kind != MODEL_NONE) {
         const uint32_t* root = reinterpret_cast<const uint32_t*>(hb + o_root);
         const PlanNode* nodes = reinterpret_cast<const PlanNode*>(hb + o_nodes);
         const uint8_t* tout = hb + o_tout;
@@ -317,12 +319,14 @@ static int enqueue_kernels(ugvc_ctx* ctx, Lane& l, const uint8_t* d_text, size_t
     launch_k1(p, d_text, d_line_start, d_n_records, l.b.raw, l.b.cap_records, d_recinfo, l.d_err, ctx->d_counts,
               ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[2], st));
-    launch_k2(p, l.b.raw, l.b.cap_records, d_n_records, l.b.feats, l.d_err, ctx->sm_count, st);
+    const bool has_model = p.h.model_kind != MODEL_NONE;
+    if (has_model) launch_k2(p, l.b.raw, l.b.cap_records, d_n_records, l.b.feats, l.d_err, ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[3], st));
-    launch_k3(p, l.b.feats, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual, ctx->d_counts,
-              ctx->sm_count, st);
+    if (has_model)
+        launch_k3(p, l.b.feats, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual, ctx->d_counts,
+                  ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[4], st));
-    ctx->launches += 6;
+    ctx->launches += has_model ? 6 : 4;
     CU(cudaGetLastError());
     return UGVC_OK;
 }

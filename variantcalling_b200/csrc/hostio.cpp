@@ -422,9 +422,9 @@ void splice_one(const uint8_t* line, size_t len, const ugvc_recinfo& ri, bool wi
 
 extern "C" int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_start, const ugvc_recinfo* recinfo,
                                        const uint8_t* low_score, const double* qual, int64_t n_records,
-                                       int overwrite_qual, int with_model, const char* blacklist_text,
-                                       const int64_t* blacklist_off, uint8_t* out, size_t capacity,
-                                       int64_t* out_line_start, int n_threads) {
+                                       int overwrite_qual, int with_model, const int32_t* blacklist_code,
+                                       const char* blacklist_table, const int64_t* blacklist_table_off,
+                                       uint8_t* out, size_t capacity, int64_t* out_line_start, int n_threads) {
     if (!text || !line_start || !recinfo || n_records < 0) return UGVC_E_ARG;
     if (with_model && (!low_score || !qual)) return UGVC_E_ARG;
     n_threads = clamp_threads(n_threads);
@@ -442,9 +442,10 @@ extern "C" int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_
             const size_t len = (size_t)(line_start[i + 1] - line_start[i] - 1);
             const char* bl = nullptr;
             size_t bl_len = 0;
-            if (blacklist_text && blacklist_off) {
-                bl = blacklist_text + blacklist_off[i];
-                bl_len = (size_t)(blacklist_off[i + 1] - blacklist_off[i]);
+            if (blacklist_code && blacklist_table && blacklist_table_off) {
+                const int32_t code = blacklist_code[i];
+                bl = blacklist_table + blacklist_table_off[code];
+                bl_len = (size_t)(blacklist_table_off[code + 1] - blacklist_table_off[code]);
             }
             splice_one(line, len, recinfo[i], with_model != 0, with_model && low_score[i] != 0,
                        with_model ? qual[i] : 0.0, overwrite_qual != 0, bl, bl_len, o);

@@ -549,6 +549,7 @@ __global__ void __launch_bounds__(K1_TPB) k1_parse(const __grid_constant__ DevPl
                 cg |= ref_len == 3 && ((ra[0] == 'G' && ra[1] == 'G' && ra[2] == 'C') ||
                                        (ra[0] == 'C' && ra[1] == 'C' && ra[2] == 'G'));
                 n_alleles = 1;
+                ri.flags |= (unsigned)(ref_len > 0xFFFFFF ? 0xFFFFFF : ref_len) << 8;
                 malformed |= (*p != '\t');
                 if (!malformed) {
                     const uint8_t* aa = p + 1;

@@ -1,0 +1,318 @@
+#!/env/python
+"""POST-GATK variant filtering -- B200-native drop-in for the reference tool.
+
+Mirrors ``ugbio_utils/src/filtering/ugbio_filtering/filter_variants_pipeline.py``:
+same flags (``parse_args``, :20-70), same ``run(argv)`` entry (argv without the
+program name, :78-80), same model-pickle contract (``mf["xgb"]``,
+``mf["transformer"]``, :89-94), same header edits (:106-113), same contig
+iteration (header order or ``--limit_to_contigs``; empty contigs skipped,
+:116-127), same FILTER / TREE_SCORE / QUAL / BLACKLST rules (:188-228), same
+log lines incl. ``Variant filtering run: success|failed`` and re-raise (:233-240).
+
+What differs is where the work happens: per contig the bgzip'ed text is inflated
+by the multi-threaded C++ reader, shipped to the GPU in batches through
+``ugvc_submit_batch`` / ``ugvc_collect_batch`` (K0 line index, K1 field parse,
+K2 feature assembly, K3 inference + score + decision), and the output lines are
+spliced from the original bytes and BGZF-compressed on the host; the ``.tbi`` is
+written directly (the reference shells out to ``bcftools index -t``, :231).
+
+Not lowered yet (raise ``NotImplementedError`` instead of a silent approximation):
+``--treat_multiallelics`` and ``--recalibrate_genotype``.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import logging
+import os.path
+import pickle
+import sys
+
+import numpy as np
+
+from variantcalling_b200 import bgzf_io, lib
+from variantcalling_b200 import model_compiler as MC
+from variantcalling_b200.vcf_header import VcfHeader
+
+
+def parse_args(argv: list[str]) -> argparse.Namespace:
+    ap_var = argparse.ArgumentParser(prog="filter_variants_pipeline.py", description="Filter VCF")
+    ap_var.add_argument("--input_file", help="Name of the input VCF file (requires .tbi index)", type=str,
+                        required=True)
+    ap_var.add_argument("--model_file", help="Pickle model file", type=str, required=False)
+    ap_var.add_argument("--blacklist", help="Blacklist file", type=str, required=False)
+    ap_var.add_argument("--custom_annotations",
+                        help="Custom INFO annotations to read from the VCF (multiple possible)", required=False,
+                        type=str, default=None, action="append")
+    ap_var.add_argument("--blacklist_cg_insertions", help="Should CCG/GGC insertions be filtered out?",
+                        action="store_true")
+    ap_var.add_argument("--treat_multiallelics",
+                        help="Should special treatment be applied to multiallelic and spanning deletions",
+                        default=False, action="store_true")
+    ap_var.add_argument("--recalibrate_genotype", help="Use if the model allows to re-call genotype", default=False,
+                        action="store_true")
+    ap_var.add_argument("--overwrite_qual_tag", help="Write the score to QUAL field in addition to TREE_SCORE/GQ",
+                        default=False, action="store_true")
+    ap_var.add_argument("--decision_threshold", help="Decision threshold for filtering variants (default: 30)",
+                        type=float, default=30.0)
+    ap_var.add_argument("--ref_fasta", help="Reference FASTA file (only required for multiallelic treatment)",
+                        required=False, type=str)
+    ap_var.add_argument("--output_file", help="Output VCF file", type=str, required=True)
+    ap_var.add_argument("--limit_to_contigs", help="Limit filtering to these contigs", nargs="+", type=str,
+                        default=None)
+    # B200 host knobs (not in the reference; defaults need no tuning)
+    ap_var.add_argument("--device", help="CUDA device index (default: LOCAL_RANK or 0)", type=int, default=None)
+    ap_var.add_argument("--batch_mb", help="VCF text per GPU batch, MiB", type=int, default=256)
+    ap_var.add_argument("--io_threads", help="Host threads for BGZF inflate/deflate/splice (0 = all)", type=int,
+                        default=0)
+    return ap_var.parse_args(argv)
+
+
+def _load_pickle(path: str):
+    with open(path, "rb") as fh:
+        return pickle.load(fh)  # noqa: S301  (the reference's own contract, :91)
+
+
+def _blacklist_positions(blacklists, contig: str) -> list[tuple[str, np.ndarray]]:
+    """[(annotation, sorted positions on this contig)] from reference-style Blacklist objects
+    (``blacklist.py:10-55``: ``.blacklist`` is a set of (chrom, pos), ``.annotation`` a name)."""
+    out = []
+    for bl in blacklists:
+        sel = getattr(bl, "selection_fcn", None)
+        name = getattr(sel, "__name__", "") or getattr(sel, "name", "") or str(sel)
+        if sel is not None and "ALL" not in str(name).upper() and not getattr(bl, "select_all", False):
+            raise NotImplementedError(
+                f"blacklist {bl.annotation!r}: only selection_fcn = VariantSelectionFunctions.ALL is lowered")
+        pos = np.fromiter((p for (c, p) in bl.blacklist if c == contig), dtype=np.int64)
+        out.append((bl.annotation, np.sort(pos)))
+    return out
+
+
+class _Splicer:
+    """Output side: splice + BGZF append + bookkeeping for the tabix index."""
+
+    def __init__(self, path: str, threads: int):
+        self.writer = bgzf_io.BgzfWriter(path, n_threads=threads)
+        self.threads = threads
+        self.names: list[str] = []
+        self.contig_of, self.beg, self.end, self.u_start, self.u_end = [], [], [], [], []
+        self.L = lib.load_library()
+
+    def write_header(self, lines: list[str]):
+        self.writer.write(("\n".join(lines) + "\n").encode())
+
+    def write_batch(self, contig: str, text: np.ndarray, res: dict, *, with_model: bool, overwrite_qual: bool,
+                    bl_code, bl_table: bytes, bl_off: np.ndarray):
+        n = res["n_records"]
+        if n == 0:
+            return
+        max_bl = int(np.diff(bl_off).max()) if bl_off is not None and bl_off.size > 1 else 0
+        cap = int(text.size + n * (80 + max_bl) + 1024)
+        out = np.empty(cap, dtype=np.uint8)
+        out_ls = np.empty(n + 1, dtype=np.int64)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        table = np.frombuffer(bl_table, dtype=np.uint8) if bl_code is not None and bl_table else None
+        nb = self.L.ugvc_splice_records(
+            p(text), p(res["line_start"]), p(res["recinfo"]), p(res.get("low_score")), p(res.get("qual")), n,
+            int(overwrite_qual), int(with_model), p(bl_code), p(table), p(bl_off) if table is not None else None,
+            p(out), out.size, p(out_ls), self.threads)
+        if nb < 0:
+            raise OSError(f"splice failed (ugvc code {nb})")
+        base = self.writer.uoffset
+        self.writer.write(out[:nb])
+        if not self.names or self.names[-1] != contig:
+            self.names.append(contig)
+        ri = res["recinfo"]
+        self.contig_of.append(np.full(n, len(self.names) - 1, dtype=np.int32))
+        self.beg.append(ri["pos"].astype(np.int64) - 1)
+        self.end.append(ri["pos"].astype(np.int64) - 1 + np.maximum(1, (ri["flags"] >> 8).astype(np.int64)))
+        self.u_start.append(base + out_ls[:-1])
+        self.u_end.append(base + out_ls[1:])
+
+    def close(self, path: str):
+        self.writer.close()
+        if self.contig_of:
+            cat = np.concatenate
+            us, ue = cat(self.u_start), cat(self.u_end)
+            vs = self.writer.virtual_offsets(us)
+            ve = self.writer.virtual_offsets(ue - 1) + np.uint64(1)
+            payload = bgzf_io.build_tbi(self.names, cat(self.contig_of), cat(self.beg), cat(self.end), vs, ve)
+        else:
+            z = np.zeros(0, np.int64)
+            payload = bgzf_io.build_tbi([], z, z, z, z.astype(np.uint64), z.astype(np.uint64))
+        bgzf_io.write_tbi(path + ".tbi", payload)
+
+
+def _split_batches(text: np.ndarray, limit: int):
+    """Yield [begin, end) byte ranges of whole lines, each at most ``limit`` bytes (a single
+    longer line becomes its own batch)."""
+    n, b = text.size, 0
+    while b < n:
+        e = min(n, b + limit)
+        if e < n:
+            back = text[b:e][::-1]
+            k = int(np.argmax(back == 10))  # noqa: PLR2004
+            if back[k] == 10:  # noqa: PLR2004
+                e -= k
+            else:  # no newline inside the window: extend to the end of this line
+                fwd = np.flatnonzero(text[e:] == 10)  # noqa: PLR2004
+                e = n if fwd.size == 0 else e + int(fwd[0]) + 1
+        yield b, e
+        b = e
+
+
+def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
+    "POST-GATK variant filtering"
+    args = parse_args(argv)
+    logging.basicConfig(format="%(asctime)s %(message)s", level=logging.INFO)
+    logger = logging.getLogger(__name__)
+
+    try:
+        model = None
+        transformer = None
+        blacklists = None
+
+        if args.model_file is not None:
+            logger.info(f"Loading model from {args.model_file}")
+            mf = _load_pickle(args.model_file)
+            model = mf["xgb"]
+            transformer = mf["transformer"]
+        if args.blacklist is not None:
+            logger.info(f"Loading blacklist from {args.blacklist}")
+            blacklists = _load_pickle(args.blacklist)
+        if args.treat_multiallelics and args.ref_fasta is None:
+            raise ValueError("Reference FASTA file is required for multiallelic treatment")
+        if not os.path.exists(args.input_file):
+            raise RuntimeError(f"Input file {args.input_file} does not exist")
+        if not os.path.exists(args.input_file + ".tbi"):
+            raise RuntimeError(f"Index file {args.input_file}.tbi does not exist")
+        if args.treat_multiallelics or args.recalibrate_genotype:
+            raise NotImplementedError(
+                "--treat_multiallelics / --recalibrate_genotype are not lowered to the GPU path yet "
+                "(SURVEY.md 8f-2); refusing to approximate")
+
+        header = VcfHeader(bgzf_io.read_header_text(args.input_file))
+        with_model = args.model_file is not None
+        with_bl = args.blacklist is not None or args.blacklist_cg_insertions
+        out_header = header.edited_lines(with_model=with_model, with_blacklist=with_bl)
+        index = bgzf_io.read_tbi(args.input_file + ".tbi")
+
+        device = args.device if args.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
+        ctx = lib.Context(device)  # raises without a CUDA device: there is no CPU path
+        plan = None
+        if with_model:
+            if model is None or transformer is None:
+                raise ValueError("Model and transformer must be loaded before applying classifier")
+            plan = MC.compile_plan(header, transformer, model, args.custom_annotations)
+        else:
+            plan = MC.compile_plan_no_model(header)
+        ctx.load_plan(plan.blob)
+        batch_bytes = max(1, args.batch_mb) << 20
+        n_lanes = 2
+        reserved = (0, 0)
+
+        out = _Splicer(args.output_file, args.io_threads)
+        out.write_header(out_header)
+        totals = {"n_records": 0, "n_low_score": 0, "n_cg": 0, "n_blacklisted": 0}
+        contigs = list(header.contigs.keys()) if args.limit_to_contigs is None else list(args.limit_to_contigs)
+        for contig in contigs:
+            contig = str(contig)
+            logger.info(f"Filtering variants from {contig}")
+            if contig not in index:
+                logger.info(f"No variants found on {contig}")
+                continue
+            vb, ve = index[contig]
+            text = bgzf_io.inflate(args.input_file, vb, ve, n_threads=args.io_threads)
+            if text.size == 0:
+                logger.info(f"No variants found on {contig}")
+                continue
+            if text[-1] != 10:  # noqa: PLR2004
+                text = np.concatenate((text, np.array([10], dtype=np.uint8)))
+            n_contig = int(np.count_nonzero(text == 10))  # noqa: PLR2004
+            logger.info(f"{n_contig} variants found on {contig}")
+            if blacklists is not None:
+                logger.info("Applying blacklist")
+            if args.blacklist_cg_insertions:
+                logger.info("Marking CG insertions")
+            bl_pos = _blacklist_positions(blacklists, contig) if blacklists is not None else []
+
+            ranges = list(_split_batches(text, batch_bytes))
+            need = (max(e - b for b, e in ranges) + 4096,
+                    max(int(np.count_nonzero(text[b:e] == 10)) for b, e in ranges) + 128)  # noqa: PLR2004
+            if need[0] > reserved[0] or need[1] > reserved[1]:
+                reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))
+                ctx.reserve(reserved[0], reserved[1], n_lanes)
+
+            logger.info("Writing records")
+            inflight: list[tuple[int, int, int]] = []
+
+            def finish(item, contig=contig, text=text, bl_pos=bl_pos):
+                lane, b, e = item
+                cap = int(np.count_nonzero(text[b:e] == 10)) + 1  # noqa: PLR2004
+                outs = ctx.alloc_outputs(cap, want_recinfo=True)
+                n = ctx.collect(lane, outs, cap)
+                res = ctx.trim_outputs(outs, n)
+                bl_code, bl_table, bl_off = None, b"", None
+                if with_bl:
+                    ri = res["recinfo"]
+                    code = np.zeros(n, dtype=np.int32)
+                    parts = []  # (bit weight, annotation) in merge order: CG first, then each blacklist
+                    w = 1
+                    if args.blacklist_cg_insertions:
+                        code += (ri["flags"] & 1).astype(np.int32) * w
+                        parts.append("CG_NON_HMER_INDEL")
+                        w *= 2
+                    for ann, pos in bl_pos:
+                        hit = np.isin(ri["pos"].astype(np.int64), pos)
+                        code += hit.astype(np.int32) * w
+                        parts.append(ann)
+                        w *= 2
+                    strings = []
+                    for c in range(w):
+                        vals = [parts[k] if (c >> k) & 1 else "PASS" for k in range(len(parts))]
+                        strings.append(";".join(vals).encode())
+                    bl_table = b"".join(strings)
+                    bl_off = np.concatenate(([0], np.cumsum([len(s) for s in strings]))).astype(np.int64)
+                    bl_code = code
+                    totals["n_blacklisted"] += int(np.count_nonzero(code))
+                    totals["n_cg"] += int(np.count_nonzero(ri["flags"] & 1))
+                out.write_batch(contig, text[b:e], res, with_model=with_model,
+                                overwrite_qual=args.overwrite_qual_tag, bl_code=bl_code, bl_table=bl_table,
+                                bl_off=bl_off)
+                totals["n_records"] += n
+                if with_model:
+                    totals["n_low_score"] += int(res["low_score"].sum())
+
+            for bi, (b, e) in enumerate(ranges):
+                lane = bi % n_lanes
+                if len(inflight) == n_lanes:
+                    finish(inflight.pop(0))
+                chunk = text[b:e]
+                ctx.submit(lane, chunk, chunk.size, args.decision_threshold)
+                inflight.append((lane, b, e))
+            while inflight:
+                finish(inflight.pop(0))
+            logger.info(f"{contig} done")
+
+        out.close(args.output_file)
+        ctx.close()
+        logger.info(
+            f"{totals['n_records']} records written: {totals['n_low_score']} LOW_SCORE, "
+            f"{totals['n_records'] - totals['n_low_score']} not LOW_SCORE, {totals['n_blacklisted']} blacklisted")
+        logger.info("Variant filtering run: success")
+        return totals
+
+    except Exception as err:
+        exc_info = sys.exc_info()
+        logger.error(exc_info[:2])
+        logger.exception(err)
+        logger.error("Variant filtering run: failed")
+        raise err
+
+
+def main():
+    run(sys.argv[1:])
+
+
+if __name__ == "__main__":
+    main()

@@ -549,3 +549,13 @@ def compile_plan(header: VcfHeader | str | bytes, transformer, model, custom_inf
             + _pad8(dicts_packed) + _pad8(strings_packed) + _pad8(feats_packed) + _pad8(checks_packed) + m["section"])
     return Plan(blob=blob, n_features=n_feat, n_classes=m["n_classes"], n_slots=len(slots), tags=tag_names,
                 feature_names=b.feature_names, model_kind=m["kind"], classes=m.get("classes", []))
+
+
+def compile_plan_no_model(header: VcfHeader | str | bytes) -> Plan:
+    """Plan for runs without ``--model_file``: only K0/K1 run (line index, POS, column
+    offsets, CG flag) so the writer can apply the blacklist / PASS-fill rules."""
+    if not isinstance(header, VcfHeader):
+        header = VcfHeader(header)
+    hdr = struct.pack("<16I4d", PLAN_MAGIC, PLAN_VERSION, 0, 0, 0, 0, 0, 0, 2, 1, 0, 0, 0, 0, CMP_LE, 0,
+                      0.0, 0.0, 0.0, 0.0)
+    return Plan(blob=_pad8(hdr), n_features=0, n_classes=2, n_slots=0, tags=[], feature_names=[], model_kind=0)
