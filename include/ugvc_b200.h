@@ -182,6 +182,11 @@ int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_start, cons
                             const char* blacklist_table, const int64_t* blacklist_table_off,
                             uint8_t* out, size_t capacity, int64_t* out_line_start, int n_threads);
 
+/* ---- test hook ------------------------------------------------------------ */
+/* K1's numeric-literal parser (csrc/numparse.h) compiled for the host: parses one token of
+ * `text` (NUL-terminated); returns 0 ok / 1 missing (".") / 2 not exactly parseable. */
+int ugvc_test_parse_float(const char* text, float* out_f32, double* out_f64, int* out_consumed);
+
 #ifdef __cplusplus
 }
 #endif

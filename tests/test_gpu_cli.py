@@ -1,0 +1,125 @@
+"""GPU: the drop-in CLI (`python ugvc filter_variants_pipeline ...`) end to end on a synthetic
+bgzip'ed VCF (BASELINE.json configs[0], plumbing): output records equal the oracle's writer
+output line for line, header edits match, the .tbi indexes the output."""
+import gzip
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import ref_pipeline as R
+from oracle.vcf_reader import OracleVariantFile
+from tests import util
+from variantcalling_b200 import bgzf_io
+from variantcalling_b200 import filter_variants_pipeline as fvp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Blacklist:  # same attribute contract as ugbio_filtering.blacklist.Blacklist (blacklist.py:10-34)
+    def __init__(self, blacklist, annotation, description=""):
+        self.blacklist, self.annotation, self.description = blacklist, annotation, description
+        self.selection_fcn = None  # VariantSelectionFunctions.ALL
+
+
+@pytest.fixture(scope="module")
+def job(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli")
+    # ~13 k records in chr1:1-5 Mb like the reference's system-test fixtures (SURVEY.md 8d cfg 1)
+    ds = util.make_dataset(n_records=13000, n_custom=4, seed=5, region=("chr1", 1, 5_000_000))
+    extra = util.make_dataset(n_records=800, n_custom=4, seed=6, contigs={"chr2": 242193529, "chr3": 198295559})
+    lines = ds["lines"] + extra["lines"]
+    header = ds["header"]
+    ds["lines"], ds["vf"] = lines, OracleVariantFile(("\n".join(header) + "\n" + "\n".join(lines) + "\n").encode())
+    ds["labels"] = np.concatenate((ds["labels"], extra["labels"]))
+    _, tr, x = util.fit_transformer(ds)
+    model = util.fit_model("gb_small", x, ds["labels"])
+    vcf = str(d / "in.vcf.gz")
+    bgzf_io.write_vcf_gz(vcf, header, lines)
+    mpath = str(d / "model.pkl")
+    with open(mpath, "wb") as fh:
+        pickle.dump({"transformer": tr, "xgb": model, "xgb_recall_precision": None}, fh)
+    pos = [int(l.split("\t")[1]) for l in ds["lines"][:4000:400]]
+    bl = [Blacklist({("chr1", p) for p in pos[:6]}, "ILLUMINA_FP"), Blacklist({("chr1", pos[2]), ("chr9", 5)}, "COHORT_FP")]
+    blpath = str(d / "bl.pkl")
+    with open(blpath, "wb") as fh:
+        pickle.dump(bl, fh)
+    return dict(dir=d, vcf=vcf, model=mpath, bl=blpath, bl_objs=bl, ds=ds, tr=tr, model_obj=model)
+
+
+def read_out(path):
+    text = gzip.open(path).read().decode().split("\n")[:-1]
+    return [l for l in text if l.startswith("#")], [l for l in text if not l.startswith("#")]
+
+
+def test_cli_matches_oracle_with_model_blacklist_and_cg(job):
+    out = str(job["dir"] / "out1.vcf.gz")
+    argv = ["--input_file", job["vcf"], "--model_file", job["model"], "--output_file", out, "--blacklist", job["bl"],
+            "--blacklist_cg_insertions"]
+    for c in job["ds"]["customs"]:
+        argv += ["--custom_annotations", c]
+    totals = fvp.run(argv)
+    bls = [(b.blacklist, b.annotation) for b in job["bl_objs"]]
+    exp = R.filter_variants(job["ds"]["vf"], job["model_obj"], job["tr"], custom_annotations=job["ds"]["customs"],
+                            blacklist_cg=True, position_blacklists=bls)
+    hdr, recs = read_out(out)
+    assert hdr == exp["header"]
+    assert len(recs) == len(exp["lines"]) == totals["n_records"]
+    bad = [i for i, (a, b) in enumerate(zip(recs, exp["lines"])) if a != b]
+    assert not bad, f"{len(bad)} records differ, first: {recs[bad[0]]!r} vs {exp['lines'][bad[0]]!r}"
+    assert sum("BLACKLST=" in r for r in recs) > 6
+    # value counts like the reference's system test goldens (FILTER column)
+    got_counts = {k: sum(r.split("\t")[6] == k for r in recs) for k in ("PASS", "LOW_SCORE")}
+    want_counts = {k: sum(f == k for f in exp["filters"]) for k in ("PASS", "LOW_SCORE")}
+    assert got_counts == want_counts and totals["n_low_score"] == sum("LOW_SCORE" in f for f in exp["filters"])
+    # the index selects each contig of the output
+    idx = bgzf_io.read_tbi(out + ".tbi")
+    assert list(idx) == ["chr1", "chr2", "chr3"]
+    for c, (vb, ve) in idx.items():
+        got = bgzf_io.inflate(out, vb, ve).tobytes().decode().split("\n")[:-1]
+        assert got == [r for r in recs if r.split("\t", 1)[0] == c]
+
+
+def test_cli_overwrite_qual_threshold_and_limit_contigs(job):
+    out = str(job["dir"] / "out2.vcf.gz")
+    argv = ["--input_file", job["vcf"], "--model_file", job["model"], "--output_file", out, "--overwrite_qual_tag",
+            "--decision_threshold", "12.5", "--limit_to_contigs", "chr3", "chr1", "chrNOPE"]
+    for c in job["ds"]["customs"]:
+        argv += ["--custom_annotations", c]
+    fvp.run(argv)
+    exp = R.filter_variants(job["ds"]["vf"], job["model_obj"], job["tr"], custom_annotations=job["ds"]["customs"],
+                            decision_threshold=12.5, overwrite_qual_tag=True, limit_to_contigs=["chr3", "chr1", "chrNOPE"])
+    _, recs = read_out(out)
+    assert recs == exp["lines"] and recs[0].startswith("chr3\t")
+
+
+def test_cli_without_model_fills_pass_and_marks_cg(job):
+    out = str(job["dir"] / "out3.vcf.gz")
+    fvp.run(["--input_file", job["vcf"], "--output_file", out, "--blacklist_cg_insertions"])
+    exp = R.filter_variants(job["ds"]["vf"], None, None, blacklist_cg=True)
+    hdr, recs = read_out(out)
+    assert hdr == exp["header"] and recs == exp["lines"]
+    assert not any("TREE_SCORE" in r for r in recs) and not any(r.split("\t")[6] == "." for r in recs)
+
+
+def test_python_ugvc_entry_point_and_error_contract(job):
+    out = str(job["dir"] / "out4.vcf.gz")
+    cmd = [sys.executable, "ugvc", "filter_variants_pipeline", "--input_file", job["vcf"], "--model_file", job["model"],
+           "--output_file", out]
+    for c in job["ds"]["customs"]:
+        cmd += ["--custom_annotations", c]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Variant filtering run: success" in r.stderr and os.path.exists(out + ".tbi")
+    # missing index -> RuntimeError + "failed" line + non-zero exit (filter_variants_pipeline.py:101-104,235-240)
+    lonely = str(job["dir"] / "lonely.vcf.gz")
+    with open(job["vcf"], "rb") as a, open(lonely, "wb") as b:
+        b.write(a.read())
+    r = subprocess.run(cmd[:4] + [lonely] + cmd[5:], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "Variant filtering run: failed" in r.stderr and "does not exist" in r.stderr
+    with pytest.raises(ValueError, match="Reference FASTA"):
+        fvp.run(["--input_file", job["vcf"], "--output_file", out, "--treat_multiallelics"])

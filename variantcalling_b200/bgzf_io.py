@@ -259,7 +259,6 @@ def write_vcf_gz(path: str, header_lines: list[str], record_lines: list[str], n_
     u_start = len(hdr) + np.concatenate(([0], np.cumsum(lens)[:-1]))
     u_end = u_start + lens
     vs = w.virtual_offsets(u_start)
-    # the end of the last record of a block is the start of the next block: htslib reports
-    # one-past-the-end the same way, and readers only need end >= true end
-    ve = w.virtual_offsets(np.minimum(u_end, w.uoffset - 1)) + np.uint64(1)
+    # one past the record's last byte, expressed inside the block that holds that byte
+    ve = w.virtual_offsets(u_end - 1) + np.uint64(1)
     write_tbi(path + ".tbi", build_tbi(names, np.array(contig_of), np.array(beg), np.array(end), vs, ve))

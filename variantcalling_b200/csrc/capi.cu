@@ -34,6 +34,7 @@ struct ugvc_ctx {
     DevPlan plan{};
     uint8_t* d_plan = nullptr;
     uint8_t* d_htab = nullptr;
+    uint2* d_nodes = nullptr;
     std::vector<Lane> lanes;
     size_t cap_bytes = 0, cap_records = 0;
     long long* d_counts = nullptr;
@@ -112,6 +113,7 @@ extern "C" void ugvc_free(ugvc_ctx* ctx) {
     for (auto& l : ctx->lanes) free_lane(l);
     cudaFree(ctx->d_plan);
     cudaFree(ctx->d_htab);
+    cudaFree(ctx->d_nodes);
     cudaFree(ctx->d_counts);
     delete ctx;
 }
@@ -127,7 +129,7 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     if (h.magic != UGVC_PLAN_MAGIC) return fail(ctx, UGVC_E_PLAN, "bad plan magic");
     if (h.version != UGVC_PLAN_VERSION) return fail(ctx, UGVC_E_PLAN, "plan version mismatch");
     if (h.n_tags > UGVC_MAX_TAGS || h.n_slots > UGVC_MAX_SLOTS || h.n_features > UGVC_MAX_FEATURES ||
-        h.n_checks > 64 || h.n_classes < 2 || h.n_classes > UGVC_MAX_CLASSES || h.n_outputs < 1 || h.n_outputs > UGVC_MAX_CLASSES)
+        h.n_checks > 64 || h.n_dicts > 64 || h.n_dict_strings > 96 || h.n_classes < 2 || h.n_classes > UGVC_MAX_CLASSES || h.n_outputs < 1 || h.n_outputs > UGVC_MAX_CLASSES)
         return fail(ctx, UGVC_E_PLAN, "plan dimensions out of range");
     size_t off = align8(sizeof(PlanHeader));
     const size_t o_tags = off;
@@ -173,9 +175,9 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     for (uint32_t t = 0; t < h.n_tags; ++t) {
         if (tags[t].len == 0 || tags[t].len > UGVC_NAME_MAX) return fail(ctx, UGVC_E_PLAN, "bad tag name length");
         if ((uint32_t)tags[t].first_slot + tags[t].n_slots > h.n_slots) return fail(ctx, UGVC_E_PLAN, "tag slots out of range");
-        unsigned hash = 2166136261u;
-        for (int i = 0; i < tags[t].len; ++i) hash = (hash ^ (uint8_t)tags[t].name[i]) * 16777619u;
-        unsigned idx = (hash ^ (hash >> 8) ^ (hash >> 16)) & 255u;
+        unsigned long long kw[3];
+        memcpy(kw, tags[t].name, 24);
+        unsigned idx = ugvc_key_hash(kw[0], kw[1], kw[2], tags[t].len);
         while (htab[idx] != 0xFF) idx = (idx + 1) & 255u;
         htab[idx] = (uint8_t)t;
     }
@@ -217,10 +219,48 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
             }
         }
     }
+    // device form of the forest: leaves become absorbing nodes (threshold = quiet NaN carrying the
+    // leaf row, right child = itself) so a fixed-depth, branch-free walk ends on them; right
+    // children are absolute indices.  Also the depth of the deepest leaf.
+    std::vector<uint2> dev_nodes;
+    uint32_t max_depth = 0;
+    if (h.model_kind != MODEL_LOGISTIC && h.model_kind != MODEL_NONE) {
+        const uint32_t* root = reinterpret_cast<const uint32_t*>(hb + o_root);
+        const PlanNode* nodes = reinterpret_cast<const PlanNode*>(hb + o_nodes);
+        if (h.n_nodes >= (1u << 24) || h.n_leaf_rows >= (1u << 22) || h.n_features > 255)
+            return fail(ctx, UGVC_E_PLAN, "forest too large for the device node format");
+        dev_nodes.resize(h.n_nodes);
+        std::vector<uint32_t> depth(h.n_nodes, 0);
+        for (uint32_t t = 0; t < h.n_trees; ++t) {
+            const uint32_t r0 = root[t], n = root[t + 1] - root[t];
+            if (n) depth[r0] = 0;
+            for (uint32_t i = 0; i < n; ++i) {  // preorder: parents precede children
+                const PlanNode& nd = nodes[r0 + i];
+                if (nd.feature >= 0) {
+                    uint32_t thr;
+                    memcpy(&thr, &nd.value, 4);
+                    dev_nodes[r0 + i] = make_uint2(thr, (uint32_t)nd.feature | ((r0 + nd.right) << 8));
+                    depth[r0 + i + 1] = depth[r0 + i] + 1;
+                    depth[r0 + nd.right] = depth[r0 + i] + 1;
+                } else {
+                    int32_t leaf;
+                    memcpy(&leaf, &nd.value, 4);
+                    dev_nodes[r0 + i] = make_uint2(0x7FC00000u | (uint32_t)leaf, (r0 + i) << 8);
+                    if (depth[r0 + i] > max_depth) max_depth = depth[r0 + i];
+                }
+            }
+        }
+    }
     cudaFree(ctx->d_plan);
     cudaFree(ctx->d_htab);
+    cudaFree(ctx->d_nodes);
     ctx->d_plan = nullptr;
     ctx->d_htab = nullptr;
+    ctx->d_nodes = nullptr;
+    if (!dev_nodes.empty()) {
+        CU(cudaMalloc(&ctx->d_nodes, dev_nodes.size() * sizeof(uint2)));
+        CU(cudaMemcpy(ctx->d_nodes, dev_nodes.data(), dev_nodes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
     CU(cudaMalloc(&ctx->d_plan, off));
     CU(cudaMemcpy(ctx->d_plan, blob, off, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&ctx->d_htab, 256));
@@ -239,11 +279,20 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     p.tree_root = reinterpret_cast<const uint32_t*>(d + o_root);
     p.tree_out = d + o_tout;
     p.nodes = reinterpret_cast<const PlanNode*>(d + o_nodes);
+    p.dev_nodes = ctx->d_nodes;
+    p.max_depth = max_depth;
     p.leaves = reinterpret_cast<const double*>(d + o_leaves);
     p.htab = ctx->d_htab;
     p.first_fixed_slot = first_fixed;
-    if (k1_smem_bytes(p) > 227 * 1024 || k3_smem_bytes(p) > 227 * 1024)
+    if (k1_smem_bytes(p) > 227 * 1024 || k3_smem_bytes(p) > 227 * 1024 || !k3_plan_fits(p))
         return fail(ctx, UGVC_E_PLAN, "plan needs more shared memory than one sm_100 CTA has");
+    if (h.model_kind != MODEL_LOGISTIC && h.model_kind != MODEL_NONE) {
+        const uint32_t* root = reinterpret_cast<const uint32_t*>(hb + o_root);
+        const unsigned cap = k3_chunk_nodes_cap(p);
+        for (uint32_t t = 0; t < h.n_trees; ++t)
+            if (root[t + 1] - root[t] > cap)
+                return fail(ctx, UGVC_E_PLAN, "a single tree does not fit the shared-memory forest buffer");
+    }
     CU(kernels_configure(p));
     ctx->has_plan = true;
     // a new plan changes the slot/feature counts: lanes must be re-reserved

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/ugvc_b200.h"
+#include "numparse.h"
 
 namespace {
 
@@ -474,4 +475,16 @@ extern "C" int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_
     }
     if (out_line_start) out_line_start[n_records] = (int64_t)total;
     return (int64_t)total;
+}
+
+// The K1 numeric-literal parser compiled for the host (same header as the device code), so
+// the CPU tests can check it against strtod on millions of literals.
+extern "C" int ugvc_test_parse_float(const char* text, float* out_f32, double* out_f64, int* out_consumed) {
+    UgvcPtrSrc s{reinterpret_cast<const uint8_t*>(text)};
+    double v = 0.0;
+    const int st = ugvc_parse_num(s, v);
+    if (out_f64) *out_f64 = v;
+    if (out_f32) *out_f32 = (float)v;
+    if (out_consumed) *out_consumed = (int)(s.p - reinterpret_cast<const uint8_t*>(text));
+    return st;
 }

@@ -20,10 +20,12 @@
 
 #include <math.h>
 
+#include "numparse.h"
+
 #define WARP 32
 #define K1_TPB 128
 #define K2_TPB 256
-#define K3_TPB 128
+#define K3_TPB 256
 
 // ------------------------------------------------------------------------------------------
 // small helpers
@@ -164,121 +166,140 @@ void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* chunk_first, int
 // ------------------------------------------------------------------------------------------
 // K1: field parse
 // ------------------------------------------------------------------------------------------
-__constant__ double c_pow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
-                                   1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+// One thread per record.  The record's bytes are consumed through a 64-bit register window
+// (aligned 8-byte loads through L1; delimiter search is SWAR over the window with
+// __vcmpeq4), keys and short string values are gathered into three 64-bit registers and
+// matched word-wise against the plan tables in shared memory, numbers go through
+// numparse.h.  The scanning primitives are real (non-inlined) functions taking and returning
+// the cursor by value: the kernel body stays small enough for the instruction cache while
+// the 32 lanes of a warp sit in different fields of different records.
+#define K1_MAX_STRINGS 96
+#define K1_MAX_DICTS 64
+// fixed layout of the shared-memory plan tables, then the slot tile
+#define K1_OFF_TAGS 0
+#define K1_OFF_STRINGS (K1_OFF_TAGS + UGVC_MAX_TAGS * 32)
+#define K1_OFF_SLOTS (K1_OFF_STRINGS + K1_MAX_STRINGS * 32)
+#define K1_OFF_DICTS (K1_OFF_SLOTS + 256 * 4)
+#define K1_OFF_HTAB (K1_OFF_DICTS + K1_MAX_DICTS * 4)
+#define K1_OFF_TILE (K1_OFF_HTAB + 256)
 
-struct K1Shared {
-    const PlanTag* tags;
-    const PlanSlot* slots;
-    const PlanDict* dicts;
-    const PlanString* strings;
-    const uint8_t* htab;
-    uint32_t* tile;  // [n_slots][K1_TPB]
+extern __shared__ __align__(16) uint8_t k1_smem[];
+__device__ __forceinline__ const PlanTag* s_tags() { return reinterpret_cast<const PlanTag*>(k1_smem + K1_OFF_TAGS); }
+__device__ __forceinline__ const PlanString* s_strings() { return reinterpret_cast<const PlanString*>(k1_smem + K1_OFF_STRINGS); }
+__device__ __forceinline__ const PlanSlot* s_slots() { return reinterpret_cast<const PlanSlot*>(k1_smem + K1_OFF_SLOTS); }
+__device__ __forceinline__ const PlanDict* s_dicts() { return reinterpret_cast<const PlanDict*>(k1_smem + K1_OFF_DICTS); }
+__device__ __forceinline__ const uint8_t* s_htab() { return k1_smem + K1_OFF_HTAB; }
+__device__ __forceinline__ uint32_t* s_tile() { return reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_TILE); }
+
+struct Cur {
+    const unsigned long long* wp;  // next aligned word
+    unsigned long long w;          // unread bytes of the current word, next byte lowest
+    int n;                         // how many (1..8)
+    __device__ __forceinline__ void init(const uint8_t* p) {
+        const unsigned off = (unsigned)(reinterpret_cast<uintptr_t>(p) & 7u);
+        wp = reinterpret_cast<const unsigned long long*>(p - off);
+        w = __ldg(wp++) >> (8 * off);
+        n = 8 - (int)off;
+    }
+    __device__ __forceinline__ unsigned peek() const { return (unsigned)w & 0xFFu; }
+    __device__ __forceinline__ void adv() {
+        w >>= 8;
+        if (--n == 0) {
+            w = __ldg(wp++);
+            n = 8;
+        }
+    }
+    __device__ __forceinline__ void refill() {
+        w = __ldg(wp++);
+        n = 8;
+    }
+    __device__ __forceinline__ const uint8_t* ptr() const { return reinterpret_cast<const uint8_t*>(wp) - n; }
 };
 
-enum { NUM_OK = 0, NUM_MISSING = 1, NUM_BAD = 2 };
-
-__device__ __forceinline__ bool is_digit(unsigned c) { return (c - '0') <= 9u; }
-__device__ __forceinline__ unsigned lower(unsigned c) { return c | 0x20u; }
-
-// Parse one numeric token starting at p (htslib: strtod -> float32 for Float, strtol for
-// Integer).  On return p is one past the token.  The double is exactly strtod's result for
-// every literal with <= 19 significant digits whose decimal exponent fits Clinger's exact
-// window; anything else reports NUM_BAD (never a silently different value).
-__device__ int parse_num(const uint8_t*& p, double& out) {
-    unsigned c = *p;
-    bool neg = false;
-    if (c == '-' || c == '+') {
-        neg = (c == '-');
-        c = *++p;
-    }
-    unsigned long long m = 0;
-    int exp10 = 0;
-    bool any = false, inexact = false;
-    while (is_digit(c)) {
-        any = true;
-        const unsigned d = c - '0';
-        if (m < 1844674407370955161ull) m = m * 10 + d;
-        else { ++exp10; inexact |= (d != 0); }
-        c = *++p;
-    }
-    if (c == '.') {
-        c = *++p;
-        while (is_digit(c)) {
-            any = true;
-            const unsigned d = c - '0';
-            if (m < 1844674407370955161ull) { m = m * 10 + d; --exp10; }
-            else inexact |= (d != 0);
-            c = *++p;
-        }
-        if (!any) {  // a lone "." (possibly signed): missing
-            out = 0.0;
-            return neg ? NUM_BAD : NUM_MISSING;
-        }
-    }
-    if (!any) {
-        // nan / inf / infinity (any case), as strtod accepts them
-        const unsigned a = lower(c);
-        if (a == 'n' && lower(p[1]) == 'a' && lower(p[2]) == 'n') {
-            p += 3;
-            out = __longlong_as_double(0x7FF8000000000000ll);
-            return NUM_OK;
-        }
-        if (a == 'i' && lower(p[1]) == 'n' && lower(p[2]) == 'f') {
-            p += 3;
-            if (lower(p[0]) == 'i' && lower(p[1]) == 'n' && lower(p[2]) == 'i' && lower(p[3]) == 't' &&
-                lower(p[4]) == 'y')
-                p += 5;
-            out = neg ? -INFINITY : INFINITY;
-            return NUM_OK;
-        }
-        out = 0.0;
-        return NUM_BAD;
-    }
-    if (lower(c) == 'e') {
-        const uint8_t* q = p + 1;
-        unsigned e = *q;
-        bool eneg = false;
-        if (e == '-' || e == '+') {
-            eneg = (e == '-');
-            e = *++q;
-        }
-        if (is_digit(e)) {
-            int ev = 0;
-            while (is_digit(e)) {
-                if (ev < 100000) ev = ev * 10 + (int)(e - '0');
-                e = *++q;
-            }
-            exp10 += eneg ? -ev : ev;
-            p = q;
-        }
-    }
+struct Key {
+    unsigned long long k0, k1, k2;
+    int len;
+};
+struct KeyCur {
+    Cur c;
+    Key k;
+};
+struct NumCur {
+    Cur c;
     double v;
-    if (m == 0) {
-        v = 0.0;
-    } else if (inexact || m > (1ull << 53)) {
-        out = 0.0;
-        return NUM_BAD;
-    } else if (exp10 == 0) {
-        v = (double)m;
-    } else if (exp10 > 0 && exp10 <= 22) {
-        v = (double)m * c_pow10[exp10];
-    } else if (exp10 < 0 && exp10 >= -22) {
-        v = (double)m / c_pow10[-exp10];
-    } else if (exp10 > 22 && exp10 <= 22 + 15) {
-        // m * 10^(exp10-22) may still be an exact integer <= 2^53
-        const double scaled = (double)m * c_pow10[exp10 - 22];
-        if (scaled > 9007199254740992.0) {
-            out = 0.0;
-            return NUM_BAD;
+    int st;
+};
+
+#define B4(ch) ((unsigned)(ch) * 0x01010101u)
+
+// 0xFF in every byte of w that equals tab, newline or one of the two pattern bytes (consumed
+// bytes of the window are zero and never match)
+__device__ __forceinline__ unsigned long long delim_mask(unsigned long long w, unsigned a4, unsigned b4) {
+    const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
+    // tab (0x09) and newline (0x0A): the only bytes of a VCF line in 0x08..0x0B
+    const unsigned ml = __vcmpeq4(lo & 0xFCFCFCFCu, 0x08080808u) | __vcmpeq4(lo, a4) | __vcmpeq4(lo, b4);
+    const unsigned mh = __vcmpeq4(hi & 0xFCFCFCFCu, 0x08080808u) | __vcmpeq4(hi, a4) | __vcmpeq4(hi, b4);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+// advance to the first byte that is tab, newline or a pattern byte
+__device__ __noinline__ Cur skip_until(Cur c, unsigned a4, unsigned b4) {
+    for (;;) {
+        const unsigned long long m = delim_mask(c.w, a4, b4);
+        if (m) {
+            const int k = (__ffsll((long long)m) - 1) >> 3;
+            c.w >>= 8 * k;
+            c.n -= k;
+            return c;
         }
-        v = scaled * 1e22;
-    } else {
-        out = 0.0;
-        return NUM_BAD;
+        c.refill();
     }
-    out = neg ? -v : v;
-    return NUM_OK;
+}
+
+__device__ __forceinline__ void key_append(Key& key, unsigned long long bytes, int k) {
+    const int pos = key.len;
+    key.len = pos + k;
+    if (k == 0 || pos >= 24) return;
+    const int sh = (pos & 7) * 8;
+    const unsigned long long lo = bytes << sh;
+    const unsigned long long hi = sh ? (bytes >> (64 - sh)) : 0ull;
+    const int word = pos >> 3;
+    if (word == 0) {
+        key.k0 |= lo;
+        key.k1 |= hi;
+    } else if (word == 1) {
+        key.k1 |= lo;
+        key.k2 |= hi;
+    } else {
+        key.k2 |= lo;
+    }
+}
+
+// gather the bytes up to (not including) the first tab / newline / pattern byte
+__device__ __noinline__ KeyCur take_until(Cur c, unsigned a4, unsigned b4) {
+    KeyCur r;
+    r.k.k0 = r.k.k1 = r.k.k2 = 0ull;
+    r.k.len = 0;
+    for (;;) {
+        const unsigned long long m = delim_mask(c.w, a4, b4);
+        if (m) {
+            const int k = (__ffsll((long long)m) - 1) >> 3;  // 0..7
+            key_append(r.k, c.w & ((1ull << (8 * k)) - 1ull), k);
+            c.w >>= 8 * k;
+            c.n -= k;
+            r.c = c;
+            return r;
+        }
+        key_append(r.k, c.w, c.n);
+        c.refill();
+    }
+}
+
+__device__ __noinline__ NumCur parse_num_cur(Cur c) {
+    NumCur r;
+    r.st = ugvc_parse_num(c, r.v);
+    r.c = c;
+    return r;
 }
 
 __device__ __forceinline__ unsigned base_code(unsigned c) {
@@ -287,47 +308,39 @@ __device__ __forceinline__ unsigned base_code(unsigned c) {
 }
 __device__ __forceinline__ unsigned motif_code(unsigned c) { return c == 'N' ? 5u : base_code(c); }
 
-__device__ __forceinline__ bool bytes_equal(const uint8_t* a, const char* b, int n) {
-    for (int i = 0; i < n; ++i)
-        if (a[i] != (uint8_t)b[i]) return false;
-    return true;
-}
-
-__device__ __forceinline__ int find_tag(const K1Shared& sp, const uint8_t* key, int len, unsigned hash) {
-    if (len <= 0 || len > UGVC_NAME_MAX) return -1;
-    unsigned idx = (hash ^ (hash >> 8) ^ (hash >> 16)) & 255u;
+__device__ __noinline__ int find_tag(Key key) {
+    if (key.len <= 0 || key.len > UGVC_NAME_MAX) return -1;
+    unsigned idx = ugvc_key_hash(key.k0, key.k1, key.k2, key.len);
     for (int probe = 0; probe < 256; ++probe) {
-        const unsigned t = sp.htab[idx];
+        const unsigned t = s_htab()[idx];
         if (t == 0xFFu) return -1;
-        const PlanTag& tg = sp.tags[t];
-        if (tg.len == len && bytes_equal(key, tg.name, len)) return (int)t;
+        const unsigned long long* tw = reinterpret_cast<const unsigned long long*>(&s_tags()[t]);
+        if (tw[0] == key.k0 && tw[1] == key.k1 && tw[2] == key.k2 && (int)(tw[3] & 0xFFu) == key.len) return (int)t;
         idx = (idx + 1) & 255u;
     }
     return -1;
 }
 
-__device__ __forceinline__ void store_slot(const K1Shared& sp, int slot, uint32_t bits) {
-    sp.tile[slot * K1_TPB + threadIdx.x] = bits;
-}
-__device__ __forceinline__ void store_slot_f(const K1Shared& sp, int slot, float v) {
-    store_slot(sp, slot, __float_as_uint(v));
-}
+__device__ __forceinline__ void store_slot(int slot, uint32_t bits) { s_tile()[slot * K1_TPB + threadIdx.x] = bits; }
+__device__ __forceinline__ void store_slot_f(int slot, float v) { store_slot(slot, __float_as_uint(v)); }
 
-__device__ uint32_t reduce_string(const K1Shared& sp, const PlanSlot& sl, const uint8_t* a, const uint8_t* b) {
-    const int n = (int)(b - a);
+#define CH3(a, b, c) ((unsigned long long)(a) | ((unsigned long long)(b) << 8) | ((unsigned long long)(c) << 16))
+
+__device__ __forceinline__ uint32_t reduce_string(const PlanSlot sl, const Key& k) {
     switch (sl.reducer) {
         case RED_BASE:
-            return __float_as_uint(n == 1 ? (float)base_code(a[0]) : 0.0f);
+            return __float_as_uint(k.len == 1 ? (float)base_code((unsigned)k.k0 & 0xFFu) : 0.0f);
         case RED_INSDEL:
-            if (n == 3 && a[0] == 'i' && a[1] == 'n' && a[2] == 's') return __float_as_uint(-1.0f);
-            if (n == 3 && a[0] == 'd' && a[1] == 'e' && a[2] == 'l') return __float_as_uint(1.0f);
-            if (n == 2 && a[0] == 'N' && a[1] == 'A') return __float_as_uint(0.0f);
+            if (k.len == 3 && k.k0 == CH3('i', 'n', 's')) return __float_as_uint(-1.0f);
+            if (k.len == 3 && k.k0 == CH3('d', 'e', 'l')) return __float_as_uint(1.0f);
+            if (k.len == 2 && k.k0 == CH3('N', 'A', 0)) return __float_as_uint(0.0f);
             return RAW_ERR;
         case RED_DICT: {
-            const PlanDict d = sp.dicts[sl.dict];
+            const PlanDict d = s_dicts()[sl.dict];
             for (int i = 0; i < d.n_strings; ++i) {
-                const PlanString& s = sp.strings[d.first_string + i];
-                if (s.len == n && bytes_equal(a, s.s, n)) return __float_as_uint((float)i);
+                const unsigned long long* sw = reinterpret_cast<const unsigned long long*>(&s_strings()[d.first_string + i]);
+                if (sw[0] == k.k0 && sw[1] == k.k1 && sw[2] == k.k2 && (int)(sw[3] & 0xFFu) == k.len)
+                    return __float_as_uint((float)i);
             }
             return RAW_ERR;
         }
@@ -336,128 +349,127 @@ __device__ uint32_t reduce_string(const K1Shared& sp, const PlanSlot& sl, const 
     }
 }
 
-// Decode one tag value that starts at p; vend is the character that ends a value in this
-// column (';' in INFO, ':' in the sample column).  Leaves p on the terminating character.
-__device__ void parse_value(const K1Shared& sp, const PlanTag& tg, unsigned kind, const uint8_t*& p,
-                            unsigned vend) {
-    const int s0 = tg.first_slot, s1 = tg.first_slot + tg.n_slots;
-    for (int s = s0; s < s1; ++s) store_slot(sp, s, RAW_MISSING);
+// Decode one tag value starting at the cursor.  vend ends a value in this column (';' in INFO,
+// ':' in the sample column).  The plan lays a tag's slots out as elements 0..n_elem-1 followed
+// by at most one whole-value slot, so element e lands in slot first_slot + e.  Returns the
+// cursor somewhere inside / at the end of the value; the caller skips to vend.
+__device__ __noinline__ Cur parse_value(int t, unsigned kind, Cur c, unsigned vend) {
+    const PlanTag tg = s_tags()[t];
+    const unsigned whole = tg.whole_red;
+    const int s0 = tg.first_slot;
+    const int n_elem = (int)tg.n_slots - (whole != 0xFFu ? 1 : 0);
     const unsigned type = kind & KIND_TYPE_MASK;
     const bool scalar = (kind & KIND_SCALAR) != 0;
-    const uint8_t* vstart = p;
-    int e = 0;
+    const unsigned v4 = B4(vend), c4 = B4(',');
     if (type == KIND_FLAG) {
-        while (*p != vend && *p != '\t' && *p != '\n') ++p;
-        return;
+        for (int s = s0; s < s0 + (int)tg.n_slots; ++s) store_slot(s, RAW_MISSING);
+        return c;
     }
-    for (;;) {
-        const uint8_t* a = p;
-        double val = 0.0;
-        int st = NUM_OK;
-        if (type == KIND_INT || type == KIND_FLOAT) {
-            st = parse_num(p, val);
-            unsigned c = *p;
-            if (c != ',' && c != vend && c != '\t' && c != '\n') {  // trailing garbage in the token
-                st = NUM_BAD;
-                while (c != ',' && c != vend && c != '\t' && c != '\n') c = *++p;
-            }
-        } else {
-            unsigned c = *p;
-            if (scalar)
-                while (c != vend && c != '\t' && c != '\n') c = *++p;
-            else
-                while (c != ',' && c != vend && c != '\t' && c != '\n') c = *++p;
+    if (whole == RED_MOTIF_L || whole == RED_MOTIF_R) {
+        // list(x): characters of a str, elements of a tuple (only single-character elements can
+        // match a base) -- transformers.py:36-60
+        if (type != KIND_STR) {
+            store_slot(tg.whole_slot, RAW_ERR);
+            return c;
         }
-        for (int s = s0; s < s1; ++s) {
-            const PlanSlot sl = sp.slots[s];
-            if (sl.elem != e) continue;
-            if (sl.reducer == RED_NUM) {
-                if (type == KIND_INT) {
-                    if (st == NUM_OK) {
-                        // htslib keeps int32; features are fp32 downstream
-                        store_slot_f(sp, s, (float)(long long)val);
-                    } else
-                        store_slot(sp, s, st == NUM_MISSING ? RAW_MISSING : RAW_ERR);
-                } else if (type == KIND_FLOAT) {
-                    if (st == NUM_OK) {
-                        const float f = (float)val;  // float32(strtod(text)), round-to-nearest-even
-                        store_slot(sp, s, isnan(f) ? RAW_MISSING : __float_as_uint(f));
-                    } else
-                        store_slot(sp, s, st == NUM_MISSING ? RAW_MISSING : RAW_ERR);
-                } else
-                    store_slot(sp, s, RAW_ERR);
-            } else if (sl.reducer <= RED_DICT) {
-                store_slot(sp, s, type == KIND_STR ? reduce_string(sp, sl, a, p) : RAW_ERR);
+        double num = 0.0, scale = 1.0;
+        const bool left = whole == RED_MOTIF_L;
+        unsigned ch = c.peek();
+        int elen = 0;
+        unsigned first = 0;
+        for (;;) {
+            const bool end = (ch == vend || ch == '\t' || ch == '\n');
+            unsigned code = 0;
+            bool emit = false;
+            if (scalar) {
+                if (!end) {
+                    code = motif_code(ch);
+                    emit = true;
+                }
+            } else if (end || ch == ',') {
+                code = elen == 1 ? motif_code(first) : 0u;
+                emit = true;
+                elen = 0;
+            } else {
+                if (elen == 0) first = ch;
+                ++elen;
             }
+            if (emit) {
+                if (left) {
+                    num += scale * (double)code;
+                    scale *= 10.0;
+                } else
+                    num = num * 10.0 + (double)code;
+            }
+            if (end) break;
+            c.adv();
+            ch = c.peek();
+        }
+        store_slot_f(tg.whole_slot, (float)num);
+        return c;
+    }
+    if (whole == RED_GT_HOM) {
+        const KeyCur r = take_until(c, v4, v4);
+        const bool hom = r.k.len == 3 && (r.k.k0 == CH3('1', '/', '1') || r.k.k0 == CH3('1', '|', '1'));
+        store_slot_f(tg.whole_slot, hom ? 1.0f : 0.0f);
+        return r.c;
+    }
+    if (whole == RED_STRNUM) {
+        const NumCur r = parse_num_cur(c);
+        const unsigned ch = r.c.peek();
+        const bool ok = r.st == NUM_OK && (ch == vend || ch == '\t' || ch == '\n') && !isnan(r.v);
+        store_slot(tg.whole_slot, ok ? __float_as_uint((float)r.v) : RAW_ERR);
+        return r.c;
+    }
+    const bool count_all = whole == RED_LEN;
+    int e = 0;
+    for (;;) {
+        if (type == KIND_INT || type == KIND_FLOAT) {
+            NumCur r = parse_num_cur(c);
+            c = r.c;
+            const unsigned ch = c.peek();
+            if (ch != ',' && ch != vend && ch != '\t' && ch != '\n') {  // trailing garbage in the token
+                r.st = NUM_BAD;
+                c = skip_until(c, c4, v4);
+            }
+            if (e < n_elem) {
+                uint32_t bits;
+                if (s_slots()[s0 + e].reducer != RED_NUM) bits = RAW_ERR;
+                else if (r.st != NUM_OK) bits = r.st == NUM_MISSING ? RAW_MISSING : RAW_ERR;
+                else if (type == KIND_INT) bits = __float_as_uint((float)(long long)r.v);  // htslib int32 -> fp32
+                else {
+                    const float f = (float)r.v;  // float32(strtod(text))
+                    bits = isnan(f) ? RAW_MISSING : __float_as_uint(f);
+                }
+                store_slot(s0 + e, bits);
+            }
+        } else if (e < n_elem) {
+            const KeyCur r = take_until(c, scalar ? v4 : c4, v4);
+            c = r.c;
+            store_slot(s0 + e, reduce_string(s_slots()[s0 + e], r.k));
+        } else {
+            c = skip_until(c, scalar ? v4 : c4, v4);
         }
         ++e;
-        if (*p == ',' && !(scalar && type == KIND_STR)) {
-            ++p;
+        if (c.peek() == ',' && !(scalar && type == KIND_STR) && (e < n_elem || count_all)) {
+            c.adv();
             continue;
         }
         break;
     }
-    // whole-value reducers
-    for (int s = s0; s < s1; ++s) {
-        const PlanSlot sl = sp.slots[s];
-        if (sl.elem != ELEM_WHOLE) continue;
-        switch (sl.reducer) {
-            case RED_LEN:
-                store_slot_f(sp, s, (float)e);
-                break;
-            case RED_MOTIF_L:
-            case RED_MOTIF_R: {
-                // list(x): characters of a str, elements of a tuple (only single-character
-                // elements can match a base) -- transformers.py:36-60
-                double num = 0.0, scale = 1.0;
-                const bool left = sl.reducer == RED_MOTIF_L;
-                const uint8_t* q = vstart;
-                if (type != KIND_STR) {
-                    store_slot(sp, s, RAW_ERR);
-                    break;
-                }
-                while (q < p) {
-                    unsigned code;
-                    if (scalar) {
-                        code = motif_code(*q++);
-                    } else {
-                        const uint8_t* ea = q;
-                        while (q < p && *q != ',') ++q;
-                        code = (q - ea == 1) ? motif_code(*ea) : 0u;
-                        if (q < p) ++q;  // skip ','
-                    }
-                    if (left) {
-                        num += scale * (double)code;
-                        scale *= 10.0;
-                    } else
-                        num = num * 10.0 + (double)code;
-                }
-                store_slot_f(sp, s, (float)num);
-                break;
-            }
-            case RED_STRNUM: {
-                const uint8_t* q = vstart;
-                double v;
-                const int st = parse_num(q, v);
-                store_slot(sp, s, (st == NUM_OK && q == p && !isnan(v)) ? __float_as_uint((float)v) : RAW_ERR);
-                break;
-            }
-            case RED_GT_HOM: {
-                const bool hom = (p - vstart == 3) && vstart[0] == '1' && (vstart[1] == '/' || vstart[1] == '|') &&
-                                 vstart[2] == '1';
-                store_slot_f(sp, s, hom ? 1.0f : 0.0f);
-                break;
-            }
-            default:
-                break;
-        }
-    }
+    for (int m = e; m < n_elem; ++m) store_slot(s0 + m, RAW_MISSING);  // vector shorter than needed
+    if (count_all) store_slot_f(tg.whole_slot, (float)e);
+    return c;
 }
 
-__device__ __forceinline__ const uint8_t* skip_to(const uint8_t* p, unsigned d0) {
-    unsigned c = *p;
-    while (c != d0 && c != '\t' && c != '\n') c = *++p;
-    return p;
+__device__ __forceinline__ bool key_is_cg(const Key& k) {
+    // an allele equal to GGC or CCG (blacklist.py:85-101: tuple membership)
+    return k.len == 3 && (k.k0 == CH3('G', 'G', 'C') || k.k0 == CH3('C', 'C', 'G'));
+}
+
+__device__ __forceinline__ void set_tag_missing(int t) {
+    const PlanTag tg = s_tags()[t];
+    for (int s = tg.first_slot; s < tg.first_slot + tg.n_slots; ++s) store_slot(s, RAW_MISSING);
 }
 
 __global__ void __launch_bounds__(K1_TPB) k1_parse(const __grid_constant__ DevPlan plan,
@@ -467,224 +479,190 @@ __global__ void __launch_bounds__(K1_TPB) k1_parse(const __grid_constant__ DevPl
                                                    uint32_t* __restrict__ raw, size_t row_stride,
                                                    ugvc_recinfo* __restrict__ recinfo, unsigned long long* err,
                                                    long long* counts) {
-    extern __shared__ __align__(16) uint8_t smem[];
     // shared-memory copies of the small plan tables
     const int n_tags = plan.h.n_tags, n_slots = plan.h.n_slots;
-    PlanTag* s_tags = reinterpret_cast<PlanTag*>(smem);
-    PlanSlot* s_slots = reinterpret_cast<PlanSlot*>(s_tags + n_tags);
-    PlanDict* s_dicts = reinterpret_cast<PlanDict*>(s_slots + ((n_slots + 1) & ~1));
-    PlanString* s_strings = reinterpret_cast<PlanString*>(s_dicts + ((plan.h.n_dicts + 1) & ~1));
-    uint8_t* s_htab = reinterpret_cast<uint8_t*>(s_strings + plan.h.n_dict_strings);
-    uint32_t* s_tile = reinterpret_cast<uint32_t*>(s_htab + 256);
     {
         const uint32_t* src;
         uint32_t* dst;
         src = reinterpret_cast<const uint32_t*>(plan.tags);
-        dst = reinterpret_cast<uint32_t*>(s_tags);
+        dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_TAGS);
         for (int i = threadIdx.x; i < n_tags * 8; i += K1_TPB) dst[i] = src[i];
+        src = reinterpret_cast<const uint32_t*>(plan.strings);
+        dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_STRINGS);
+        for (int i = threadIdx.x; i < (int)plan.h.n_dict_strings * 8; i += K1_TPB) dst[i] = src[i];
         src = reinterpret_cast<const uint32_t*>(plan.slots);
-        dst = reinterpret_cast<uint32_t*>(s_slots);
+        dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_SLOTS);
         for (int i = threadIdx.x; i < n_slots; i += K1_TPB) dst[i] = src[i];
         src = reinterpret_cast<const uint32_t*>(plan.dicts);
-        dst = reinterpret_cast<uint32_t*>(s_dicts);
+        dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_DICTS);
         for (int i = threadIdx.x; i < (int)plan.h.n_dicts; i += K1_TPB) dst[i] = src[i];
-        src = reinterpret_cast<const uint32_t*>(plan.strings);
-        dst = reinterpret_cast<uint32_t*>(s_strings);
-        for (int i = threadIdx.x; i < (int)plan.h.n_dict_strings * 8; i += K1_TPB) dst[i] = src[i];
-        for (int i = threadIdx.x; i < 256; i += K1_TPB) s_htab[i] = plan.htab[i];
+        for (int i = threadIdx.x; i < 256; i += K1_TPB) k1_smem[K1_OFF_HTAB + i] = plan.htab[i];
     }
-    K1Shared sp;
-    sp.tags = s_tags;
-    sp.slots = s_slots;
-    sp.dicts = s_dicts;
-    sp.strings = s_strings;
-    sp.htab = s_htab;
-    sp.tile = s_tile;
     __syncthreads();
-
+    const unsigned tab4 = B4('\t');
     const long long n_rec = *n_records_p;
     const long long n_tiles = (n_rec + K1_TPB - 1) / K1_TPB;
     unsigned cg_local = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // every slot starts ABSENT (the reference's defaultdict(lambda: None))
-        for (int i = threadIdx.x; i < n_slots * K1_TPB; i += K1_TPB) s_tile[i] = RAW_ABSENT;
+        for (int i = threadIdx.x; i < n_slots * K1_TPB; i += K1_TPB) s_tile()[i] = RAW_ABSENT;
         __syncthreads();
         const long long rec = tile * K1_TPB + threadIdx.x;
         if (rec < n_rec) {
-            const int64_t ls = line_start[rec];
-            const uint8_t* const line = text + ls;
-            const uint8_t* p = line;
+            const uint8_t* const line = text + line_start[rec];
+            Cur c;
+            c.init(line);
             ugvc_recinfo ri;
             ri.flags = 0;
             bool malformed = false;
             // ---- CHROM
-            p = skip_to(p, '\t');
-            malformed |= (*p != '\t');
+            c = skip_until(c, tab4, tab4);
+            malformed |= (c.peek() != '\t');
             // ---- POS
             long long pos = 0;
             if (!malformed) {
-                ++p;
-                unsigned c = *p;
-                while (is_digit(c)) {
-                    pos = pos * 10 + (c - '0');
-                    c = *++p;
+                c.adv();
+                unsigned ch = c.peek();
+                while (ugvc_is_digit(ch)) {
+                    pos = pos * 10 + (ch - '0');
+                    c.adv();
+                    ch = c.peek();
                 }
-                malformed |= (*p != '\t');
+                malformed |= (ch != '\t');
             }
             ri.pos = (int32_t)pos;
             // ---- ID
             if (!malformed) {
-                p = skip_to(p + 1, '\t');
-                malformed |= (*p != '\t');
+                c.adv();
+                c = skip_until(c, tab4, tab4);
+                malformed |= (c.peek() != '\t');
             }
             // ---- REF / ALT -> allele codes, indel flag, CG flag
             float a0 = 0.f, a1 = 0.f;
             bool a1_missing = true, indel = false, cg = false;
             int n_alleles = 0;
             if (!malformed) {
-                const uint8_t* ra = p + 1;
-                p = skip_to(ra, '\t');
-                const int ref_len = (int)(p - ra);
-                a0 = ref_len == 1 ? (float)base_code(ra[0]) : 0.f;
-                cg |= ref_len == 3 && ((ra[0] == 'G' && ra[1] == 'G' && ra[2] == 'C') ||
-                                       (ra[0] == 'C' && ra[1] == 'C' && ra[2] == 'G'));
+                c.adv();
+                KeyCur r = take_until(c, tab4, tab4);
+                c = r.c;
+                const int ref_len = r.k.len;
+                a0 = ref_len == 1 ? (float)base_code((unsigned)r.k.k0 & 0xFFu) : 0.f;
+                cg |= key_is_cg(r.k);
                 n_alleles = 1;
                 ri.flags |= (unsigned)(ref_len > 0xFFFFFF ? 0xFFFFFF : ref_len) << 8;
-                malformed |= (*p != '\t');
+                malformed |= (c.peek() != '\t');
                 if (!malformed) {
-                    const uint8_t* aa = p + 1;
-                    if (aa[0] == '.' && (aa[1] == '\t' || aa[1] == '\n')) {
-                        p = aa + 1;  // ALT "." -> alleles == (REF,)
-                    } else {
-                        for (;;) {
-                            p = skip_to(aa, ',');
-                            const int alen = (int)(p - aa);
-                            if (n_alleles == 1) {
-                                a1 = alen == 1 ? (float)base_code(aa[0]) : 0.f;
-                                a1_missing = false;
-                            }
-                            indel |= (alen != ref_len);
-                            cg |= alen == 3 && ((aa[0] == 'G' && aa[1] == 'G' && aa[2] == 'C') ||
-                                                (aa[0] == 'C' && aa[1] == 'C' && aa[2] == 'G'));
-                            ++n_alleles;
-                            if (*p != ',') break;
-                            aa = p + 1;
+                    c.adv();
+                    for (;;) {
+                        r = take_until(c, B4(','), tab4);
+                        c = r.c;
+                        if (n_alleles == 1 && r.k.len == 1 && (r.k.k0 & 0xFFu) == '.' && c.peek() != ',')
+                            break;  // ALT "." -> alleles == (REF,)
+                        if (n_alleles == 1) {
+                            a1 = r.k.len == 1 ? (float)base_code((unsigned)r.k.k0 & 0xFFu) : 0.f;
+                            a1_missing = false;
                         }
+                        indel |= (r.k.len != ref_len);
+                        cg |= key_is_cg(r.k);
+                        ++n_alleles;
+                        if (c.peek() != ',') break;
+                        c.adv();
                     }
-                    malformed |= (*p != '\t');
+                    malformed |= (c.peek() != '\t');
                 }
             }
             // ---- QUAL
             uint32_t qual_bits = RAW_MISSING;
-            unsigned off;
-            off = (unsigned)(p + 1 - line);
+            unsigned off = (unsigned)(c.ptr() + 1 - line);
             ri.qual_off = off > 0xFFFFu ? 0xFFFFu : (uint16_t)off;
             if (!malformed) {
-                ++p;
-                if (p[0] == '.' && p[1] == '\t') {
-                    ++p;
-                } else {
-                    double qv;
-                    const int st = parse_num(p, qv);
-                    if (st == NUM_OK && *p == '\t') {
-                        const float f = (float)qv;
-                        qual_bits = isnan(f) ? RAW_MISSING : __float_as_uint(f);
-                    } else {
-                        qual_bits = RAW_ERR;
-                        p = skip_to(p, '\t');
-                    }
+                c.adv();
+                const NumCur r = parse_num_cur(c);
+                c = r.c;
+                if (c.peek() != '\t') {
+                    qual_bits = RAW_ERR;
+                    c = skip_until(c, tab4, tab4);
+                } else if (r.st == NUM_OK) {
+                    const float f = (float)r.v;
+                    qual_bits = isnan(f) ? RAW_MISSING : __float_as_uint(f);
+                } else if (r.st == NUM_BAD) {
+                    qual_bits = RAW_ERR;
                 }
-                malformed |= (*p != '\t');
+                malformed |= (c.peek() != '\t');
             }
             // ---- FILTER (kept as bytes; only its position is reported)
-            off = (unsigned)(p + 1 - line);
+            off = (unsigned)(c.ptr() + 1 - line);
             ri.filter_off = off > 0xFFFFu ? 0xFFFFu : (uint16_t)off;
             if (!malformed) {
-                p = skip_to(p + 1, '\t');
-                malformed |= (*p != '\t');
+                c.adv();
+                c = skip_until(c, tab4, tab4);
+                malformed |= (c.peek() != '\t');
             }
             // ---- INFO
-            off = (unsigned)(p + 1 - line);
+            off = (unsigned)(c.ptr() + 1 - line);
             ri.info_off = off > 0xFFFFu ? 0xFFFFu : (uint16_t)off;
             if (!malformed) {
-                ++p;
-                if (p[0] == '.' && (p[1] == '\t' || p[1] == '\n')) {
-                    ++p;
-                } else {
-                    for (;;) {
-                        const uint8_t* key = p;
-                        unsigned hash = 2166136261u, c = *p;
-                        while (c != '=' && c != ';' && c != '\t' && c != '\n') {
-                            hash = (hash ^ c) * 16777619u;
-                            c = *++p;
-                        }
-                        const int t = find_tag(sp, key, (int)(p - key), hash);
-                        const unsigned kind = t >= 0 ? s_tags[t].info_kind : 0u;
-                        if (c == '=') {
-                            ++p;
-                            if (kind)
-                                parse_value(sp, s_tags[t], kind, p, ';');
-                            p = skip_to(p, ';');
-                        } else if (kind) {  // key without a value: typed None / ()
-                            for (int s = s_tags[t].first_slot; s < s_tags[t].first_slot + s_tags[t].n_slots; ++s)
-                                store_slot(sp, s, RAW_MISSING);
-                        }
-                        if (*p == ';') {
-                            ++p;
-                            continue;
-                        }
-                        break;
+                c.adv();
+                const unsigned semi4 = B4(';'), eq4 = B4('=');
+                for (;;) {
+                    const KeyCur r = take_until(c, eq4, semi4);
+                    c = r.c;
+                    const unsigned ch = c.peek();
+                    const int t = find_tag(r.k);
+                    const unsigned kind = t >= 0 ? s_tags()[t].info_kind : 0u;
+                    if (ch == '=') {
+                        c.adv();
+                        if (kind) c = parse_value(t, kind, c, ';');
+                        c = skip_until(c, semi4, semi4);
+                    } else if (kind) {  // key without a value: typed None / ()
+                        set_tag_missing(t);
                     }
+                    if (c.peek() == ';') {
+                        c.adv();
+                        continue;
+                    }
+                    break;
                 }
             }
             // ---- FORMAT + first sample (FORMAT values override INFO values of the same
             //      name: the reference builds its per-record dict from info.items() +
             //      samples[0].items(), vcftools.py:69-86)
-            off = (unsigned)(p + 1 - line);
+            off = (unsigned)(c.ptr() + 1 - line);
             ri.format_off = off > 0xFFFFu ? 0xFFFFu : (uint16_t)off;
-            if (!malformed && *p == '\t') {
-                const uint8_t* fk = p + 1;
-                const uint8_t* sv = skip_to(fk, '\t');
-                bool have_sample = (*sv == '\t');
-                if (have_sample) ++sv;
-                if (!(fk[0] == '.' && (fk[1] == '\t' || fk[1] == '\n'))) {
-                    for (;;) {
-                        const uint8_t* key = fk;
-                        unsigned hash = 2166136261u, c = *fk;
-                        while (c != ':' && c != '\t' && c != '\n') {
-                            hash = (hash ^ c) * 16777619u;
-                            c = *++fk;
-                        }
-                        const int t = find_tag(sp, key, (int)(fk - key), hash);
-                        const unsigned kind = t >= 0 ? s_tags[t].fmt_kind : 0u;
-                        if (have_sample) {
-                            if (kind)
-                                parse_value(sp, s_tags[t], kind, sv, ':');
-                            sv = skip_to(sv, ':');
-                            if (*sv == ':')
-                                ++sv;
-                            else
-                                have_sample = false;
-                        } else if (kind) {  // trailing sub-fields dropped: missing
-                            for (int s = s_tags[t].first_slot; s < s_tags[t].first_slot + s_tags[t].n_slots; ++s)
-                                store_slot(sp, s, RAW_MISSING);
-                        }
-                        if (*fk == ':') {
-                            ++fk;
-                            continue;
-                        }
-                        break;
+            if (!malformed && c.peek() == '\t') {
+                c.adv();
+                const unsigned col4 = B4(':');
+                Cur sv = skip_until(c, tab4, tab4);
+                bool have_sample = (sv.peek() == '\t');
+                if (have_sample) sv.adv();
+                for (;;) {
+                    const KeyCur r = take_until(c, col4, col4);
+                    c = r.c;
+                    const int t = find_tag(r.k);
+                    const unsigned kind = t >= 0 ? s_tags()[t].fmt_kind : 0u;
+                    if (have_sample) {
+                        if (kind) sv = parse_value(t, kind, sv, ':');
+                        sv = skip_until(sv, col4, col4);
+                        if (sv.peek() == ':') sv.adv();
+                        else have_sample = false;
+                    } else if (kind) {  // trailing sub-fields dropped: missing
+                        set_tag_missing(t);
                     }
+                    if (c.peek() == ':') {
+                        c.adv();
+                        continue;
+                    }
+                    break;
                 }
             }
             // ---- fixed-column slots
             for (int s = plan.first_fixed_slot; s < n_slots; ++s) {
-                switch (s_slots[s].reducer) {
-                    case RED_FIX_QUAL: store_slot(sp, s, qual_bits); break;
-                    case RED_FIX_ALLELE0: store_slot_f(sp, s, a0); break;
-                    case RED_FIX_ALLELE1: store_slot(sp, s, a1_missing ? RAW_MISSING : __float_as_uint(a1)); break;
-                    case RED_FIX_INDEL: store_slot_f(sp, s, indel ? 1.f : 0.f); break;
-                    case RED_FIX_NALLELES: store_slot_f(sp, s, (float)n_alleles); break;
+                switch (s_slots()[s].reducer) {
+                    case RED_FIX_QUAL: store_slot(s, qual_bits); break;
+                    case RED_FIX_ALLELE0: store_slot_f(s, a0); break;
+                    case RED_FIX_ALLELE1: store_slot(s, a1_missing ? RAW_MISSING : __float_as_uint(a1)); break;
+                    case RED_FIX_INDEL: store_slot_f(s, indel ? 1.f : 0.f); break;
+                    case RED_FIX_NALLELES: store_slot_f(s, (float)n_alleles); break;
                     default: break;
                 }
             }
@@ -697,31 +675,27 @@ __global__ void __launch_bounds__(K1_TPB) k1_parse(const __grid_constant__ DevPl
         // coalesced columnar write-out of the slot tile
         const long long base = tile * K1_TPB;
         const int valid = (int)min((long long)K1_TPB, n_rec - base);
-        for (int s = 0; s < n_slots; ++s)
-            if (threadIdx.x < valid) raw[(size_t)s * row_stride + base + threadIdx.x] = s_tile[s * K1_TPB + threadIdx.x];
+        if (threadIdx.x < valid) {
+            uint32_t* dst = raw + base + threadIdx.x;
+            const uint32_t* src = s_tile() + threadIdx.x;
+#pragma unroll 4
+            for (int s = 0; s < n_slots; ++s) dst[(size_t)s * row_stride] = src[s * K1_TPB];
+        }
         __syncthreads();
     }
-    // CG-insertion counter: warp ballot-free reduction, one atomic per warp
+    // CG-insertion counter: one atomic per warp
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) cg_local += __shfl_xor_sync(0xffffffffu, cg_local, s);
     if ((threadIdx.x & 31) == 0 && cg_local) atomicAdd((unsigned long long*)&counts[3], (unsigned long long)cg_local);
 }
 
-size_t k1_smem_bytes(const DevPlan& plan) {
-    size_t b = (size_t)plan.h.n_tags * sizeof(PlanTag);
-    b += (size_t)((plan.h.n_slots + 1) & ~1u) * sizeof(PlanSlot);
-    b += (size_t)((plan.h.n_dicts + 1) & ~1u) * sizeof(PlanDict);
-    b += (size_t)plan.h.n_dict_strings * sizeof(PlanString);
-    b += 256;
-    b += (size_t)plan.h.n_slots * K1_TPB * 4;
-    return b;
-}
+size_t k1_smem_bytes(const DevPlan& plan) { return (size_t)K1_OFF_TILE + (size_t)plan.h.n_slots * K1_TPB * 4; }
 
 void launch_k1(const DevPlan& plan, const uint8_t* d_text, const int64_t* line_start, const int64_t* d_n_records,
                uint32_t* raw, size_t row_stride, ugvc_recinfo* recinfo, unsigned long long* d_err,
                long long* d_counts, int sm_count, cudaStream_t st) {
     const size_t smem = k1_smem_bytes(plan);
-    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     k1_parse<<<sm_count * per_sm, K1_TPB, smem, st>>>(plan, d_text, line_start, d_n_records, raw, row_stride, recinfo,
@@ -777,30 +751,63 @@ void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, cons
 // ------------------------------------------------------------------------------------------
 // K3: inference + score math + FILTER decision
 // ------------------------------------------------------------------------------------------
+// One thread per record, one persistent CTA per SM.  Shared memory holds the feature tile
+// [F][K3_TPB] (column f of a record tile is one coalesced row of the column-major matrix) and
+// the forest in device form (8-byte nodes; leaves are absorbing: threshold = quiet NaN carrying
+// the leaf row, right child = itself).  Trees are walked eight at a time with a fixed number of
+// steps (the depth of the deepest leaf), branch-free, so eight independent load chains per
+// thread hide the shared-memory latency; leaf values are then added in tree order in the
+// arithmetic of the library that trained the model (fp64 for sklearn, fp32 for xgboost).
+#define K3_CHAINS 8
+
 __device__ __forceinline__ double expit64(double x) { return 1.0 / (1.0 + exp(-x)); }
 
 template <int CMP>
-__device__ __forceinline__ int walk_tree(const PlanNode* __restrict__ nodes, const float* __restrict__ x_col,
-                                         int stride) {
-    // preorder layout: left child is the next node; returns the leaf row
-    int n = 0;
-    for (;;) {
-        const PlanNode nd = nodes[n];
-        if (nd.feature < 0) return __float_as_int(nd.value);
-        const float x = x_col[nd.feature * stride];
-        const bool left = (CMP == CMP_LE) ? (x <= nd.value) : (x < nd.value);
-        n = left ? n + 1 : (int)nd.right;
+__device__ __forceinline__ void walk8(const uint2* __restrict__ s_nodes, const uint32_t* __restrict__ s_roots,
+                                      unsigned chunk_first_node, unsigned tr, unsigned tr_end, int depth,
+                                      const float* __restrict__ x, int leaf[K3_CHAINS]) {
+    unsigned n[K3_CHAINS];
+    uint2 nd[K3_CHAINS];
+#pragma unroll
+    for (int j = 0; j < K3_CHAINS; ++j) {
+        const unsigned t = tr + j < tr_end ? tr + j : tr;  // pad with a repeat (result ignored)
+        n[j] = s_roots[t] - chunk_first_node;
     }
+    for (int d = 0; d <= depth; ++d) {
+#pragma unroll
+        for (int j = 0; j < K3_CHAINS; ++j) nd[j] = s_nodes[n[j]];
+#pragma unroll
+        for (int j = 0; j < K3_CHAINS; ++j) {
+            const float xv = x[(nd[j].y & 0xFFu) * K3_TPB];
+            const float thr = __uint_as_float(nd[j].x);
+            const bool left = (CMP == CMP_LE) ? (xv <= thr) : (xv < thr);  // false on a leaf (NaN)
+            n[j] = left ? n[j] + 1 : (nd[j].y >> 8) - chunk_first_node;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < K3_CHAINS; ++j) leaf[j] = (int)(nd[j].x & 0x3FFFFFu);
 }
 
-__global__ void __launch_bounds__(K3_TPB) k3_infer(const __grid_constant__ DevPlan plan,
-                                                   const float* __restrict__ feats, size_t row_stride,
-                                                   const int64_t* __restrict__ n_records_p, double threshold,
-                                                   uint8_t* __restrict__ low_score, float* __restrict__ probs,
-                                                   double* __restrict__ qual_out, long long* counts) {
+__global__ void __launch_bounds__(K3_TPB, 1) k3_infer(const __grid_constant__ DevPlan plan,
+                                                      const float* __restrict__ feats, size_t row_stride,
+                                                      const int64_t* __restrict__ n_records_p, double threshold,
+                                                      uint8_t* __restrict__ low_score, float* __restrict__ probs,
+                                                      double* __restrict__ qual_out, long long* counts,
+                                                      unsigned chunk_nodes_cap) {
     extern __shared__ __align__(16) uint8_t smem3[];
-    float* tile = reinterpret_cast<float*>(smem3);  // [F][K3_TPB]
     const int F = plan.h.n_features, K = plan.h.n_classes, O = plan.h.n_outputs;
+    const unsigned n_trees = plan.h.n_trees;
+    const bool forest = plan.h.model_kind != MODEL_LOGISTIC;
+    float* tile = reinterpret_cast<float*>(smem3);  // [F][K3_TPB]
+    uint2* s_nodes = reinterpret_cast<uint2*>(smem3 + (size_t)F * K3_TPB * sizeof(float));
+    uint32_t* s_roots = reinterpret_cast<uint32_t*>(s_nodes + chunk_nodes_cap);  // [n_trees + 1]
+    const bool resident = forest && plan.h.n_nodes <= chunk_nodes_cap;  // whole forest fits: stage once
+    if (forest) {
+        for (unsigned i = threadIdx.x; i <= n_trees; i += K3_TPB) s_roots[i] = plan.tree_root[i];
+        if (resident)
+            for (unsigned i = threadIdx.x; i < plan.h.n_nodes; i += K3_TPB) s_nodes[i] = plan.dev_nodes[i];
+    }
+    const int depth = (int)plan.max_depth;
     const long long n_rec = *n_records_p;
     const long long n_tiles = (n_rec + K3_TPB - 1) / K3_TPB;
     unsigned n_low = 0, n_seen = 0;
@@ -808,110 +815,177 @@ __global__ void __launch_bounds__(K3_TPB) k3_infer(const __grid_constant__ DevPl
         const long long rec = t * K3_TPB + threadIdx.x;
         const bool active = rec < n_rec;
         __syncthreads();
-        // stage the feature tile: row f of the column-major matrix is a coalesced 512 B read
-        for (int f = 0; f < F; ++f) tile[f * K3_TPB + threadIdx.x] = active ? feats[(size_t)f * row_stride + rec] : 0.f;
+        {
+            const float* src = feats + rec;
+#pragma unroll 8
+            for (int f = 0; f < F; ++f) tile[f * K3_TPB + threadIdx.x] = active ? __ldg(src + (size_t)f * row_stride) : 0.f;
+        }
         __syncthreads();
-        if (!active) continue;
         const float* x = tile + threadIdx.x;
-        double p[UGVC_MAX_CLASSES];
+        double p[UGVC_MAX_CLASSES] = {0.0, 0.0, 0.0, 0.0};
+        double z[UGVC_MAX_CLASSES];   // fp64 accumulators (sklearn) ...
+        float zf[UGVC_MAX_CLASSES];   // ... fp32 accumulators (xgboost)
+#pragma unroll
+        for (int o = 0; o < UGVC_MAX_CLASSES; ++o) {
+            z[o] = plan.h.model_kind == MODEL_RF_SKLEARN ? 0.0 : plan.h.init[o];
+            zf[o] = (float)plan.h.init[o];
+        }
+        if (forest) {
+            // tree chunks: [c0, c1) are whole trees whose nodes fit the shared-memory buffer
+            unsigned c0 = 0;
+            while (c0 < n_trees) {
+                unsigned c1 = n_trees;
+                unsigned first_node = 0;
+                if (!resident) {
+                    first_node = s_roots[c0];
+                    c1 = c0;
+                    while (c1 < n_trees && s_roots[c1 + 1] - first_node <= chunk_nodes_cap) ++c1;
+                    if (c1 == c0) c1 = c0 + 1;  // cannot happen: load_plan checks every tree fits
+                    __syncthreads();
+                    const unsigned cnt = s_roots[c1] - first_node;
+                    for (unsigned i = threadIdx.x; i < cnt; i += K3_TPB) s_nodes[i] = plan.dev_nodes[first_node + i];
+                    __syncthreads();
+                }
+                for (unsigned tr = c0; tr < c1; tr += K3_CHAINS) {
+                    int leaf[K3_CHAINS];
+                    if (plan.h.cmp_mode == CMP_LE) walk8<CMP_LE>(s_nodes, s_roots, first_node, tr, c1, depth, x, leaf);
+                    else walk8<CMP_LT>(s_nodes, s_roots, first_node, tr, c1, depth, x, leaf);
+                    if (plan.h.model_kind == MODEL_GB_SKLEARN && O == 1) {
+                        // raw += learning_rate * leaf (pre-scaled on the host), fp64, tree order
+#pragma unroll
+                        for (int j = 0; j < K3_CHAINS; ++j)
+                            if (tr + j < c1) z[0] = __dadd_rn(z[0], __ldg(&plan.leaves[leaf[j]]));
+                    } else if (plan.h.model_kind == MODEL_RF_SKLEARN) {
+                        // sum of per-leaf class fractions, fp64, tree order
+#pragma unroll
+                        for (int j = 0; j < K3_CHAINS; ++j)
+                            if (tr + j < c1) {
+                                const double* lv = plan.leaves + (size_t)leaf[j] * plan.h.leaf_width;
+#pragma unroll
+                                for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
+                                    if (k < K) z[k] = __dadd_rn(z[k], __ldg(&lv[k]));
+                            }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < K3_CHAINS; ++j)
+                            if (tr + j < c1) {
+                                const int o = plan.tree_out[tr + j];
+                                const double add = __ldg(&plan.leaves[leaf[j]]);
+                                const float addf = (float)add;
+#pragma unroll
+                                for (int k = 0; k < UGVC_MAX_CLASSES; ++k) {
+                                    z[k] = o == k ? __dadd_rn(z[k], add) : z[k];
+                                    zf[k] = o == k ? __fadd_rn(zf[k], addf) : zf[k];
+                                }
+                            }
+                    }
+                }
+                c0 = c1;
+            }
+        }
+        if (!active) continue;
         switch (plan.h.model_kind) {
             case MODEL_LOGISTIC: {
-                double z[UGVC_MAX_CLASSES];
-                for (int o = 0; o < O; ++o) {
-                    double acc = 0.0;
-                    const double* w = plan.coef + (size_t)o * F;
-                    for (int f = 0; f < F; ++f) acc = fma((double)x[f * K3_TPB], __ldg(&w[f]), acc);
-                    z[o] = acc + plan.intercept[o];
-                }
-                if (O == 1) {
-                    p[1] = expit64(z[0]);
-                    p[0] = 1.0 - p[1];
-                } else {
-                    double mx = z[0];
-                    for (int o = 1; o < O; ++o) mx = fmax(mx, z[o]);
-                    double s = 0.0;
-                    for (int o = 0; o < O; ++o) {
-                        p[o] = exp(z[o] - mx);
-                        s += p[o];
+                // sklearn LogisticRegression: fp64 decision, expit / softmax
+#pragma unroll
+                for (int o = 0; o < UGVC_MAX_CLASSES; ++o) {
+                    if (o < O) {
+                        double acc = 0.0;
+                        const double* w = plan.coef + (size_t)o * F;
+                        for (int f = 0; f < F; ++f) acc = fma((double)x[f * K3_TPB], __ldg(&w[f]), acc);
+                        z[o] = acc + plan.intercept[o];
                     }
-                    for (int o = 0; o < O; ++o) p[o] /= s;
                 }
-                break;
             }
+            // fall through: same link as the fp64 boosting model
             case MODEL_GB_SKLEARN: {
-                // raw = init + sum_t (learning_rate * leaf_t) in fp64, tree order
-                // (sklearn _gradient_boosting.predict_stages); leaves are pre-scaled on the host
-                double z[UGVC_MAX_CLASSES];
-                for (int o = 0; o < O; ++o) z[o] = plan.h.init[o];
-                for (unsigned tr = 0; tr < plan.h.n_trees; ++tr) {
-                    const int leaf = walk_tree<CMP_LE>(plan.nodes + plan.tree_root[tr], x, K3_TPB);
-                    const int o = plan.tree_out[tr];
-                    z[o] = __dadd_rn(z[o], plan.leaves[leaf]);
-                }
                 if (O == 1) {
                     p[1] = expit64(z[0]);
                     p[0] = 1.0 - p[1];
-                } else {
-                    // softmax as exp(raw - logsumexp(raw))
+                } else if (plan.h.model_kind == MODEL_LOGISTIC) {
                     double mx = z[0];
-                    for (int o = 1; o < O; ++o) mx = fmax(mx, z[o]);
+#pragma unroll
+                    for (int o = 1; o < UGVC_MAX_CLASSES; ++o)
+                        if (o < O) mx = fmax(mx, z[o]);
                     double s = 0.0;
-                    for (int o = 0; o < O; ++o) s += exp(z[o] - mx);
+#pragma unroll
+                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                        if (o < O) {
+                            p[o] = exp(z[o] - mx);
+                            s += p[o];
+                        }
+#pragma unroll
+                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                        if (o < O) p[o] /= s;
+                } else {
+                    // sklearn multiclass boosting: exp(raw - logsumexp(raw))
+                    double mx = z[0];
+#pragma unroll
+                    for (int o = 1; o < UGVC_MAX_CLASSES; ++o)
+                        if (o < O) mx = fmax(mx, z[o]);
+                    double s = 0.0;
+#pragma unroll
+                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                        if (o < O) s += exp(z[o] - mx);
                     const double lse = mx + log(s);
-                    for (int o = 0; o < O; ++o) p[o] = exp(z[o] - lse);
+#pragma unroll
+                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                        if (o < O) p[o] = exp(z[o] - lse);
                 }
                 break;
             }
             case MODEL_RF_SKLEARN: {
-                // mean over trees of the per-leaf class fractions, fp64, tree order
-                for (int k = 0; k < K; ++k) p[k] = 0.0;
-                for (unsigned tr = 0; tr < plan.h.n_trees; ++tr) {
-                    const int leaf = walk_tree<CMP_LE>(plan.nodes + plan.tree_root[tr], x, K3_TPB);
-                    const double* lv = plan.leaves + (size_t)leaf * plan.h.leaf_width;
-                    for (int k = 0; k < K; ++k) p[k] = __dadd_rn(p[k], lv[k]);
-                }
-                for (int k = 0; k < K; ++k) p[k] = p[k] / (double)plan.h.n_trees;
+#pragma unroll
+                for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
+                    if (k < K) p[k] = z[k] / (double)n_trees;
                 break;
             }
             case MODEL_XGB: {
-                // xgboost CPU predictor: fp32 margin accumulated in tree order, fp32 sigmoid / softmax
-                float z[UGVC_MAX_CLASSES];
-                for (int o = 0; o < O; ++o) z[o] = (float)plan.h.init[o];
-                for (unsigned tr = 0; tr < plan.h.n_trees; ++tr) {
-                    const int leaf = walk_tree<CMP_LT>(plan.nodes + plan.tree_root[tr], x, K3_TPB);
-                    const int o = plan.tree_out[tr];
-                    z[o] = __fadd_rn(z[o], (float)plan.leaves[leaf]);
-                }
+                // xgboost CPU predictor: fp32 margins, fp32 sigmoid / softmax
                 if (O == 1) {
-                    const float p1 = 1.0f / (1.0f + expf(-z[0]));
+                    const float p1 = 1.0f / (1.0f + expf(-zf[0]));
                     p[1] = (double)p1;
                     p[0] = (double)(1.0f - p1);
                 } else {
-                    float mx = z[0];
-                    for (int o = 1; o < O; ++o) mx = fmaxf(mx, z[o]);
+                    float mx = zf[0];
+#pragma unroll
+                    for (int o = 1; o < UGVC_MAX_CLASSES; ++o)
+                        if (o < O) mx = fmaxf(mx, zf[o]);
                     double s = 0.0;
-                    float e[UGVC_MAX_CLASSES];
-                    for (int o = 0; o < O; ++o) {
-                        e[o] = expf(z[o] - mx);
-                        s += (double)e[o];
-                    }
-                    for (int o = 0; o < O; ++o) p[o] = (double)(e[o] / (float)s);
+                    float e[UGVC_MAX_CLASSES] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                        if (o < O) {
+                            e[o] = expf(zf[o] - mx);
+                            s += (double)e[o];
+                        }
+#pragma unroll
+                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                        if (o < O) p[o] = (double)(e[o] / (float)s);
                 }
                 break;
             }
             default:
-                for (int k = 0; k < K; ++k) p[k] = 0.0;
+                break;
         }
         // phred = -10 log10(lik + 1e-10); qual = clip(30 + ph[0] - min(ph[1:]), 0, inf)   (fp64)
-        double ph0 = -10.0 * log10(p[0] + 1e-10);
+        const double ph0 = -10.0 * log10(p[0] + 1e-10);
         double mn = -10.0 * log10(p[1] + 1e-10);
-        for (int k = 2; k < K; ++k) mn = fmin(mn, -10.0 * log10(p[k] + 1e-10));
+#pragma unroll
+        for (int k = 2; k < UGVC_MAX_CLASSES; ++k)
+            if (k < K) mn = fmin(mn, -10.0 * log10(p[k] + 1e-10));
         double q = __dadd_rn(__dadd_rn(30.0, ph0), -mn);
         q = q < 0.0 ? 0.0 : q;
         const bool low = q <= threshold;
         low_score[rec] = low ? 1 : 0;
         qual_out[rec] = q;
-        for (int k = 0; k < K; ++k) probs[(size_t)rec * K + k] = (float)p[k];
+        if (K == 2) {
+            *reinterpret_cast<float2*>(&probs[(size_t)rec * 2]) = make_float2((float)p[0], (float)p[1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
+                if (k < K) probs[(size_t)rec * K + k] = (float)p[k];
+        }
         n_low += low ? 1u : 0u;
         n_seen += 1u;
     }
@@ -928,17 +1002,38 @@ __global__ void __launch_bounds__(K3_TPB) k3_infer(const __grid_constant__ DevPl
     }
 }
 
-size_t k3_smem_bytes(const DevPlan& plan) { return (size_t)plan.h.n_features * K3_TPB * sizeof(float); }
+#define K3_SMEM_BUDGET (224u * 1024u)
+// nodes the shared-memory forest buffer holds (0 for linear models)
+static unsigned k3_chunk_nodes(const DevPlan& plan) {
+    if (plan.h.model_kind == MODEL_LOGISTIC || plan.h.model_kind == MODEL_NONE) return 0;
+    const size_t tile = (size_t)plan.h.n_features * K3_TPB * sizeof(float);
+    const size_t roots = ((size_t)plan.h.n_trees + 2) * sizeof(uint32_t);
+    if (tile + roots + 4096 > K3_SMEM_BUDGET) return 0;
+    const size_t room = (K3_SMEM_BUDGET - tile - roots) / sizeof(uint2);
+    return (unsigned)(room < plan.h.n_nodes ? room : plan.h.n_nodes);
+}
+size_t k3_smem_bytes(const DevPlan& plan) {
+    size_t b = (size_t)plan.h.n_features * K3_TPB * sizeof(float);
+    const unsigned cap = k3_chunk_nodes(plan);
+    if (cap) b += (size_t)cap * sizeof(uint2) + ((size_t)plan.h.n_trees + 2) * sizeof(uint32_t);
+    return b;
+}
+unsigned k3_chunk_nodes_cap(const DevPlan& plan) { return k3_chunk_nodes(plan); }
+bool k3_plan_fits(const DevPlan& plan) {
+    if (plan.h.model_kind == MODEL_LOGISTIC || plan.h.model_kind == MODEL_NONE)
+        return (size_t)plan.h.n_features * K3_TPB * sizeof(float) <= K3_SMEM_BUDGET;
+    return k3_chunk_nodes(plan) > 0;
+}
 
 void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const int64_t* d_n_records,
                double threshold, uint8_t* low_score, float* probs, double* qual, long long* d_counts,
                int sm_count, cudaStream_t st) {
     const size_t smem = k3_smem_bytes(plan);
-    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    int per_sm = (int)((K3_SMEM_BUDGET) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 4) per_sm = 4;
     k3_infer<<<sm_count * per_sm, K3_TPB, smem, st>>>(plan, feats, row_stride, d_n_records, threshold, low_score,
-                                                      probs, qual, d_counts);
+                                                      probs, qual, d_counts, k3_chunk_nodes(plan));
 }
 
 cudaError_t kernels_configure(const DevPlan& plan) {

@@ -19,7 +19,9 @@ struct DevPlan {
     const double* intercept;
     const uint32_t* tree_root;
     const uint8_t* tree_out;
-    const PlanNode* nodes;
+    const PlanNode* nodes;     // blob form (host validation)
+    const uint2* dev_nodes;    // device form: x = threshold bits (leaf: quiet NaN | leaf row), y = feature | right_abs << 8
+    uint32_t max_depth;        // deepest leaf over all trees
     const double* leaves;
     const uint8_t* htab;       // 256-entry open-addressing table: tag index or 0xFF
     uint32_t first_fixed_slot; // slots [first_fixed_slot, n_slots) are TAG_FIXED
@@ -64,4 +66,6 @@ void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const
                int sm_count, cudaStream_t st);
 size_t k1_smem_bytes(const DevPlan& plan);
 size_t k3_smem_bytes(const DevPlan& plan);
+bool k3_plan_fits(const DevPlan& plan);
+unsigned k3_chunk_nodes_cap(const DevPlan& plan);
 cudaError_t kernels_configure(const DevPlan& plan);

@@ -8,13 +8,13 @@
 #include <stdint.h>
 
 #define UGVC_PLAN_MAGIC 0x50564755u /* "UGVP" */
-#define UGVC_PLAN_VERSION 4u
+#define UGVC_PLAN_VERSION 6u
 
-#define UGVC_MAX_TAGS 160
+#define UGVC_MAX_TAGS 128
 #define UGVC_MAX_SLOTS 250
 #define UGVC_MAX_FEATURES 250
 #define UGVC_MAX_CLASSES 4
-#define UGVC_NAME_MAX 23
+#define UGVC_NAME_MAX 24
 
 // ---- value kinds of a tag in one header section (INFO or FORMAT) -----------
 enum : uint8_t {
@@ -82,8 +82,9 @@ enum : uint32_t {
     CMP_LT = 1,  // go left when x <  thr (xgboost)
 };
 
-#pragma pack(push, 1)
-struct PlanHeader {
+// All records are naturally aligned so that device code can fetch them with single 32/64-bit
+// loads (shared memory copies and __ldg).
+struct alignas(8) PlanHeader {
     uint32_t magic, version;
     uint32_t n_tags, n_slots, n_features, n_dicts, n_dict_strings;
     uint32_t model_kind, n_classes, n_outputs; // n_outputs: margins/prob columns the model produces (1 for binary GB/LR/XGB)
@@ -92,34 +93,37 @@ struct PlanHeader {
     double init[UGVC_MAX_CLASSES]; // GB init raw / XGB base margin / LR intercepts are in their own section
 };
 
-struct PlanTag {              // 32 bytes
-    char name[24];            // not NUL-terminated when len == 24 is never allowed: len <= 23
+struct alignas(8) PlanTag {   // 32 bytes
+    char name[24];            // zero padded; compared as three 64-bit words
     uint8_t len;
     uint8_t info_kind;        // KIND_* | KIND_SCALAR, as declared by ##INFO
     uint8_t fmt_kind;         // as declared by ##FORMAT
     uint8_t first_slot;
     uint8_t n_slots;
-    uint8_t pad[3];
+    uint8_t whole_red;        // RED_* of the tag's whole-value slot, 0xFF if none
+    uint8_t whole_slot;       // slot index of that reducer
+    uint8_t pad;
 };
 
-struct PlanSlot {             // 4 bytes
+struct alignas(4) PlanSlot {  // 4 bytes
     uint8_t tag;              // index into tags, or TAG_FIXED
     uint8_t elem;             // element index, or ELEM_WHOLE
     uint8_t reducer;          // RED_*
     uint8_t dict;             // dictionary index for RED_DICT
 };
 
-struct PlanDict {             // 4 bytes
+struct alignas(4) PlanDict {  // 4 bytes
     uint16_t first_string;
     uint16_t n_strings;
 };
 
-struct PlanString {           // 32 bytes
-    char s[31];
+struct alignas(8) PlanString {  // 32 bytes
+    char s[24];               // zero padded; compared as three 64-bit words
     uint8_t len;
+    uint8_t pad[7];
 };
 
-struct PlanFeature {          // 12 bytes
+struct alignas(4) PlanFeature {  // 12 bytes
     uint16_t slot;
     uint8_t absent_pol;       // POL_*
     uint8_t missing_pol;
@@ -127,19 +131,34 @@ struct PlanFeature {          // 12 bytes
     float missing_val;
 };
 
-struct PlanCheck {            // 8 bytes: the reference raises unless the slot value satisfies the bound
+struct alignas(4) PlanCheck {  // 8 bytes: the reference raises unless the slot value satisfies the bound
     uint16_t slot;
     uint8_t kind;             // 0: value <= bound, 1: value >= bound
     uint8_t pad;
     float bound;
 };
 
-struct PlanNode {             // 8 bytes, preorder layout: left child = this + 1
+struct alignas(8) PlanNode {  // 8 bytes, preorder layout: left child = this + 1
     float value;              // internal: threshold (fp32); leaf: bit pattern of the int32 leaf row
     int16_t feature;          // < 0 for a leaf
     uint16_t right;           // index of the right child relative to the tree root
 };
-#pragma pack(pop)
+static_assert(sizeof(PlanHeader) == 96 && sizeof(PlanTag) == 32 && sizeof(PlanSlot) == 4 && sizeof(PlanDict) == 4 &&
+                  sizeof(PlanString) == 32 && sizeof(PlanFeature) == 12 && sizeof(PlanCheck) == 8 &&
+                  sizeof(PlanNode) == 8,
+              "plan record layout");
+
+// Hash of a tag name held as three little-endian 64-bit words (+ length); the host builds the
+// 256-entry open-addressing table with the same function the device probes it with.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline unsigned ugvc_key_hash(unsigned long long k0, unsigned long long k1, unsigned long long k2, int len) {
+    unsigned long long h = k0 ^ (k1 * 0x9E3779B97F4A7C15ull) ^ (k2 * 0xC2B2AE3D27D4EB4Full) ^ (unsigned long long)len;
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 33;
+    return (unsigned)(h & 255u);
+}
 
 // Section order after PlanHeader (each padded to 8 bytes):
 //   PlanTag[n_tags], PlanSlot[n_slots], PlanDict[n_dicts], PlanString[n_dict_strings],

@@ -117,6 +117,7 @@ __device__ void gen_record(S& s, uint64_t seed, long long rec, long long total, 
         if (rec < r1) break;
         cum += c_contig_len[c];
     }
+    if (c >= N_CONTIGS) c = N_CONTIGS - 1;  // rec >= total: keep generating on the last contig
     const long long n_c = r1 - r0 > 0 ? r1 - r0 : 1;
     const double step = (double)c_contig_len[c] / (double)n_c;
     long long pos = 1 + (long long)(((double)(rec - r0) + (double)r.uni()) * step);

@@ -72,6 +72,8 @@ SIGNATURES = {
                                             C.POINTER(C.c_uint64), _vp, _sz, C.POINTER(_sz)]),
     "ugvc_splice_records": (C.c_int64, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp,
                                         _vp, _sz, _vp, C.c_int]),
+    "ugvc_test_parse_float": (C.c_int, [C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_int)]),
 }
 
 _lib = None

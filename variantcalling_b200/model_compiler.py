@@ -35,8 +35,9 @@ import numpy as np
 from variantcalling_b200.vcf_header import VcfHeader
 
 PLAN_MAGIC = 0x50564755
-PLAN_VERSION = 4
-MAX_TAGS, MAX_SLOTS, MAX_FEATURES, MAX_CLASSES, NAME_MAX = 160, 250, 250, 4, 23
+PLAN_VERSION = 6
+MAX_TAGS, MAX_SLOTS, MAX_FEATURES, MAX_CLASSES, NAME_MAX = 128, 250, 250, 4, 24
+MAX_DICTS, MAX_STRINGS = 64, 96
 
 KIND_INT, KIND_FLOAT, KIND_STR, KIND_FLAG, KIND_SCALAR = 1, 2, 3, 4, 8
 (RED_NUM, RED_BASE, RED_INSDEL, RED_DICT, RED_MOTIF_L, RED_MOTIF_R, RED_STRNUM, RED_GT_HOM, RED_LEN) = range(9)
@@ -165,9 +166,11 @@ class _Builder:
         for c in cats:
             if not isinstance(c, str):
                 raise PlanError(f"OrdinalEncoder category {c!r} is not a string")
-            if len(c.encode()) > 31:  # noqa: PLR2004
-                raise PlanError(f"category string {c!r} longer than 31 bytes")
+            if len(c.encode()) > 24:  # noqa: PLR2004
+                raise PlanError(f"category string {c!r} longer than 24 bytes")
             strs.append(c)
+        if strs in self.dicts:
+            return self.dicts.index(strs)
         self.dicts.append(strs)
         return len(self.dicts) - 1
 
@@ -513,14 +516,34 @@ def compile_plan(header: VcfHeader | str | bytes, transformer, model, custom_inf
         if len(tag.encode()) > NAME_MAX:
             raise PlanError(f"tag name {tag!r} longer than {NAME_MAX} bytes")
         first = len(slots)
+        # K1 contract: element slots 0..k-1 (each element once, gaps filled with unused numeric
+        # slots), then at most one whole-value slot
+        by_elem: dict[int, _SlotReq] = {}
+        whole_req = None
         for r in reqs:
-            key = (r.tag, r.elem, r.reducer, r.dict_id)
-            if r.tag == tag and key not in slot_index:
-                slot_index[key] = len(slots)
-                slots.append((ti, r.elem, r.reducer, r.dict_id))
+            if r.tag != tag:
+                continue
+            if r.elem == ELEM_WHOLE:
+                if whole_req is not None and (whole_req.reducer, whole_req.dict_id) != (r.reducer, r.dict_id):
+                    raise PlanError(f"tag {tag}: more than one whole-value reducer")
+                whole_req = r
+            else:
+                prev = by_elem.get(r.elem)
+                if prev is not None and (prev.reducer, prev.dict_id) != (r.reducer, r.dict_id):
+                    raise PlanError(f"tag {tag}: element {r.elem} is reduced in two different ways")
+                by_elem[r.elem] = r
+        for e in range(max(by_elem) + 1 if by_elem else 0):
+            r = by_elem.get(e) or _SlotReq(tag, e, RED_NUM)
+            slot_index[(tag, e, r.reducer, r.dict_id)] = len(slots)
+            slots.append((ti, e, r.reducer, r.dict_id))
+        if whole_req is not None:
+            slot_index[(tag, ELEM_WHOLE, whole_req.reducer, whole_req.dict_id)] = len(slots)
+            slots.append((ti, ELEM_WHOLE, whole_req.reducer, whole_req.dict_id))
         ik, fk = b.kinds(tag)
         name_b = tag.encode()
-        tags_packed.append(struct.pack("<24sBBBBB3x", name_b, len(name_b), ik, fk, first, len(slots) - first))
+        whole_red, whole_slot = (whole_req.reducer, len(slots) - 1) if whole_req is not None else (0xFF, 0)
+        tags_packed.append(struct.pack("<24sBBBBBBBx", name_b, len(name_b), ik, fk, first, len(slots) - first,
+                                       whole_red, whole_slot))
     for r in reqs:
         key = (r.tag, r.elem, r.reducer, r.dict_id)
         if r.tag is None and key not in slot_index:
@@ -532,12 +555,14 @@ def compile_plan(header: VcfHeader | str | bytes, transformer, model, custom_inf
     def sid(r: _SlotReq) -> int:
         return slot_index[(r.tag, r.elem, r.reducer, r.dict_id)]
 
+    if len(b.dicts) > MAX_DICTS or sum(len(d) for d in b.dicts) > MAX_STRINGS:
+        raise PlanError("too many OrdinalEncoder categories for the K1 dictionary tables")
     strings = []
     dicts_packed = b""
     for d in b.dicts:
         dicts_packed += struct.pack("<HH", len(strings), len(d))
         strings.extend(d)
-    strings_packed = b"".join(struct.pack("<31sB", s.encode(), len(s.encode())) for s in strings)
+    strings_packed = b"".join(struct.pack("<24sB7x", s.encode(), len(s.encode())) for s in strings)
     feats_packed = b"".join(
         struct.pack("<HBBff", sid(f.slot), f.absent[0], f.missing[0], f.absent[1], f.missing[1]) for f in b.features)
     checks_packed = b"".join(struct.pack("<HBxf", sid(c[0]), c[1], c[2]) for c in b.checks)
