@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 #include "numparse.h"
 
@@ -181,7 +182,7 @@ void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* chunk_first, int
 #define K1_OFF_SLOTS (K1_OFF_STRINGS + K1_MAX_STRINGS * 32)
 #define K1_OFF_DICTS (K1_OFF_SLOTS + 256 * 4)
 #define K1_OFF_HTAB (K1_OFF_DICTS + K1_MAX_DICTS * 4)
-#define K1_OFF_TILE (K1_OFF_HTAB + 256)
+#define K1_SMEM_BYTES (K1_OFF_HTAB + 256)
 
 extern __shared__ __align__(16) uint8_t k1_smem[];
 __device__ __forceinline__ const PlanTag* s_tags() { return reinterpret_cast<const PlanTag*>(k1_smem + K1_OFF_TAGS); }
@@ -189,7 +190,6 @@ __device__ __forceinline__ const PlanString* s_strings() { return reinterpret_ca
 __device__ __forceinline__ const PlanSlot* s_slots() { return reinterpret_cast<const PlanSlot*>(k1_smem + K1_OFF_SLOTS); }
 __device__ __forceinline__ const PlanDict* s_dicts() { return reinterpret_cast<const PlanDict*>(k1_smem + K1_OFF_DICTS); }
 __device__ __forceinline__ const uint8_t* s_htab() { return k1_smem + K1_OFF_HTAB; }
-__device__ __forceinline__ uint32_t* s_tile() { return reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_TILE); }
 
 struct Cur {
     const unsigned long long* wp;  // next aligned word
@@ -232,14 +232,17 @@ struct NumCur {
 
 #define B4(ch) ((unsigned)(ch) * 0x01010101u)
 
-// 0xFF in every byte of w that equals tab, newline or one of the two pattern bytes (consumed
-// bytes of the window are zero and never match)
+// Bit 7 set in the FIRST byte of w that equals tab, newline or one of the two pattern bytes
+// (bytes above the first match may carry false positives -- only the lowest set bit is used;
+// consumed bytes of the window are zero and never match).  Classic has-zero-byte SWAR on
+// 64-bit words: sm_100 has no byte-compare instruction (__vcmpeq4 is emulated).
+__device__ __forceinline__ unsigned long long has_zero(unsigned long long x) {
+    return (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;
+}
 __device__ __forceinline__ unsigned long long delim_mask(unsigned long long w, unsigned a4, unsigned b4) {
-    const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
-    // tab (0x09) and newline (0x0A): the only bytes of a VCF line in 0x08..0x0B
-    const unsigned ml = __vcmpeq4(lo & 0xFCFCFCFCu, 0x08080808u) | __vcmpeq4(lo, a4) | __vcmpeq4(lo, b4);
-    const unsigned mh = __vcmpeq4(hi & 0xFCFCFCFCu, 0x08080808u) | __vcmpeq4(hi, a4) | __vcmpeq4(hi, b4);
-    return ((unsigned long long)mh << 32) | ml;
+    const unsigned long long a8 = ((unsigned long long)a4 << 32) | a4, b8 = ((unsigned long long)b4 << 32) | b4;
+    // tab (0x09) and newline (0x0A) are the only bytes of a VCF line in 0x08..0x0B
+    return has_zero((w & 0xFCFCFCFCFCFCFCFCull) ^ 0x0808080808080808ull) | has_zero(w ^ a8) | has_zero(w ^ b8);
 }
 
 // advance to the first byte that is tab, newline or a pattern byte
@@ -302,6 +305,47 @@ __device__ __noinline__ NumCur parse_num_cur(Cur c) {
     return r;
 }
 
+struct IntCur {
+    Cur c;
+    int v;
+    int st;
+};
+// "[+-]digits" or "." -> int (saturating at int32); anything else in the token is NUM_BAD
+__device__ __noinline__ IntCur parse_int_cur(Cur c) {
+    IntCur r;
+    unsigned ch = c.peek();
+    bool neg = false;
+    if (ch == '-' || ch == '+') {
+        neg = ch == '-';
+        c.adv();
+        ch = c.peek();
+    }
+    unsigned m = 0;
+    int nd = 0;
+    bool ovf = false;
+    while (ugvc_is_digit(ch)) {
+        const unsigned d = ch - '0';
+        ovf |= m > 214748364u || (m == 214748364u && d > 7u);
+        m = m * 10u + d;
+        ++nd;
+        c.adv();
+        ch = c.peek();
+    }
+    r.st = NUM_OK;
+    if (nd == 0) {
+        if (ch == '.' && !neg) {
+            c.adv();
+            r.st = NUM_MISSING;
+        } else
+            r.st = NUM_BAD;
+    } else if (ovf) {
+        r.st = NUM_BAD;  // outside int32: htslib rejects the value
+    }
+    r.v = neg ? -(int)m : (int)m;
+    r.c = c;
+    return r;
+}
+
 __device__ __forceinline__ unsigned base_code(unsigned c) {
     // {A:1, T:2, G:3, C:4}  (transformers.py:72-77)
     return c == 'A' ? 1u : c == 'T' ? 2u : c == 'G' ? 3u : c == 'C' ? 4u : 0u;
@@ -321,8 +365,17 @@ __device__ __noinline__ int find_tag(Key key) {
     return -1;
 }
 
-__device__ __forceinline__ void store_slot(int slot, uint32_t bits) { s_tile()[slot * K1_TPB + threadIdx.x] = bits; }
-__device__ __forceinline__ void store_slot_f(int slot, float v) { store_slot(slot, __float_as_uint(v)); }
+// Slot stores go straight to the columnar batch raw[slot][record] (rows were pre-filled with
+// RAW_ABSENT by k1_fill).  A warp's lanes hit different rows at different times, so these are
+// 4-byte partial-sector writes that L2 merges (8 neighbouring records share a sector); keeping
+// the tile out of shared memory is what lets ~2x more warps stay resident, and this kernel is
+// bound by latency per warp, not by store bandwidth.
+struct RawOut {
+    uint32_t* col;      // &raw[0][record]
+    size_t stride;      // elements between slot rows
+};
+__device__ __forceinline__ void store_slot(const RawOut& o, int slot, uint32_t bits) { o.col[(size_t)slot * o.stride] = bits; }
+__device__ __forceinline__ void store_slot_f(const RawOut& o, int slot, float v) { store_slot(o, slot, __float_as_uint(v)); }
 
 #define CH3(a, b, c) ((unsigned long long)(a) | ((unsigned long long)(b) << 8) | ((unsigned long long)(c) << 16))
 
@@ -353,7 +406,7 @@ __device__ __forceinline__ uint32_t reduce_string(const PlanSlot sl, const Key& 
 // ':' in the sample column).  The plan lays a tag's slots out as elements 0..n_elem-1 followed
 // by at most one whole-value slot, so element e lands in slot first_slot + e.  Returns the
 // cursor somewhere inside / at the end of the value; the caller skips to vend.
-__device__ __noinline__ Cur parse_value(int t, unsigned kind, Cur c, unsigned vend) {
+__device__ __noinline__ Cur parse_value(RawOut o, int t, unsigned kind, Cur c, unsigned vend) {
     const PlanTag tg = s_tags()[t];
     const unsigned whole = tg.whole_red;
     const int s0 = tg.first_slot;
@@ -362,14 +415,14 @@ __device__ __noinline__ Cur parse_value(int t, unsigned kind, Cur c, unsigned ve
     const bool scalar = (kind & KIND_SCALAR) != 0;
     const unsigned v4 = B4(vend), c4 = B4(',');
     if (type == KIND_FLAG) {
-        for (int s = s0; s < s0 + (int)tg.n_slots; ++s) store_slot(s, RAW_MISSING);
+        for (int s = s0; s < s0 + (int)tg.n_slots; ++s) store_slot(o, s, RAW_MISSING);
         return c;
     }
     if (whole == RED_MOTIF_L || whole == RED_MOTIF_R) {
         // list(x): characters of a str, elements of a tuple (only single-character elements can
         // match a base) -- transformers.py:36-60
         if (type != KIND_STR) {
-            store_slot(tg.whole_slot, RAW_ERR);
+            store_slot(o, tg.whole_slot, RAW_ERR);
             return c;
         }
         double num = 0.0, scale = 1.0;
@@ -405,26 +458,42 @@ __device__ __noinline__ Cur parse_value(int t, unsigned kind, Cur c, unsigned ve
             c.adv();
             ch = c.peek();
         }
-        store_slot_f(tg.whole_slot, (float)num);
+        store_slot_f(o, tg.whole_slot, (float)num);
         return c;
     }
     if (whole == RED_GT_HOM) {
         const KeyCur r = take_until(c, v4, v4);
         const bool hom = r.k.len == 3 && (r.k.k0 == CH3('1', '/', '1') || r.k.k0 == CH3('1', '|', '1'));
-        store_slot_f(tg.whole_slot, hom ? 1.0f : 0.0f);
+        store_slot_f(o, tg.whole_slot, hom ? 1.0f : 0.0f);
         return r.c;
     }
     if (whole == RED_STRNUM) {
         const NumCur r = parse_num_cur(c);
         const unsigned ch = r.c.peek();
         const bool ok = r.st == NUM_OK && (ch == vend || ch == '\t' || ch == '\n') && !isnan(r.v);
-        store_slot(tg.whole_slot, ok ? __float_as_uint((float)r.v) : RAW_ERR);
+        store_slot(o, tg.whole_slot, ok ? __float_as_uint((float)r.v) : RAW_ERR);
         return r.c;
     }
     const bool count_all = whole == RED_LEN;
     int e = 0;
     for (;;) {
-        if (type == KIND_INT || type == KIND_FLOAT) {
+        if (type == KIND_INT) {
+            // Integer tags (htslib int32): digits only, no binary64 round trip
+            IntCur r = parse_int_cur(c);
+            c = r.c;
+            const unsigned ch = c.peek();
+            if (ch != ',' && ch != vend && ch != '\t' && ch != '\n') {
+                r.st = NUM_BAD;
+                c = skip_until(c, c4, v4);
+            }
+            if (e < n_elem) {
+                uint32_t bits;
+                if (s_slots()[s0 + e].reducer != RED_NUM) bits = RAW_ERR;
+                else if (r.st != NUM_OK) bits = r.st == NUM_MISSING ? RAW_MISSING : RAW_ERR;
+                else bits = __float_as_uint((float)r.v);
+                store_slot(o, s0 + e, bits);
+            }
+        } else if (type == KIND_FLOAT) {
             NumCur r = parse_num_cur(c);
             c = r.c;
             const unsigned ch = c.peek();
@@ -436,17 +505,16 @@ __device__ __noinline__ Cur parse_value(int t, unsigned kind, Cur c, unsigned ve
                 uint32_t bits;
                 if (s_slots()[s0 + e].reducer != RED_NUM) bits = RAW_ERR;
                 else if (r.st != NUM_OK) bits = r.st == NUM_MISSING ? RAW_MISSING : RAW_ERR;
-                else if (type == KIND_INT) bits = __float_as_uint((float)(long long)r.v);  // htslib int32 -> fp32
                 else {
                     const float f = (float)r.v;  // float32(strtod(text))
                     bits = isnan(f) ? RAW_MISSING : __float_as_uint(f);
                 }
-                store_slot(s0 + e, bits);
+                store_slot(o, s0 + e, bits);
             }
         } else if (e < n_elem) {
             const KeyCur r = take_until(c, scalar ? v4 : c4, v4);
             c = r.c;
-            store_slot(s0 + e, reduce_string(s_slots()[s0 + e], r.k));
+            store_slot(o, s0 + e, reduce_string(s_slots()[s0 + e], r.k));
         } else {
             c = skip_until(c, scalar ? v4 : c4, v4);
         }
@@ -457,8 +525,8 @@ __device__ __noinline__ Cur parse_value(int t, unsigned kind, Cur c, unsigned ve
         }
         break;
     }
-    for (int m = e; m < n_elem; ++m) store_slot(s0 + m, RAW_MISSING);  // vector shorter than needed
-    if (count_all) store_slot_f(tg.whole_slot, (float)e);
+    for (int m = e; m < n_elem; ++m) store_slot(o, s0 + m, RAW_MISSING);  // vector shorter than needed
+    if (count_all) store_slot_f(o, tg.whole_slot, (float)e);
     return c;
 }
 
@@ -467,12 +535,12 @@ __device__ __forceinline__ bool key_is_cg(const Key& k) {
     return k.len == 3 && (k.k0 == CH3('G', 'G', 'C') || k.k0 == CH3('C', 'C', 'G'));
 }
 
-__device__ __forceinline__ void set_tag_missing(int t) {
+__device__ __forceinline__ void set_tag_missing(const RawOut& o, int t) {
     const PlanTag tg = s_tags()[t];
-    for (int s = tg.first_slot; s < tg.first_slot + tg.n_slots; ++s) store_slot(s, RAW_MISSING);
+    for (int s = tg.first_slot; s < tg.first_slot + tg.n_slots; ++s) store_slot(o, s, RAW_MISSING);
 }
 
-__global__ void __launch_bounds__(K1_TPB) k1_parse(const __grid_constant__ DevPlan plan,
+__global__ void __launch_bounds__(K1_TPB, 8) k1_parse(const __grid_constant__ DevPlan plan,
                                                    const uint8_t* __restrict__ text,
                                                    const int64_t* __restrict__ line_start,
                                                    const int64_t* __restrict__ n_records_p,
@@ -504,12 +572,12 @@ __global__ void __launch_bounds__(K1_TPB) k1_parse(const __grid_constant__ DevPl
     const long long n_tiles = (n_rec + K1_TPB - 1) / K1_TPB;
     unsigned cg_local = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // every slot starts ABSENT (the reference's defaultdict(lambda: None))
-        for (int i = threadIdx.x; i < n_slots * K1_TPB; i += K1_TPB) s_tile()[i] = RAW_ABSENT;
-        __syncthreads();
         const long long rec = tile * K1_TPB + threadIdx.x;
         if (rec < n_rec) {
             const uint8_t* const line = text + line_start[rec];
+            RawOut o;
+            o.col = raw + rec;
+            o.stride = row_stride;
             Cur c;
             c.init(line);
             ugvc_recinfo ri;
@@ -612,10 +680,10 @@ __global__ void __launch_bounds__(K1_TPB) k1_parse(const __grid_constant__ DevPl
                     const unsigned kind = t >= 0 ? s_tags()[t].info_kind : 0u;
                     if (ch == '=') {
                         c.adv();
-                        if (kind) c = parse_value(t, kind, c, ';');
+                        if (kind) c = parse_value(o, t, kind, c, ';');
                         c = skip_until(c, semi4, semi4);
                     } else if (kind) {  // key without a value: typed None / ()
-                        set_tag_missing(t);
+                        set_tag_missing(o, t);
                     }
                     if (c.peek() == ';') {
                         c.adv();
@@ -641,12 +709,12 @@ __global__ void __launch_bounds__(K1_TPB) k1_parse(const __grid_constant__ DevPl
                     const int t = find_tag(r.k);
                     const unsigned kind = t >= 0 ? s_tags()[t].fmt_kind : 0u;
                     if (have_sample) {
-                        if (kind) sv = parse_value(t, kind, sv, ':');
+                        if (kind) sv = parse_value(o, t, kind, sv, ':');
                         sv = skip_until(sv, col4, col4);
                         if (sv.peek() == ':') sv.adv();
                         else have_sample = false;
                     } else if (kind) {  // trailing sub-fields dropped: missing
-                        set_tag_missing(t);
+                        set_tag_missing(o, t);
                     }
                     if (c.peek() == ':') {
                         c.adv();
@@ -658,11 +726,11 @@ __global__ void __launch_bounds__(K1_TPB) k1_parse(const __grid_constant__ DevPl
             // ---- fixed-column slots
             for (int s = plan.first_fixed_slot; s < n_slots; ++s) {
                 switch (s_slots()[s].reducer) {
-                    case RED_FIX_QUAL: store_slot(s, qual_bits); break;
-                    case RED_FIX_ALLELE0: store_slot_f(s, a0); break;
-                    case RED_FIX_ALLELE1: store_slot(s, a1_missing ? RAW_MISSING : __float_as_uint(a1)); break;
-                    case RED_FIX_INDEL: store_slot_f(s, indel ? 1.f : 0.f); break;
-                    case RED_FIX_NALLELES: store_slot_f(s, (float)n_alleles); break;
+                    case RED_FIX_QUAL: store_slot(o, s, qual_bits); break;
+                    case RED_FIX_ALLELE0: store_slot_f(o, s, a0); break;
+                    case RED_FIX_ALLELE1: store_slot(o, s, a1_missing ? RAW_MISSING : __float_as_uint(a1)); break;
+                    case RED_FIX_INDEL: store_slot_f(o, s, indel ? 1.f : 0.f); break;
+                    case RED_FIX_NALLELES: store_slot_f(o, s, (float)n_alleles); break;
                     default: break;
                 }
             }
@@ -671,17 +739,6 @@ __global__ void __launch_bounds__(K1_TPB) k1_parse(const __grid_constant__ DevPl
             cg_local += cg ? 1u : 0u;
             if (recinfo) *reinterpret_cast<uint4*>(&recinfo[rec]) = *reinterpret_cast<const uint4*>(&ri);
         }
-        __syncthreads();
-        // coalesced columnar write-out of the slot tile
-        const long long base = tile * K1_TPB;
-        const int valid = (int)min((long long)K1_TPB, n_rec - base);
-        if (threadIdx.x < valid) {
-            uint32_t* dst = raw + base + threadIdx.x;
-            const uint32_t* src = s_tile() + threadIdx.x;
-#pragma unroll 4
-            for (int s = 0; s < n_slots; ++s) dst[(size_t)s * row_stride] = src[s * K1_TPB];
-        }
-        __syncthreads();
     }
     // CG-insertion counter: one atomic per warp
 #pragma unroll
@@ -689,7 +746,21 @@ __global__ void __launch_bounds__(K1_TPB) k1_parse(const __grid_constant__ DevPl
     if ((threadIdx.x & 31) == 0 && cg_local) atomicAdd((unsigned long long*)&counts[3], (unsigned long long)cg_local);
 }
 
-size_t k1_smem_bytes(const DevPlan& plan) { return (size_t)K1_OFF_TILE + (size_t)plan.h.n_slots * K1_TPB * 4; }
+size_t k1_smem_bytes(const DevPlan&) { return (size_t)K1_SMEM_BYTES; }
+
+// every slot of every record starts ABSENT (the reference's defaultdict(lambda: None)):
+// coalesced 16-byte stores over the first n_records columns of each slot row
+__global__ void __launch_bounds__(256) k1_fill(uint32_t* __restrict__ raw, size_t row_stride, int n_slots,
+                                               const int64_t* __restrict__ n_records_p) {
+    const long long n_rec = *n_records_p;
+    const long long quads = (n_rec + 3) >> 2;  // rows are 16-byte aligned and padded (cap is a multiple of 128)
+    const uint4 v = make_uint4(RAW_ABSENT, RAW_ABSENT, RAW_ABSENT, RAW_ABSENT);
+    for (int s = blockIdx.y; s < n_slots; s += gridDim.y) {
+        uint4* row = reinterpret_cast<uint4*>(raw + (size_t)s * row_stride);
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += (long long)gridDim.x * blockDim.x)
+            row[i] = v;
+    }
+}
 
 void launch_k1(const DevPlan& plan, const uint8_t* d_text, const int64_t* line_start, const int64_t* d_n_records,
                uint32_t* raw, size_t row_stride, ugvc_recinfo* recinfo, unsigned long long* d_err,
@@ -698,6 +769,12 @@ void launch_k1(const DevPlan& plan, const uint8_t* d_text, const int64_t* line_s
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
+    static const int tune = getenv("UGVC_K1_CTAS_PER_SM") ? atoi(getenv("UGVC_K1_CTAS_PER_SM")) : 0;  // profiling knob
+    if (tune > 0 && tune < per_sm) per_sm = tune;
+    if (plan.h.n_slots) {
+        const dim3 fgrid((unsigned)(sm_count * 2), (unsigned)(plan.h.n_slots < 16 ? plan.h.n_slots : 16));
+        k1_fill<<<fgrid, 256, 0, st>>>(raw, row_stride, (int)plan.h.n_slots, d_n_records);
+    }
     k1_parse<<<sm_count * per_sm, K1_TPB, smem, st>>>(plan, d_text, line_start, d_n_records, raw, row_stride, recinfo,
                                                       d_err, d_counts);
 }
