@@ -307,6 +307,10 @@ def main():  # noqa: C901, PLR0912, PLR0915
     if rank == 0:
         log(f"[bench] rank0: {n_mine} records, {total_bytes / 1e9:.2f} GB text in HBM, {len(batches)} batches, "
             f"mean line {total_bytes / max(1, n_mine):.1f} B")
+    # the usual INFO key order / FORMAT column, learned from the head of the input like the CLI does
+    head = bytes(d_text[batches[0][0]: batches[0][0] + min(batches[0][1], 1 << 20)].cpu().numpy())
+    info_order, fmt_order = lib.learn_key_order(head[: head.rfind(b"\n") + 1])
+    ctx.set_key_order(info_order, fmt_order)
     max_b = max(b[2] for b in batches)
     d_low = torch.empty(n_mine, dtype=torch.uint8, device="cuda")
     d_probs = torch.empty((n_mine, K), dtype=torch.float32, device="cuda")

@@ -77,6 +77,13 @@ int ugvc_version(void);
 int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes);
 int ugvc_plan_info(const ugvc_ctx* ctx, int32_t* n_features, int32_t* n_classes, int32_t* n_slots);
 
+/* Optional: the order in which records carry their INFO keys (';'-separated key names, a
+ * trailing '!' marks a key that appears without a value) and the usual FORMAT column (e.g.
+ * "GT:AD:DP:GQ:PL"), learned by the host from the first records of the file.  K1 then steps
+ * through that order warp-uniformly; records that deviate fall back to the generic key lookup,
+ * results are identical either way.  NULL / "" clears.  Belongs to the loaded plan. */
+int ugvc_set_key_order(ugvc_ctx* ctx, const char* info_keys, const char* format_keys);
+
 /* Size the context's device workspace: n_pipeline independent batch lanes, each
  * for up to max_bytes of VCF text and max_records records. */
 int ugvc_reserve(ugvc_ctx* ctx, size_t max_bytes, size_t max_records, int n_pipeline);

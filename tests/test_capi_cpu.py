@@ -51,3 +51,16 @@ def test_synth_header_host_call():
     h = lib.synth_header(40)
     assert h.startswith("##fileformat=VCFv4.2") and h.rstrip().endswith("SAMPLE1")
     assert h.count("##INFO=<ID=ANN") == 35 and "##contig=<ID=chrY" in h
+
+
+def test_learn_key_order():
+    from variantcalling_b200 import synth
+
+    _, lines, _ = synth.generate(synth.SynthSpec(n_records=1500, n_custom=40))
+    info, fmt = lib.learn_key_order(("\n".join(lines) + "\n").encode())
+    keys = info.split(";")
+    assert keys[:5] == ["AC", "AF", "AN", "BaseQRankSum", "DP"] and fmt == "GT:AD:DP:GQ:PL"
+    assert keys[28:33] == synth.BASE_CUSTOM and keys[-1] == "ANN34" and len(keys) == 68
+    # inconsistent orders are left to the generic path; valueless keys carry a '!' marker
+    assert lib.learn_key_order(b"c\t1\t.\tA\tC\t1\t.\tB=1;A=2\tGT\t0/1\nc\t2\t.\tA\tC\t1\t.\tA=2;B=1\tGT\t0/1\n")[0] == ""
+    assert lib.learn_key_order(b"c\t1\t.\tA\tC\t1\t.\tA=2;DB;Z=1\n")[0] == "A;DB!;Z"

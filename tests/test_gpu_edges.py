@@ -50,11 +50,14 @@ def test_features_equal_reference_transformer_golden(gpu_ctx, golden):
     plan = MC.compile_plan(VcfHeader(hdr), golden["tr"], model, golden["customs"])
     gpu_ctx.load_plan(plan.blob)
     gpu_ctx.reserve(len(body) + 64, len(recs) + 8, 1)
-    res = gpu_ctx.filter_batch(body)
-    feats = gpu_ctx.debug_features(res["n_records"]).T
     want = golden["feats_ref"].astype(np.float32)
-    bad = np.argwhere(feats != want)
-    assert bad.size == 0, f"{len(bad)} mismatches, first {bad[0]}: {feats[tuple(bad[0])]} vs {want[tuple(bad[0])]}"
+    for mode in ("generic", "learned"):
+        if mode == "learned":
+            gpu_ctx.set_key_order(*lib.learn_key_order(body))
+        res = gpu_ctx.filter_batch(body)
+        feats = gpu_ctx.debug_features(res["n_records"]).T
+        bad = np.argwhere(feats != want)
+        assert bad.size == 0, f"[{mode}] {len(bad)} mismatches, first {bad[0]}: {feats[tuple(bad[0])]} vs {want[tuple(bad[0])]}"
     exp = R.filter_variants(golden["vf"], model, golden["tr"], custom_annotations=golden["customs"])
     assert np.array_equal(res["low_score"].astype(bool), np.array(["LOW_SCORE" in f.split(";") for f in exp["filters"]]))
     np.testing.assert_allclose(res["probs"], exp["probs"], atol=1e-5, rtol=0)
@@ -90,6 +93,7 @@ def test_inputs_the_reference_raises_on_raise_here_too(gpu_ctx, golden, case):
         R.filter_variants(OracleVariantFile(text), model, golden["tr"], custom_annotations=golden["customs"])
     plan = MC.compile_plan(VcfHeader(hdr), golden["tr"], model, golden["customs"])
     gpu_ctx.load_plan(plan.blob)
+    gpu_ctx.set_key_order(*lib.learn_key_order(("\n".join(recs) + "\n").encode()))
     gpu_ctx.reserve(1 << 20, 4096, 1)
     with pytest.raises(lib.UgvcDataError):
         gpu_ctx.filter_batch(("\n".join(new_recs) + "\n").encode())

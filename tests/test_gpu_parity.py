@@ -6,6 +6,7 @@ import pytest
 
 from oracle import ref_pipeline as R
 from tests import util
+from variantcalling_b200 import lib
 from variantcalling_b200 import model_compiler as MC
 from variantcalling_b200.vcf_header import VcfHeader
 
@@ -20,11 +21,21 @@ def ds():
     return d
 
 
-@pytest.mark.parametrize("kind", ["lr", "gb_small", "rf", "gb"])
-def test_filter_batch_matches_oracle(gpu_ctx, ds, kind):
+WRONG_ORDER = "X_RM;X_LM;DP;AC;NOPE;QD;AF!;SOR;AN"  # deliberately scrambled / partly bogus schedule
+
+
+@pytest.mark.parametrize("kind,order", [("lr", "none"), ("gb_small", "learned"), ("rf", "wrong"), ("gb", "learned"),
+                                        ("gb_small", "none")])
+def test_filter_batch_matches_oracle(gpu_ctx, ds, kind, order):
     model = util.fit_model(kind, ds["x"], ds["labels"])
     plan = MC.compile_plan(VcfHeader(ds["header_text"]), ds["tr"], model, ds["customs"])
     gpu_ctx.load_plan(plan.blob)
+    if order == "learned":  # K1's schedule-driven path
+        info, fmt = lib.learn_key_order(ds["text"])
+        assert info.startswith("AC;AF;AN") and fmt == "GT:AD:DP:GQ:PL"
+        gpu_ctx.set_key_order(info, fmt)
+    elif order == "wrong":  # a bad schedule must only cost speed, never change results
+        gpu_ctx.set_key_order(WRONG_ORDER, "GT:DP")
     gpu_ctx.reserve(len(ds["text"]) + 1024, len(ds["lines"]) + 16, 1)
     gpu_ctx.counts_reset()
     res = gpu_ctx.filter_batch(ds["text"], 30.0)

@@ -35,6 +35,9 @@ struct ugvc_ctx {
     uint8_t* d_plan = nullptr;
     uint8_t* d_htab = nullptr;
     uint2* d_nodes = nullptr;
+    std::vector<PlanTag> h_tags;   // host copy for name lookups
+    DevSchedule sched{};           // learned key order (empty: generic path only)
+    SchedEntry* d_sched = nullptr;
     std::vector<Lane> lanes;
     size_t cap_bytes = 0, cap_records = 0;
     long long* d_counts = nullptr;
@@ -114,6 +117,7 @@ extern "C" void ugvc_free(ugvc_ctx* ctx) {
     cudaFree(ctx->d_plan);
     cudaFree(ctx->d_htab);
     cudaFree(ctx->d_nodes);
+    cudaFree(ctx->d_sched);
     cudaFree(ctx->d_counts);
     delete ctx;
 }
@@ -295,10 +299,80 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     }
     CU(kernels_configure(p));
     ctx->has_plan = true;
+    ctx->h_tags.assign(tags, tags + h.n_tags);
+    cudaFree(ctx->d_sched);  // a key order belongs to a plan
+    ctx->d_sched = nullptr;
+    ctx->sched = DevSchedule{};
     // a new plan changes the slot/feature counts: lanes must be re-reserved
     for (auto& l : ctx->lanes) free_lane(l);
     ctx->lanes.clear();
     ctx->cap_bytes = ctx->cap_records = 0;
+    return UGVC_OK;
+}
+
+static int find_host_tag(const ugvc_ctx* ctx, const std::string& name) {
+    for (size_t t = 0; t < ctx->h_tags.size(); ++t)
+        if (ctx->h_tags[t].len == name.size() && memcmp(ctx->h_tags[t].name, name.data(), name.size()) == 0) return (int)t;
+    return -1;
+}
+
+extern "C" int ugvc_set_key_order(ugvc_ctx* ctx, const char* info_keys, const char* format_keys) {
+    if (!ctx) return UGVC_E_ARG;
+    if (!ctx->has_plan) return fail(ctx, UGVC_E_STATE, "set_key_order: load a plan first");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    std::vector<SchedEntry> entries;
+    if (info_keys) {
+        const char* p = info_keys;
+        while (*p && entries.size() < UGVC_MAX_SCHED) {
+            const char* e = p;
+            while (*e && *e != ';') ++e;
+            std::string key(p, e);
+            p = *e ? e + 1 : e;
+            if (key.empty()) continue;
+            SchedEntry se;
+            memset(&se, 0, sizeof(se));
+            se.is_flag = key.back() == '!' ? 1 : 0;
+            if (se.is_flag) key.pop_back();
+            if (key.empty() || key.size() > 23) continue;  // longer keys simply take the generic path
+            se.tag = (int16_t)find_host_tag(ctx, key);
+            std::string bytes = key + (se.is_flag ? "" : "=");
+            se.len = (uint8_t)bytes.size();
+            memcpy(se.w, bytes.data(), bytes.size());
+            entries.push_back(se);
+        }
+    }
+    DevSchedule sc{};
+    cudaFree(ctx->d_sched);
+    ctx->d_sched = nullptr;
+    if (!entries.empty()) {
+        CU(cudaMalloc(&ctx->d_sched, entries.size() * sizeof(SchedEntry)));
+        CU(cudaMemcpy(ctx->d_sched, entries.data(), entries.size() * sizeof(SchedEntry), cudaMemcpyHostToDevice));
+        sc.info = ctx->d_sched;
+        sc.n_info = (int)entries.size();
+    }
+    if (format_keys && *format_keys) {
+        const std::string f(format_keys);
+        if (f.size() <= 24) {
+            int n = 0;
+            size_t b = 0;
+            bool ok = true;
+            while (b <= f.size() && ok) {
+                size_t e = f.find(':', b);
+                if (e == std::string::npos) e = f.size();
+                if (n >= UGVC_MAX_FMT_KEYS) { ok = false; break; }
+                sc.fmt_tag[n++] = (int16_t)find_host_tag(ctx, f.substr(b, e - b));
+                b = e + 1;
+                if (e == f.size()) break;
+            }
+            if (ok) {
+                sc.n_fmt = n;
+                sc.fmt_len = (int)f.size();
+                memcpy(sc.fmt_w, f.data(), f.size());
+            }
+        }
+    }
+    ctx->sched = sc;
     return UGVC_OK;
 }
 
@@ -365,7 +439,7 @@ static int enqueue_kernels(ugvc_ctx* ctx, Lane& l, const uint8_t* d_text, size_t
     if (timing) CU(cudaEventRecord(ev[0], st));
     launch_k0(d_text, n_bytes, l.b.chunk_first, d_line_start, line_cap, d_n_records, l.d_err, ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[1], st));
-    launch_k1(p, d_text, d_line_start, d_n_records, l.b.raw, l.b.cap_records, d_recinfo, l.d_err, ctx->d_counts,
+    launch_k1(p, ctx->sched, d_text, d_line_start, d_n_records, l.b.raw, l.b.cap_records, d_recinfo, l.d_err, ctx->d_counts,
               ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[2], st));
     const bool has_model = p.h.model_kind != MODEL_NONE;
@@ -375,7 +449,7 @@ static int enqueue_kernels(ugvc_ctx* ctx, Lane& l, const uint8_t* d_text, size_t
         launch_k3(p, l.b.feats, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual, ctx->d_counts,
                   ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[4], st));
-    ctx->launches += has_model ? 6 : 4;
+    ctx->launches += (has_model ? 6 : 4) + (p.h.n_slots ? 1 : 0);
     CU(cudaGetLastError());
     return UGVC_OK;
 }

@@ -182,7 +182,8 @@ void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* chunk_first, int
 #define K1_OFF_SLOTS (K1_OFF_STRINGS + K1_MAX_STRINGS * 32)
 #define K1_OFF_DICTS (K1_OFF_SLOTS + 256 * 4)
 #define K1_OFF_HTAB (K1_OFF_DICTS + K1_MAX_DICTS * 4)
-#define K1_SMEM_BYTES (K1_OFF_HTAB + 256)
+#define K1_OFF_SCHED (K1_OFF_HTAB + 256)
+#define K1_SMEM_BYTES (K1_OFF_SCHED + UGVC_MAX_SCHED * 32)
 
 extern __shared__ __align__(16) uint8_t k1_smem[];
 __device__ __forceinline__ const PlanTag* s_tags() { return reinterpret_cast<const PlanTag*>(k1_smem + K1_OFF_TAGS); }
@@ -190,30 +191,41 @@ __device__ __forceinline__ const PlanString* s_strings() { return reinterpret_ca
 __device__ __forceinline__ const PlanSlot* s_slots() { return reinterpret_cast<const PlanSlot*>(k1_smem + K1_OFF_SLOTS); }
 __device__ __forceinline__ const PlanDict* s_dicts() { return reinterpret_cast<const PlanDict*>(k1_smem + K1_OFF_DICTS); }
 __device__ __forceinline__ const uint8_t* s_htab() { return k1_smem + K1_OFF_HTAB; }
+__device__ __forceinline__ const SchedEntry* s_sched() { return reinterpret_cast<const SchedEntry*>(k1_smem + K1_OFF_SCHED); }
 
+// Look-ahead cursor: two consecutive aligned 8-byte words of the line (the second one is always
+// already loaded, so the next load is issued a word ahead of its use) and a byte offset into
+// the first.  peek8() is the next 8 bytes of the stream whatever the alignment.
 struct Cur {
-    const unsigned long long* wp;  // next aligned word
-    unsigned long long w;          // unread bytes of the current word, next byte lowest
-    int n;                         // how many (1..8)
+    const unsigned long long* wp;  // word after hi
+    unsigned long long lo, hi;
+    int sh;                        // bytes of lo already consumed (0..7)
     __device__ __forceinline__ void init(const uint8_t* p) {
-        const unsigned off = (unsigned)(reinterpret_cast<uintptr_t>(p) & 7u);
-        wp = reinterpret_cast<const unsigned long long*>(p - off);
-        w = __ldg(wp++) >> (8 * off);
-        n = 8 - (int)off;
+        sh = (int)(reinterpret_cast<uintptr_t>(p) & 7u);
+        wp = reinterpret_cast<const unsigned long long*>(p - sh);
+        lo = __ldg(wp++);
+        hi = __ldg(wp++);
     }
-    __device__ __forceinline__ unsigned peek() const { return (unsigned)w & 0xFFu; }
+    __device__ __forceinline__ unsigned peek() const { return (unsigned)(lo >> (8 * sh)) & 0xFFu; }
+    __device__ __forceinline__ unsigned long long peek8() const {
+        return sh ? ((lo >> (8 * sh)) | (hi << (64 - 8 * sh))) : lo;
+    }
     __device__ __forceinline__ void adv() {
-        w >>= 8;
-        if (--n == 0) {
-            w = __ldg(wp++);
-            n = 8;
+        if (++sh == 8) {
+            sh = 0;
+            lo = hi;
+            hi = __ldg(wp++);
         }
     }
-    __device__ __forceinline__ void refill() {
-        w = __ldg(wp++);
-        n = 8;
+    __device__ __forceinline__ void advance(int k) {  // 0 <= k <= 8
+        sh += k;
+        if (sh >= 8) {
+            sh -= 8;
+            lo = hi;
+            hi = __ldg(wp++);
+        }
     }
-    __device__ __forceinline__ const uint8_t* ptr() const { return reinterpret_cast<const uint8_t*>(wp) - n; }
+    __device__ __forceinline__ const uint8_t* ptr() const { return reinterpret_cast<const uint8_t*>(wp - 2) + sh; }
 };
 
 struct Key {
@@ -233,9 +245,9 @@ struct NumCur {
 #define B4(ch) ((unsigned)(ch) * 0x01010101u)
 
 // Bit 7 set in the FIRST byte of w that equals tab, newline or one of the two pattern bytes
-// (bytes above the first match may carry false positives -- only the lowest set bit is used;
-// consumed bytes of the window are zero and never match).  Classic has-zero-byte SWAR on
-// 64-bit words: sm_100 has no byte-compare instruction (__vcmpeq4 is emulated).
+// (bytes above the first match may carry false positives -- only the lowest set bit is used).
+// Classic has-zero-byte SWAR on 64-bit words: sm_100 has no byte-compare instruction
+// (__vcmpeq4 is emulated with five instructions).
 __device__ __forceinline__ unsigned long long has_zero(unsigned long long x) {
     return (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;
 }
@@ -245,17 +257,15 @@ __device__ __forceinline__ unsigned long long delim_mask(unsigned long long w, u
     return has_zero((w & 0xFCFCFCFCFCFCFCFCull) ^ 0x0808080808080808ull) | has_zero(w ^ a8) | has_zero(w ^ b8);
 }
 
-// advance to the first byte that is tab, newline or a pattern byte
+// advance to the first byte that is tab, newline or a pattern byte (8 bytes of look-ahead per step)
 __device__ __noinline__ Cur skip_until(Cur c, unsigned a4, unsigned b4) {
     for (;;) {
-        const unsigned long long m = delim_mask(c.w, a4, b4);
+        const unsigned long long m = delim_mask(c.peek8(), a4, b4);
         if (m) {
-            const int k = (__ffsll((long long)m) - 1) >> 3;
-            c.w >>= 8 * k;
-            c.n -= k;
+            c.advance((__ffsll((long long)m) - 1) >> 3);
             return c;
         }
-        c.refill();
+        c.advance(8);
     }
 }
 
@@ -284,17 +294,17 @@ __device__ __noinline__ KeyCur take_until(Cur c, unsigned a4, unsigned b4) {
     r.k.k0 = r.k.k1 = r.k.k2 = 0ull;
     r.k.len = 0;
     for (;;) {
-        const unsigned long long m = delim_mask(c.w, a4, b4);
+        const unsigned long long x = c.peek8();
+        const unsigned long long m = delim_mask(x, a4, b4);
         if (m) {
             const int k = (__ffsll((long long)m) - 1) >> 3;  // 0..7
-            key_append(r.k, c.w & ((1ull << (8 * k)) - 1ull), k);
-            c.w >>= 8 * k;
-            c.n -= k;
+            key_append(r.k, x & ((1ull << (8 * k)) - 1ull), k);
+            c.advance(k);
             r.c = c;
             return r;
         }
-        key_append(r.k, c.w, c.n);
-        c.refill();
+        key_append(r.k, x, 8);
+        c.advance(8);
     }
 }
 
@@ -310,7 +320,7 @@ struct IntCur {
     int v;
     int st;
 };
-// "[+-]digits" or "." -> int (saturating at int32); anything else in the token is NUM_BAD
+// "[+-]digits" or "." -> int (int32 range, else NUM_BAD); anything else in the token is NUM_BAD
 __device__ __noinline__ IntCur parse_int_cur(Cur c) {
     IntCur r;
     unsigned ch = c.peek();
@@ -530,6 +540,40 @@ __device__ __noinline__ Cur parse_value(RawOut o, int t, unsigned kind, Cur c, u
     return c;
 }
 
+// Does the stream at c start with the len bytes w[]?  On success out stands right after them.
+__device__ __forceinline__ bool match_bytes(const Cur& c, const unsigned long long w0, const unsigned long long w1,
+                                            const unsigned long long w2, int len, Cur& out) {
+    Cur t = c;
+    unsigned long long x = t.peek8();
+    if (len <= 8) {
+        const unsigned long long mask = len == 8 ? ~0ull : ((1ull << (8 * len)) - 1ull);
+        if ((x & mask) != w0) return false;
+        t.advance(len);
+        out = t;
+        return true;
+    }
+    if (x != w0) return false;
+    t.advance(8);
+    x = t.peek8();
+    int rem = len - 8;
+    if (rem <= 8) {
+        const unsigned long long mask = rem == 8 ? ~0ull : ((1ull << (8 * rem)) - 1ull);
+        if ((x & mask) != w1) return false;
+        t.advance(rem);
+        out = t;
+        return true;
+    }
+    if (x != w1) return false;
+    t.advance(8);
+    x = t.peek8();
+    rem -= 8;
+    const unsigned long long mask = rem >= 8 ? ~0ull : ((1ull << (8 * rem)) - 1ull);
+    if ((x & mask) != w2) return false;
+    t.advance(rem > 8 ? 8 : rem);
+    out = t;
+    return true;
+}
+
 __device__ __forceinline__ bool key_is_cg(const Key& k) {
     // an allele equal to GGC or CCG (blacklist.py:85-101: tuple membership)
     return k.len == 3 && (k.k0 == CH3('G', 'G', 'C') || k.k0 == CH3('C', 'C', 'G'));
@@ -541,7 +585,8 @@ __device__ __forceinline__ void set_tag_missing(const RawOut& o, int t) {
 }
 
 __global__ void __launch_bounds__(K1_TPB, 8) k1_parse(const __grid_constant__ DevPlan plan,
-                                                   const uint8_t* __restrict__ text,
+                                                      const __grid_constant__ DevSchedule sched,
+                                                      const uint8_t* __restrict__ text,
                                                    const int64_t* __restrict__ line_start,
                                                    const int64_t* __restrict__ n_records_p,
                                                    uint32_t* __restrict__ raw, size_t row_stride,
@@ -565,6 +610,9 @@ __global__ void __launch_bounds__(K1_TPB, 8) k1_parse(const __grid_constant__ De
         dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_DICTS);
         for (int i = threadIdx.x; i < (int)plan.h.n_dicts; i += K1_TPB) dst[i] = src[i];
         for (int i = threadIdx.x; i < 256; i += K1_TPB) k1_smem[K1_OFF_HTAB + i] = plan.htab[i];
+        src = reinterpret_cast<const uint32_t*>(sched.info);
+        dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_SCHED);
+        for (int i = threadIdx.x; i < sched.n_info * 8; i += K1_TPB) dst[i] = src[i];
     }
     __syncthreads();
     const unsigned tab4 = B4('\t');
@@ -672,7 +720,33 @@ __global__ void __launch_bounds__(K1_TPB, 8) k1_parse(const __grid_constant__ De
             if (!malformed) {
                 c.adv();
                 const unsigned semi4 = B4(';'), eq4 = B4('=');
-                for (;;) {
+                bool in_info = true;
+                // (1) step through the learned key order: every lane of the warp looks for the same
+                //     key at the same time, so the lanes that have it decode the same type together
+                for (int j = 0; j < sched.n_info; ++j) {
+                    if (in_info) {
+                        const SchedEntry e = s_sched()[j];
+                        Cur t;
+                        if (match_bytes(c, e.w[0], e.w[1], e.w[2], e.len, t)) {
+                            const unsigned nxt = t.peek();
+                            const unsigned kind = e.tag >= 0 ? s_tags()[e.tag].info_kind : 0u;
+                            if (!e.is_flag) {
+                                c = t;
+                                if (kind) c = parse_value(o, e.tag, kind, c, ';');
+                                c = skip_until(c, semi4, semi4);
+                            } else if (nxt == ';' || nxt == '\t' || nxt == '\n') {
+                                c = t;
+                                if (kind) set_tag_missing(o, e.tag);  // key without a value: typed None / ()
+                            } else {
+                                continue;  // a longer key with this prefix: not this entry
+                            }
+                            if (c.peek() == ';') c.adv();
+                            else in_info = false;  // tab / newline: the INFO column is finished
+                        }
+                    }
+                }
+                // (2) whatever is left (keys off the schedule, another order): generic path
+                while (in_info) {
                     const KeyCur r = take_until(c, eq4, semi4);
                     c = r.c;
                     const unsigned ch = c.peek();
@@ -685,11 +759,8 @@ __global__ void __launch_bounds__(K1_TPB, 8) k1_parse(const __grid_constant__ De
                     } else if (kind) {  // key without a value: typed None / ()
                         set_tag_missing(o, t);
                     }
-                    if (c.peek() == ';') {
-                        c.adv();
-                        continue;
-                    }
-                    break;
+                    if (c.peek() == ';') c.adv();
+                    else in_info = false;
                 }
             }
             // ---- FORMAT + first sample (FORMAT values override INFO values of the same
@@ -700,27 +771,56 @@ __global__ void __launch_bounds__(K1_TPB, 8) k1_parse(const __grid_constant__ De
             if (!malformed && c.peek() == '\t') {
                 c.adv();
                 const unsigned col4 = B4(':');
-                Cur sv = skip_until(c, tab4, tab4);
-                bool have_sample = (sv.peek() == '\t');
-                if (have_sample) sv.adv();
-                for (;;) {
-                    const KeyCur r = take_until(c, col4, col4);
-                    c = r.c;
-                    const int t = find_tag(r.k);
-                    const unsigned kind = t >= 0 ? s_tags()[t].fmt_kind : 0u;
-                    if (have_sample) {
-                        if (kind) sv = parse_value(o, t, kind, sv, ':');
-                        sv = skip_until(sv, col4, col4);
-                        if (sv.peek() == ':') sv.adv();
-                        else have_sample = false;
-                    } else if (kind) {  // trailing sub-fields dropped: missing
-                        set_tag_missing(o, t);
+                Cur sv;
+                bool spec = false;
+                if (sched.n_fmt > 0) {
+                    // the usual FORMAT column, compared as a whole: its sub-fields are then decoded
+                    // in the known order, the same tag in every lane
+                    Cur t;
+                    if (match_bytes(c, sched.fmt_w[0], sched.fmt_w[1], sched.fmt_w[2], sched.fmt_len, t) &&
+                        (t.peek() == '\t' || t.peek() == '\n')) {
+                        spec = true;
+                        sv = t;
                     }
-                    if (c.peek() == ':') {
-                        c.adv();
-                        continue;
+                }
+                if (spec) {
+                    bool have_sample = (sv.peek() == '\t');
+                    if (have_sample) sv.adv();
+                    for (int j = 0; j < sched.n_fmt; ++j) {
+                        const int t = sched.fmt_tag[j];
+                        const unsigned kind = t >= 0 ? s_tags()[t].fmt_kind : 0u;
+                        if (have_sample) {
+                            if (kind) sv = parse_value(o, t, kind, sv, ':');
+                            sv = skip_until(sv, col4, col4);
+                            if (sv.peek() == ':') sv.adv();
+                            else have_sample = false;
+                        } else if (kind) {  // trailing sub-fields dropped: missing
+                            set_tag_missing(o, t);
+                        }
                     }
-                    break;
+                } else {
+                    sv = skip_until(c, tab4, tab4);
+                    bool have_sample = (sv.peek() == '\t');
+                    if (have_sample) sv.adv();
+                    for (;;) {
+                        const KeyCur r = take_until(c, col4, col4);
+                        c = r.c;
+                        const int t = find_tag(r.k);
+                        const unsigned kind = t >= 0 ? s_tags()[t].fmt_kind : 0u;
+                        if (have_sample) {
+                            if (kind) sv = parse_value(o, t, kind, sv, ':');
+                            sv = skip_until(sv, col4, col4);
+                            if (sv.peek() == ':') sv.adv();
+                            else have_sample = false;
+                        } else if (kind) {  // trailing sub-fields dropped: missing
+                            set_tag_missing(o, t);
+                        }
+                        if (c.peek() == ':') {
+                            c.adv();
+                            continue;
+                        }
+                        break;
+                    }
                 }
             }
             // ---- fixed-column slots
@@ -762,7 +862,8 @@ __global__ void __launch_bounds__(256) k1_fill(uint32_t* __restrict__ raw, size_
     }
 }
 
-void launch_k1(const DevPlan& plan, const uint8_t* d_text, const int64_t* line_start, const int64_t* d_n_records,
+void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_text, const int64_t* line_start,
+               const int64_t* d_n_records,
                uint32_t* raw, size_t row_stride, ugvc_recinfo* recinfo, unsigned long long* d_err,
                long long* d_counts, int sm_count, cudaStream_t st) {
     const size_t smem = k1_smem_bytes(plan);
@@ -775,7 +876,7 @@ void launch_k1(const DevPlan& plan, const uint8_t* d_text, const int64_t* line_s
         const dim3 fgrid((unsigned)(sm_count * 2), (unsigned)(plan.h.n_slots < 16 ? plan.h.n_slots : 16));
         k1_fill<<<fgrid, 256, 0, st>>>(raw, row_stride, (int)plan.h.n_slots, d_n_records);
     }
-    k1_parse<<<sm_count * per_sm, K1_TPB, smem, st>>>(plan, d_text, line_start, d_n_records, raw, row_stride, recinfo,
+    k1_parse<<<sm_count * per_sm, K1_TPB, smem, st>>>(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo,
                                                       d_err, d_counts);
 }
 

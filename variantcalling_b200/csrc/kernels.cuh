@@ -27,6 +27,27 @@ struct DevPlan {
     uint32_t first_fixed_slot; // slots [first_fixed_slot, n_slots) are TAG_FIXED
 };
 
+// Learned key order ("schedule"): the INFO keys in the order records carry them and the usual
+// FORMAT column.  K1 steps through it warp-uniformly, matching "KEY=" word-wise against the
+// cursor's look-ahead; keys off the schedule take the generic hash-lookup path.
+#define UGVC_MAX_SCHED 128
+#define UGVC_MAX_FMT_KEYS 16
+struct alignas(8) SchedEntry {   // 32 bytes
+    unsigned long long w[3];     // the bytes to match ("KEY=", or "KEY" for a valueless key), zero padded
+    uint8_t len;                 // how many
+    uint8_t is_flag;             // valueless key: the next byte must end the field
+    int16_t tag;                 // plan tag index, or -1 when the value is not needed
+    uint8_t pad[4];
+};
+struct DevSchedule {
+    const SchedEntry* info;      // device array
+    int n_info;
+    int n_fmt;                   // sub-fields of the expected FORMAT column (0: none learned)
+    int fmt_len;                 // its length in bytes
+    unsigned long long fmt_w[3]; // its bytes, zero padded
+    int16_t fmt_tag[UGVC_MAX_FMT_KEYS];
+};
+
 // Error word: smaller is earlier.  (record << 24) | (column << 8) | reason
 #define UGVC_NO_ERROR 0xFFFFFFFFFFFFFFFFull
 __host__ __device__ inline unsigned long long ugvc_pack_error(long long rec, int col, int reason) {
@@ -56,7 +77,7 @@ struct LaneBuffers {
 void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* chunk_first, int64_t* line_start,
                size_t cap_records, int64_t* d_n_records, unsigned long long* d_err, int sm_count,
                cudaStream_t st);
-void launch_k1(const DevPlan& plan, const uint8_t* d_text, const int64_t* line_start, const int64_t* d_n_records,
+void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_text, const int64_t* line_start, const int64_t* d_n_records,
                uint32_t* raw, size_t row_stride, ugvc_recinfo* recinfo, unsigned long long* d_err,
                long long* d_counts, int sm_count, cudaStream_t st);
 void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, const int64_t* d_n_records, float* feats,

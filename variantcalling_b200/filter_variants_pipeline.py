@@ -210,6 +210,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         batch_bytes = max(1, args.batch_mb) << 20
         n_lanes = 2
         reserved = (0, 0)
+        key_order_set = False
 
         out = _Splicer(args.output_file, args.io_threads)
         out.write_header(out_header)
@@ -236,6 +237,10 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 logger.info("Marking CG insertions")
             bl_pos = _blacklist_positions(blacklists, contig) if blacklists is not None else []
 
+            if not key_order_set and with_model:
+                head = text[: min(text.size, 1 << 20)].tobytes()
+                ctx.set_key_order(*lib.learn_key_order(head[: head.rfind(b"\n") + 1]))
+                key_order_set = True
             ranges = list(_split_batches(text, batch_bytes))
             need = (max(e - b for b, e in ranges) + 4096,
                     max(int(np.count_nonzero(text[b:e] == 10)) for b, e in ranges) + 128)  # noqa: PLR2004

@@ -47,6 +47,7 @@ SIGNATURES = {
     "ugvc_load_plan": (C.c_int, [_vp, _vp, _sz]),
     "ugvc_plan_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ugvc_reserve": (C.c_int, [_vp, _sz, _sz, C.c_int]),
+    "ugvc_set_key_order": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
     "ugvc_filter_batch": (C.c_int, [_vp, _vp, _sz, C.c_double, _vp, _vp, _vp, _vp, _vp, _sz, _i64p]),
     "ugvc_submit_batch": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_double]),
     "ugvc_collect_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _i64p]),
@@ -177,6 +178,10 @@ class Context:
         self._check(self.lib.ugvc_plan_info(self.h, C.byref(f), C.byref(k), C.byref(s)))
         self.n_features, self.n_classes, self.n_slots = f.value, k.value, s.value
 
+    def set_key_order(self, info_keys: str | None, format_keys: str | None):
+        """Tell K1 the usual INFO key order / FORMAT column (see :func:`learn_key_order`)."""
+        self._check(self.lib.ugvc_set_key_order(self.h, (info_keys or "").encode(), (format_keys or "").encode()))
+
     def reserve(self, max_bytes: int, max_records: int, n_pipeline: int = 1):
         self._check(self.lib.ugvc_reserve(self.h, max_bytes, max_records, n_pipeline))
         self.cap_bytes, self.cap_records = max_bytes, (max_records + 127) // 128 * 128
@@ -285,3 +290,63 @@ def synth_header(n_custom: int) -> str:
     buf = C.create_string_buffer(int(n))
     lib.ugvc_synth_header(n_custom, buf, n)
     return buf.raw.decode()
+
+
+def learn_key_order(sample: bytes, max_records: int = 2000) -> tuple[str, str]:
+    """Order of the INFO keys and the most common FORMAT column over the first records of
+    ``sample`` (VCF data lines).
+
+    Every record contributes the chain key[i] -> key[i+1]; a topological order of the union
+    graph is a common supersequence of all the records' key sequences (records written by
+    GATK/htsjdk carry their keys sorted, optional keys simply missing).  Keys caught in a cycle
+    (files mixing orders) are left out and take K1's generic lookup path."""
+    import heapq
+
+    first_seen: dict[str, int] = {}
+    succ: dict[str, set] = {}
+    indeg: dict[str, int] = {}
+    formats: dict[str, int] = {}
+    n = 0
+    for line in sample.split(b"\n"):
+        if not line or line.startswith(b"#"):
+            continue
+        cols = line.split(b"\t")
+        if len(cols) < 8:  # noqa: PLR2004
+            continue
+        n += 1
+        if n > max_records:
+            break
+        if len(cols) > 8:  # noqa: PLR2004
+            f = cols[8].decode("latin-1")
+            formats[f] = formats.get(f, 0) + 1
+        if cols[7] == b".":
+            continue
+        prev = None
+        for kv in cols[7].split(b";"):
+            if not kv:
+                continue
+            key, sep, _ = kv.partition(b"=")
+            name = key.decode("latin-1") + ("" if sep else "!")
+            if ";" in name or len(name) > 24:  # noqa: PLR2004
+                prev = None
+                continue
+            if name not in first_seen:
+                first_seen[name] = len(first_seen)
+                succ[name] = set()
+                indeg[name] = 0
+            if prev is not None and prev != name and name not in succ[prev]:
+                succ[prev].add(name)
+                indeg[name] += 1
+            prev = name
+    heap = [(first_seen[k], k) for k, d in indeg.items() if d == 0]
+    heapq.heapify(heap)
+    order = []
+    while heap:
+        _, k = heapq.heappop(heap)
+        order.append(k)
+        for m in succ[k]:
+            indeg[m] -= 1
+            if indeg[m] == 0:
+                heapq.heappush(heap, (first_seen[m], m))
+    fmt = max(formats, key=formats.get) if formats else ""
+    return ";".join(order[:128]), fmt if len(fmt) <= 24 else ""  # noqa: PLR2004
