@@ -35,7 +35,8 @@ struct ugvc_ctx {
     uint8_t* d_plan = nullptr;
     uint8_t* d_htab = nullptr;
     uint2* d_nodes = nullptr;
-    std::vector<PlanTag> h_tags;   // host copy for name lookups
+    std::vector<PlanTag> h_tags;   // host copies for name lookups / decode classes
+    std::vector<PlanSlot> h_slots;
     DevSchedule sched{};           // learned key order (empty: generic path only)
     SchedEntry* d_sched = nullptr;
     std::vector<Lane> lanes;
@@ -300,6 +301,7 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     CU(kernels_configure(p));
     ctx->has_plan = true;
     ctx->h_tags.assign(tags, tags + h.n_tags);
+    ctx->h_slots.assign(slots, slots + h.n_slots);
     cudaFree(ctx->d_sched);  // a key order belongs to a plan
     ctx->d_sched = nullptr;
     ctx->sched = DevSchedule{};
@@ -314,6 +316,35 @@ static int find_host_tag(const ugvc_ctx* ctx, const std::string& name) {
     for (size_t t = 0; t < ctx->h_tags.size(); ++t)
         if (ctx->h_tags[t].len == name.size() && memcmp(ctx->h_tags[t].name, name.data(), name.size()) == 0) return (int)t;
     return -1;
+}
+
+// decode class of a tag in one header section, from the plan's slot layout
+static void classify(const ugvc_ctx* ctx, int tag, bool format, SchedEntry& se) {
+    se.tag = (int16_t)tag;
+    se.cls = CLS_SKIP;
+    if (tag < 0) return;
+    const PlanTag& tg = ctx->h_tags[tag];
+    const unsigned kind = format ? tg.fmt_kind : tg.info_kind;
+    if (!kind) return;  // not declared in this section: the value is skipped
+    se.cls = CLS_GENERIC;
+    const unsigned type = kind & KIND_TYPE_MASK;
+    const bool scalar = (kind & KIND_SCALAR) != 0;
+    const bool has_whole = tg.whole_red != 0xFF;
+    const int n_elem = (int)tg.n_slots - (has_whole ? 1 : 0);
+    se.slot0 = tg.first_slot;
+    se.n_elem = (uint8_t)n_elem;
+    bool all_num = true;
+    for (int e = 0; e < n_elem; ++e) all_num &= ctx->h_slots[tg.first_slot + e].reducer == RED_NUM;
+    if (type == KIND_INT && all_num && (!has_whole || tg.whole_red == RED_LEN)) {
+        se.cls = CLS_INT;
+        if (has_whole) se.flags |= SCHED_COUNT_ALL;
+    } else if (type == KIND_FLOAT && all_num && !has_whole) {
+        se.cls = CLS_FLOAT;
+    } else if (type == KIND_STR && scalar && n_elem == 1 && !has_whole &&
+               ctx->h_slots[tg.first_slot].reducer == RED_DICT) {
+        se.cls = CLS_DICT1;
+        se.dict = ctx->h_slots[tg.first_slot].dict;
+    }
 }
 
 extern "C" int ugvc_set_key_order(ugvc_ctx* ctx, const char* info_keys, const char* format_keys) {
@@ -332,13 +363,18 @@ extern "C" int ugvc_set_key_order(ugvc_ctx* ctx, const char* info_keys, const ch
             if (key.empty()) continue;
             SchedEntry se;
             memset(&se, 0, sizeof(se));
-            se.is_flag = key.back() == '!' ? 1 : 0;
-            if (se.is_flag) key.pop_back();
-            if (key.empty() || key.size() > 23) continue;  // longer keys simply take the generic path
-            se.tag = (int16_t)find_host_tag(ctx, key);
-            std::string bytes = key + (se.is_flag ? "" : "=");
+            const bool is_flag = key.back() == '!';
+            if (is_flag) key.pop_back();
+            const std::string bytes = key + (is_flag ? "" : "=");
+            if (key.empty() || bytes.size() > 16) continue;  // longer keys simply take the generic path
+            if (is_flag) se.flags |= SCHED_IS_FLAG;
+            classify(ctx, find_host_tag(ctx, key), false, se);
             se.len = (uint8_t)bytes.size();
-            memcpy(se.w, bytes.data(), bytes.size());
+            unsigned char buf[16] = {0};
+            memcpy(buf, bytes.data(), bytes.size());
+            memcpy(&se.w0, buf, 8);
+            memcpy(&se.w1, buf + 8, 8);
+            se.m0 = bytes.size() >= 8 ? ~0ull : ((1ull << (8 * bytes.size())) - 1ull);
             entries.push_back(se);
         }
     }
@@ -357,13 +393,18 @@ extern "C" int ugvc_set_key_order(ugvc_ctx* ctx, const char* info_keys, const ch
             int n = 0;
             size_t b = 0;
             bool ok = true;
-            while (b <= f.size() && ok) {
+            for (;;) {
                 size_t e = f.find(':', b);
                 if (e == std::string::npos) e = f.size();
-                if (n >= UGVC_MAX_FMT_KEYS) { ok = false; break; }
-                sc.fmt_tag[n++] = (int16_t)find_host_tag(ctx, f.substr(b, e - b));
-                b = e + 1;
+                if (n >= UGVC_MAX_FMT_KEYS) {
+                    ok = false;
+                    break;
+                }
+                memset(&sc.fmt[n], 0, sizeof(SchedEntry));
+                classify(ctx, find_host_tag(ctx, f.substr(b, e - b)), true, sc.fmt[n]);
+                ++n;
                 if (e == f.size()) break;
+                b = e + 1;
             }
             if (ok) {
                 sc.n_fmt = n;

@@ -25,6 +25,9 @@
 
 #define WARP 32
 #define K1_TPB 128
+#ifndef K1_MIN_CTAS
+#define K1_MIN_CTAS 8  // resident CTAs per SM the register allocation targets (profiled: see DESIGN.md)
+#endif
 #define K2_TPB 256
 #define K3_TPB 256
 
@@ -540,40 +543,6 @@ __device__ __noinline__ Cur parse_value(RawOut o, int t, unsigned kind, Cur c, u
     return c;
 }
 
-// Does the stream at c start with the len bytes w[]?  On success out stands right after them.
-__device__ __forceinline__ bool match_bytes(const Cur& c, const unsigned long long w0, const unsigned long long w1,
-                                            const unsigned long long w2, int len, Cur& out) {
-    Cur t = c;
-    unsigned long long x = t.peek8();
-    if (len <= 8) {
-        const unsigned long long mask = len == 8 ? ~0ull : ((1ull << (8 * len)) - 1ull);
-        if ((x & mask) != w0) return false;
-        t.advance(len);
-        out = t;
-        return true;
-    }
-    if (x != w0) return false;
-    t.advance(8);
-    x = t.peek8();
-    int rem = len - 8;
-    if (rem <= 8) {
-        const unsigned long long mask = rem == 8 ? ~0ull : ((1ull << (8 * rem)) - 1ull);
-        if ((x & mask) != w1) return false;
-        t.advance(rem);
-        out = t;
-        return true;
-    }
-    if (x != w1) return false;
-    t.advance(8);
-    x = t.peek8();
-    rem -= 8;
-    const unsigned long long mask = rem >= 8 ? ~0ull : ((1ull << (8 * rem)) - 1ull);
-    if ((x & mask) != w2) return false;
-    t.advance(rem > 8 ? 8 : rem);
-    out = t;
-    return true;
-}
-
 __device__ __forceinline__ bool key_is_cg(const Key& k) {
     // an allele equal to GGC or CCG (blacklist.py:85-101: tuple membership)
     return k.len == 3 && (k.k0 == CH3('G', 'G', 'C') || k.k0 == CH3('C', 'C', 'G'));
@@ -584,7 +553,63 @@ __device__ __forceinline__ void set_tag_missing(const RawOut& o, int t) {
     for (int s = tg.first_slot; s < tg.first_slot + tg.n_slots; ++s) store_slot(o, s, RAW_MISSING);
 }
 
-__global__ void __launch_bounds__(K1_TPB, 8) k1_parse(const __grid_constant__ DevPlan plan,
+// Decode the value of a scheduled key (every lane that gets here holds the same key, so the
+// class switch is warp-uniform) and leave the cursor on the byte that ends the field.
+// meta = the entry's last 8 bytes: len | cls<<8 | slot0<<16 | n_elem<<24 | dict<<32 | flags<<40 | tag<<48
+__device__ __noinline__ Cur decode_sched(RawOut o, unsigned long long meta, Cur c, unsigned vend) {
+    const unsigned cls = (unsigned)(meta >> 8) & 0xFFu;
+    const int slot0 = (int)((meta >> 16) & 0xFFu), n_elem = (int)((meta >> 24) & 0xFFu);
+    const unsigned flags = (unsigned)(meta >> 40) & 0xFFu;
+    const unsigned v4 = B4(vend), c4 = B4(',');
+    if (cls == CLS_INT || cls == CLS_FLOAT) {
+        const bool count_all = (flags & SCHED_COUNT_ALL) != 0;
+        int e = 0;
+        for (;;) {
+            uint32_t bits;
+            if (cls == CLS_INT) {
+                const IntCur r = parse_int_cur(c);  // htslib int32 -> fp32 feature
+                c = r.c;
+                bits = r.st == NUM_OK ? __float_as_uint((float)r.v) : (r.st == NUM_MISSING ? RAW_MISSING : RAW_ERR);
+            } else {
+                const NumCur r = parse_num_cur(c);  // float32(strtod(text))
+                c = r.c;
+                const float f = (float)r.v;
+                bits = r.st == NUM_OK ? (isnan(f) ? RAW_MISSING : __float_as_uint(f))
+                                      : (r.st == NUM_MISSING ? RAW_MISSING : RAW_ERR);
+            }
+            const unsigned ch = c.peek();
+            if (ch != ',' && ch != vend && ch != '\t' && ch != '\n') {  // trailing garbage in the token
+                bits = RAW_ERR;
+                c = skip_until(c, c4, v4);
+            }
+            if (e < n_elem) store_slot(o, slot0 + e, bits);
+            ++e;
+            if (c.peek() == ',' && (e < n_elem || count_all)) {
+                c.adv();
+                continue;
+            }
+            break;
+        }
+        for (int m = e; m < n_elem; ++m) store_slot(o, slot0 + m, RAW_MISSING);  // vector shorter than needed
+        if (count_all) store_slot_f(o, slot0 + n_elem, (float)e);
+    } else if (cls == CLS_DICT1) {
+        const KeyCur r = take_until(c, v4, v4);
+        c = r.c;
+        PlanSlot sl;
+        sl.reducer = RED_DICT;
+        sl.dict = (uint8_t)((meta >> 32) & 0xFFu);
+        store_slot(o, slot0, reduce_string(sl, r.k));
+    } else if (cls == CLS_GENERIC) {
+        const int tag = (int)(short)(meta >> 48);
+        const unsigned kind = vend == ':' ? s_tags()[tag].fmt_kind : s_tags()[tag].info_kind;
+        c = parse_value(o, tag, kind, c, vend);
+    }
+    const unsigned ch = c.peek();
+    if (ch != vend && ch != '\t' && ch != '\n') c = skip_until(c, v4, v4);
+    return c;
+}
+
+__global__ void __launch_bounds__(K1_TPB, K1_MIN_CTAS) k1_parse(const __grid_constant__ DevPlan plan,
                                                       const __grid_constant__ DevSchedule sched,
                                                       const uint8_t* __restrict__ text,
                                                    const int64_t* __restrict__ line_start,
@@ -722,26 +747,43 @@ __global__ void __launch_bounds__(K1_TPB, 8) k1_parse(const __grid_constant__ De
                 const unsigned semi4 = B4(';'), eq4 = B4('=');
                 bool in_info = true;
                 // (1) step through the learned key order: every lane of the warp looks for the same
-                //     key at the same time, so the lanes that have it decode the same type together
+                //     key at the same time (one masked 8-byte compare against the cached
+                //     look-ahead), so the lanes that have it decode the same type together
+                unsigned long long x = c.peek8();
                 for (int j = 0; j < sched.n_info; ++j) {
                     if (in_info) {
-                        const SchedEntry e = s_sched()[j];
-                        Cur t;
-                        if (match_bytes(c, e.w[0], e.w[1], e.w[2], e.len, t)) {
-                            const unsigned nxt = t.peek();
-                            const unsigned kind = e.tag >= 0 ? s_tags()[e.tag].info_kind : 0u;
-                            if (!e.is_flag) {
-                                c = t;
-                                if (kind) c = parse_value(o, e.tag, kind, c, ';');
-                                c = skip_until(c, semi4, semi4);
-                            } else if (nxt == ';' || nxt == '\t' || nxt == '\n') {
-                                c = t;
-                                if (kind) set_tag_missing(o, e.tag);  // key without a value: typed None / ()
+                        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&s_sched()[j]);  // w0, m0
+                        if ((x & a.y) == a.x) {
+                            const ulonglong2 b = *(reinterpret_cast<const ulonglong2*>(&s_sched()[j]) + 1);  // w1, meta
+                            const int len = (int)(b.y & 0xFFu);
+                            Cur t = c;
+                            bool ok = true;
+                            if (len > 8) {
+                                t.advance(8);
+                                const int rem = len - 8;
+                                const unsigned long long mask = rem >= 8 ? ~0ull : ((1ull << (8 * rem)) - 1ull);
+                                ok = (t.peek8() & mask) == b.x;
+                                t.advance(rem);
                             } else {
-                                continue;  // a longer key with this prefix: not this entry
+                                t.advance(len);
                             }
-                            if (c.peek() == ';') c.adv();
-                            else in_info = false;  // tab / newline: the INFO column is finished
+                            if (ok) {
+                                if ((b.y >> 40) & SCHED_IS_FLAG) {  // valueless key: must end right here
+                                    const unsigned nxt = t.peek();
+                                    ok = nxt == ';' || nxt == '\t' || nxt == '\n';
+                                    if (ok) {
+                                        c = t;
+                                        if (((b.y >> 8) & 0xFFu) != CLS_SKIP) set_tag_missing(o, (int)(short)(b.y >> 48));
+                                    }
+                                } else {
+                                    c = decode_sched(o, b.y, t, ';');
+                                }
+                            }
+                            if (ok) {
+                                if (c.peek() == ';') c.adv();
+                                else in_info = false;  // tab / newline: the INFO column is finished
+                                x = c.peek8();
+                            }
                         }
                     }
                 }
@@ -776,26 +818,33 @@ __global__ void __launch_bounds__(K1_TPB, 8) k1_parse(const __grid_constant__ De
                 if (sched.n_fmt > 0) {
                     // the usual FORMAT column, compared as a whole: its sub-fields are then decoded
                     // in the known order, the same tag in every lane
-                    Cur t;
-                    if (match_bytes(c, sched.fmt_w[0], sched.fmt_w[1], sched.fmt_w[2], sched.fmt_len, t) &&
-                        (t.peek() == '\t' || t.peek() == '\n')) {
-                        spec = true;
-                        sv = t;
+                    Cur t = c;
+                    int rem = sched.fmt_len;
+                    spec = true;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        if (rem > 0) {
+                            const unsigned long long mask = rem >= 8 ? ~0ull : ((1ull << (8 * rem)) - 1ull);
+                            spec &= (t.peek8() & mask) == sched.fmt_w[i];
+                            t.advance(rem >= 8 ? 8 : rem);
+                            rem -= 8;
+                        }
                     }
+                    spec &= (t.peek() == '\t' || t.peek() == '\n');
+                    sv = t;
                 }
                 if (spec) {
                     bool have_sample = (sv.peek() == '\t');
                     if (have_sample) sv.adv();
                     for (int j = 0; j < sched.n_fmt; ++j) {
-                        const int t = sched.fmt_tag[j];
-                        const unsigned kind = t >= 0 ? s_tags()[t].fmt_kind : 0u;
+                        const unsigned long long meta = reinterpret_cast<const unsigned long long*>(&sched.fmt[j])[3];
+                        const unsigned cls = (unsigned)(meta >> 8) & 0xFFu;
                         if (have_sample) {
-                            if (kind) sv = parse_value(o, t, kind, sv, ':');
-                            sv = skip_until(sv, col4, col4);
+                            sv = decode_sched(o, meta, sv, ':');
                             if (sv.peek() == ':') sv.adv();
                             else have_sample = false;
-                        } else if (kind) {  // trailing sub-fields dropped: missing
-                            set_tag_missing(o, t);
+                        } else if (cls != CLS_SKIP) {  // trailing sub-fields dropped: missing
+                            set_tag_missing(o, (int)(short)(meta >> 48));
                         }
                     }
                 } else {

@@ -31,13 +31,26 @@ struct DevPlan {
 // FORMAT column.  K1 steps through it warp-uniformly, matching "KEY=" word-wise against the
 // cursor's look-ahead; keys off the schedule take the generic hash-lookup path.
 #define UGVC_MAX_SCHED 128
-#define UGVC_MAX_FMT_KEYS 16
+#define UGVC_MAX_FMT_KEYS 8
+enum : uint8_t {
+    CLS_SKIP = 0,     // value not needed
+    CLS_GENERIC = 1,  // any tag: parse_value()
+    CLS_INT = 2,      // n_elem Integer elements (+ element count when SCHED_COUNT_ALL)
+    CLS_FLOAT = 3,    // n_elem Float elements
+    CLS_DICT1 = 4,    // scalar String looked up in one dictionary
+};
+#define SCHED_IS_FLAG 1u
+#define SCHED_COUNT_ALL 2u
 struct alignas(8) SchedEntry {   // 32 bytes
-    unsigned long long w[3];     // the bytes to match ("KEY=", or "KEY" for a valueless key), zero padded
-    uint8_t len;                 // how many
-    uint8_t is_flag;             // valueless key: the next byte must end the field
-    int16_t tag;                 // plan tag index, or -1 when the value is not needed
-    uint8_t pad[4];
+    unsigned long long w0, m0;   // first 8 bytes to match ("KEY=", or "KEY" for a valueless key) and their mask
+    unsigned long long w1;       // bytes 8..15, zero padded (len > 8)
+    uint8_t len;                 // bytes to match (<= 16; longer keys are not scheduled)
+    uint8_t cls;                 // CLS_*
+    uint8_t slot0;               // first slot of the tag
+    uint8_t n_elem;              // element slots
+    uint8_t dict;                // CLS_DICT1
+    uint8_t flags;               // SCHED_*
+    int16_t tag;                 // plan tag index, or -1
 };
 struct DevSchedule {
     const SchedEntry* info;      // device array
@@ -45,7 +58,7 @@ struct DevSchedule {
     int n_fmt;                   // sub-fields of the expected FORMAT column (0: none learned)
     int fmt_len;                 // its length in bytes
     unsigned long long fmt_w[3]; // its bytes, zero padded
-    int16_t fmt_tag[UGVC_MAX_FMT_KEYS];
+    SchedEntry fmt[UGVC_MAX_FMT_KEYS];  // per sub-field: cls / slot0 / n_elem / dict / flags / tag
 };
 
 // Error word: smaller is earlier.  (record << 24) | (column << 8) | reason

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libugvc_b200.so")
+LIB_PATH = os.environ.get("UGVC_LIB_PATH") or os.path.join(_HERE, "libugvc_b200.so")  # env: profiling builds
 
 UGVC_OK, UGVC_E_CUDA, UGVC_E_ARG, UGVC_E_PLAN, UGVC_E_DATA, UGVC_E_IO, UGVC_E_STATE = 0, -1, -2, -3, -4, -5, -6
 
