@@ -437,7 +437,7 @@ extern "C" int ugvc_reserve(ugvc_ctx* ctx, size_t max_bytes, size_t max_records,
     ctx->cap_bytes = max_bytes;
     ctx->cap_records = max_records;
     ctx->lanes.resize(n_pipeline);
-    const size_t n_chunks = (max_bytes + K0_CHUNK_BYTES - 1) / K0_CHUNK_BYTES + 1;
+    const size_t n_chunks = 2 * ((max_bytes + K0_TILE_BYTES_HOST - 1) / K0_TILE_BYTES_HOST + 2);  // uint32 words
     const DevPlan& p = ctx->plan;
     for (auto& l : ctx->lanes) {
         CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
@@ -490,7 +490,7 @@ static int enqueue_kernels(ugvc_ctx* ctx, Lane& l, const uint8_t* d_text, size_t
         launch_k3(p, l.b.feats, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual, ctx->d_counts,
                   ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[4], st));
-    ctx->launches += (has_model ? 6 : 4) + (p.h.n_slots ? 1 : 0);
+    ctx->launches += (has_model ? 4 : 2) + (p.h.n_slots ? 1 : 0);
     CU(cudaGetLastError());
     return UGVC_OK;
 }

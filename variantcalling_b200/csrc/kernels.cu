@@ -29,7 +29,6 @@
 #define K1_MIN_CTAS 8  // resident CTAs per SM the register allocation targets (profiled: see DESIGN.md)
 #endif
 #define K2_TPB 256
-#define K3_TPB 256
 
 // ------------------------------------------------------------------------------------------
 // small helpers
@@ -48,123 +47,132 @@ __device__ __forceinline__ uint4 ld_stream16(const uint4* p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K0: line index
+// K0: line index (single pass)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k0_count(const uint8_t* __restrict__ text, size_t n_bytes,
-                                                uint32_t* __restrict__ chunk_count, size_t n_chunks) {
-    const int lane = threadIdx.x & 31;
-    size_t warp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
-    for (size_t c = warp; c < n_chunks; c += n_warps) {
-        const size_t base = c * K0_CHUNK_BYTES;
-        unsigned cnt = 0;
+// One read of the text.  Tiles of 16 KiB are claimed in order from an atomic ticket; each thread
+// turns its 64 contiguous bytes into a 64-bit newline mask, the block scans the pop-counts, the
+// tile's running record count comes from a decoupled look-back over the tile-state words
+// (bit 63: inclusive prefix published, bit 62: aggregate published), and the line starts are
+// written straight from the masks -- no second pass over the text.
+#define K0_TPB 256
+#define K0_TILE_BYTES (K0_TPB * 64)
+#define K0_FLAG_AGG (1ull << 62)
+#define K0_FLAG_INC (1ull << 63)
+#define K0_VAL_MASK ((1ull << 62) - 1ull)
+
+__device__ __forceinline__ unsigned long long nl_mask64(const uint8_t* __restrict__ text, size_t off, size_t n_bytes) {
+    unsigned long long m = 0;
+    if (off + 64 <= n_bytes) {
 #pragma unroll
-        for (int it = 0; it < K0_CHUNK_BYTES / 512; ++it) {
-            const size_t off = base + (size_t)it * 512 + (size_t)lane * 16;
-            if (off + 16 <= n_bytes) {
-                uint4 v = ld_stream16(reinterpret_cast<const uint4*>(text + off));
-                cnt += nl_count4(v.x) + nl_count4(v.y) + nl_count4(v.z) + nl_count4(v.w);
-            } else {
-                for (size_t q = off; q < n_bytes && q < off + 16; ++q) cnt += (text[q] == '\n');
-            }
+        for (int q = 0; q < 4; ++q) {
+            const uint4 v = ld_stream16(reinterpret_cast<const uint4*>(text + off) + q);
+            const unsigned long long part = (unsigned long long)(nl_bits4(v.x) | (nl_bits4(v.y) << 4) |
+                                                                 (nl_bits4(v.z) << 8) | (nl_bits4(v.w) << 12));
+            m |= part << (16 * q);
         }
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
-        if (lane == 0) chunk_count[c] = cnt;
+    } else {
+        for (size_t q = off; q < n_bytes && q < off + 64; ++q)
+            if (text[q] == '\n') m |= 1ull << (q - off);
     }
+    return m;
 }
 
-// single block: exclusive scan of chunk counts in place; publishes n_records
-__global__ void __launch_bounds__(1024) k0_scan(uint32_t* __restrict__ chunk, size_t n_chunks,
-                                                const uint8_t* __restrict__ text, size_t n_bytes,
-                                                int64_t* __restrict__ line_start, size_t cap_records,
-                                                int64_t* __restrict__ n_records, unsigned long long* err) {
-    __shared__ unsigned long long part[1024];
-    const int t = threadIdx.x;
-    const size_t per = (n_chunks + 1023) / 1024;
-    const size_t lo = (size_t)t * per, hi = min(lo + per, n_chunks);
-    unsigned long long s = 0;
-    for (size_t i = lo; i < hi; ++i) s += chunk[i];
-    part[t] = s;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (int d = 1; d < 1024; d <<= 1) {
-        unsigned long long v = (t >= d) ? part[t - d] : 0;
+__global__ void __launch_bounds__(K0_TPB) k0_index(const uint8_t* __restrict__ text, size_t n_bytes,
+                                                   unsigned long long* __restrict__ tile_state,
+                                                   unsigned int* __restrict__ ticket, size_t n_tiles,
+                                                   int64_t* __restrict__ line_start, size_t cap_records,
+                                                   int64_t* __restrict__ n_records, unsigned long long* err) {
+    __shared__ unsigned s_warp[K0_TPB / 32];
+    __shared__ unsigned long long s_excl;
+    __shared__ unsigned s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
         __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    unsigned long long run = (t == 0) ? 0 : part[t - 1];
-    for (size_t i = lo; i < hi; ++i) {
-        unsigned c = chunk[i];
-        chunk[i] = (uint32_t)run;
-        run += c;
-    }
-    if (t == 1023) {
-        long long total = (long long)part[1023];
-        if (n_bytes > 0 && text[n_bytes - 1] != '\n') {  // contract: the batch ends with '\n'
-            atomicMin(err, ugvc_pack_error(total, 0xFFFF, REASON_MALFORMED_LINE));
-        }
-        if ((size_t)total > cap_records) {
-            atomicMin(err, ugvc_pack_error((long long)cap_records, 0xFFFF, REASON_TOO_MANY_ELEMS));
-            total = (long long)cap_records;
-        }
-        *n_records = total;
-        line_start[0] = 0;
-    }
-}
-
-__global__ void __launch_bounds__(256) k0_write(const uint8_t* __restrict__ text, size_t n_bytes,
-                                                const uint32_t* __restrict__ chunk_first, size_t n_chunks,
-                                                int64_t* __restrict__ line_start, size_t cap_records) {
-    const int lane = threadIdx.x & 31;
-    size_t warp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
-    for (size_t c = warp; c < n_chunks; c += n_warps) {
-        const size_t base = c * K0_CHUNK_BYTES;
-        size_t rec = chunk_first[c];
-#pragma unroll 1
-        for (int it = 0; it < K0_CHUNK_BYTES / 512; ++it) {
-            const size_t off = base + (size_t)it * 512 + (size_t)lane * 16;
-            unsigned mask = 0;
-            if (off + 16 <= n_bytes) {
-                uint4 v = ld_stream16(reinterpret_cast<const uint4*>(text + off));
-                mask = nl_bits4(v.x) | (nl_bits4(v.y) << 4) | (nl_bits4(v.z) << 8) | (nl_bits4(v.w) << 12);
-            } else {
-                for (size_t q = off; q < n_bytes && q < off + 16; ++q)
-                    if (text[q] == '\n') mask |= 1u << (q - off);
-            }
-            unsigned cnt = __popc(mask), incl = cnt;
+        const size_t tile = s_tile;
+        if (tile >= n_tiles) break;
+        const size_t off = tile * K0_TILE_BYTES + (size_t)threadIdx.x * 64;
+        unsigned long long mask = off < n_bytes ? nl_mask64(text, off, n_bytes) : 0ull;
+        const unsigned cnt = __popcll(mask);
+        unsigned incl = cnt;
 #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                unsigned v = __shfl_up_sync(0xffffffffu, incl, s);
-                if (lane >= s) incl += v;
-            }
-            const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-            size_t idx = rec + (incl - cnt);
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (idx + 1 <= cap_records) line_start[idx + 1] = (int64_t)(off + b + 1);
-                ++idx;
-            }
-            rec += total;
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
         }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned warp_base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < K0_TPB / 32; ++w) {
+            const unsigned v = s_warp[w];
+            if (w < warp) warp_base += v;
+            total += v;
+        }
+        if (threadIdx.x == 0) {
+            // publish the aggregate, then look back for the exclusive prefix
+            unsigned long long excl = 0;
+            if (tile == 0) {
+                atomicExch(&tile_state[0], K0_FLAG_INC | (unsigned long long)total);
+            } else {
+                atomicExch(&tile_state[tile], K0_FLAG_AGG | (unsigned long long)total);
+                size_t p = tile;
+                while (p > 0) {
+                    --p;
+                    unsigned long long st;
+                    do {
+                        st = atomicAdd(&tile_state[p], 0ull);
+                    } while ((st & (K0_FLAG_AGG | K0_FLAG_INC)) == 0);
+                    excl += st & K0_VAL_MASK;
+                    if (st & K0_FLAG_INC) break;
+                }
+                atomicExch(&tile_state[tile], K0_FLAG_INC | (excl + total));
+            }
+            s_excl = excl;
+            if (tile == n_tiles - 1) {
+                long long all = (long long)(excl + total);
+                if (n_bytes > 0 && text[n_bytes - 1] != '\n')  // contract: the batch ends with '\n'
+                    atomicMin(err, ugvc_pack_error(all, 0xFFFF, REASON_MALFORMED_LINE));
+                if ((size_t)all > cap_records) {
+                    atomicMin(err, ugvc_pack_error((long long)cap_records, 0xFFFF, REASON_TOO_MANY_ELEMS));
+                    all = (long long)cap_records;
+                }
+                *n_records = all;
+                line_start[0] = 0;
+            }
+        }
+        __syncthreads();
+        size_t idx = (size_t)s_excl + warp_base + (incl - cnt);
+        while (mask) {
+            const int b = __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            if (idx + 1 <= cap_records) line_start[idx + 1] = (int64_t)(off + b + 1);
+            ++idx;
+        }
+        __syncthreads();  // s_tile / s_excl are rewritten by the next round
     }
 }
 
-void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* chunk_first, int64_t* line_start,
+__global__ void k0_empty(int64_t* __restrict__ line_start, int64_t* __restrict__ n_records) {
+    *n_records = 0;
+    line_start[0] = 0;
+}
+
+void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* scratch, int64_t* line_start,
                size_t cap_records, int64_t* d_n_records, unsigned long long* d_err, int sm_count,
                cudaStream_t st) {
-    const size_t n_chunks = (n_bytes + K0_CHUNK_BYTES - 1) / K0_CHUNK_BYTES;
-    const size_t warps_per_block = 8;
-    size_t blocks = (n_chunks + warps_per_block - 1) / warps_per_block;
-    const size_t max_blocks = (size_t)sm_count * 8;
-    if (blocks > max_blocks) blocks = max_blocks;
-    if (blocks == 0) blocks = 1;
-    k0_count<<<(unsigned)blocks, 256, 0, st>>>(d_text, n_bytes, chunk_first, n_chunks);
-    k0_scan<<<1, 1024, 0, st>>>(chunk_first, n_chunks, d_text, n_bytes, line_start, cap_records, d_n_records, d_err);
-    k0_write<<<(unsigned)blocks, 256, 0, st>>>(d_text, n_bytes, chunk_first, n_chunks, line_start, cap_records);
+    // scratch: [0] ticket (padded to 8 bytes), then one 64-bit state word per tile
+    const size_t n_tiles = (n_bytes + K0_TILE_BYTES - 1) / K0_TILE_BYTES;
+    if (n_tiles == 0) {
+        k0_empty<<<1, 1, 0, st>>>(line_start, d_n_records);
+        return;
+    }
+    cudaMemsetAsync(scratch, 0, 8 + n_tiles * sizeof(unsigned long long), st);
+    size_t blocks = n_tiles < (size_t)sm_count * 8 ? n_tiles : (size_t)sm_count * 8;
+    k0_index<<<(unsigned)blocks, K0_TPB, 0, st>>>(d_text, n_bytes,
+                                                  reinterpret_cast<unsigned long long*>(scratch) + 1,
+                                                  reinterpret_cast<unsigned int*>(scratch), n_tiles, line_start,
+                                                  cap_records, d_n_records, d_err);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -989,7 +997,7 @@ void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, cons
 
 __device__ __forceinline__ double expit64(double x) { return 1.0 / (1.0 + exp(-x)); }
 
-template <int CMP>
+template <int CMP, int TPB>
 __device__ __forceinline__ void walk8(const uint2* __restrict__ s_nodes, const uint32_t* __restrict__ s_roots,
                                       unsigned chunk_first_node, unsigned tr, unsigned tr_end, int depth,
                                       const float* __restrict__ x, int leaf[K3_CHAINS]) {
@@ -1005,7 +1013,7 @@ __device__ __forceinline__ void walk8(const uint2* __restrict__ s_nodes, const u
         for (int j = 0; j < K3_CHAINS; ++j) nd[j] = s_nodes[n[j]];
 #pragma unroll
         for (int j = 0; j < K3_CHAINS; ++j) {
-            const float xv = x[(nd[j].y & 0xFFu) * K3_TPB];
+            const float xv = x[(nd[j].y & 0xFFu) * TPB];
             const float thr = __uint_as_float(nd[j].x);
             const bool left = (CMP == CMP_LE) ? (xv <= thr) : (xv < thr);  // false on a leaf (NaN)
             n[j] = left ? n[j] + 1 : (nd[j].y >> 8) - chunk_first_node;
@@ -1015,7 +1023,8 @@ __device__ __forceinline__ void walk8(const uint2* __restrict__ s_nodes, const u
     for (int j = 0; j < K3_CHAINS; ++j) leaf[j] = (int)(nd[j].x & 0x3FFFFFu);
 }
 
-__global__ void __launch_bounds__(K3_TPB, 1) k3_infer(const __grid_constant__ DevPlan plan,
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 1) k3_infer(const __grid_constant__ DevPlan plan,
                                                       const float* __restrict__ feats, size_t row_stride,
                                                       const int64_t* __restrict__ n_records_p, double threshold,
                                                       uint8_t* __restrict__ low_score, float* __restrict__ probs,
@@ -1025,27 +1034,27 @@ __global__ void __launch_bounds__(K3_TPB, 1) k3_infer(const __grid_constant__ De
     const int F = plan.h.n_features, K = plan.h.n_classes, O = plan.h.n_outputs;
     const unsigned n_trees = plan.h.n_trees;
     const bool forest = plan.h.model_kind != MODEL_LOGISTIC;
-    float* tile = reinterpret_cast<float*>(smem3);  // [F][K3_TPB]
-    uint2* s_nodes = reinterpret_cast<uint2*>(smem3 + (size_t)F * K3_TPB * sizeof(float));
+    float* tile = reinterpret_cast<float*>(smem3);  // [F][TPB]
+    uint2* s_nodes = reinterpret_cast<uint2*>(smem3 + (size_t)F * TPB * sizeof(float));
     uint32_t* s_roots = reinterpret_cast<uint32_t*>(s_nodes + chunk_nodes_cap);  // [n_trees + 1]
     const bool resident = forest && plan.h.n_nodes <= chunk_nodes_cap;  // whole forest fits: stage once
     if (forest) {
-        for (unsigned i = threadIdx.x; i <= n_trees; i += K3_TPB) s_roots[i] = plan.tree_root[i];
+        for (unsigned i = threadIdx.x; i <= n_trees; i += TPB) s_roots[i] = plan.tree_root[i];
         if (resident)
-            for (unsigned i = threadIdx.x; i < plan.h.n_nodes; i += K3_TPB) s_nodes[i] = plan.dev_nodes[i];
+            for (unsigned i = threadIdx.x; i < plan.h.n_nodes; i += TPB) s_nodes[i] = plan.dev_nodes[i];
     }
     const int depth = (int)plan.max_depth;
     const long long n_rec = *n_records_p;
-    const long long n_tiles = (n_rec + K3_TPB - 1) / K3_TPB;
+    const long long n_tiles = (n_rec + TPB - 1) / TPB;
     unsigned n_low = 0, n_seen = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const long long rec = t * K3_TPB + threadIdx.x;
+        const long long rec = t * TPB + threadIdx.x;
         const bool active = rec < n_rec;
         __syncthreads();
         {
             const float* src = feats + rec;
 #pragma unroll 8
-            for (int f = 0; f < F; ++f) tile[f * K3_TPB + threadIdx.x] = active ? __ldg(src + (size_t)f * row_stride) : 0.f;
+            for (int f = 0; f < F; ++f) tile[f * TPB + threadIdx.x] = active ? __ldg(src + (size_t)f * row_stride) : 0.f;
         }
         __syncthreads();
         const float* x = tile + threadIdx.x;
@@ -1070,13 +1079,13 @@ __global__ void __launch_bounds__(K3_TPB, 1) k3_infer(const __grid_constant__ De
                     if (c1 == c0) c1 = c0 + 1;  // cannot happen: load_plan checks every tree fits
                     __syncthreads();
                     const unsigned cnt = s_roots[c1] - first_node;
-                    for (unsigned i = threadIdx.x; i < cnt; i += K3_TPB) s_nodes[i] = plan.dev_nodes[first_node + i];
+                    for (unsigned i = threadIdx.x; i < cnt; i += TPB) s_nodes[i] = plan.dev_nodes[first_node + i];
                     __syncthreads();
                 }
                 for (unsigned tr = c0; tr < c1; tr += K3_CHAINS) {
                     int leaf[K3_CHAINS];
-                    if (plan.h.cmp_mode == CMP_LE) walk8<CMP_LE>(s_nodes, s_roots, first_node, tr, c1, depth, x, leaf);
-                    else walk8<CMP_LT>(s_nodes, s_roots, first_node, tr, c1, depth, x, leaf);
+                    if (plan.h.cmp_mode == CMP_LE) walk8<CMP_LE, TPB>(s_nodes, s_roots, first_node, tr, c1, depth, x, leaf);
+                    else walk8<CMP_LT, TPB>(s_nodes, s_roots, first_node, tr, c1, depth, x, leaf);
                     if (plan.h.model_kind == MODEL_GB_SKLEARN && O == 1) {
                         // raw += learning_rate * leaf (pre-scaled on the host), fp64, tree order
 #pragma unroll
@@ -1119,7 +1128,7 @@ __global__ void __launch_bounds__(K3_TPB, 1) k3_infer(const __grid_constant__ De
                     if (o < O) {
                         double acc = 0.0;
                         const double* w = plan.coef + (size_t)o * F;
-                        for (int f = 0; f < F; ++f) acc = fma((double)x[f * K3_TPB], __ldg(&w[f]), acc);
+                        for (int f = 0; f < F; ++f) acc = fma((double)x[f * TPB], __ldg(&w[f]), acc);
                         z[o] = acc + plan.intercept[o];
                     }
                 }
@@ -1230,25 +1239,36 @@ __global__ void __launch_bounds__(K3_TPB, 1) k3_infer(const __grid_constant__ De
 }
 
 #define K3_SMEM_BUDGET (224u * 1024u)
+static size_t k3_forest_bytes(const DevPlan& plan) {
+    if (plan.h.model_kind == MODEL_LOGISTIC || plan.h.model_kind == MODEL_NONE) return 0;
+    return (size_t)plan.h.n_nodes * sizeof(uint2);
+}
+static size_t k3_roots_bytes(const DevPlan& plan) { return ((size_t)plan.h.n_trees + 2) * sizeof(uint32_t); }
+// records per CTA: 384 when the feature tile and the whole forest still fit, else 256
+static int k3_tpb(const DevPlan& plan) {
+    const size_t forest = k3_forest_bytes(plan);
+    if (forest == 0) return 256;
+    const size_t need384 = (size_t)plan.h.n_features * 384 * sizeof(float) + forest + k3_roots_bytes(plan);
+    return need384 <= K3_SMEM_BUDGET ? 384 : 256;
+}
 // nodes the shared-memory forest buffer holds (0 for linear models)
 static unsigned k3_chunk_nodes(const DevPlan& plan) {
-    if (plan.h.model_kind == MODEL_LOGISTIC || plan.h.model_kind == MODEL_NONE) return 0;
-    const size_t tile = (size_t)plan.h.n_features * K3_TPB * sizeof(float);
-    const size_t roots = ((size_t)plan.h.n_trees + 2) * sizeof(uint32_t);
+    if (k3_forest_bytes(plan) == 0) return 0;
+    const size_t tile = (size_t)plan.h.n_features * k3_tpb(plan) * sizeof(float);
+    const size_t roots = k3_roots_bytes(plan);
     if (tile + roots + 4096 > K3_SMEM_BUDGET) return 0;
     const size_t room = (K3_SMEM_BUDGET - tile - roots) / sizeof(uint2);
     return (unsigned)(room < plan.h.n_nodes ? room : plan.h.n_nodes);
 }
 size_t k3_smem_bytes(const DevPlan& plan) {
-    size_t b = (size_t)plan.h.n_features * K3_TPB * sizeof(float);
+    size_t b = (size_t)plan.h.n_features * k3_tpb(plan) * sizeof(float);
     const unsigned cap = k3_chunk_nodes(plan);
-    if (cap) b += (size_t)cap * sizeof(uint2) + ((size_t)plan.h.n_trees + 2) * sizeof(uint32_t);
+    if (cap) b += (size_t)cap * sizeof(uint2) + k3_roots_bytes(plan);
     return b;
 }
 unsigned k3_chunk_nodes_cap(const DevPlan& plan) { return k3_chunk_nodes(plan); }
 bool k3_plan_fits(const DevPlan& plan) {
-    if (plan.h.model_kind == MODEL_LOGISTIC || plan.h.model_kind == MODEL_NONE)
-        return (size_t)plan.h.n_features * K3_TPB * sizeof(float) <= K3_SMEM_BUDGET;
+    if (k3_forest_bytes(plan) == 0) return (size_t)plan.h.n_features * 256 * sizeof(float) <= K3_SMEM_BUDGET;
     return k3_chunk_nodes(plan) > 0;
 }
 
@@ -1259,13 +1279,19 @@ void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const
     int per_sm = (int)((K3_SMEM_BUDGET) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
-    k3_infer<<<sm_count * per_sm, K3_TPB, smem, st>>>(plan, feats, row_stride, d_n_records, threshold, low_score,
-                                                      probs, qual, d_counts, k3_chunk_nodes(plan));
+    if (k3_tpb(plan) == 384)
+        k3_infer<384><<<sm_count * per_sm, 384, smem, st>>>(plan, feats, row_stride, d_n_records, threshold, low_score,
+                                                            probs, qual, d_counts, k3_chunk_nodes(plan));
+    else
+        k3_infer<256><<<sm_count * per_sm, 256, smem, st>>>(plan, feats, row_stride, d_n_records, threshold, low_score,
+                                                            probs, qual, d_counts, k3_chunk_nodes(plan));
 }
 
 cudaError_t kernels_configure(const DevPlan& plan) {
     cudaError_t e = cudaFuncSetAttribute(k1_parse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)k1_smem_bytes(plan));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k3_infer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_smem_bytes(plan));
+    e = cudaFuncSetAttribute(k3_infer<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k3_infer<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
 }

@@ -85,7 +85,7 @@ struct LaneBuffers {
     double* qual;              // [cap_records]
 };
 
-#define K0_CHUNK_BYTES 4096
+#define K0_TILE_BYTES_HOST 16384  // one 64-bit look-back state word per 16 KiB tile
 
 void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* chunk_first, int64_t* line_start,
                size_t cap_records, int64_t* d_n_records, unsigned long long* d_err, int sm_count,
