@@ -52,6 +52,7 @@ typedef struct ugvc_recinfo {
     uint16_t info_off;    /* offset of the INFO column */
     uint16_t format_off;  /* offset one past the tab after INFO (== line length + 1 when there is no FORMAT column) */
     uint32_t flags;       /* bit0: an allele equals GGC or CCG (blacklist_cg_insertions, blacklist.py:85-101);
+                             bits 1..7: number of alleles (saturating at 127), for --recalibrate_genotype;
                              bits 8..31: length of REF (saturating), for the tabix index of the output */
 } ugvc_recinfo;
 
@@ -113,6 +114,12 @@ int ugvc_collect_batch(ugvc_ctx* ctx, int lane, uint8_t* out_low_score, float* o
 int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n_bytes, double threshold,
                        uint8_t* d_low_score, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
                        int64_t* d_line_start, size_t capacity_records, int64_t* d_n_records, void* stream);
+
+/* --recalibrate_genotype (filter_variants_pipeline.py:203-215): ask K3 to keep the per-class
+ * phreds -10*log10(p + 1e-10) of the host-buffer lanes (takes effect at the next ugvc_reserve)
+ * and fetch them (N x n_classes fp64) after ugvc_collect_batch. */
+int ugvc_enable_phreds(ugvc_ctx* ctx, int on);
+int ugvc_collect_phreds(ugvc_ctx* ctx, int lane, double* out, size_t capacity_records);
 
 /* Blocking: waits for `stream` and surfaces a data error (UGVC_E_DATA) of the last
  * ugvc_filter_device call. */
@@ -180,13 +187,17 @@ int ugvc_bgzf_deflate_to_file(const char* path, const char* mode, const uint8_t*
  * and TREE_SCORE (and optionally QUAL, BLACKLST) spliced in, exactly the rules of
  * filter_variants_pipeline.py:188-228.  blacklist_code (may be NULL) selects,
  * per record, one ';'-joined annotation string of blacklist_table (string c is
- * bytes [table_off[c], table_off[c+1])) as the BLACKLST value; out_line_start (may be
+ * bytes [table_off[c], table_off[c+1])) as the BLACKLST value.  phreds != NULL selects the
+ * --recalibrate_genotype rules instead of TREE_SCORE (:203-215): GQ = int(2nd smallest - smallest
+ * phred), PL = int(phreds[:n_genotypes]), GT = genotype of the smallest PL, QUAL = GQ (float) when
+ * overwrite_qual, all on the first sample.  out_line_start (may be
  * NULL, n_records + 1 entries) receives the offset of every output line.
  * Returns bytes written. */
 int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_start, const ugvc_recinfo* recinfo,
                             const uint8_t* low_score, const double* qual, int64_t n_records,
                             int overwrite_qual, int with_model, const int32_t* blacklist_code,
                             const char* blacklist_table, const int64_t* blacklist_table_off,
+                            const double* phreds, int n_classes,
                             uint8_t* out, size_t capacity, int64_t* out_line_start, int n_threads);
 
 /* ---- test hook ------------------------------------------------------------ */

@@ -198,8 +198,32 @@ def edited_header_lines(header_lines: list[str], *, with_model: bool, with_black
     return out[:chrom_at] + add + out[chrom_at:]
 
 
+def recalibrated_sample_columns(cols: list[str], phreds_row, gq: float, n_alleles: int) -> list[str]:
+    """GT / GQ / PL of the first sample, filter_variants_pipeline.py:203-215 (pysam setters:
+    existing FORMAT keys keep their place, new ones are appended; phasing is kept)."""
+    keys = [] if cols[8] == "." else cols[8].split(":")
+    vals = cols[9].split(":")
+    vals += ["."] * (len(keys) - len(vals))
+    n_pl = (n_alleles + 1) * n_alleles // 2
+    pl = [int(x) for x in phreds_row[:n_pl]]
+    gt = get_gt_from_pl_idx(int(np.argmin(pl)))
+    sep = "|" if "GT" in keys and "|" in vals[keys.index("GT")] else "/"
+
+    def put(key, val):
+        if key in keys:
+            vals[keys.index(key)] = val
+        else:
+            keys.append(key)
+            vals.append(val)
+
+    put("GQ", str(int(gq)))
+    put("PL", ",".join(str(v) for v in pl))
+    put("GT", sep.join(str(a) for a in gt))
+    return cols[:8] + [":".join(keys), ":".join(vals)] + cols[10:]
+
+
 def write_record(rec: OracleRecord, qual: float | None, threshold: float, *, overwrite_qual: bool,
-                 blacklist_value: str | None) -> tuple[str, list[str]]:
+                 blacklist_value: str | None, recal: tuple | None = None) -> tuple[str, list[str]]:
     """Apply filter_variants_pipeline.py:188-228 to one record; returns (line, filter keys).
 
     Untouched columns keep their input bytes (the product splices rather than
@@ -215,15 +239,21 @@ def write_record(rec: OracleRecord, qual: float | None, threshold: float, *, ove
                 keys.remove("PASS")
             if "LOW_SCORE" not in keys:
                 keys.append("LOW_SCORE")
-        score_txt = "TREE_SCORE=" + format_float_g(qual)
-        for i, kv in enumerate(info):
-            if kv.split("=", 1)[0] == "TREE_SCORE":
-                info[i] = score_txt
-                break
-        else:
-            info.append(score_txt)
-        if overwrite_qual:
-            cols[5] = format_float_g(qual)
+        if recal is None:
+            score_txt = "TREE_SCORE=" + format_float_g(qual)
+            for i, kv in enumerate(info):
+                if kv.split("=", 1)[0] == "TREE_SCORE":
+                    info[i] = score_txt
+                    break
+            else:
+                info.append(score_txt)
+            if overwrite_qual:
+                cols[5] = format_float_g(qual)
+        else:  # --recalibrate_genotype: GQ / PL / GT instead of TREE_SCORE, QUAL = gq
+            phreds_row, gq = recal
+            if overwrite_qual:
+                cols[5] = format_float_g(gq)
+            cols = recalibrated_sample_columns(cols, phreds_row, gq, len(rec.alleles))
     if blacklist_value is not None and blacklist_value != "PASS":
         vals = [v for v in blacklist_value.split(";") if v != "PASS"]
         if vals:
@@ -244,7 +274,8 @@ def write_record(rec: OracleRecord, qual: float | None, threshold: float, *, ove
 def filter_variants(vcf: OracleVariantFile, model, transformer, *, custom_annotations=None,
                     decision_threshold: float = 30.0, blacklist_cg: bool = False,
                     position_blacklists: list | None = None, overwrite_qual_tag: bool = False,
-                    limit_to_contigs: list[str] | None = None, timings: dict | None = None) -> dict:
+                    limit_to_contigs: list[str] | None = None, timings: dict | None = None,
+                    recalibrate_genotype: bool = False) -> dict:
     """The serial contig loop of filter_variants_pipeline.py:116-229 (model branch
     without ``--treat_multiallelics`` / ``--recalibrate_genotype``).
 
@@ -273,7 +304,7 @@ def filter_variants(vcf: OracleVariantFile, model, transformer, *, custom_annota
             blacklist = pd.Series("PASS", index=df.index, dtype=str)
         if blacklist_cg:
             blacklist = merge_blacklists([blacklist_cg_insertions(df), blacklist])
-        quals = None
+        quals = phreds = gq = None
         if model is not None:
             t0 = time.perf_counter()
             x = transform_features(df, transformer)
@@ -284,7 +315,7 @@ def filter_variants(vcf: OracleVariantFile, model, transformer, *, custom_annota
             scores = model.predict_proba(x_in)
             tick("predict", t0)
             t0 = time.perf_counter()
-            _, quals, _ = score_math(scores)
+            phreds, quals, gq = score_math(scores)
             tick("score", t0)
             all_quals.append(quals)
             all_probs.append(np.asarray(scores, dtype=np.float64))
@@ -294,7 +325,8 @@ def filter_variants(vcf: OracleVariantFile, model, transformer, *, custom_annota
         for i, rec in enumerate(vcf.fetch(str(contig))):  # PARSE #2, like the reference's fetch iterator
             line, keys = write_record(
                 rec, None if quals is None else float(quals[i]), decision_threshold,
-                overwrite_qual=overwrite_qual_tag, blacklist_value=None if bl_values is None else bl_values[i])
+                overwrite_qual=overwrite_qual_tag, blacklist_value=None if bl_values is None else bl_values[i],
+                recal=(phreds[i], float(gq[i])) if (recalibrate_genotype and quals is not None) else None)
             out_lines.append(line)
             out_filters.append(";".join(keys))
         tick("write", t0)

@@ -123,3 +123,36 @@ def test_python_ugvc_entry_point_and_error_contract(job):
     assert r.returncode != 0 and "Variant filtering run: failed" in r.stderr and "does not exist" in r.stderr
     with pytest.raises(ValueError, match="Reference FASTA"):
         fvp.run(["--input_file", job["vcf"], "--output_file", out, "--treat_multiallelics"])
+
+
+def test_cli_recalibrate_genotype_three_class_model(job):
+    """--recalibrate_genotype with an exact-GT style 3-class model: GT / GQ / PL rewritten from the
+    per-class phreds, no TREE_SCORE, QUAL = GQ when overwriting (filter_variants_pipeline.py:203-215)."""
+    ds = job["ds"]
+    _, tr, x = util.fit_transformer(ds)
+    y3 = np.where(x[:, 2] > 0, 2, ds["labels"])  # hom-alt calls get class 2: labels 0 / 1 / 2
+    model = util.fit_model("gb3", x, y3)
+    assert len(model.classes_) == 3
+    mpath = str(job["dir"] / "model3.pkl")
+    with open(mpath, "wb") as fh:
+        pickle.dump({"transformer": tr, "xgb": model}, fh)
+    out = str(job["dir"] / "out5.vcf.gz")
+    argv = ["--input_file", job["vcf"], "--model_file", mpath, "--output_file", out, "--recalibrate_genotype",
+            "--overwrite_qual_tag"]
+    for c in ds["customs"]:
+        argv += ["--custom_annotations", c]
+    fvp.run(argv)
+    exp = R.filter_variants(ds["vf"], model, tr, custom_annotations=ds["customs"], recalibrate_genotype=True,
+                            overwrite_qual_tag=True)
+    _, recs = read_out(out)
+    assert len(recs) == len(exp["lines"])
+    bad = [i for i, (a, b) in enumerate(zip(recs, exp["lines"])) if a != b]
+    # int() of a phred sits on an integer boundary for ~1 record in 10^5 when the device log10 and
+    # NumPy's differ in the last ulp; everything else must match byte for byte
+    assert len(bad) <= 1, f"{len(bad)} records differ, first: {recs[bad[0]]!r} vs {exp['lines'][bad[0]]!r}"
+    assert not any("TREE_SCORE" in r for r in recs)
+    gts = {}
+    for r in recs:
+        g = r.split("\t")[9].split(":")[0]
+        gts[g] = gts.get(g, 0) + 1
+    assert set(gts) <= {"0/0", "0/1", "1/1"} and len(gts) == 3

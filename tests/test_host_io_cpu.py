@@ -54,7 +54,8 @@ def _recinfo_for(lines):
     for i, ln in enumerate(lines):
         cols = ln.split("\t")
         start = lambda k: len("\t".join(cols[:k])) + 1  # noqa: E731
-        ri[i] = (int(cols[1]), start(5), start(6), start(7), start(8), (len(cols[3]) << 8))
+        n_alleles = 1 + (0 if cols[4] == "." else cols[4].count(",") + 1)
+        ri[i] = (int(cols[1]), start(5), start(6), start(7), start(8), (len(cols[3]) << 8) | (n_alleles << 1))
     return ri
 
 
@@ -79,7 +80,7 @@ def test_splicer_matches_oracle_writer(overwrite_qual):
     out_ls = np.empty(len(lines) + 1, dtype=np.int64)
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     n = lib.load_library().ugvc_splice_records(p(buf), p(ls), p(ri), p(low), p(quals), len(lines), int(overwrite_qual),
-                                               1, p(codes), p(table), p(off), p(out), out.size, p(out_ls), 2)
+                                               1, p(codes), p(table), p(off), None, 0, p(out), out.size, p(out_ls), 2)
     assert n > 0
     got = out[:n].tobytes().decode().split("\n")[:-1]
     vf = OracleVariantFile(("\n".join(hdr) + "\n" + "\n".join(lines) + "\n").encode())
@@ -97,6 +98,39 @@ def test_splicer_without_model_only_fills_pass():
     ri = _recinfo_for(lines)
     out = np.empty(256, dtype=np.uint8)
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-    n = lib.load_library().ugvc_splice_records(p(buf), p(ls), p(ri), None, None, 2, 0, 0, None, None, None, p(out),
-                                               out.size, None, 1)
+    n = lib.load_library().ugvc_splice_records(p(buf), p(ls), p(ri), None, None, 2, 0, 0, None, None, None, None, 0,
+                                               p(out), out.size, None, 1)
     assert out[:n].tobytes().decode() == "c1\t1\t.\tA\tC\t5\tPASS\tX=1\nc1\t2\t.\tA\tC\t5\tq10\t.\n"
+
+
+@pytest.mark.parametrize("overwrite_qual", [False, True])
+def test_splicer_recalibrate_genotype_matches_oracle(overwrite_qual):
+    """--recalibrate_genotype writer rules (filter_variants_pipeline.py:203-215): GQ / PL / GT of the
+    first sample, no TREE_SCORE, QUAL = gq when overwriting."""
+    hdr = ["##fileformat=VCFv4.2", "##contig=<ID=c1,length=100>",
+           "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS\tS2"]
+    lines = ["c1\t1\t.\tA\tC\t5.5\tPASS\tX=1\tGT:AD:DP:GQ:PL\t0/1:3,4:7:50:10,0,90\t1/1:0,9:9:20:90,20,0",
+             "c1\t2\t.\tA\tC\t.\t.\t.\tGT:PL\t1|1:0,0,0\t.",
+             "c1\t3\trs\tAT\tA\t7\tq10\tY=2\tGT:DP\t0/1:3\t./.",
+             "c1\t4\t.\tA\tC,G\t7\t.\tY=2\tGT:GQ:PL\t1/2:9:9,8,7,6,5,4\t0/0"]
+    rng = np.random.default_rng(4)
+    probs = rng.dirichlet(np.ones(3), size=len(lines))
+    probs[1] = [0.2, 0.2, 0.6]
+    phreds, quals, gq = R.score_math(probs)
+    low = (quals <= 30.0).astype(np.uint8)
+    text = ("\n".join(lines) + "\n").encode()
+    buf = np.frombuffer(text, dtype=np.uint8)
+    ls = np.concatenate(([0], np.cumsum([len(l) + 1 for l in lines]))).astype(np.int64)
+    ri = _recinfo_for(lines)
+    out = np.empty(len(text) + 1024, dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    ph = np.ascontiguousarray(phreds)
+    n = lib.load_library().ugvc_splice_records(p(buf), p(ls), p(ri), p(low), p(quals), len(lines), int(overwrite_qual),
+                                               1, None, None, None, p(ph), 3, p(out), out.size, None, 2)
+    assert n > 0
+    got = out[:n].tobytes().decode().split("\n")[:-1]
+    vf = OracleVariantFile(("\n".join(hdr) + "\n" + "\n".join(lines) + "\n").encode())
+    want = [R.write_record(rec, float(quals[i]), 30.0, overwrite_qual=overwrite_qual, blacklist_value=None,
+                           recal=(phreds[i], float(gq[i])))[0] for i, rec in enumerate(vf)]
+    assert got == want
+    assert all("TREE_SCORE" not in g for g in got) and got[3].split("\t")[8] == "GT:GQ:PL"

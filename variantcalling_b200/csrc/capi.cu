@@ -44,6 +44,7 @@ struct ugvc_ctx {
     long long* d_counts = nullptr;
     int64_t launches = 0;
     bool timing = false;
+    bool want_phreds = false;
     float stage_ms[4] = {0, 0, 0, 0};
     int64_t err_record = -1;
     int32_t err_column = -1, err_reason = 0;
@@ -102,6 +103,7 @@ static void free_lane(Lane& l) {
     cudaFree(l.b.low_score);
     cudaFree(l.b.probs);
     cudaFree(l.b.qual);
+    cudaFree(l.b.phreds);
     cudaFree(l.d_err);
     if (l.h_n) cudaFreeHost(l.h_n);
     if (l.h_err) cudaFreeHost(l.h_err);
@@ -453,6 +455,7 @@ extern "C" int ugvc_reserve(ugvc_ctx* ctx, size_t max_bytes, size_t max_records,
         CU(cudaMalloc(&l.b.low_score, max_records));
         CU(cudaMalloc(&l.b.probs, max_records * p.h.n_classes * sizeof(float)));
         CU(cudaMalloc(&l.b.qual, max_records * sizeof(double)));
+        if (ctx->want_phreds) CU(cudaMalloc(&l.b.phreds, max_records * p.h.n_classes * sizeof(double)));
         CU(cudaMalloc(&l.d_err, sizeof(unsigned long long)));
         CU(cudaHostAlloc(&l.h_n, sizeof(int64_t), cudaHostAllocDefault));
         CU(cudaHostAlloc(&l.h_err, sizeof(unsigned long long), cudaHostAllocDefault));
@@ -487,8 +490,8 @@ static int enqueue_kernels(ugvc_ctx* ctx, Lane& l, const uint8_t* d_text, size_t
     if (has_model) launch_k2(p, l.b.raw, l.b.cap_records, d_n_records, l.b.feats, l.d_err, ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[3], st));
     if (has_model)
-        launch_k3(p, l.b.feats, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual, ctx->d_counts,
-                  ctx->sm_count, st);
+        launch_k3(p, l.b.feats, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual,
+                  d_low == l.b.low_score ? l.b.phreds : nullptr, ctx->d_counts, ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[4], st));
     ctx->launches += (has_model ? 4 : 2) + (p.h.n_slots ? 1 : 0);
     CU(cudaGetLastError());
@@ -604,6 +607,25 @@ extern "C" int ugvc_device_status(ugvc_ctx* ctx, void* stream) {
     unsigned long long e;
     CU(cudaMemcpy(&e, l.d_err, sizeof(e), cudaMemcpyDeviceToHost));
     return decode_error(ctx, e);
+}
+
+extern "C" int ugvc_enable_phreds(ugvc_ctx* ctx, int on) {
+    // takes effect at the next ugvc_reserve
+    if (!ctx) return UGVC_E_ARG;
+    ctx->want_phreds = on != 0;
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_collect_phreds(ugvc_ctx* ctx, int lane, double* out, size_t capacity_records) {
+    if (!ctx || !out || lane < 0 || lane >= (int)ctx->lanes.size()) return UGVC_E_ARG;
+    Lane& l = ctx->lanes[lane];
+    if (!l.b.phreds) return fail(ctx, UGVC_E_STATE, "collect_phreds: call ugvc_enable_phreds before ugvc_reserve");
+    if ((size_t)l.last_n > capacity_records) return fail(ctx, UGVC_E_ARG, "collect_phreds: capacity too small");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(l.stream));
+    if (l.last_n)
+        CU(cudaMemcpy(out, l.b.phreds, (size_t)l.last_n * ctx->plan.h.n_classes * sizeof(double), cudaMemcpyDeviceToHost));
+    return UGVC_OK;
 }
 
 extern "C" int ugvc_counts_reset(ugvc_ctx* ctx) {

@@ -10,6 +10,7 @@
 #include <zlib.h>
 
 #include <atomic>
+#include <algorithm>
 #include <string>
 #include <thread>
 #include <vector>
@@ -297,8 +298,86 @@ inline bool piece_is(const Piece& a, const char* s) {
 // htslib prints INFO/QUAL floats (float32) with %g semantics
 int format_g(double q, char* buf, size_t cap) { return snprintf(buf, cap, "%g", (double)(float)q); }
 
+// triangular PL index -> (a, b) with a <= b  (multiallelics.py:257-277)
+void gt_from_pl_idx(int idx, int& a, int& b) {
+    int count = 0, n_alleles = 0;
+    while (count < idx + 1) {
+        count += n_alleles;
+        ++n_alleles;
+    }
+    b = n_alleles - 2;
+    a = idx - (count - n_alleles) - 1;
+}
+
+// rewrite GT / GQ / PL of the first sample (filter_variants_pipeline.py:203-215)
+void recalibrated_sample(const uint8_t* fmt, size_t len, const double* ph, int n_pl, double gq, std::string& out) {
+    // fmt = "FORMAT\tSAMPLE1[\tSAMPLE2...]"
+    size_t ftab = 0;
+    while (ftab < len && fmt[ftab] != '\t') ++ftab;
+    std::vector<std::string> keys, vals;
+    {
+        size_t s = 0;
+        for (size_t e = 0; e <= ftab; ++e)
+            if (e == ftab || fmt[e] == ':') {
+                keys.emplace_back(reinterpret_cast<const char*>(fmt + s), e - s);
+                s = e + 1;
+            }
+    }
+    size_t s1 = ftab < len ? ftab + 1 : len, s1e = s1;
+    while (s1e < len && fmt[s1e] != '\t') ++s1e;
+    {
+        size_t s = s1;
+        for (size_t e = s1; e <= s1e; ++e)
+            if (e == s1e || fmt[e] == ':') {
+                vals.emplace_back(reinterpret_cast<const char*>(fmt + s), e - s);
+                s = e + 1;
+            }
+    }
+    if (keys.size() == 1 && keys[0] == ".") keys.clear();
+    vals.resize(keys.size(), ".");
+    char sep = '/';
+    std::vector<int> pl(n_pl);
+    int best = 0;
+    for (int k = 0; k < n_pl; ++k) {
+        pl[k] = (int)ph[k];  // int(): truncation
+        if (pl[k] < pl[best]) best = k;
+    }
+    int a = 0, b = 0;
+    gt_from_pl_idx(best, a, b);
+    auto set = [&](const char* key, const std::string& v) {
+        for (size_t i = 0; i < keys.size(); ++i)
+            if (keys[i] == key) {
+                vals[i] = v;
+                return;
+            }
+        keys.emplace_back(key);
+        vals.push_back(v);
+    };
+    for (size_t i = 0; i < keys.size(); ++i)
+        if (keys[i] == "GT" && vals[i].find('|') != std::string::npos) sep = '|';
+    set("GQ", std::to_string((int)gq));
+    std::string pls;
+    for (int k = 0; k < n_pl; ++k) {
+        if (k) pls.push_back(',');
+        pls += std::to_string(pl[k]);
+    }
+    set("PL", pls);
+    set("GT", std::to_string(a) + sep + std::to_string(b));
+    for (size_t i = 0; i < keys.size(); ++i) {
+        if (i) out.push_back(':');
+        out += keys[i];
+    }
+    out.push_back('\t');
+    for (size_t i = 0; i < vals.size(); ++i) {
+        if (i) out.push_back(':');
+        out += vals[i];
+    }
+    if (s1e < len) out.append(reinterpret_cast<const char*>(fmt + s1e), len - s1e);  // other samples untouched
+}
+
 void splice_one(const uint8_t* line, size_t len, const ugvc_recinfo& ri, bool with_model, bool low, double qual,
-                bool overwrite_qual, const char* bl, size_t bl_len, std::string& out) {
+                bool overwrite_qual, const char* bl, size_t bl_len, const double* ph, int n_classes,
+                std::string& out) {
     size_t off[4] = {ri.qual_off, ri.filter_off, ri.info_off, ri.format_off};
     if (ri.qual_off == 0xFFFF || ri.filter_off == 0xFFFF || ri.info_off == 0xFFFF || ri.format_off == 0xFFFF) {
         // long line: recount the tabs
@@ -317,10 +396,30 @@ void splice_one(const uint8_t* line, size_t len, const ugvc_recinfo& ri, bool wi
         return;
     }
     char num[48];
+    // --recalibrate_genotype: gq = second smallest - smallest phred
+    const bool recal = with_model && ph != nullptr;
+    double gq = 0.0;
+    int n_pl = 0;
+    if (recal) {
+        double m1 = ph[0], m2 = ph[1];
+        if (m2 < m1) std::swap(m1, m2);
+        for (int k = 2; k < n_classes; ++k) {
+            if (ph[k] < m1) {
+                m2 = m1;
+                m1 = ph[k];
+            } else if (ph[k] < m2)
+                m2 = ph[k];
+        }
+        gq = m2 - m1;
+        const int na = (int)((ri.flags >> 1) & 0x7Fu);
+        n_pl = (na + 1) * na / 2;
+        if (n_pl > n_classes) n_pl = n_classes;
+        if (n_pl < 1) n_pl = 1;
+    }
     // columns 1-5 incl. trailing tab
     out.append(reinterpret_cast<const char*>(line), q0);
     // QUAL
-    if (with_model && overwrite_qual) out.append(num, (size_t)format_g(qual, num, sizeof(num)));
+    if (with_model && overwrite_qual) out.append(num, (size_t)format_g(recal ? gq : qual, num, sizeof(num)));
     else out.append(reinterpret_cast<const char*>(line + q0), f0 - 1 - q0);
     out.push_back('\t');
     // FILTER
@@ -358,9 +457,9 @@ void splice_one(const uint8_t* line, size_t len, const ugvc_recinfo& ri, bool wi
         const uint8_t* ip = line + i0;
         const size_t il = x0 - 1 - i0;
         size_t written = 0;
-        bool done_score = !with_model, done_bl = (bl_len == 0);
+        bool done_score = !with_model || recal, done_bl = (bl_len == 0);
         std::string score;
-        if (with_model) {
+        if (with_model && !recal) {
             score = "TREE_SCORE=";
             score.append(num, (size_t)format_g(qual, num, sizeof(num)));
         }
@@ -411,10 +510,11 @@ void splice_one(const uint8_t* line, size_t len, const ugvc_recinfo& ri, bool wi
         }
         if (!written) out.push_back('.');
     }
-    // FORMAT + samples (with the tab before them), untouched
+    // FORMAT + samples (with the tab before them): untouched unless genotypes are recalibrated
     if (x0 <= len) {
         out.push_back('\t');
-        out.append(reinterpret_cast<const char*>(line + x0), len - x0);
+        if (recal) recalibrated_sample(line + x0, len - x0, ph, n_pl, gq, out);
+        else out.append(reinterpret_cast<const char*>(line + x0), len - x0);
     }
     out.push_back('\n');
 }
@@ -425,7 +525,8 @@ extern "C" int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_
                                        const uint8_t* low_score, const double* qual, int64_t n_records,
                                        int overwrite_qual, int with_model, const int32_t* blacklist_code,
                                        const char* blacklist_table, const int64_t* blacklist_table_off,
-                                       uint8_t* out, size_t capacity, int64_t* out_line_start, int n_threads) {
+                                       const double* phreds, int n_classes, uint8_t* out, size_t capacity,
+                                       int64_t* out_line_start, int n_threads) {
     if (!text || !line_start || !recinfo || n_records < 0) return UGVC_E_ARG;
     if (with_model && (!low_score || !qual)) return UGVC_E_ARG;
     n_threads = clamp_threads(n_threads);
@@ -449,7 +550,8 @@ extern "C" int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_
                 bl_len = (size_t)(blacklist_table_off[code + 1] - blacklist_table_off[code]);
             }
             splice_one(line, len, recinfo[i], with_model != 0, with_model && low_score[i] != 0,
-                       with_model ? qual[i] : 0.0, overwrite_qual != 0, bl, bl_len, o);
+                       with_model ? qual[i] : 0.0, overwrite_qual != 0, bl, bl_len,
+                       phreds ? phreds + (size_t)i * n_classes : nullptr, n_classes, o);
             if (out_line_start) lens[t].push_back((int64_t)(o.size() - before));
         }
     };

@@ -49,13 +49,14 @@ __device__ __forceinline__ uint4 ld_stream16(const uint4* p) {
 // ------------------------------------------------------------------------------------------
 // K0: line index (single pass)
 // ------------------------------------------------------------------------------------------
-// One read of the text.  Tiles of 16 KiB are claimed in order from an atomic ticket; each thread
-// turns its 64 contiguous bytes into a 64-bit newline mask, the block scans the pop-counts, the
+// One read of the text.  Tiles of 64 KiB are claimed in order from an atomic ticket; each thread
+// turns its 256 contiguous bytes into four 64-bit newline masks, the block scans the pop-counts, the
 // tile's running record count comes from a decoupled look-back over the tile-state words
 // (bit 63: inclusive prefix published, bit 62: aggregate published), and the line starts are
 // written straight from the masks -- no second pass over the text.
 #define K0_TPB 256
-#define K0_TILE_BYTES (K0_TPB * 64)
+#define K0_SEGS 4
+#define K0_TILE_BYTES (K0_TPB * 64 * K0_SEGS)
 #define K0_FLAG_AGG (1ull << 62)
 #define K0_FLAG_INC (1ull << 63)
 #define K0_VAL_MASK ((1ull << 62) - 1ull)
@@ -91,9 +92,15 @@ __global__ void __launch_bounds__(K0_TPB) k0_index(const uint8_t* __restrict__ t
         __syncthreads();
         const size_t tile = s_tile;
         if (tile >= n_tiles) break;
-        const size_t off = tile * K0_TILE_BYTES + (size_t)threadIdx.x * 64;
-        unsigned long long mask = off < n_bytes ? nl_mask64(text, off, n_bytes) : 0ull;
-        const unsigned cnt = __popcll(mask);
+        // each thread owns K0_SEGS * 64 contiguous bytes
+        const size_t off = tile * K0_TILE_BYTES + (size_t)threadIdx.x * (64 * K0_SEGS);
+        unsigned long long mask[K0_SEGS];
+        unsigned cnt = 0;
+#pragma unroll
+        for (int g = 0; g < K0_SEGS; ++g) {
+            mask[g] = off + 64 * g < n_bytes ? nl_mask64(text, off + 64 * g, n_bytes) : 0ull;
+            cnt += __popcll(mask[g]);
+        }
         unsigned incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -143,11 +150,15 @@ __global__ void __launch_bounds__(K0_TPB) k0_index(const uint8_t* __restrict__ t
         }
         __syncthreads();
         size_t idx = (size_t)s_excl + warp_base + (incl - cnt);
-        while (mask) {
-            const int b = __ffsll((long long)mask) - 1;
-            mask &= mask - 1;
-            if (idx + 1 <= cap_records) line_start[idx + 1] = (int64_t)(off + b + 1);
-            ++idx;
+#pragma unroll
+        for (int g = 0; g < K0_SEGS; ++g) {
+            unsigned long long m = mask[g];
+            while (m) {
+                const int b = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                if (idx + 1 <= cap_records) line_start[idx + 1] = (int64_t)(off + 64 * g + b + 1);
+                ++idx;
+            }
         }
         __syncthreads();  // s_tile / s_excl are rewritten by the next round
     }
@@ -893,6 +904,7 @@ __global__ void __launch_bounds__(K1_TPB, K1_MIN_CTAS) k1_parse(const __grid_con
             }
             if (malformed) atomicMin(err, ugvc_pack_error(rec, 0xFFFF, REASON_MALFORMED_LINE));
             if (cg) ri.flags |= 1u;
+            ri.flags |= (unsigned)(n_alleles > 127 ? 127 : n_alleles) << 1;
             cg_local += cg ? 1u : 0u;
             if (recinfo) *reinterpret_cast<uint4*>(&recinfo[rec]) = *reinterpret_cast<const uint4*>(&ri);
         }
@@ -1028,8 +1040,8 @@ __global__ void __launch_bounds__(TPB, 1) k3_infer(const __grid_constant__ DevPl
                                                       const float* __restrict__ feats, size_t row_stride,
                                                       const int64_t* __restrict__ n_records_p, double threshold,
                                                       uint8_t* __restrict__ low_score, float* __restrict__ probs,
-                                                      double* __restrict__ qual_out, long long* counts,
-                                                      unsigned chunk_nodes_cap) {
+                                                      double* __restrict__ qual_out, double* __restrict__ phred_out,
+                                                      long long* counts, unsigned chunk_nodes_cap) {
     extern __shared__ __align__(16) uint8_t smem3[];
     const int F = plan.h.n_features, K = plan.h.n_classes, O = plan.h.n_outputs;
     const unsigned n_trees = plan.h.n_trees;
@@ -1205,11 +1217,19 @@ __global__ void __launch_bounds__(TPB, 1) k3_infer(const __grid_constant__ DevPl
                 break;
         }
         // phred = -10 log10(lik + 1e-10); qual = clip(30 + ph[0] - min(ph[1:]), 0, inf)   (fp64)
-        const double ph0 = -10.0 * log10(p[0] + 1e-10);
-        double mn = -10.0 * log10(p[1] + 1e-10);
+        double ph[UGVC_MAX_CLASSES];
+#pragma unroll
+        for (int k = 0; k < UGVC_MAX_CLASSES; ++k) ph[k] = k < K ? -10.0 * log10(p[k] + 1e-10) : 0.0;
+        const double ph0 = ph[0];
+        double mn = ph[1];
 #pragma unroll
         for (int k = 2; k < UGVC_MAX_CLASSES; ++k)
-            if (k < K) mn = fmin(mn, -10.0 * log10(p[k] + 1e-10));
+            if (k < K) mn = fmin(mn, ph[k]);
+        if (phred_out) {  // --recalibrate_genotype: PL / GQ come from the per-class phreds
+#pragma unroll
+            for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
+                if (k < K) phred_out[(size_t)rec * K + k] = ph[k];
+        }
         double q = __dadd_rn(__dadd_rn(30.0, ph0), -mn);
         q = q < 0.0 ? 0.0 : q;
         const bool low = q <= threshold;
@@ -1273,18 +1293,18 @@ bool k3_plan_fits(const DevPlan& plan) {
 }
 
 void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const int64_t* d_n_records,
-               double threshold, uint8_t* low_score, float* probs, double* qual, long long* d_counts,
-               int sm_count, cudaStream_t st) {
+               double threshold, uint8_t* low_score, float* probs, double* qual, double* phreds,
+               long long* d_counts, int sm_count, cudaStream_t st) {
     const size_t smem = k3_smem_bytes(plan);
     int per_sm = (int)((K3_SMEM_BUDGET) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
     if (k3_tpb(plan) == 384)
         k3_infer<384><<<sm_count * per_sm, 384, smem, st>>>(plan, feats, row_stride, d_n_records, threshold, low_score,
-                                                            probs, qual, d_counts, k3_chunk_nodes(plan));
+                                                            probs, qual, phreds, d_counts, k3_chunk_nodes(plan));
     else
         k3_infer<256><<<sm_count * per_sm, 256, smem, st>>>(plan, feats, row_stride, d_n_records, threshold, low_score,
-                                                            probs, qual, d_counts, k3_chunk_nodes(plan));
+                                                            probs, qual, phreds, d_counts, k3_chunk_nodes(plan));
 }
 
 cudaError_t kernels_configure(const DevPlan& plan) {

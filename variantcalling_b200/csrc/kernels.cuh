@@ -83,9 +83,10 @@ struct LaneBuffers {
     uint8_t* low_score;        // [cap_records]
     float* probs;              // [cap_records][n_classes]
     double* qual;              // [cap_records]
+    double* phreds;            // [cap_records][n_classes], only with ugvc_enable_phreds
 };
 
-#define K0_TILE_BYTES_HOST 16384  // one 64-bit look-back state word per 16 KiB tile
+#define K0_TILE_BYTES_HOST 65536  // one 64-bit look-back state word per 64 KiB tile
 
 void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* chunk_first, int64_t* line_start,
                size_t cap_records, int64_t* d_n_records, unsigned long long* d_err, int sm_count,
@@ -96,8 +97,8 @@ void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_t
 void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, const int64_t* d_n_records, float* feats,
                unsigned long long* d_err, int sm_count, cudaStream_t st);
 void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const int64_t* d_n_records,
-               double threshold, uint8_t* low_score, float* probs, double* qual, long long* d_counts,
-               int sm_count, cudaStream_t st);
+               double threshold, uint8_t* low_score, float* probs, double* qual, double* phreds,
+               long long* d_counts, int sm_count, cudaStream_t st);
 size_t k1_smem_bytes(const DevPlan& plan);
 size_t k3_smem_bytes(const DevPlan& plan);
 bool k3_plan_fits(const DevPlan& plan);

@@ -17,7 +17,8 @@ spliced from the original bytes and BGZF-compressed on the host; the ``.tbi`` is
 written directly (the reference shells out to ``bcftools index -t``, :231).
 
 Not lowered yet (raise ``NotImplementedError`` instead of a silent approximation):
-``--treat_multiallelics`` and ``--recalibrate_genotype``.
+``--treat_multiallelics``.  ``--recalibrate_genotype`` alone is supported: K3
+keeps the per-class phreds and the splicer rewrites GT / GQ / PL of the first sample (:203-215).
 """
 from __future__ import annotations
 
@@ -102,12 +103,12 @@ class _Splicer:
         self.writer.write(("\n".join(lines) + "\n").encode())
 
     def write_batch(self, contig: str, text: np.ndarray, res: dict, *, with_model: bool, overwrite_qual: bool,
-                    bl_code, bl_table: bytes, bl_off: np.ndarray):
+                    bl_code, bl_table: bytes, bl_off: np.ndarray, phreds: np.ndarray | None = None):
         n = res["n_records"]
         if n == 0:
             return
         max_bl = int(np.diff(bl_off).max()) if bl_off is not None and bl_off.size > 1 else 0
-        cap = int(text.size + n * (80 + max_bl) + 1024)
+        cap = int(text.size + n * (96 + max_bl + (16 * phreds.shape[1] if phreds is not None else 0)) + 1024)
         out = np.empty(cap, dtype=np.uint8)
         out_ls = np.empty(n + 1, dtype=np.int64)
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
@@ -115,7 +116,7 @@ class _Splicer:
         nb = self.L.ugvc_splice_records(
             p(text), p(res["line_start"]), p(res["recinfo"]), p(res.get("low_score")), p(res.get("qual")), n,
             int(overwrite_qual), int(with_model), p(bl_code), p(table), p(bl_off) if table is not None else None,
-            p(out), out.size, p(out_ls), self.threads)
+            p(phreds), 0 if phreds is None else int(phreds.shape[1]), p(out), out.size, p(out_ls), self.threads)
         if nb < 0:
             raise OSError(f"splice failed (ugvc code {nb})")
         base = self.writer.uoffset
@@ -186,10 +187,9 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             raise RuntimeError(f"Input file {args.input_file} does not exist")
         if not os.path.exists(args.input_file + ".tbi"):
             raise RuntimeError(f"Index file {args.input_file}.tbi does not exist")
-        if args.treat_multiallelics or args.recalibrate_genotype:
+        if args.treat_multiallelics:
             raise NotImplementedError(
-                "--treat_multiallelics / --recalibrate_genotype are not lowered to the GPU path yet "
-                "(SURVEY.md 8f-2); refusing to approximate")
+                "--treat_multiallelics is not lowered to the GPU path yet (SURVEY.md 8f-2); refusing to approximate")
 
         header = VcfHeader(bgzf_io.read_header_text(args.input_file))
         with_model = args.model_file is not None
@@ -207,6 +207,9 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         else:
             plan = MC.compile_plan_no_model(header)
         ctx.load_plan(plan.blob)
+        recal = bool(args.recalibrate_genotype and with_model)
+        if recal:
+            ctx.enable_phreds(True)
         batch_bytes = max(1, args.batch_mb) << 20
         n_lanes = 2
         reserved = (0, 0)
@@ -257,6 +260,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 outs = ctx.alloc_outputs(cap, want_recinfo=True)
                 n = ctx.collect(lane, outs, cap)
                 res = ctx.trim_outputs(outs, n)
+                phreds = np.ascontiguousarray(ctx.collect_phreds(lane, n)) if recal else None
                 bl_code, bl_table, bl_off = None, b"", None
                 if with_bl:
                     ri = res["recinfo"]
@@ -283,7 +287,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                     totals["n_cg"] += int(np.count_nonzero(ri["flags"] & 1))
                 out.write_batch(contig, text[b:e], res, with_model=with_model,
                                 overwrite_qual=args.overwrite_qual_tag, bl_code=bl_code, bl_table=bl_table,
-                                bl_off=bl_off)
+                                bl_off=bl_off, phreds=phreds)
                 totals["n_records"] += n
                 if with_model:
                     totals["n_low_score"] += int(res["low_score"].sum())

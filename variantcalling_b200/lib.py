@@ -72,7 +72,9 @@ SIGNATURES = {
     "ugvc_bgzf_deflate_to_file": (C.c_int, [C.c_char_p, C.c_char_p, _vp, _sz, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(C.c_uint64), _vp, _sz, C.POINTER(_sz)]),
     "ugvc_splice_records": (C.c_int64, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp,
-                                        _vp, _sz, _vp, C.c_int]),
+                                        _vp, C.c_int, _vp, _sz, _vp, C.c_int]),
+    "ugvc_enable_phreds": (C.c_int, [_vp, C.c_int]),
+    "ugvc_collect_phreds": (C.c_int, [_vp, C.c_int, _vp, _sz]),
     "ugvc_test_parse_float": (C.c_int, [C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_double),
                                         C.POINTER(C.c_int)]),
 }
@@ -222,6 +224,14 @@ class Context:
                                                 _ptr(out.get("qual")), _ptr(out.get("recinfo")),
                                                 _ptr(out.get("line_start")), capacity, C.byref(n)))
         return n.value
+
+    def enable_phreds(self, on: bool = True):
+        self._check(self.lib.ugvc_enable_phreds(self.h, int(on)))
+
+    def collect_phreds(self, lane: int, n: int) -> np.ndarray:
+        out = np.empty((max(1, n), self.n_classes), np.float64)
+        self._check(self.lib.ugvc_collect_phreds(self.h, lane, _ptr(out), out.shape[0]))
+        return out[:n]
 
     # ---- device-resident hot path (pointers are ints, e.g. torch.Tensor.data_ptr())
     def filter_device(self, d_text: int, n_bytes: int, threshold: float, d_low: int, d_probs: int, d_qual: int,
