@@ -61,6 +61,8 @@ def test_learn_key_order():
     keys = info.split(";")
     assert keys[:5] == ["AC", "AF", "AN", "BaseQRankSum", "DP"] and fmt == "GT:AD:DP:GQ:PL"
     assert keys[28:33] == synth.BASE_CUSTOM and keys[-1] == "ANN34" and len(keys) == 68
+    dense = lib.learn_key_order(("\n".join(lines) + "\n").encode(), min_presence=0.5)[0].split(";")
+    assert dense[-1] == "X_RM" and len(dense) == 28        # the 15 %-present annotations can be left out
     # inconsistent orders are left to the generic path; valueless keys carry a '!' marker
     assert lib.learn_key_order(b"c\t1\t.\tA\tC\t1\t.\tB=1;A=2\tGT\t0/1\nc\t2\t.\tA\tC\t1\t.\tA=2;B=1\tGT\t0/1\n")[0] == ""
     assert lib.learn_key_order(b"c\t1\t.\tA\tC\t1\t.\tA=2;DB;Z=1\n")[0] == "A;DB!;Z"
