@@ -379,7 +379,7 @@ def main():  # noqa: C901, PLR0912, PLR0915
     S, F = ctx.n_slots, ctx.n_features
     rec_per_launch = n_mine / len(batches)
     text_per_launch = total_bytes / len(batches)
-    alg_bytes = {  # algorithmic (compulsory) bytes per launch, DESIGN.md section 4
+    alg_bytes = {  # algorithmic (compulsory) bytes per launch, DESIGN.md section 3
         "k0_line_index": text_per_launch + 8 * rec_per_launch,
         "k1_field_parse": text_per_launch + rec_per_launch * (8 + 4 * S + 16),
         "k2_feature_assembly": rec_per_launch * 4 * (S + F),
@@ -390,8 +390,14 @@ def main():  # noqa: C901, PLR0912, PLR0915
     achieved = alg_bytes[dom] / (stage_ms[dom] / 1e3) / 1e9
     path_bytes = total_bytes / max(1, n_mine) + 4 * K + 9  # B_alg per record, SURVEY.md 8d
     kernels_ms_per_step = sum(stage_sum) / args.steps
+    # DRAM bytes per record of each kernel from the committed `ncu --set full` capture
+    # (profiles/r1_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum over the records of that launch)
+    ncu_traffic_per_record = {"k1_field_parse": 958.0, "k3_inference": 320.0}
+    traffic = ncu_traffic_per_record.get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": None if traffic is None else traffic * rec_per_launch,
+                "traffic_source": "profiles/r1_ncu_full_summary.csv (ncu --set full, per launch, scaled to this launch size)",
+                "algorithmic_bytes_per_launch": alg_bytes[dom], "peak_source": peak_src,
                 "stage_ms_per_launch": stage_ms, "launches_timed": n_calls,
                 "path": {"bytes_per_record": path_bytes,
                          "achieved": path_bytes * n_mine / (kernels_ms_per_step / 1e3) / 1e9,

@@ -572,6 +572,17 @@ __device__ __forceinline__ void set_tag_missing(const RawOut& o, int t) {
     for (int s = tg.first_slot; s < tg.first_slot + tg.n_slots; ++s) store_slot(o, s, RAW_MISSING);
 }
 
+// number of leading ASCII digits in the 8 look-ahead bytes (0..8)
+__device__ __forceinline__ int leading_digits(unsigned long long x) {
+    const unsigned long long hi = 0xF0F0F0F0F0F0F0F0ull, three = 0x3030303030303030ull;
+    // a byte is a digit iff its high nibble is 3 and stays 3 after adding 6
+    const unsigned long long nd = ((x & hi) ^ three) | (((x + 0x0606060606060606ull) & hi) ^ three);
+    return nd ? ((__ffsll((long long)nd) - 1) >> 3) : 8;
+}
+__device__ __forceinline__ bool is_term(unsigned ch, unsigned vend) {
+    return ch == ',' || ch == vend || ch == '\t' || ch == '\n';
+}
+
 // Decode the value of a scheduled key (every lane that gets here holds the same key, so the
 // class switch is warp-uniform) and leave the cursor on the byte that ends the field.
 // meta = the entry's last 8 bytes: len | cls<<8 | slot0<<16 | n_elem<<24 | dict<<32 | flags<<40 | tag<<48
@@ -585,16 +596,46 @@ __device__ __noinline__ Cur decode_sched(RawOut o, unsigned long long meta, Cur 
         int e = 0;
         for (;;) {
             uint32_t bits;
+            // fast paths on the 8-byte look-ahead: a short unsigned integer, or digits '.' digits,
+            // ending inside the window; anything else goes through the full parsers
+            const unsigned long long x = c.peek8();
+            const int k1 = leading_digits(x);
+            bool fast = false;
             if (cls == CLS_INT) {
-                const IntCur r = parse_int_cur(c);  // htslib int32 -> fp32 feature
-                c = r.c;
-                bits = r.st == NUM_OK ? __float_as_uint((float)r.v) : (r.st == NUM_MISSING ? RAW_MISSING : RAW_ERR);
+                if (k1 >= 1 && k1 <= 7 && is_term((unsigned)(x >> (8 * k1)) & 0xFFu, vend)) {
+                    unsigned v = 0;
+                    for (int i = 0; i < k1; ++i) v = v * 10u + ((unsigned)(x >> (8 * i)) & 0xFu);
+                    bits = __float_as_uint((float)v);
+                    c.advance(k1);
+                    fast = true;
+                }
+                if (!fast) {
+                    const IntCur r = parse_int_cur(c);  // htslib int32 -> fp32 feature
+                    c = r.c;
+                    bits = r.st == NUM_OK ? __float_as_uint((float)r.v) : (r.st == NUM_MISSING ? RAW_MISSING : RAW_ERR);
+                }
             } else {
-                const NumCur r = parse_num_cur(c);  // float32(strtod(text))
-                c = r.c;
-                const float f = (float)r.v;
-                bits = r.st == NUM_OK ? (isnan(f) ? RAW_MISSING : __float_as_uint(f))
-                                      : (r.st == NUM_MISSING ? RAW_MISSING : RAW_ERR);
+                if (k1 >= 1 && k1 <= 5 && ((unsigned)(x >> (8 * k1)) & 0xFFu) == '.') {
+                    const unsigned long long y = x >> (8 * (k1 + 1));
+                    const int k2 = leading_digits(y | (0xFFull << (8 * (7 - k1))));  // bytes past the window: non-digits
+                    if (k2 >= 1 && k1 + 1 + k2 <= 7 && is_term((unsigned)(y >> (8 * k2)) & 0xFFu, vend)) {
+                        unsigned m = 0;
+                        for (int i = 0; i < k1; ++i) m = m * 10u + ((unsigned)(x >> (8 * i)) & 0xFu);
+                        for (int i = 0; i < k2; ++i) m = m * 10u + ((unsigned)(y >> (8 * i)) & 0xFu);
+                        // Clinger: m < 2^24 and 10^k2 are exact doubles, one correctly rounded division
+                        const float f = (float)((double)m / ugvc_ten(k2));
+                        bits = __float_as_uint(f);
+                        c.advance(k1 + 1 + k2);
+                        fast = true;
+                    }
+                }
+                if (!fast) {
+                    const NumCur r = parse_num_cur(c);  // float32(strtod(text))
+                    c = r.c;
+                    const float f = (float)r.v;
+                    bits = r.st == NUM_OK ? (isnan(f) ? RAW_MISSING : __float_as_uint(f))
+                                          : (r.st == NUM_MISSING ? RAW_MISSING : RAW_ERR);
+                }
             }
             const unsigned ch = c.peek();
             if (ch != ',' && ch != vend && ch != '\t' && ch != '\n') {  // trailing garbage in the token
@@ -612,12 +653,34 @@ __device__ __noinline__ Cur decode_sched(RawOut o, unsigned long long meta, Cur 
         for (int m = e; m < n_elem; ++m) store_slot(o, slot0 + m, RAW_MISSING);  // vector shorter than needed
         if (count_all) store_slot_f(o, slot0 + n_elem, (float)e);
     } else if (cls == CLS_DICT1) {
-        const KeyCur r = take_until(c, v4, v4);
-        c = r.c;
-        PlanSlot sl;
-        sl.reducer = RED_DICT;
-        sl.dict = (uint8_t)((meta >> 32) & 0xFFu);
-        store_slot(o, slot0, reduce_string(sl, r.k));
+        // category strings of up to 7 bytes are compared against the look-ahead directly
+        const PlanDict d = s_dicts()[(meta >> 32) & 0xFFu];
+        const unsigned long long x = c.peek8();
+        int found = -1;
+        bool all_short = true;
+        for (int i = 0; i < d.n_strings; ++i) {
+            const PlanString* ps = &s_strings()[d.first_string + i];
+            const int L = ps->len;
+            all_short &= L <= 7;
+            if (L <= 7) {
+                const unsigned long long w0 = *reinterpret_cast<const unsigned long long*>(ps);
+                const unsigned nxt = (unsigned)(x >> (8 * L)) & 0xFFu;
+                if ((x & ((1ull << (8 * L)) - 1ull)) == w0 && (nxt == vend || nxt == '\t' || nxt == '\n')) found = i;
+            }
+        }
+        if (found >= 0) {
+            store_slot_f(o, slot0, (float)found);
+            c.advance(s_strings()[d.first_string + found].len);
+        } else if (all_short) {
+            store_slot(o, slot0, RAW_ERR);  // unknown category
+        } else {
+            const KeyCur r = take_until(c, v4, v4);
+            c = r.c;
+            PlanSlot sl;
+            sl.reducer = RED_DICT;
+            sl.dict = (uint8_t)((meta >> 32) & 0xFFu);
+            store_slot(o, slot0, reduce_string(sl, r.k));
+        }
     } else if (cls == CLS_GENERIC) {
         const int tag = (int)(short)(meta >> 48);
         const unsigned kind = vend == ':' ? s_tags()[tag].fmt_kind : s_tags()[tag].info_kind;
@@ -936,9 +999,12 @@ void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_t
                uint32_t* raw, size_t row_stride, ugvc_recinfo* recinfo, unsigned long long* d_err,
                long long* d_counts, int sm_count, cudaStream_t st) {
     const size_t smem = k1_smem_bytes(plan);
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    // persistent grid: exactly the CTAs that can be resident (registers and shared memory decide)
+    static int occ = 0;
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_parse, K1_TPB, smem) != cudaSuccess || occ < 1) occ = 1;
+    }
+    int per_sm = occ;
     static const int tune = getenv("UGVC_K1_CTAS_PER_SM") ? atoi(getenv("UGVC_K1_CTAS_PER_SM")) : 0;  // profiling knob
     if (tune > 0 && tune < per_sm) per_sm = tune;
     if (plan.h.n_slots) {
