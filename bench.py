@@ -241,6 +241,7 @@ def main():  # noqa: C901, PLR0912, PLR0915
     ap.add_argument("--cpu-sample-per-worker", type=int, default=8000)
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (0 = same as --steps)")
     ap.add_argument("--lanes", type=int, default=3)
+    ap.add_argument("--min-presence", type=float, default=None, help="learn_key_order presence threshold (profiling)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -309,7 +310,8 @@ def main():  # noqa: C901, PLR0912, PLR0915
             f"mean line {total_bytes / max(1, n_mine):.1f} B")
     # the usual INFO key order / FORMAT column, learned from the head of the input like the CLI does
     head = bytes(d_text[batches[0][0]: batches[0][0] + min(batches[0][1], 1 << 20)].cpu().numpy())
-    info_order, fmt_order = lib.learn_key_order(head[: head.rfind(b"\n") + 1])
+    kw = {} if args.min_presence is None else {"min_presence": args.min_presence}
+    info_order, fmt_order = lib.learn_key_order(head[: head.rfind(b"\n") + 1], **kw)
     ctx.set_key_order(info_order, fmt_order)
     max_b = max(b[2] for b in batches)
     d_low = torch.empty(n_mine, dtype=torch.uint8, device="cuda")
