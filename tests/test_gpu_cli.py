@@ -156,3 +156,39 @@ def test_cli_recalibrate_genotype_three_class_model(job):
         g = r.split("\t")[9].split(":")[0]
         gts[g] = gts.get(g, 0) + 1
     assert set(gts) <= {"0/0", "0/1", "1/1"} and len(gts) == 3
+
+
+def test_cli_small_batches_long_lines_and_rescoring(job):
+    """Several batches per contig (--batch_mb 1), a record longer than 64 KiB (saturated column
+    offsets: the splicer recounts tabs), and re-filtering an already filtered file (TREE_SCORE /
+    LOW_SCORE already declared and present: replaced in place, header lines not duplicated)."""
+    ds = job["ds"]
+    lines = list(ds["lines"][:6000])
+    big = lines[100].split("\t")
+    big[3] = "A" + "CGT" * 24000           # 72 kB REF allele
+    big[4] = "A"
+    lines[100] = "\t".join(big)
+    vcf = str(job["dir"] / "in_long.vcf.gz")
+    bgzf_io.write_vcf_gz(vcf, ds["header"], lines)
+    out1 = str(job["dir"] / "out6.vcf.gz")
+    argv = ["--input_file", vcf, "--model_file", job["model"], "--output_file", out1, "--batch_mb", "1"]
+    for c in ds["customs"]:
+        argv += ["--custom_annotations", c]
+    fvp.run(argv)
+    vf = OracleVariantFile(("\n".join(ds["header"]) + "\n" + "\n".join(lines) + "\n").encode())
+    exp = R.filter_variants(vf, job["model_obj"], job["tr"], custom_annotations=ds["customs"])
+    hdr1, recs1 = read_out(out1)
+    assert hdr1 == exp["header"] and recs1 == exp["lines"]
+    assert len(recs1[100]) > 72000 and "TREE_SCORE=" in recs1[100]
+    # second pass over the filtered output with another threshold
+    out2 = str(job["dir"] / "out7.vcf.gz")
+    fvp.run(["--input_file", out1, "--model_file", job["model"], "--output_file", out2, "--decision_threshold", "5",
+             "--batch_mb", "1"] + [a for c in ds["customs"] for a in ("--custom_annotations", c)])
+    vf2 = OracleVariantFile(("\n".join(hdr1) + "\n" + "\n".join(recs1) + "\n").encode())
+    exp2 = R.filter_variants(vf2, job["model_obj"], job["tr"], custom_annotations=ds["customs"], decision_threshold=5.0)
+    hdr2, recs2 = read_out(out2)
+    assert hdr2 == exp2["header"] == hdr1      # nothing added twice
+    assert recs2 == exp2["lines"]
+    assert all(r.count("TREE_SCORE=") == 1 for r in recs2)
+    assert any(r.split("\t")[6] == "LOW_SCORE" for r in recs1) and sum("LOW_SCORE" in r.split("\t")[6] for r in recs2) >= \
+        sum("LOW_SCORE" in r.split("\t")[6] for r in recs1)

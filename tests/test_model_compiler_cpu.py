@@ -84,3 +84,41 @@ def test_xgboost_json_lowering():
 def test_no_model_plan():
     p = MC.compile_plan_no_model("##fileformat=VCFv4.2\n#CHROM\tPOS\n")
     assert p.n_features == 0 and len(p.blob) == 96
+
+
+@pytest.mark.parametrize("vtype,extra_info", [("deep_variant", ["VAF"]), ("joint_callset", []),
+                                              ("deep_variant_extended", ["MQ0_REF", "MQ0_ALT", "LS_REF"])])
+def test_other_vcf_flavours_lower_or_fail_loudly(ds, vtype, extra_info):
+    """The DeepVariant / joint feature lists (transformers.py:241-265,289-290) lower through the
+    same entries; a flavour whose tags the header lacks is a PlanError, never a silent zero."""
+    from sklearn.linear_model import LogisticRegression
+
+    from variantcalling_b200 import transformers as T
+    from variantcalling_b200.tprep_constants import VcfType
+
+    tr = T.get_transformer(VcfType(vtype), None)
+    names = [e[0] for e in tr.transformers]
+    assert names[:4] == ["ad", "gt", "gq", "pl"]
+    hdr = ds["header_text"]
+    if vtype == "deep_variant":
+        hdr = hdr.replace("##FORMAT=<ID=PL", '##FORMAT=<ID=VAF,Number=A,Type=Float,Description="v">\n##FORMAT=<ID=PL')
+        df = ds["df"].copy()
+        df["vaf"] = [(0.5,)] * len(df)
+        import pandas as pd
+        with pd.option_context("future.infer_string", False):
+            x = tr.fit_transform(df)
+        model = LogisticRegression(max_iter=20).fit(x.to_numpy(dtype=float), ds["labels"])
+        plan = MC.compile_plan(VcfHeader(hdr), tr, model, None)
+        assert plan.feature_names[-1] == "vaf" and plan.n_features == 22
+    elif vtype == "joint_callset":
+        import pandas as pd
+        with pd.option_context("future.infer_string", False):
+            x = tr.fit_transform(ds["df"])
+        model = LogisticRegression(max_iter=20).fit(x.to_numpy(dtype=float), ds["labels"])
+        plan = MC.compile_plan(VcfHeader(hdr), tr, model, None)
+        assert plan.n_features == 21 and plan.feature_names[-1] == "x_gcc"
+    else:
+        # the synthetic header has no MQ0_REF ... tags: lowering must refuse, not guess
+        tr.transformers_ = [(n, t, c) for (n, t, c) in tr.transformers]
+        with pytest.raises(MC.PlanError):
+            MC.compile_plan(VcfHeader(hdr), tr, None, None)

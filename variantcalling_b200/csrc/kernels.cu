@@ -1018,6 +1018,23 @@ void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_t
 // ------------------------------------------------------------------------------------------
 // K2: feature assembly
 // ------------------------------------------------------------------------------------------
+// Four consecutive records per thread: every slot row and every feature row is touched with
+// 16-byte loads / stores (rows are 512-byte aligned), policies applied lane-wise.
+__device__ __forceinline__ float k2_apply(uint32_t bits, const PlanFeature& pf, long long rec, int f,
+                                          unsigned long long* err) {
+    float v = __uint_as_float(bits);
+    if (bits == RAW_ABSENT) {
+        if (pf.absent_pol == POL_VALUE) v = pf.absent_val;
+        else atomicMin(err, ugvc_pack_error(rec, f, REASON_BAD_VALUE));
+    } else if (bits == RAW_MISSING) {
+        if (pf.missing_pol == POL_VALUE) v = pf.missing_val;
+        else atomicMin(err, ugvc_pack_error(rec, f, REASON_NULL_FEATURE));
+    } else if (bits == RAW_ERR) {
+        atomicMin(err, ugvc_pack_error(rec, f, REASON_BAD_VALUE));
+    }
+    return v;
+}
+
 __global__ void __launch_bounds__(K2_TPB) k2_features(const __grid_constant__ DevPlan plan,
                                                       const uint32_t* __restrict__ raw, size_t row_stride,
                                                       const int64_t* __restrict__ n_records_p,
@@ -1027,31 +1044,34 @@ __global__ void __launch_bounds__(K2_TPB) k2_features(const __grid_constant__ De
     for (int i = threadIdx.x; i < F; i += K2_TPB) s_feat[i] = plan.feats[i];
     __syncthreads();
     const long long n_rec = *n_records_p;
-    for (long long rec = (long long)blockIdx.x * K2_TPB + threadIdx.x; rec < n_rec;
-         rec += (long long)gridDim.x * K2_TPB) {
-#pragma unroll 4
+    const long long n_quads = (n_rec + 3) >> 2;
+    for (long long q = (long long)blockIdx.x * K2_TPB + threadIdx.x; q < n_quads; q += (long long)gridDim.x * K2_TPB) {
+        const long long rec = q << 2;
+        // records past n_rec inside the last quad: rows are padded to a multiple of 128, the values
+        // there are the ABSENT fill and are never reported (only rec < n_rec can raise)
+        const int live = (int)(n_rec - rec < 4 ? n_rec - rec : 4);
+#pragma unroll 2
         for (int f = 0; f < F; ++f) {
             const PlanFeature pf = s_feat[f];
-            const uint32_t bits = __ldg(&raw[(size_t)pf.slot * row_stride + rec]);
-            float v = __uint_as_float(bits);
-            if (bits == RAW_ABSENT) {
-                if (pf.absent_pol == POL_VALUE) v = pf.absent_val;
-                else atomicMin(err, ugvc_pack_error(rec, f, REASON_BAD_VALUE));
-            } else if (bits == RAW_MISSING) {
-                if (pf.missing_pol == POL_VALUE) v = pf.missing_val;
-                else atomicMin(err, ugvc_pack_error(rec, f, REASON_NULL_FEATURE));
-            } else if (bits == RAW_ERR) {
-                atomicMin(err, ugvc_pack_error(rec, f, REASON_BAD_VALUE));
-            }
-            feats[(size_t)f * row_stride + rec] = v;
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(raw + (size_t)pf.slot * row_stride + rec));
+            float4 v;
+            v.x = k2_apply(b.x, pf, rec, f, err);
+            v.y = live > 1 ? k2_apply(b.y, pf, rec + 1, f, err) : 0.f;
+            v.z = live > 2 ? k2_apply(b.z, pf, rec + 2, f, err) : 0.f;
+            v.w = live > 3 ? k2_apply(b.w, pf, rec + 3, f, err) : 0.f;
+            *reinterpret_cast<float4*>(feats + (size_t)f * row_stride + rec) = v;
         }
         for (unsigned c = 0; c < plan.h.n_checks; ++c) {
             const PlanCheck ck = plan.checks[c];
-            const uint32_t bits = __ldg(&raw[(size_t)ck.slot * row_stride + rec]);
-            if (bits == RAW_ABSENT || bits == RAW_MISSING) continue;  // handled by the feature policies
-            const float v = __uint_as_float(bits);
-            const bool ok = ck.kind == 0 ? (v <= ck.bound) : (v >= ck.bound);
-            if (!ok) atomicMin(err, ugvc_pack_error(rec, 0xFFFF, ck.kind == 0 ? REASON_TOO_MANY_ELEMS : REASON_BAD_VALUE));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(raw + (size_t)ck.slot * row_stride + rec));
+            const uint32_t bits[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i >= live || bits[i] == RAW_ABSENT || bits[i] == RAW_MISSING) continue;  // handled by the feature policies
+                const float v = __uint_as_float(bits[i]);
+                const bool ok = ck.kind == 0 ? (v <= ck.bound) : (v >= ck.bound);
+                if (!ok) atomicMin(err, ugvc_pack_error(rec + i, 0xFFFF, ck.kind == 0 ? REASON_TOO_MANY_ELEMS : REASON_BAD_VALUE));
+            }
         }
     }
 }

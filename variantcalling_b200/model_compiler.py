@@ -233,6 +233,8 @@ class _Builder:
                 return
             if rest == ["ordinal"]:
                 enc = trans.steps[-1][1]
+                if not hasattr(enc, "categories_"):
+                    raise PlanError(f"entry {name!r}: the OrdinalEncoder is not fitted")
                 did = self.add_dict(list(enc.categories_[0]))
                 self.add(name, _SlotReq(tag, 0, RED_DICT, did), (E, 0.0), (E, 0.0))
                 return
@@ -270,6 +272,8 @@ class _Builder:
         if len(steps) == 2 and steps[0] == "impute:none:'FALSE'" and steps[1] == "ordinal":  # noqa: PLR2004
             tag = self.tag_of(single_col())
             self.require(tag, scalar=True, types=(KIND_STR,))
+            if not hasattr(trans.steps[-1][1], "categories_"):
+                raise PlanError(f"entry {name!r}: the OrdinalEncoder is not fitted")
             cats = list(trans.steps[-1][1].categories_[0])
             did = self.add_dict(cats)
             absent = (V, float(cats.index("FALSE"))) if "FALSE" in cats else (E, 0.0)
