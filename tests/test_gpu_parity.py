@@ -65,3 +65,41 @@ def test_filter_batch_matches_oracle(gpu_ctx, ds, kind, order):
         assert (ri["qual_off"][i], ri["filter_off"][i], ri["info_off"][i], ri["format_off"][i]) == (
             start(5), start(6), start(7), start(8))
         assert ds["text"][ls[i]:ls[i + 1] - 1].decode() == line
+
+
+@pytest.mark.parametrize("n_class", [2, 3])
+def test_xgboost_json_model_path(gpu_ctx, ds, n_class):
+    """MODEL_XGB (x < t, fp32 margins in tree order, fp32 sigmoid / softmax) against the NumPy
+    restatement of xgboost's predictor on an xgboost-format JSON document."""
+    from oracle import xgb_predictor as XP
+
+    y = ds["labels"] if n_class == 2 else np.where(ds["x"][:, 2] > 0, 2, ds["labels"])
+    gb = util.fit_model("gb_small" if n_class == 2 else "gb3", ds["x"], y)
+    doc = XP.sklearn_gb_to_xgb_json(gb)
+    plan = MC.compile_plan(VcfHeader(ds["header_text"]), ds["tr"], doc, ds["customs"])
+    assert plan.model_kind == MC.MODEL_XGB and plan.n_classes == n_class
+    gpu_ctx.load_plan(plan.blob)
+    gpu_ctx.set_key_order(*lib.learn_key_order(ds["text"]))
+    gpu_ctx.reserve(len(ds["text"]) + 1024, len(ds["lines"]) + 16, 1)
+    res = gpu_ctx.filter_batch(ds["text"], 30.0)
+    want = XP.predict_proba(doc, ds["x"].astype(np.float32))
+    np.testing.assert_allclose(res["probs"], want, atol=2e-6, rtol=0)
+    _, quals, _ = R.score_math(want)
+    np.testing.assert_allclose(res["qual"], quals, atol=2e-4, rtol=0)
+    far = np.abs(quals - 30.0) > 1e-3  # fp32 expf may differ by an ulp between libm and CUDA near the threshold
+    assert np.array_equal(res["low_score"].astype(bool)[far], (quals <= 30.0)[far])
+    if n_class == 2:  # same trees, same prior: sklearn's fp64 evaluation agrees to fp32 accuracy
+        assert np.abs(gb.predict_proba(ds["x"]) - want).max() < 1e-5
+
+
+def test_multinomial_logistic_regression(gpu_ctx, ds):
+    y = np.where(ds["x"][:, 2] > 0, 2, ds["labels"])
+    model = util.fit_model("lr", ds["x"], y)
+    assert model.coef_.shape[0] == 3
+    plan = MC.compile_plan(VcfHeader(ds["header_text"]), ds["tr"], model, ds["customs"])
+    gpu_ctx.load_plan(plan.blob)
+    gpu_ctx.reserve(len(ds["text"]) + 1024, len(ds["lines"]) + 16, 1)
+    res = gpu_ctx.filter_batch(ds["text"], 30.0)
+    exp = R.filter_variants(ds["vf"], model, ds["tr"], custom_annotations=ds["customs"])
+    np.testing.assert_allclose(res["probs"], exp["probs"], atol=TOL, rtol=0)
+    assert np.array_equal(res["low_score"].astype(bool), np.array(["LOW_SCORE" in f.split(";") for f in exp["filters"]]))
