@@ -1091,7 +1091,9 @@ void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, cons
 // steps (the depth of the deepest leaf), branch-free, so eight independent load chains per
 // thread hide the shared-memory latency; leaf values are then added in tree order in the
 // arithmetic of the library that trained the model (fp64 for sklearn, fp32 for xgboost).
+#ifndef K3_CHAINS
 #define K3_CHAINS 8
+#endif
 
 __device__ __forceinline__ double expit64(double x) { return 1.0 / (1.0 + exp(-x)); }
 
@@ -1355,6 +1357,8 @@ static int k3_tpb(const DevPlan& plan) {
     const size_t forest = k3_forest_bytes(plan);
     if (forest == 0) return 256;
     const size_t need384 = (size_t)plan.h.n_features * 384 * sizeof(float) + forest + k3_roots_bytes(plan);
+    static const int force = getenv("UGVC_K3_TPB") ? atoi(getenv("UGVC_K3_TPB")) : 0;  // profiling knob
+    if (force == 256 || force == 384) return force == 384 && need384 > K3_SMEM_BUDGET ? 256 : force;
     return need384 <= K3_SMEM_BUDGET ? 384 : 256;
 }
 // nodes the shared-memory forest buffer holds (0 for linear models)
