@@ -264,6 +264,8 @@ def main():  # noqa: C901, PLR0912, PLR0915
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own logger (version banner, NCCL_DEBUG output) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist  # noqa: PLC0415
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
