@@ -1,21 +1,23 @@
 // kernels.cu -- the hot path of filter_variants_pipeline as sm_100a CUDA kernels.
 //
-//   K0  line index     : newline scan of the VCF text -> line_start[], n_records
-//   K1  field parse    : one thread per record walks the 8 fixed columns, the INFO
-//                        key=value list and the FORMAT/sample pair, decodes the tags
-//                        the plan needs with htslib's typing rules (int32 / float32 /
-//                        dictionary-encoded strings) into a shared-memory slot tile that
-//                        is written out as coalesced columnar rows raw[slot][record]
-//                        (replaces vcftools.py:63-89 + :196-214 of the reference)
+//   K0  line index      : one pass over the VCF text (decoupled look-back) -> line_start[], n_records
+//   K1  field parse     : one thread per record walks the 8 fixed columns, the INFO key=value
+//                         list and the FORMAT/sample pair and decodes the tags the plan needs
+//                         with htslib's typing rules (int32 / float32 / dictionary-encoded
+//                         strings) straight into the columnar batch raw[slot][record]; keys are
+//                         visited in the learned order so the lanes of a warp decode the same
+//                         type together, keys off that order take a generic hash-lookup path
+//                         (replaces vcftools.py:63-89 + :196-214 of the reference)
 //   K2  feature assembly: raw slots -> fp32 feature matrix feats[feature][record] with the
-//                        fitted transformer's missing/absent policies (transformers.py:221-344)
-//   K3  inference      : feature tile staged in shared memory, tree-ensemble / logistic
-//                        evaluation in the reference library's own arithmetic order,
-//                        fp64 phred/qual math and the FILTER decision fused in
-//                        (variant_filtering_utils.py:123-124, filter_variants_pipeline.py:170-195)
+//                         fitted transformer's missing/absent policies (transformers.py:221-344)
+//   K3  inference       : feature tile + forest staged in shared memory, tree-ensemble /
+//                         logistic evaluation in the training library's own arithmetic order,
+//                         fp64 phred/qual math and the FILTER decision fused in
+//                         (variant_filtering_utils.py:123-124, filter_variants_pipeline.py:170-195)
 //
-// No tensor cores: there is no dense contraction on this path; the kernels are
-// byte/integer work bounded by HBM and by instruction issue.
+// No tensor cores: there is no dense contraction on this path.  K0/K2 are HBM-side kernels,
+// K1 is bound by instruction fetch and per-warp latency, K3 by shared-memory wavefronts
+// (DESIGN.md sections 3 and 6 carry the measurements).
 #include "kernels.cuh"
 
 #include <math.h>
@@ -23,7 +25,6 @@
 
 #include "numparse.h"
 
-#define WARP 32
 #define K1_TPB 128
 #ifndef K1_MIN_CTAS
 #define K1_MIN_CTAS 8  // resident CTAs per SM the register allocation targets (profiled: see DESIGN.md)
@@ -33,7 +34,6 @@
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned nl_count4(unsigned w) { return __popc(__vcmpeq4(w, 0x0A0A0A0Au)) >> 3; }
 __device__ __forceinline__ unsigned nl_bits4(unsigned w) {
     unsigned m = __vcmpeq4(w, 0x0A0A0A0Au);
     return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
