@@ -21,7 +21,7 @@ def ds():
 def test_plan_layout(ds, kind, model_kind):
     model = util.fit_model(kind, ds["x"], ds["labels"])
     plan = MC.compile_plan(VcfHeader(ds["header_text"]), ds["tr"], model, ds["customs"])
-    hdr = struct.unpack_from("<16I4d", plan.blob, 0)
+    hdr = struct.unpack_from("<15I2H4d", plan.blob, 0)
     assert hdr[0] == MC.PLAN_MAGIC and hdr[1] == MC.PLAN_VERSION
     assert hdr[4] == plan.n_features == ds["x"].shape[1] == 46
     assert hdr[7] == model_kind and hdr[8] == 2

@@ -136,7 +136,7 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     if (h.magic != UGVC_PLAN_MAGIC) return fail(ctx, UGVC_E_PLAN, "bad plan magic");
     if (h.version != UGVC_PLAN_VERSION) return fail(ctx, UGVC_E_PLAN, "plan version mismatch");
     if (h.n_tags > UGVC_MAX_TAGS || h.n_slots > UGVC_MAX_SLOTS || h.n_features > UGVC_MAX_FEATURES ||
-        h.n_checks > 64 || h.n_dicts > 64 || h.n_dict_strings > 96 || h.n_classes < 2 || h.n_classes > UGVC_MAX_CLASSES || h.n_outputs < 1 || h.n_outputs > UGVC_MAX_CLASSES)
+        h.n_checks > 64 || h.n_combines > 16 || h.n_dicts > 64 || h.n_dict_strings > 96 || h.n_classes < 2 || h.n_classes > UGVC_MAX_CLASSES || h.n_outputs < 1 || h.n_outputs > UGVC_MAX_CLASSES)
         return fail(ctx, UGVC_E_PLAN, "plan dimensions out of range");
     size_t off = align8(sizeof(PlanHeader));
     const size_t o_tags = off;
@@ -151,6 +151,8 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     off = align8(off + (size_t)h.n_features * sizeof(PlanFeature));
     const size_t o_checks = off;
     off = align8(off + (size_t)h.n_checks * sizeof(PlanCheck));
+    const size_t o_combines = off;
+    off = align8(off + (size_t)h.n_combines * sizeof(PlanCombine));
     size_t o_coef = 0, o_icpt = 0, o_root = 0, o_tout = 0, o_nodes = 0, o_leaves = 0;
     if (h.model_kind == MODEL_LOGISTIC) {
         o_coef = off;
@@ -182,9 +184,9 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     for (uint32_t t = 0; t < h.n_tags; ++t) {
         if (tags[t].len == 0 || tags[t].len > UGVC_NAME_MAX) return fail(ctx, UGVC_E_PLAN, "bad tag name length");
         if ((uint32_t)tags[t].first_slot + tags[t].n_slots > h.n_slots) return fail(ctx, UGVC_E_PLAN, "tag slots out of range");
-        unsigned long long kw[3];
-        memcpy(kw, tags[t].name, 24);
-        unsigned idx = ugvc_key_hash(kw[0], kw[1], kw[2], tags[t].len);
+        unsigned long long kw[4];
+        memcpy(kw, tags[t].name, 32);
+        unsigned idx = ugvc_key_hash(kw[0], kw[1], kw[2], kw[3], tags[t].len);
         while (htab[idx] != 0xFF) idx = (idx + 1) & 255u;
         htab[idx] = (uint8_t)t;
     }
@@ -204,6 +206,10 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
         const PlanCheck* checks = reinterpret_cast<const PlanCheck*>(hb + o_checks);
         for (uint32_t c = 0; c < h.n_checks; ++c)
             if (checks[c].slot >= h.n_slots) return fail(ctx, UGVC_E_PLAN, "check slot out of range");
+        const PlanCombine* comb = reinterpret_cast<const PlanCombine*>(hb + o_combines);
+        for (uint32_t c = 0; c < h.n_combines; ++c)
+            if (comb[c].slot_b >= h.n_slots || comb[c].feature >= h.n_features)
+                return fail(ctx, UGVC_E_PLAN, "combine entry out of range");
     }
     if (h.model_kind != MODEL_LOGISTIC && h.model_kind != MODEL_NONE) {
         const uint32_t* root = reinterpret_cast<const uint32_t*>(hb + o_root);
@@ -281,6 +287,7 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     p.strings = reinterpret_cast<const PlanString*>(d + o_strings);
     p.feats = reinterpret_cast<const PlanFeature*>(d + o_feats);
     p.checks = reinterpret_cast<const PlanCheck*>(d + o_checks);
+    p.combines = reinterpret_cast<const PlanCombine*>(d + o_combines);
     p.coef = reinterpret_cast<const double*>(d + o_coef);
     p.intercept = reinterpret_cast<const double*>(d + o_icpt);
     p.tree_root = reinterpret_cast<const uint32_t*>(d + o_root);

@@ -200,7 +200,7 @@ void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* scratch, int64_t
 #define K1_MAX_DICTS 64
 // fixed layout of the shared-memory plan tables, then the slot tile
 #define K1_OFF_TAGS 0
-#define K1_OFF_STRINGS (K1_OFF_TAGS + UGVC_MAX_TAGS * 32)
+#define K1_OFF_STRINGS (K1_OFF_TAGS + UGVC_MAX_TAGS * 40)
 #define K1_OFF_SLOTS (K1_OFF_STRINGS + K1_MAX_STRINGS * 32)
 #define K1_OFF_DICTS (K1_OFF_SLOTS + 256 * 4)
 #define K1_OFF_HTAB (K1_OFF_DICTS + K1_MAX_DICTS * 4)
@@ -251,8 +251,8 @@ struct Cur {
 };
 
 struct Key {
-    unsigned long long k0, k1, k2;
-    int len;
+    unsigned long long k0, k1, k2, k3;  // the first 32 bytes, little-endian, zero padded
+    int len;                             // the true length (may exceed 32: then nothing matches)
 };
 struct KeyCur {
     Cur c;
@@ -294,7 +294,7 @@ __device__ __noinline__ Cur skip_until(Cur c, unsigned a4, unsigned b4) {
 __device__ __forceinline__ void key_append(Key& key, unsigned long long bytes, int k) {
     const int pos = key.len;
     key.len = pos + k;
-    if (k == 0 || pos >= 24) return;
+    if (k == 0 || pos >= 32) return;
     const int sh = (pos & 7) * 8;
     const unsigned long long lo = bytes << sh;
     const unsigned long long hi = sh ? (bytes >> (64 - sh)) : 0ull;
@@ -305,15 +305,18 @@ __device__ __forceinline__ void key_append(Key& key, unsigned long long bytes, i
     } else if (word == 1) {
         key.k1 |= lo;
         key.k2 |= hi;
-    } else {
+    } else if (word == 2) {
         key.k2 |= lo;
+        key.k3 |= hi;
+    } else {
+        key.k3 |= lo;
     }
 }
 
 // gather the bytes up to (not including) the first tab / newline / pattern byte
 __device__ __noinline__ KeyCur take_until(Cur c, unsigned a4, unsigned b4) {
     KeyCur r;
-    r.k.k0 = r.k.k1 = r.k.k2 = 0ull;
+    r.k.k0 = r.k.k1 = r.k.k2 = r.k.k3 = 0ull;
     r.k.len = 0;
     for (;;) {
         const unsigned long long x = c.peek8();
@@ -386,12 +389,13 @@ __device__ __forceinline__ unsigned motif_code(unsigned c) { return c == 'N' ? 5
 
 __device__ __noinline__ int find_tag(Key key) {
     if (key.len <= 0 || key.len > UGVC_NAME_MAX) return -1;
-    unsigned idx = ugvc_key_hash(key.k0, key.k1, key.k2, key.len);
+    unsigned idx = ugvc_key_hash(key.k0, key.k1, key.k2, key.k3, key.len);
     for (int probe = 0; probe < 256; ++probe) {
         const unsigned t = s_htab()[idx];
         if (t == 0xFFu) return -1;
         const unsigned long long* tw = reinterpret_cast<const unsigned long long*>(&s_tags()[t]);
-        if (tw[0] == key.k0 && tw[1] == key.k1 && tw[2] == key.k2 && (int)(tw[3] & 0xFFu) == key.len) return (int)t;
+        if (tw[0] == key.k0 && tw[1] == key.k1 && tw[2] == key.k2 && tw[3] == key.k3 && (int)(tw[4] & 0xFFu) == key.len)
+            return (int)t;
         idx = (idx + 1) & 255u;
     }
     return -1;
@@ -432,6 +436,39 @@ __device__ __forceinline__ uint32_t reduce_string(const PlanSlot sl, const Key& 
         default:
             return RAW_ERR;
     }
+}
+
+// tuple of region names -> code of the (sorted) subset; transformers.py:108-123.  Rarely used
+// (CNV flavour): kept out of line so the hot decoders stay small.
+__device__ __noinline__ Cur parse_region(RawOut o, int slot, unsigned type, bool scalar, Cur c, unsigned vend) {
+    const unsigned v4 = B4(vend), c4 = B4(',');
+    if (type != KIND_STR) {
+        store_slot(o, slot, RAW_ERR);
+        return c;
+    }
+    const PlanDict d = s_dicts()[s_slots()[slot].dict];
+    unsigned mask = 0;
+    bool bad = d.n_strings != 3;
+    for (;;) {
+        const KeyCur r = take_until(c, scalar ? v4 : c4, v4);
+        c = r.c;
+        int hit = -1;
+        for (int i = 0; i < 3 && !bad; ++i) {
+            const unsigned long long* sw = reinterpret_cast<const unsigned long long*>(&s_strings()[d.first_string + i]);
+            if (sw[0] == r.k.k0 && sw[1] == r.k.k1 && sw[2] == r.k.k2 && (int)(sw[3] & 0xFFu) == r.k.len) hit = i;
+        }
+        bad |= hit < 0 || (mask & (1u << hit));  // unknown or repeated name: KeyError in the reference
+        if (hit >= 0) mask |= 1u << hit;
+        if (c.peek() == ',' && !scalar) {
+            c.adv();
+            continue;
+        }
+        break;
+    }
+    // subsets of the sorted names enumerated by size, then lexicographically, from 1
+    const float code = (float)((0x87645321u >> (4 * (mask & 7u))) & 0xFu);
+    store_slot(o, slot, bad ? RAW_ERR : __float_as_uint(code));
+    return c;
 }
 
 // Decode one tag value starting at the cursor.  vend ends a value in this column (';' in INFO,
@@ -493,6 +530,7 @@ __device__ __noinline__ Cur parse_value(RawOut o, int t, unsigned kind, Cur c, u
         store_slot_f(o, tg.whole_slot, (float)num);
         return c;
     }
+    if (whole == RED_REGION) return parse_region(o, tg.whole_slot, type, scalar, c, vend);
     if (whole == RED_GT_HOM) {
         const KeyCur r = take_until(c, v4, v4);
         const bool hom = r.k.len == 3 && (r.k.k0 == CH3('1', '/', '1') || r.k.k0 == CH3('1', '|', '1'));
@@ -706,7 +744,7 @@ __global__ void __launch_bounds__(K1_TPB, K1_MIN_CTAS) k1_parse(const __grid_con
         uint32_t* dst;
         src = reinterpret_cast<const uint32_t*>(plan.tags);
         dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_TAGS);
-        for (int i = threadIdx.x; i < n_tags * 8; i += K1_TPB) dst[i] = src[i];
+        for (int i = threadIdx.x; i < n_tags * 10; i += K1_TPB) dst[i] = src[i];
         src = reinterpret_cast<const uint32_t*>(plan.strings);
         dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_STRINGS);
         for (int i = threadIdx.x; i < (int)plan.h.n_dict_strings * 8; i += K1_TPB) dst[i] = src[i];
@@ -1025,10 +1063,10 @@ __device__ __forceinline__ float k2_apply(uint32_t bits, const PlanFeature& pf, 
     float v = __uint_as_float(bits);
     if (bits == RAW_ABSENT) {
         if (pf.absent_pol == POL_VALUE) v = pf.absent_val;
-        else atomicMin(err, ugvc_pack_error(rec, f, REASON_BAD_VALUE));
+        else if (pf.absent_pol == POL_ERROR) atomicMin(err, ugvc_pack_error(rec, f, REASON_BAD_VALUE));
     } else if (bits == RAW_MISSING) {
         if (pf.missing_pol == POL_VALUE) v = pf.missing_val;
-        else atomicMin(err, ugvc_pack_error(rec, f, REASON_NULL_FEATURE));
+        else if (pf.missing_pol == POL_ERROR) atomicMin(err, ugvc_pack_error(rec, f, REASON_NULL_FEATURE));
     } else if (bits == RAW_ERR) {
         atomicMin(err, ugvc_pack_error(rec, f, REASON_BAD_VALUE));
     }
@@ -1060,6 +1098,25 @@ __global__ void __launch_bounds__(K2_TPB) k2_features(const __grid_constant__ De
             v.z = live > 2 ? k2_apply(b.z, pf, rec + 2, f, err) : 0.f;
             v.w = live > 3 ? k2_apply(b.w, pf, rec + 3, f, err) : 0.f;
             *reinterpret_cast<float4*>(feats + (size_t)f * row_stride + rec) = v;
+        }
+        for (unsigned c = 0; c < plan.h.n_combines; ++c) {
+            // feature = max(feature, slot_b), nulls skipped (DataFrame.max(axis=1), transformers.py:200-201)
+            const PlanCombine cb = plan.combines[c];
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(raw + (size_t)cb.slot_b * row_stride + rec));
+            float4* dst = reinterpret_cast<float4*>(feats + (size_t)cb.feature * row_stride + rec);
+            float4 a = *dst;
+            const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
+            float* av = &a.x;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool b_null = bb[i] == RAW_ABSENT || bb[i] == RAW_MISSING;
+                if (bb[i] == RAW_ERR && i < live) atomicMin(err, ugvc_pack_error(rec + i, cb.feature, REASON_BAD_VALUE));
+                const float bv = __uint_as_float(bb[i]);
+                const float r = isnan(av[i]) ? (b_null ? av[i] : bv) : (b_null ? av[i] : fmaxf(av[i], bv));
+                if (isnan(r) && i < live) atomicMin(err, ugvc_pack_error(rec + i, cb.feature, REASON_NULL_FEATURE));
+                av[i] = r;
+            }
+            *dst = a;
         }
         for (unsigned c = 0; c < plan.h.n_checks; ++c) {
             const PlanCheck ck = plan.checks[c];

@@ -15,6 +15,7 @@ struct DevPlan {
     const PlanString* strings;
     const PlanFeature* feats;
     const PlanCheck* checks;
+    const PlanCombine* combines;
     const double* coef;
     const double* intercept;
     const uint32_t* tree_root;

@@ -8,13 +8,13 @@
 #include <stdint.h>
 
 #define UGVC_PLAN_MAGIC 0x50564755u /* "UGVP" */
-#define UGVC_PLAN_VERSION 6u
+#define UGVC_PLAN_VERSION 8u
 
 #define UGVC_MAX_TAGS 128
 #define UGVC_MAX_SLOTS 250
 #define UGVC_MAX_FEATURES 250
 #define UGVC_MAX_CLASSES 4
-#define UGVC_NAME_MAX 24
+#define UGVC_NAME_MAX 32
 
 // ---- value kinds of a tag in one header section (INFO or FORMAT) -----------
 enum : uint8_t {
@@ -38,6 +38,8 @@ enum : uint8_t {
     RED_STRNUM = 6,   // scalar string parsed as a number (pd.to_numeric)    (transformers.py:326-333)
     RED_GT_HOM = 7,   // FORMAT/GT == (1,1) -> 1 else 0                      (transformers.py:94-98)
     RED_LEN = 8,      // number of elements of the value
+    RED_REGION = 9,   // whole value: subset of the three region names in dictionary `dict` -> 1..8
+                      // (transformers.py:108-123), unknown / repeated name -> ERR
     // fixed columns (tag == TAG_FIXED)
     RED_FIX_QUAL = 16,     // QUAL as float32, "." -> MISSING
     RED_FIX_ALLELE0 = 17,  // allele_encode(REF)
@@ -57,6 +59,7 @@ enum : uint8_t {
 enum : uint8_t {
     POL_VALUE = 0,  // substitute the given constant
     POL_ERROR = 1,  // the reference raises / produces a null -> UGVC_E_DATA
+    POL_NULL = 2,   // keep a null (NaN) for a PlanCombine to resolve
 };
 
 // reasons reported by ugvc_last_data_error
@@ -89,12 +92,12 @@ struct alignas(8) PlanHeader {
     uint32_t n_tags, n_slots, n_features, n_dicts, n_dict_strings;
     uint32_t model_kind, n_classes, n_outputs; // n_outputs: margins/prob columns the model produces (1 for binary GB/LR/XGB)
     uint32_t n_trees, n_nodes, n_leaf_rows, leaf_width, cmp_mode;
-    uint32_t n_checks;
+    uint16_t n_checks, n_combines;
     double init[UGVC_MAX_CLASSES]; // GB init raw / XGB base margin / LR intercepts are in their own section
 };
 
-struct alignas(8) PlanTag {   // 32 bytes
-    char name[24];            // zero padded; compared as three 64-bit words
+struct alignas(8) PlanTag {   // 40 bytes
+    char name[32];            // zero padded; compared as four 64-bit words
     uint8_t len;
     uint8_t info_kind;        // KIND_* | KIND_SCALAR, as declared by ##INFO
     uint8_t fmt_kind;         // as declared by ##FORMAT
@@ -138,23 +141,32 @@ struct alignas(4) PlanCheck {  // 8 bytes: the reference raises unless the slot 
     float bound;
 };
 
+struct alignas(4) PlanCombine {  // 8 bytes: feature = max(feature, slot_b) skipping nulls (DataFrame.max(axis=1))
+    uint16_t feature;
+    uint16_t slot_b;
+    uint8_t op;               // 0: max, nulls skipped; still null -> the reference's _validate_data asserts
+    uint8_t pad[3];
+};
+
 struct alignas(8) PlanNode {  // 8 bytes, preorder layout: left child = this + 1
     float value;              // internal: threshold (fp32); leaf: bit pattern of the int32 leaf row
     int16_t feature;          // < 0 for a leaf
     uint16_t right;           // index of the right child relative to the tree root
 };
-static_assert(sizeof(PlanHeader) == 96 && sizeof(PlanTag) == 32 && sizeof(PlanSlot) == 4 && sizeof(PlanDict) == 4 &&
+static_assert(sizeof(PlanHeader) == 96 && sizeof(PlanTag) == 40 && sizeof(PlanSlot) == 4 && sizeof(PlanDict) == 4 &&
                   sizeof(PlanString) == 32 && sizeof(PlanFeature) == 12 && sizeof(PlanCheck) == 8 &&
-                  sizeof(PlanNode) == 8,
+                  sizeof(PlanCombine) == 8 && sizeof(PlanNode) == 8,
               "plan record layout");
 
-// Hash of a tag name held as three little-endian 64-bit words (+ length); the host builds the
+// Hash of a tag name held as four little-endian 64-bit words (+ length); the host builds the
 // 256-entry open-addressing table with the same function the device probes it with.
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-static inline unsigned ugvc_key_hash(unsigned long long k0, unsigned long long k1, unsigned long long k2, int len) {
-    unsigned long long h = k0 ^ (k1 * 0x9E3779B97F4A7C15ull) ^ (k2 * 0xC2B2AE3D27D4EB4Full) ^ (unsigned long long)len;
+static inline unsigned ugvc_key_hash(unsigned long long k0, unsigned long long k1, unsigned long long k2,
+                                     unsigned long long k3, int len) {
+    unsigned long long h = k0 ^ (k1 * 0x9E3779B97F4A7C15ull) ^ (k2 * 0xC2B2AE3D27D4EB4Full) ^
+                           (k3 * 0x165667B19E3779F9ull) ^ (unsigned long long)len;
     h *= 0xFF51AFD7ED558CCDull;
     h ^= h >> 33;
     return (unsigned)(h & 255u);
@@ -162,7 +174,7 @@ static inline unsigned ugvc_key_hash(unsigned long long k0, unsigned long long k
 
 // Section order after PlanHeader (each padded to 8 bytes):
 //   PlanTag[n_tags], PlanSlot[n_slots], PlanDict[n_dicts], PlanString[n_dict_strings],
-//   PlanFeature[n_features], PlanCheck[n_checks],
+//   PlanFeature[n_features], PlanCheck[n_checks], PlanCombine[n_combines],
 //   MODEL_LOGISTIC : double coef[n_outputs * n_features], double intercept[n_outputs]
 //   forests        : uint32 tree_root[n_trees + 1], uint8 tree_out[n_trees] (output column of each tree),
 //                    PlanNode[n_nodes], double leaves[n_leaf_rows * leaf_width]

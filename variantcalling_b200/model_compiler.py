@@ -35,15 +35,16 @@ import numpy as np
 from variantcalling_b200.vcf_header import VcfHeader
 
 PLAN_MAGIC = 0x50564755
-PLAN_VERSION = 6
-MAX_TAGS, MAX_SLOTS, MAX_FEATURES, MAX_CLASSES, NAME_MAX = 128, 250, 250, 4, 24
+PLAN_VERSION = 8
+MAX_TAGS, MAX_SLOTS, MAX_FEATURES, MAX_CLASSES, NAME_MAX = 128, 250, 250, 4, 32
 MAX_DICTS, MAX_STRINGS = 64, 96
 
 KIND_INT, KIND_FLOAT, KIND_STR, KIND_FLAG, KIND_SCALAR = 1, 2, 3, 4, 8
-(RED_NUM, RED_BASE, RED_INSDEL, RED_DICT, RED_MOTIF_L, RED_MOTIF_R, RED_STRNUM, RED_GT_HOM, RED_LEN) = range(9)
+(RED_NUM, RED_BASE, RED_INSDEL, RED_DICT, RED_MOTIF_L, RED_MOTIF_R, RED_STRNUM, RED_GT_HOM, RED_LEN,
+ RED_REGION) = range(10)
 RED_FIX_QUAL, RED_FIX_ALLELE0, RED_FIX_ALLELE1, RED_FIX_INDEL, RED_FIX_NALLELES = 16, 17, 18, 19, 20
 TAG_FIXED, ELEM_WHOLE = 0xFF, 0xFF
-POL_VALUE, POL_ERROR = 0, 1
+POL_VALUE, POL_ERROR, POL_NULL = 0, 1, 2
 MODEL_LOGISTIC, MODEL_GB_SKLEARN, MODEL_RF_SKLEARN, MODEL_XGB = 1, 2, 3, 4
 CMP_LE, CMP_LT = 0, 1
 
@@ -127,6 +128,7 @@ class _Builder:
         self.features: list[_Feature] = []
         self.feature_names: list[str] = []
         self.checks: list[tuple[_SlotReq, int, float]] = []
+        self.combines: list[tuple[int, _SlotReq]] = []  # (feature index, second slot): max, nulls skipped
         self.dicts: list[list[str]] = []
 
     # ---- tag typing
@@ -287,6 +289,47 @@ class _Builder:
                 self.add(name, _SlotReq(tag, ELEM_WHOLE, RED_STRNUM), (V, 0.0), (E, 0.0))
             else:
                 self.add(name, _SlotReq(tag, 0, RED_NUM), (V, 0.0), (V, 0.0))
+            return
+        # ---- CNV flavour (transformers.py:291-313)
+        if steps == ["fn:svtype_encode_df"]:
+            tag = self.tag_of(single_col())
+            self.require(tag, scalar=True, types=(KIND_STR,))
+            did = self.add_dict(["NEUTRAL", "DEL", "DUP"])  # index == svtype_encode code (transformers.py:80-83)
+            self.add(name, _SlotReq(tag, 0, RED_DICT, did), (E, 0.0), (E, 0.0))
+            return
+        if steps == ["fn:copy_number_encode_df"]:
+            if len(col_list) != 2:  # noqa: PLR2004
+                raise PlanError(f"entry {name!r}: copy_number_encode_df takes two columns")
+            tags = [self.tag_of(c) for c in col_list]
+            for tag in tags:
+                self.require(tag, scalar=True, types=NUM)
+            n = POL_NULL
+            self.add(name, _SlotReq(tags[0], 0, RED_NUM), (n, 0.0), (n, 0.0))
+            self.combines.append((len(self.features) - 1, _SlotReq(tags[1], 0, RED_NUM)))
+            return
+        if steps == ["fn:cnv_source_encode_df"]:
+            tag = self.tag_of(single_col())
+            self.require(tag, scalar=False, types=(KIND_STR,))
+            # index == cnv_source_encode code; index 0 is a string no VCF value can equal
+            did = self.add_dict(["\x01", "cn.mops", "cnvpytor"])
+            self.add(name, _SlotReq(tag, 0, RED_DICT, did), (E, 0.0), (E, 0.0))
+            self.checks.append((_SlotReq(tag, ELEM_WHOLE, RED_LEN), 0, 1.0))  # len(x) != 1 -> ValueError
+            self.checks.append((_SlotReq(tag, ELEM_WHOLE, RED_LEN), 1, 1.0))
+            return
+        if steps == ["fn:region_annotation_encode_df"]:
+            from variantcalling_b200 import transformers as T
+
+            tag = self.tag_of(single_col())
+            self.require(tag, scalar=False, types=(KIND_STR,))
+            names = sorted(T._REGIONS)  # noqa: SLF001
+            lut = [1, 2, 3, 5, 4, 6, 7, 8]  # K1's table: subset bit mask (sorted names) -> code
+            enc = T._get_region_encoding()  # noqa: SLF001
+            for mask in range(8):
+                subset = tuple(nm for i, nm in enumerate(names) if mask >> i & 1)
+                if enc[subset] != lut[mask]:
+                    raise PlanError("region encoding differs from the table compiled into K1")
+            did = self.add_dict(names)
+            self.add(name, _SlotReq(tag, ELEM_WHOLE, RED_REGION, did), (V, 0.0), (E, 0.0))
             return
         raise PlanError(f"entry {name!r}: transformer {steps} is not lowered by this build")
 
@@ -506,7 +549,7 @@ def compile_plan(header: VcfHeader | str | bytes, transformer, model, custom_inf
     m = _lower_model(model, n_feat)
 
     # ---- slot layout: per-tag contiguous, fixed-column slots last
-    reqs: list[_SlotReq] = [f.slot for f in b.features] + [c[0] for c in b.checks]
+    reqs: list[_SlotReq] = [f.slot for f in b.features] + [c[0] for c in b.checks] + [c[1] for c in b.combines]
     tag_names = []
     for r in reqs:
         if r.tag is not None and r.tag not in tag_names:
@@ -546,7 +589,7 @@ def compile_plan(header: VcfHeader | str | bytes, transformer, model, custom_inf
         ik, fk = b.kinds(tag)
         name_b = tag.encode()
         whole_red, whole_slot = (whole_req.reducer, len(slots) - 1) if whole_req is not None else (0xFF, 0)
-        tags_packed.append(struct.pack("<24sBBBBBBBx", name_b, len(name_b), ik, fk, first, len(slots) - first,
+        tags_packed.append(struct.pack("<32sBBBBBBBx", name_b, len(name_b), ik, fk, first, len(slots) - first,
                                        whole_red, whole_slot))
     for r in reqs:
         key = (r.tag, r.elem, r.reducer, r.dict_id)
@@ -570,12 +613,14 @@ def compile_plan(header: VcfHeader | str | bytes, transformer, model, custom_inf
     feats_packed = b"".join(
         struct.pack("<HBBff", sid(f.slot), f.absent[0], f.missing[0], f.absent[1], f.missing[1]) for f in b.features)
     checks_packed = b"".join(struct.pack("<HBxf", sid(c[0]), c[1], c[2]) for c in b.checks)
+    combines_packed = b"".join(struct.pack("<HHB3x", c[0], sid(c[1]), 0) for c in b.combines)
     hdr = struct.pack(
-        "<16I4d", PLAN_MAGIC, PLAN_VERSION, len(tags_packed), len(slots), n_feat, len(b.dicts), len(strings),
+        "<15I2H4d", PLAN_MAGIC, PLAN_VERSION, len(tags_packed), len(slots), n_feat, len(b.dicts), len(strings),
         m["kind"], m["n_classes"], m["n_outputs"], m["n_trees"], m["n_nodes"], m["n_leaf_rows"], m["leaf_width"],
-        m["cmp"], len(b.checks), *m["init"])
+        m["cmp"], len(b.checks), len(b.combines), *m["init"])
     blob = (_pad8(hdr) + _pad8(b"".join(tags_packed)) + _pad8(b"".join(struct.pack("<4B", *s) for s in slots))
-            + _pad8(dicts_packed) + _pad8(strings_packed) + _pad8(feats_packed) + _pad8(checks_packed) + m["section"])
+            + _pad8(dicts_packed) + _pad8(strings_packed) + _pad8(feats_packed) + _pad8(checks_packed)
+            + _pad8(combines_packed) + m["section"])
     return Plan(blob=blob, n_features=n_feat, n_classes=m["n_classes"], n_slots=len(slots), tags=tag_names,
                 feature_names=b.feature_names, model_kind=m["kind"], classes=m.get("classes", []))
 
@@ -585,6 +630,6 @@ def compile_plan_no_model(header: VcfHeader | str | bytes) -> Plan:
     offsets, CG flag) so the writer can apply the blacklist / PASS-fill rules."""
     if not isinstance(header, VcfHeader):
         header = VcfHeader(header)
-    hdr = struct.pack("<16I4d", PLAN_MAGIC, PLAN_VERSION, 0, 0, 0, 0, 0, 0, 2, 1, 0, 0, 0, 0, CMP_LE, 0,
+    hdr = struct.pack("<15I2H4d", PLAN_MAGIC, PLAN_VERSION, 0, 0, 0, 0, 0, 0, 2, 1, 0, 0, 0, 0, CMP_LE, 0, 0,
                       0.0, 0.0, 0.0, 0.0)
     return Plan(blob=_pad8(hdr), n_features=0, n_classes=2, n_slots=0, tags=[], feature_names=[], model_kind=0)
