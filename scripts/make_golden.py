@@ -90,6 +90,20 @@ def main():
                         features_ref=feats, categories=json.dumps(cats))
     print("golden features", feats.shape, "categories", cats)
 
+    # ---- CNV flavour: the reference's own CNV transformer on a synthetic CNV frame
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_cnv import CUSTOM, make_cnv_vcf  # noqa: PLC0415  (fixture generator shared with the GPU test)
+
+    chdr, clines = make_cnv_vcf()
+    ctext = ("\n".join(chdr) + "\n" + "\n".join(clines) + "\n").encode()
+    cdf = R.harness_float_columns(R.get_vcf_df(OracleVariantFile(ctext), None, CUSTOM))
+    ctr = ref_t.get_transformer(RefVcfType.CNV, ["region_annotations"])
+    with pd.option_context("future.infer_string", False):
+        cx = ctr.fit_transform(cdf).to_numpy(dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "transformer_cnv.npz"), vcf_text=np.frombuffer(ctext, dtype=np.uint8),
+                        customs=np.array(CUSTOM), features_ref=cx)
+    print("golden CNV features", cx.shape)
+
     kats = {
         "tuple_break": [[[1, 2, 3], ref_t.tuple_break((1, 2, 3))], [None, ref_t.tuple_break(None)]],
         "motif_encode_left": {m: ref_t.motif_encode_left(m) for m in ["ATGC", "ACGTA", "NNACG", "acgtN", ""]},

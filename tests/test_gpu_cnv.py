@@ -65,6 +65,10 @@ def cnv():
     tr = T.get_transformer(VcfType.CNV, ["region_annotations"])
     with pd.option_context("future.infer_string", False):
         x = tr.fit_transform(df).to_numpy(dtype=np.float64)
+    import os
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "transformer_cnv.npz"))
+    assert np.array_equal(x, gold["features_ref"]), "mirror differs from the reference CNV transformer golden"
     from sklearn.ensemble import RandomForestClassifier
 
     y = (x[:, 1] + x[:, 16] > 5).astype(int)

@@ -166,3 +166,15 @@ def test_writer_rules():
     assert out[-1].startswith("#CHROM") and sum(l.startswith("##FILTER=<ID=LOW_SCORE") for l in out) == 1
     assert any(l.startswith("##INFO=<ID=TREE_SCORE,Number=1,Type=Float") for l in out)
     assert any(l.startswith("##INFO=<ID=BLACKLST,Number=.,Type=String") for l in out)
+
+
+def test_mirror_cnv_transformer_matches_reference_golden():
+    """CNV flavour (+ region_annotations): mirror == the reference module's fit_transform."""
+    z = np.load(os.path.join(GOLD, "transformer_cnv.npz"))
+    text, customs, feats_ref = bytes(z["vcf_text"]), [str(c) for c in z["customs"]], z["features_ref"]
+    df = R.harness_float_columns(R.get_vcf_df(OracleVariantFile(text), None, customs))
+    tr = T.get_transformer(VcfType.CNV, ["region_annotations"])
+    with pd.option_context("future.infer_string", False):
+        x = tr.fit_transform(df).to_numpy(dtype=np.float64)
+    assert x.shape == feats_ref.shape == (400, 19)
+    assert np.array_equal(x, feats_ref)
