@@ -110,9 +110,9 @@ int ugvc_collect_batch(ugvc_ctx* ctx, int lane, uint8_t* out_low_score, float* o
 /* d_* are device pointers sized for capacity_records (d_recinfo / d_line_start
  * may be NULL -> context scratch).  Runs on `stream` (a cudaStream_t, NULL =
  * the context's lane-0 stream) without any host synchronisation; the record
- * count lands in *d_n_records (device int64).  d_text must be 8-byte aligned, hold
- * whole lines ending with '\n', and have at least 16 readable bytes after n_bytes
- * (K1 reads aligned 8-byte words one word ahead of its cursor). */
+ * count lands in *d_n_records (device int64).  d_text must be 16-byte aligned (K0 streams the
+ * text with 16-byte loads), hold whole lines ending with '\n', and have at least 16 readable
+ * bytes after n_bytes (K1 reads aligned 8-byte words one word ahead of its cursor). */
 int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n_bytes, double threshold,
                        uint8_t* d_low_score, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
                        int64_t* d_line_start, size_t capacity_records, int64_t* d_n_records, void* stream);

@@ -103,3 +103,86 @@ def test_multinomial_logistic_regression(gpu_ctx, ds):
     exp = R.filter_variants(ds["vf"], model, ds["tr"], custom_annotations=ds["customs"])
     np.testing.assert_allclose(res["probs"], exp["probs"], atol=TOL, rtol=0)
     assert np.array_equal(res["low_score"].astype(bool), np.array(["LOW_SCORE" in f.split(";") for f in exp["filters"]]))
+
+
+def test_cfg5_precision_recall_identical_to_oracle(gpu_ctx, ds):
+    """BASELINE.json configs[4]: accuracy of the filtered call set against the synthetic truth.  With
+    the FILTER column identical, the concordance counts (tp / fp / fn after filtering) and hence
+    precision / recall are identical; this pins that end of the contract on the truth labels the
+    generator emits."""
+    model = util.fit_model("gb_small", ds["x"], ds["labels"])
+    plan = MC.compile_plan(VcfHeader(ds["header_text"]), ds["tr"], model, ds["customs"])
+    gpu_ctx.load_plan(plan.blob)
+    gpu_ctx.set_key_order(*lib.learn_key_order(ds["text"]))
+    gpu_ctx.reserve(len(ds["text"]) + 1024, len(ds["lines"]) + 16, 1)
+    res = gpu_ctx.filter_batch(ds["text"], 30.0)
+    exp = R.filter_variants(ds["vf"], model, ds["tr"], custom_annotations=ds["customs"])
+    truth = ds["labels"].astype(bool)
+
+    def stats(kept):
+        tp, fp, fn = int((kept & truth).sum()), int((kept & ~truth).sum()), int((~kept & truth).sum())
+        return tp, fp, fn, round(tp / max(1, tp + fp), 5), round(tp / max(1, tp + fn), 5)
+
+    gpu = stats(~res["low_score"].astype(bool))
+    ora = stats(np.array(["LOW_SCORE" not in f.split(";") for f in exp["filters"]]))
+    assert gpu == ora and gpu[3] > 0.5 and gpu[4] > 0.5
+
+
+def test_full_size_properties_batching_invariance(gpu_ctx):
+    """Size-independent properties at a BASELINE-scale batch (cfg 2: logistic regression, 2 M device
+    generated records): per-record results do not depend on how the text is cut into batches, the
+    pass/fail counters add up, and a second pass reproduces the first bit for bit."""
+    import torch
+
+    n, n_custom = 2_000_000, 0
+    small = util.make_dataset(n_records=3000, n_custom=n_custom, seed=1984)
+    _, tr, x = util.fit_transformer(small)
+    model = util.fit_model("lr", x, small["labels"])
+    plan = MC.compile_plan(VcfHeader(lib.synth_header(n_custom)), tr, model, [])
+    gpu_ctx.load_plan(plan.blob)
+    cap = n + 1024
+    gpu_ctx.reserve(900 << 20, cap, 1)
+    buf = torch.empty(900 << 20, dtype=torch.uint8, device="cuda")
+    nbytes = gpu_ctx.synth_device(7, 1_000_000, n, 50_000_000, n_custom, buf.data_ptr(), buf.numel() - 64)
+    head = bytes(buf[: 1 << 20].cpu().numpy())
+    gpu_ctx.set_key_order(*lib.learn_key_order(head[: head.rfind(b"\n") + 1]))
+    low = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    probs = torch.empty((cap, 2), dtype=torch.float32, device="cuda")
+    qual = torch.empty(cap, dtype=torch.float64, device="cuda")
+    ls = torch.empty(cap + 1, dtype=torch.int64, device="cuda")
+    nrec = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def run(off, nb, rec0):
+        gpu_ctx.filter_device(buf.data_ptr() + off, nb, 30.0, low.data_ptr() + rec0, probs.data_ptr() + rec0 * 8,
+                              qual.data_ptr() + rec0 * 8, cap - rec0, d_n_records=nrec.data_ptr(),
+                              d_line_start=ls.data_ptr())
+        gpu_ctx.device_status()
+        return int(nrec.item())
+
+    gpu_ctx.counts_reset()
+    assert run(0, nbytes, 0) == n
+    c1 = gpu_ctx.counts()
+    starts = ls[: n + 1].clone()
+    ref_low, ref_qual, ref_probs = low[:n].clone(), qual[:n].clone(), probs[:n].clone()
+    assert c1["n_records"] == n and c1["n_low_score"] + c1["n_pass"] == n
+    assert c1["n_low_score"] == int(ref_low.sum().item()) and 0 < c1["n_low_score"] < n
+    # second pass: bit-identical
+    low.zero_(); qual.zero_(); probs.zero_()  # noqa: E702
+    run(0, nbytes, 0)
+    assert torch.equal(low[:n], ref_low) and torch.equal(qual[:n], ref_qual) and torch.equal(probs[:n], ref_probs)
+    # seven uneven batches cut at line starts (16-byte alignment is part of the device-text contract)
+    cuts = [0]
+    host_starts = starts.cpu().numpy()
+    for frac in (0.07, 0.2, 0.21, 0.5, 0.77, 0.9):
+        r = int(n * frac)
+        while host_starts[r] % 16:
+            r += 1
+        cuts.append(r)
+    cuts.append(n)
+    low.zero_(); qual.zero_(); probs.zero_()  # noqa: E702
+    gpu_ctx.counts_reset()
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        off, end = int(starts[a].item()), int(starts[b].item())
+        assert run(off, end - off, a) == b - a
+    assert torch.equal(low[:n], ref_low) and torch.equal(qual[:n], ref_qual) and torch.equal(probs[:n], ref_probs)
+    assert gpu_ctx.counts() == c1

@@ -591,7 +591,7 @@ extern "C" int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n
     if (!ctx->has_plan || ctx->lanes.empty()) return fail(ctx, UGVC_E_STATE, "filter_device: load a plan and reserve first");
     if (n_bytes > ctx->cap_bytes) return fail(ctx, UGVC_E_ARG, "filter_device: batch larger than the reserved max_bytes");
     if (!d_text || !d_low_score || !d_probs || !d_qual) return fail(ctx, UGVC_E_ARG, "filter_device: null device pointer");
-    if (reinterpret_cast<uintptr_t>(d_text) & 7u) return fail(ctx, UGVC_E_ARG, "filter_device: d_text must be 8-byte aligned");
+    if (reinterpret_cast<uintptr_t>(d_text) & 15u) return fail(ctx, UGVC_E_ARG, "filter_device: d_text must be 16-byte aligned");
     CU(cudaSetDevice(ctx->device));
     Lane& l = ctx->lanes[0];
     if (capacity_records == 0 || capacity_records > l.b.cap_records)
