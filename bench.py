@@ -49,6 +49,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly one JSON line.  Libraries (NCCL's version banner, for one) write
+    to file descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and the JSON line
+    is written to the saved descriptor at the end."""
+    global _REAL_STDOUT  # noqa: PLW0603
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 # ------------------------------------------------------------------------------------------
 def build_model(n_train: int = 20000):
     """Train the cfg-3 model on host-generated records of the same schema."""
@@ -198,7 +221,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def _reference_worker(job):
@@ -245,6 +268,7 @@ def main():  # noqa: C901, PLR0912, PLR0915
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.warmup < 3:  # noqa: PLR2004
         args.warmup = 3
     if args.impl == "reference":
@@ -264,8 +288,6 @@ def main():  # noqa: C901, PLR0912, PLR0915
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own logger (version banner, NCCL_DEBUG output) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist  # noqa: PLC0415
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -510,7 +532,7 @@ def main():  # noqa: C901, PLR0912, PLR0915
             "counts_last_steps": {"n_records": counts_total[0], "n_low_score": counts_total[1],
                                   "n_pass": counts_total[2], "n_cg": counts_total[3]},
         }
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
