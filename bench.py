@@ -418,8 +418,8 @@ def main():  # noqa: C901, PLR0912, PLR0915
     kernels_ms_per_step = sum(stage_sum) / args.steps
     # DRAM bytes per record of each kernel from the committed `ncu --set full` capture
     # (profiles/r1_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum of one launch over its
-    # 848 538 records -- the record count follows from k1_fill's 278.32 MB = 82 slots x 4 B x records)
-    ncu_traffic_per_record = {"k1_field_parse": 1245.0, "k2_feature_assembly": 741.0, "k3_inference": 413.0}
+    # 849 481 records -- the record count follows from k1_fill's 278.63 MB = 82 slots x 4 B x records)
+    ncu_traffic_per_record = {"k1_field_parse": 1242.0, "k2_feature_assembly": 743.0, "k3_inference": 411.0}
     traffic = ncu_traffic_per_record.get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None if traffic is None else traffic * rec_per_launch,
