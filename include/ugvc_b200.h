@@ -119,7 +119,9 @@ int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n_bytes, dou
 
 /* --recalibrate_genotype (filter_variants_pipeline.py:203-215): ask K3 to keep the per-class
  * phreds -10*log10(p + 1e-10) of the host-buffer lanes (takes effect at the next ugvc_reserve)
- * and fetch them (N x n_classes fp64) after ugvc_collect_batch. */
+ * and fetch them (N x n_classes fp64) after ugvc_collect_batch.  on = 2 keeps the fp64 class
+ * likelihoods themselves instead (--treat_multiallelics merges the likelihoods of split rows on
+ * the host before the phred step, variant_filtering_utils.py:346-408). */
 int ugvc_enable_phreds(ugvc_ctx* ctx, int on);
 int ugvc_collect_phreds(ugvc_ctx* ctx, int lane, double* out, size_t capacity_records);
 

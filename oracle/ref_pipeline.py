@@ -275,13 +275,18 @@ def filter_variants(vcf: OracleVariantFile, model, transformer, *, custom_annota
                     decision_threshold: float = 30.0, blacklist_cg: bool = False,
                     position_blacklists: list | None = None, overwrite_qual_tag: bool = False,
                     limit_to_contigs: list[str] | None = None, timings: dict | None = None,
-                    recalibrate_genotype: bool = False) -> dict:
-    """The serial contig loop of filter_variants_pipeline.py:116-229 (model branch
-    without ``--treat_multiallelics`` / ``--recalibrate_genotype``).
+                    recalibrate_genotype: bool = False, treat_multiallelics: bool = False,
+                    ref_fasta: dict | None = None) -> dict:
+    """The serial contig loop of filter_variants_pipeline.py:116-229.
+
+    ``treat_multiallelics`` takes the :145-166 branch (``ref_fasta``: contig -> sequence; the
+    features / probs returned are then those of the *split* frame, in its row order).
 
     Returns dict(header=[...], lines=[...], filters=[...], quals=ndarray,
     probs=ndarray, features=ndarray).
     """
+    if treat_multiallelics and ref_fasta is None:
+        raise ValueError("Reference FASTA file is required for multiallelic treatment")
     timings = timings if timings is not None else {}
     out_lines, out_filters, all_quals, all_probs, all_feats = [], [], [], [], []
     with_bl = blacklist_cg or bool(position_blacklists)
@@ -306,6 +311,12 @@ def filter_variants(vcf: OracleVariantFile, model, transformer, *, custom_annota
             blacklist = merge_blacklists([blacklist_cg_insertions(df), blacklist])
         quals = phreds = gq = None
         if model is not None:
+            df_original = None
+            if treat_multiallelics:
+                from oracle import multiallelic_ref as MR
+
+                df_original = df.copy()
+                df = MR.process_multiallelic_spandel(df, ref_fasta[str(contig)], vcf.header)
             t0 = time.perf_counter()
             x = transform_features(df, transformer)
             tick("transform", t0)
@@ -315,7 +326,14 @@ def filter_variants(vcf: OracleVariantFile, model, transformer, *, custom_annota
             scores = model.predict_proba(x_in)
             tick("predict", t0)
             t0 = time.perf_counter()
-            phreds, quals, gq = score_math(scores)
+            if treat_multiallelics:
+                src = [i in df_original.index for i in df.index]
+                dst = [i in df.index for i in df_original.index]
+                df_original["ml_lik"] = pd.Series([list(r) for r in scores[src, :]], index=df_original.loc[dst].index)
+                df_original = MR.combine_multiallelic_spandel(df, df_original, scores)
+                phreds, quals, gq = score_math(list(df_original["ml_lik"]))
+            else:
+                phreds, quals, gq = score_math(scores)
             tick("score", t0)
             all_quals.append(quals)
             all_probs.append(np.asarray(scores, dtype=np.float64))

@@ -80,3 +80,99 @@ def test_index_helpers_known_answers():
         MR.gt_subset((0, 0), (1, 2))
     assert MR.pl_subset((10, 20, 30, 40, 50, 60), (1, 2)) == (0, 20, 30)
     assert MR.pl_subset((10, 20, 30, 40, 50, 60), (0, 2), normed=False) == (10, 40, 60)
+
+
+# ---------------------------------------------------------------- product host code (no GPU needed)
+def cpu_index(text: bytes):
+    """What the index pass (K0 + K1 with the no-model plan) returns, computed in Python."""
+    from variantcalling_b200.lib import RECINFO_DTYPE
+
+    lines = text.split(b"\n")[:-1]
+    ls = np.zeros(len(lines) + 1, dtype=np.int64)
+    ri = np.zeros(len(lines), dtype=RECINFO_DTYPE)
+    at = 0
+    for i, ln in enumerate(lines):
+        c = ln.split(b"\t")
+        ls[i] = at
+        at += len(ln) + 1
+        n_all = 1 + (0 if c[4] == b"." else c[4].count(b",") + 1)
+        ri["pos"][i] = int(c[1])
+        ri["flags"][i] = (n_all << 1) | (len(c[3]) << 8)
+    ls[-1] = at
+    return ls, ri
+
+
+def contig_text(ds, contig):
+    return ("\n".join(ln for ln in ds["lines"] if ln.split("\t", 1)[0] == contig) + "\n").encode()
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_product_split_rows_and_merge_match_the_oracle(seed):
+    """variantcalling_b200.multiallelics rewrites the split rows as VCF lines; read back through the
+    oracle loader + transformer they must give the features of the oracle's split frame, and its
+    merge must give the oracle's merged likelihoods."""
+    from tests import util
+    from variantcalling_b200 import multiallelics as PM
+    from variantcalling_b200.vcf_header import VcfHeader
+
+    ds, tr, _model, _ = util.make_multiallelic_case(seed, "lr")
+    hdr = VcfHeader(ds["header_text"])
+    rng = np.random.default_rng(seed)
+    for contig in ("chrM1", "chrM2"):
+        df = R.get_vcf_df(ds["vf"], contig, ds["customs"])
+        want_split = MR.process_multiallelic_spandel(df, ds["ref"][contig], ds["vf"].header)
+        text = contig_text(ds, contig)
+        ls, ri = cpu_index(text)
+        plan = PM.SplitPlan(hdr, hdr.loader_columns(ds["customs"]), ds["ref"][contig])
+        new_text = plan.build(np.frombuffer(text, dtype=np.uint8), ls, ri).tobytes()
+        # same overlap sets as the reference's row loop
+        sets = MR.overlapping_sets(df)
+        assert sorted(g.origin for g in plan.groups) == sorted(sum(sets, []))
+        got_df = R.get_vcf_df(OracleVariantFile(ds["header_text"].encode() + new_text), contig, ds["customs"])
+        assert got_df.shape[0] == want_split.shape[0]
+        with pd.option_context("future.infer_string", False):
+            want_x = tr.transform(R.harness_float_columns(want_split)).to_numpy(dtype=np.float64)
+            got_x = tr.transform(R.harness_float_columns(got_df)).to_numpy(dtype=np.float64)
+        bad = np.argwhere(want_x.astype(np.float32) != got_x.astype(np.float32))
+        assert bad.size == 0, (bad[:5], list(tr.get_feature_names_out())[bad[0][1]], want_x[tuple(bad[0])], got_x[tuple(bad[0])],
+                               new_text.split(b"\n")[bad[0][0]])
+        scores = rng.dirichlet(np.ones(3), size=want_split.shape[0])
+        original = df.copy()
+        src = [x in original.index for x in want_split.index]
+        dst = [x in want_split.index for x in original.index]
+        original["ml_lik"] = pd.Series([list(x) for x in scores[src, :]], index=original.loc[dst].index)
+        merged = MR.combine_multiallelic_spandel(want_split, original, scores)
+        lik = plan.merge(scores)
+        for i, want in enumerate(merged["ml_lik"]):
+            want = np.asarray(want, dtype=np.float64)
+            assert np.array_equal(lik[i, :want.size], want) and not lik[i, want.size:].any(), (i, lik[i], want)
+        ph, q, low = PM.score_math(lik, 30.0)
+        ph_o, q_o, _gq = R.score_math(list(merged["ml_lik"]))
+        assert np.array_equal(ph, ph_o) and np.array_equal(q, q_o) and np.array_equal(low, (q_o <= 30.0).astype(np.uint8))  # noqa: PLR2004
+
+
+def test_find_overlaps_equals_the_row_loop_on_random_layouts():
+    from variantcalling_b200 import multiallelics as PM
+
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        n = int(rng.integers(1, 40))
+        pos = np.sort(rng.integers(1, 60, size=n)).astype(np.int64)
+        alleles = []
+        for _i in range(n):
+            kind = rng.random()
+            ref = "A" * int(rng.integers(1, 6)) if kind < 0.4 else "A"
+            alts = ["C"]
+            if kind < 0.4 and rng.random() < 0.8:
+                alts = ["A" * int(rng.integers(1, len(ref) + 1))]
+            if rng.random() < 0.3:
+                alts.append("*")
+            if rng.random() < 0.3:
+                alts.append("AT")
+            alleles.append((ref, *alts))
+        df = pd.DataFrame({"alleles": alleles, "pos": pos})
+        want = MR.overlapping_sets(df)
+        del_len = np.array([max(len(a[0]) - len(y) for y in a) for a in alleles])
+        singles, clusters = PM.find_overlaps(pos, np.array([len(a) for a in alleles]), del_len,
+                                             np.array(["*" in a for a in alleles]))
+        assert sorted([[m] for m in singles] + clusters) == want

@@ -54,3 +54,28 @@ def fit_model(kind, x, y, seed=1984):
         raise ValueError(kind)
     m.fit(x, y)
     return m
+
+
+def make_multiallelic_case(seed=11, model_kind="rf", n_custom=3):
+    """Data set with multi-allelic sites + spanning deletions (tests/multiallelic_data.py), a
+    transformer fitted on the *split* frame (as the reference's training does, training_prep.py:220)
+    and a 3-class genotype model (0/0, 0/1, 1/1) trained on the split rows."""
+    from oracle import multiallelic_ref as MR
+    from tests import multiallelic_data as MD
+
+    ds = MD.generate(seed, n_custom=n_custom)
+    ds["vf"] = OracleVariantFile(ds["header_text"].encode() + ds["text"])
+    frames = []
+    for contig in MD.CONTIGS:
+        df = R.get_vcf_df(ds["vf"], contig, ds["customs"])
+        frames.append(MR.process_multiallelic_spandel(df, ds["ref"][contig], ds["vf"].header))
+    split = pd.concat(frames)
+    tr = T.get_transformer(VcfType.SINGLE_SAMPLE, [a.lower() for a in ds["customs"]])
+    with pd.option_context("future.infer_string", False):
+        x = tr.fit_transform(R.harness_float_columns(split)).to_numpy(dtype=np.float64)
+    y = np.array([sum(1 for g in gt if g) for gt in split["gt"]])
+    # the split genotypes alone do not carry much signal: tie the label to a few annotations too
+    rng = np.random.default_rng(seed)
+    y = np.where(rng.random(len(y)) < 0.25, rng.integers(0, 3, size=len(y)), y)
+    model = fit_model(model_kind, x, y)
+    return ds, tr, model, split

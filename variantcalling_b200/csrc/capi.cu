@@ -44,7 +44,7 @@ struct ugvc_ctx {
     long long* d_counts = nullptr;
     int64_t launches = 0;
     bool timing = false;
-    bool want_phreds = false;
+    int want_phreds = 0;  // 0: off, 1: per-class phreds, 2: per-class fp64 likelihoods
     float stage_ms[4] = {0, 0, 0, 0};
     int64_t err_record = -1;
     int32_t err_column = -1, err_reason = 0;
@@ -498,7 +498,7 @@ static int enqueue_kernels(ugvc_ctx* ctx, Lane& l, const uint8_t* d_text, size_t
     if (timing) CU(cudaEventRecord(ev[3], st));
     if (has_model)
         launch_k3(p, l.b.feats, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual,
-                  d_low == l.b.low_score ? l.b.phreds : nullptr, ctx->d_counts, ctx->sm_count, st);
+                  d_low == l.b.low_score ? l.b.phreds : nullptr, ctx->want_phreds, ctx->d_counts, ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[4], st));
     ctx->launches += (has_model ? 4 : 2) + (p.h.n_slots ? 1 : 0);
     CU(cudaGetLastError());
@@ -620,7 +620,8 @@ extern "C" int ugvc_device_status(ugvc_ctx* ctx, void* stream) {
 extern "C" int ugvc_enable_phreds(ugvc_ctx* ctx, int on) {
     // takes effect at the next ugvc_reserve
     if (!ctx) return UGVC_E_ARG;
-    ctx->want_phreds = on != 0;
+    if (on < 0 || on > 2) return fail(ctx, UGVC_E_ARG, "enable_phreds: mode must be 0, 1 or 2");
+    ctx->want_phreds = on;
     return UGVC_OK;
 }
 

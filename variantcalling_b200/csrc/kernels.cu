@@ -1186,7 +1186,8 @@ __global__ void __launch_bounds__(TPB, 1) k3_infer(const __grid_constant__ DevPl
                                                       const int64_t* __restrict__ n_records_p, double threshold,
                                                       uint8_t* __restrict__ low_score, float* __restrict__ probs,
                                                       double* __restrict__ qual_out, double* __restrict__ phred_out,
-                                                      long long* counts, unsigned chunk_nodes_cap) {
+                                                      long long* counts, unsigned chunk_nodes_cap,
+                                                      int phred_mode) {
     extern __shared__ __align__(16) uint8_t smem3[];
     const int F = plan.h.n_features, K = plan.h.n_classes, O = plan.h.n_outputs;
     const unsigned n_trees = plan.h.n_trees;
@@ -1370,10 +1371,11 @@ __global__ void __launch_bounds__(TPB, 1) k3_infer(const __grid_constant__ DevPl
 #pragma unroll
         for (int k = 2; k < UGVC_MAX_CLASSES; ++k)
             if (k < K) mn = fmin(mn, ph[k]);
-        if (phred_out) {  // --recalibrate_genotype: PL / GQ come from the per-class phreds
+        if (phred_out) {  // --recalibrate_genotype: PL / GQ come from the per-class phreds;
+                          // mode 2 (--treat_multiallelics): the fp64 likelihoods, merged on the host
 #pragma unroll
             for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
-                if (k < K) phred_out[(size_t)rec * K + k] = ph[k];
+                if (k < K) phred_out[(size_t)rec * K + k] = phred_mode == 2 ? p[k] : ph[k];
         }
         double q = __dadd_rn(__dadd_rn(30.0, ph0), -mn);
         q = q < 0.0 ? 0.0 : q;
@@ -1440,7 +1442,7 @@ bool k3_plan_fits(const DevPlan& plan) {
 }
 
 void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const int64_t* d_n_records,
-               double threshold, uint8_t* low_score, float* probs, double* qual, double* phreds,
+               double threshold, uint8_t* low_score, float* probs, double* qual, double* phreds, int phred_mode,
                long long* d_counts, int sm_count, cudaStream_t st) {
     const size_t smem = k3_smem_bytes(plan);
     int per_sm = (int)((K3_SMEM_BUDGET) / (smem + 1024));
@@ -1448,10 +1450,10 @@ void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const
     if (per_sm > 4) per_sm = 4;
     if (k3_tpb(plan) == 384)
         k3_infer<384><<<sm_count * per_sm, 384, smem, st>>>(plan, feats, row_stride, d_n_records, threshold, low_score,
-                                                            probs, qual, phreds, d_counts, k3_chunk_nodes(plan));
+                                                            probs, qual, phreds, d_counts, k3_chunk_nodes(plan), phred_mode);
     else
         k3_infer<256><<<sm_count * per_sm, 256, smem, st>>>(plan, feats, row_stride, d_n_records, threshold, low_score,
-                                                            probs, qual, phreds, d_counts, k3_chunk_nodes(plan));
+                                                            probs, qual, phreds, d_counts, k3_chunk_nodes(plan), phred_mode);
 }
 
 cudaError_t kernels_configure(const DevPlan& plan) {

@@ -98,7 +98,7 @@ void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_t
 void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, const int64_t* d_n_records, float* feats,
                unsigned long long* d_err, int sm_count, cudaStream_t st);
 void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const int64_t* d_n_records,
-               double threshold, uint8_t* low_score, float* probs, double* qual, double* phreds,
+               double threshold, uint8_t* low_score, float* probs, double* qual, double* phreds, int phred_mode,
                long long* d_counts, int sm_count, cudaStream_t st);
 size_t k1_smem_bytes(const DevPlan& plan);
 size_t k3_smem_bytes(const DevPlan& plan);
