@@ -16,9 +16,11 @@ K2 feature assembly, K3 inference + score + decision), and the output lines are
 spliced from the original bytes and BGZF-compressed on the host; the ``.tbi`` is
 written directly (the reference shells out to ``bcftools index -t``, :231).
 
-Not lowered yet (raise ``NotImplementedError`` instead of a silent approximation):
-``--treat_multiallelics``.  ``--recalibrate_genotype`` alone is supported: K3
-keeps the per-class phreds and the splicer rewrites GT / GQ / PL of the first sample (:203-215).
+``--recalibrate_genotype``: K3 keeps the per-class phreds and the splicer rewrites GT / GQ / PL of
+the first sample (:203-215).  ``--treat_multiallelics`` (:145-166): per contig, an index pass
+(K0+K1) finds the multi-allelic records and deletion clusters, their biallelic split rows are
+written as VCF lines (``variantcalling_b200/multiallelics.py``) and scored by the same kernels with
+the untouched records; the fp64 likelihoods are merged per record on the host.
 """
 from __future__ import annotations
 
@@ -31,7 +33,7 @@ import sys
 
 import numpy as np
 
-from variantcalling_b200 import bgzf_io, lib
+from variantcalling_b200 import bgzf_io, lib, multiallelics
 from variantcalling_b200 import model_compiler as MC
 from variantcalling_b200.vcf_header import VcfHeader
 
@@ -187,10 +189,6 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             raise RuntimeError(f"Input file {args.input_file} does not exist")
         if not os.path.exists(args.input_file + ".tbi"):
             raise RuntimeError(f"Index file {args.input_file}.tbi does not exist")
-        if args.treat_multiallelics:
-            raise NotImplementedError(
-                "--treat_multiallelics is not lowered to the GPU path yet (SURVEY.md 8f-2); refusing to approximate")
-
         header = VcfHeader(bgzf_io.read_header_text(args.input_file))
         with_model = args.model_file is not None
         with_bl = args.blacklist is not None or args.blacklist_cg_insertions
@@ -208,8 +206,17 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             plan = MC.compile_plan_no_model(header)
         ctx.load_plan(plan.blob)
         recal = bool(args.recalibrate_genotype and with_model)
-        if recal:
+        split_sites = bool(args.treat_multiallelics and with_model)
+        idx_ctx = None
+        if split_sites:
+            # the split rows' likelihoods are merged on the host before the phred step: K3 hands back
+            # the fp64 likelihoods; a second context with the model-less plan indexes each contig first
+            ctx.enable_phreds(2)
+            idx_ctx = lib.Context(device)
+            idx_ctx.load_plan(MC.compile_plan_no_model(header).blob)
+        elif recal:
             ctx.enable_phreds(True)
+        idx_reserved = (0, 0)
         batch_bytes = max(1, args.batch_mb) << 20
         n_lanes = 2
         reserved = (0, 0)
@@ -218,6 +225,33 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         out = _Splicer(args.output_file, args.io_threads)
         out.write_header(out_header)
         totals = {"n_records": 0, "n_low_score": 0, "n_cg": 0, "n_blacklisted": 0}
+
+        def blacklist_codes(ri, n, bl_pos):
+            """Per-record index into a table of ';'-joined blacklist annotations (merge order: CG
+            insertions first, then each blacklist; blacklist.py:64-101)."""
+            if not with_bl:
+                return None, b"", None
+            code = np.zeros(n, dtype=np.int32)
+            parts = []  # (bit weight, annotation) in merge order
+            w = 1
+            if args.blacklist_cg_insertions:
+                code += (ri["flags"] & 1).astype(np.int32) * w
+                parts.append("CG_NON_HMER_INDEL")
+                w *= 2
+            for ann, pos in bl_pos:
+                hit = np.isin(ri["pos"].astype(np.int64), pos)
+                code += hit.astype(np.int32) * w
+                parts.append(ann)
+                w *= 2
+            strings = []
+            for c in range(w):
+                vals = [parts[k] if (c >> k) & 1 else "PASS" for k in range(len(parts))]
+                strings.append(";".join(vals).encode())
+            totals["n_blacklisted"] += int(np.count_nonzero(code))
+            totals["n_cg"] += int(np.count_nonzero(ri["flags"] & 1))
+            return (code, b"".join(strings),
+                    np.concatenate(([0], np.cumsum([len(x) for x in strings]))).astype(np.int64))
+
         contigs = list(header.contigs.keys()) if args.limit_to_contigs is None else list(args.limit_to_contigs)
         for contig in contigs:
             contig = str(contig)
@@ -244,6 +278,39 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 head = text[: min(text.size, 1 << 20)].tobytes()
                 ctx.set_key_order(*lib.learn_key_order(head[: head.rfind(b"\n") + 1]))
                 key_order_set = True
+            if split_sites:
+                # --treat_multiallelics: the whole contig at once, like the reference's frame
+                # (filter_variants_pipeline.py:145-166)
+                need_idx = (text.size + 4096, n_contig + 128)
+                if need_idx[0] > idx_reserved[0] or need_idx[1] > idx_reserved[1]:
+                    idx_reserved = (max(need_idx[0], idx_reserved[0]), max(need_idx[1], idx_reserved[1]))
+                    idx_ctx.reserve(idx_reserved[0], idx_reserved[1], 1)
+                idx = idx_ctx.filter_batch(text, args.decision_threshold)
+                logger.info("Processing multiallelics -> pre-classifier")
+                sp = multiallelics.SplitPlan(header, header.loader_columns(args.custom_annotations),
+                                             multiallelics.read_fasta_contig(args.ref_fasta, contig))
+                scored_text = sp.build(text, idx["line_start"], idx["recinfo"])
+                n_scored = int(np.count_nonzero(scored_text == 10))  # noqa: PLR2004
+                need = (scored_text.size + 4096, n_scored + 128)
+                if need[0] > reserved[0] or need[1] > reserved[1]:
+                    reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))
+                    ctx.reserve(reserved[0], reserved[1], n_lanes)
+                scored = ctx.filter_batch(scored_text, args.decision_threshold, want_recinfo=False)
+                lik = sp.merge(ctx.collect_phreds(0, scored["n_records"]))
+                phreds, quals, low = multiallelics.score_math(lik, args.decision_threshold)
+                n = idx["n_records"]
+                res = {"n_records": n, "line_start": idx["line_start"], "recinfo": idx["recinfo"],
+                       "low_score": np.ascontiguousarray(low), "qual": np.ascontiguousarray(quals)}
+                bl_code, bl_table, bl_off = blacklist_codes(res["recinfo"], n, bl_pos)
+                logger.info("Writing records")
+                out.write_batch(contig, text, res, with_model=True, overwrite_qual=args.overwrite_qual_tag,
+                                bl_code=bl_code, bl_table=bl_table, bl_off=bl_off,
+                                phreds=np.ascontiguousarray(phreds) if recal else None)
+                totals["n_records"] += n
+                totals["n_low_score"] += int(low.sum())
+                logger.info(f"{contig} done")
+                continue
+
             ranges = list(_split_batches(text, batch_bytes))
             need = (max(e - b for b, e in ranges) + 4096,
                     max(int(np.count_nonzero(text[b:e] == 10)) for b, e in ranges) + 128)  # noqa: PLR2004
@@ -261,30 +328,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 n = ctx.collect(lane, outs, cap)
                 res = ctx.trim_outputs(outs, n)
                 phreds = np.ascontiguousarray(ctx.collect_phreds(lane, n)) if recal else None
-                bl_code, bl_table, bl_off = None, b"", None
-                if with_bl:
-                    ri = res["recinfo"]
-                    code = np.zeros(n, dtype=np.int32)
-                    parts = []  # (bit weight, annotation) in merge order: CG first, then each blacklist
-                    w = 1
-                    if args.blacklist_cg_insertions:
-                        code += (ri["flags"] & 1).astype(np.int32) * w
-                        parts.append("CG_NON_HMER_INDEL")
-                        w *= 2
-                    for ann, pos in bl_pos:
-                        hit = np.isin(ri["pos"].astype(np.int64), pos)
-                        code += hit.astype(np.int32) * w
-                        parts.append(ann)
-                        w *= 2
-                    strings = []
-                    for c in range(w):
-                        vals = [parts[k] if (c >> k) & 1 else "PASS" for k in range(len(parts))]
-                        strings.append(";".join(vals).encode())
-                    bl_table = b"".join(strings)
-                    bl_off = np.concatenate(([0], np.cumsum([len(s) for s in strings]))).astype(np.int64)
-                    bl_code = code
-                    totals["n_blacklisted"] += int(np.count_nonzero(code))
-                    totals["n_cg"] += int(np.count_nonzero(ri["flags"] & 1))
+                bl_code, bl_table, bl_off = blacklist_codes(res["recinfo"], n, bl_pos)
                 out.write_batch(contig, text[b:e], res, with_model=with_model,
                                 overwrite_qual=args.overwrite_qual_tag, bl_code=bl_code, bl_table=bl_table,
                                 bl_off=bl_off, phreds=phreds)
@@ -305,6 +349,8 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
 
         out.close(args.output_file)
         ctx.close()
+        if idx_ctx is not None:
+            idx_ctx.close()
         logger.info(
             f"{totals['n_records']} records written: {totals['n_low_score']} LOW_SCORE, "
             f"{totals['n_records'] - totals['n_low_score']} not LOW_SCORE, {totals['n_blacklisted']} blacklisted")

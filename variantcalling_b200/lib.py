@@ -225,7 +225,8 @@ class Context:
                                                 _ptr(out.get("line_start")), capacity, C.byref(n)))
         return n.value
 
-    def enable_phreds(self, on: bool = True):
+    def enable_phreds(self, on: bool | int = True):
+        """1/True: K3 keeps the per-class phreds; 2: the fp64 class likelihoods (--treat_multiallelics)."""
         self._check(self.lib.ugvc_enable_phreds(self.h, int(on)))
 
     def collect_phreds(self, lane: int, n: int) -> np.ndarray:
