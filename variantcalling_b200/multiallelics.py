@@ -272,6 +272,13 @@ class SplitPlan:
                 num[k] = 1
         num.update({"rpa": "R", "ru": 1, "str": 1})
         self.numbers = num
+        # per source table: column -> how to sub-sample its values (None: leave the text alone)
+        self.rule = {}
+        for is_format, table in ((False, header.info), (True, header.formats)):
+            for tag, (number, _t) in table.items():
+                col = tag.lower()
+                multi_valued = number not in ("0", "1") and num[col] != 1
+                self.rule.setdefault((is_format, col), num[col] if multi_valued else None)
         self.loaded = set(loaded_columns)          # lower-cased columns the loader keeps
         self.loaded_tags = set(loaded_columns.values())
         self.split_lines: list[bytes] = []
@@ -307,11 +314,10 @@ class SplitPlan:
                 return text
             if not is_format and col in in_format:
                 return text  # the FORMAT value is the one the loader keeps
-            table = self.header.formats if is_format else self.header.info
-            tag_number = next((nv[0] for t, nv in table.items() if t.lower() == col), "1")
-            if tag_number in ("0", "1") or self.numbers[col] == 1:
+            number = self.rule.get((is_format, col))
+            if number is None:
                 return text
-            return ",".join(_subsample(text.split(","), self.numbers[col], pair))
+            return ",".join(_subsample(text.split(","), number, pair))
 
         info, seen = [], set()
         for k, sep, v in rec.info:
