@@ -204,6 +204,36 @@ int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_start, cons
                             const double* phreds, int n_classes,
                             uint8_t* out, size_t capacity, int64_t* out_line_start, int n_threads);
 
+/* ---- concordance metrics (BASELINE configs[4]: evaluate_concordance on the filtered set) ----
+ * Precision / recall of calls against truth labels, per variant group, replacing the array work
+ * of ugbio_core/concordance/concordance_utils.py:11-188,346-458 and stats_utils.py:141-210 (which
+ * wraps sklearn.metrics.precision_recall_curve).  Group g: 0..6 = the selection functions of
+ * concordance_utils.py:266-275 in order (SNP, Non-hmer INDEL, HMER indel <= 4, (4,8), [8,10],
+ * 11,12, > 12), 7 = INDELS, 8 = H-INDELS.  Per record: scores (tree_score, fp64), pred (1 when
+ * the final FILTER is PASS), cls (0 fp, 1 tp, 2 fn, 3 tn: the classify / classify_gt column), indel,
+ * hmer_len (hmer_indel_length, < 0 for null), group (NULL = derive from indel / hmer_len, else the
+ * caller's group id per record, -1 = none).  Inputs are host arrays, or device arrays when
+ * inputs_on_device != 0.
+ *   out_counts[g][6]   = tp, fp, missed (call < truth), initial_tp, n_called (not fn), n_fn
+ *   out_curve_len[g]   = points of the raw precision/recall curve kept on the device (0 for g = 8)
+ *   out_cutoff[g]      = the 20th largest score of the group (stats_utils.py:202-207)
+ *   out_selected[g][2] = number of called records, number of true ones among them
+ * ugvc_conc_curve copies group g's raw curve: precision = tps/(tps+fps), recall = tps/tps[-1] at each
+ * distinct score, in increasing-threshold order (sklearn's order, without its final (1, 0) point). */
+#define UGVC_CONC_GROUPS 9
+#define UGVC_CONC_COUNTERS 6
+typedef struct ugvc_conc ugvc_conc;
+int ugvc_conc_create(int device, ugvc_conc** out);
+void ugvc_conc_free(ugvc_conc* h);
+const char* ugvc_conc_last_error(const ugvc_conc* h);
+long long ugvc_conc_launch_count(const ugvc_conc* h);
+int ugvc_conc_run(ugvc_conc* h, int64_t n, const double* scores, const uint8_t* pred, const uint8_t* cls,
+                  const uint8_t* indel, const int32_t* hmer_len, const int8_t* group, int inputs_on_device,
+                  int want_curves, int64_t* out_counts, int64_t* out_curve_len, double* out_cutoff,
+                  int64_t* out_selected);
+int ugvc_conc_curve(ugvc_conc* h, int group, double* precision, double* recall, double* thresholds,
+                    size_t capacity);
+
 /* ---- test hook ------------------------------------------------------------ */
 /* K1's numeric-literal parser (csrc/numparse.h) compiled for the host: parses one token of
  * `text` (NUL-terminated); returns 0 ok / 1 missing (".") / 2 not exactly parseable. */

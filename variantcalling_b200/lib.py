@@ -75,6 +75,12 @@ SIGNATURES = {
                                         _vp, C.c_int, _vp, _sz, _vp, C.c_int]),
     "ugvc_enable_phreds": (C.c_int, [_vp, C.c_int]),
     "ugvc_collect_phreds": (C.c_int, [_vp, C.c_int, _vp, _sz]),
+    "ugvc_conc_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "ugvc_conc_free": (None, [_vp]),
+    "ugvc_conc_last_error": (C.c_char_p, [_vp]),
+    "ugvc_conc_launch_count": (C.c_longlong, [_vp]),
+    "ugvc_conc_run": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "ugvc_conc_curve": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz]),
     "ugvc_test_parse_float": (C.c_int, [C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_double),
                                         C.POINTER(C.c_int)]),
 }
