@@ -54,3 +54,25 @@ def test_get_concordance_metrics_single_selection():
     for k in ("precision", "recall", "f1", "predictions"):
         np.testing.assert_array_equal(np.asarray(c[k][0]), wc[k])
     assert c["threshold"][0] == wc["threshold"]
+
+
+def test_evaluate_concordance_cli_writes_the_reference_csvs(tmp_path):
+    """`python ugvc evaluate_concordance`: .stats.csv / .thresholds.csv as evaluate_concordance.py:100-107 writes them."""
+    import pandas as pd
+
+    from variantcalling_b200 import evaluate_concordance as EC
+
+    df = make_frame(30000, 42)
+    src = str(tmp_path / "cmp.csv")
+    df.to_csv(src, index=False)
+    prefix = str(tmp_path / "out")
+    EC.run(["--input_file", src, "--output_prefix", prefix])
+    stats = pd.read_csv(prefix + ".stats.csv", sep=";")
+    want = CR.calc_accuracy_metrics(pd.read_csv(src), "classify_gt")
+    assert list(stats.columns) == ["group"] + CR.METRIC_COLUMNS and list(stats["group"]) == list(want["group"])
+    for col in CR.METRIC_COLUMNS:
+        np.testing.assert_allclose(stats[col].to_numpy(dtype=float), want[col].to_numpy(dtype=float), rtol=0, atol=1e-12)
+    thr = pd.read_csv(prefix + ".thresholds.csv")
+    want_thr = CR.calc_recall_precision_curve(pd.read_csv(src), "classify_gt")
+    assert list(thr["group"]) == list(want_thr["group"])
+    np.testing.assert_allclose(thr["threshold"].to_numpy(dtype=float), np.asarray(list(want_thr["threshold"]), dtype=float))

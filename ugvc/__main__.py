@@ -2,8 +2,9 @@
 
 The reference routes every tool through ``ugvc/__main__.py`` (simppl
 ``CommandLineInterface``, ``ugvc/__main__.py:43-54,104-105``).  This repository
-implements one tool of that CLI -- ``filter_variants_pipeline`` -- so the
-dispatcher knows exactly that name and hands ``sys.argv[2:]`` to its ``run``.
+implements the tools of the filtering hot path -- ``filter_variants_pipeline`` and the
+``evaluate_concordance`` step that scores its output against truth -- so the dispatcher knows
+exactly those names and hands ``sys.argv[2:]`` to their ``run``.
 """
 import os
 import sys
@@ -12,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-TOOLS = {"filter_variants_pipeline": "variantcalling_b200.filter_variants_pipeline"}
+TOOLS = {"filter_variants_pipeline": "variantcalling_b200.filter_variants_pipeline",
+         "evaluate_concordance": "variantcalling_b200.evaluate_concordance"}
 
 
 def main(argv=None):
