@@ -134,3 +134,58 @@ def test_splicer_recalibrate_genotype_matches_oracle(overwrite_qual):
                            recal=(phreds[i], float(gq[i])))[0] for i, rec in enumerate(vf)]
     assert got == want
     assert all("TREE_SCORE" not in g for g in got) and got[3].split("\t")[8] == "GT:GQ:PL"
+
+
+def test_output_pipeline_writer_thread_keeps_order_and_index(tmp_path):
+    """_Splicer: splice on the caller's thread, BGZF deflate + index bookkeeping on its writer thread.
+    Many small batches over three contigs -> the file holds every record in order and the .tbi selects
+    each contig; a failing write surfaces on the caller's thread."""
+    import gzip
+
+    from variantcalling_b200 import filter_variants_pipeline as fvp
+    from variantcalling_b200 import synth
+
+    header, lines, _ = synth.generate(synth.SynthSpec(n_records=6000, n_custom=2, seed=9,
+                                                      contigs={"chr1": 3_000_000, "chr2": 2_000_000, "chr3": 1_000_000}))
+    path = str(tmp_path / "out.vcf.gz")
+    sp = fvp._Splicer(path, 2)  # noqa: SLF001
+    sp.write_header(header)
+    rng = np.random.default_rng(0)
+    want = []
+    at = 0
+    while at < len(lines):
+        contig = lines[at].split("\t", 1)[0]
+        stop = at
+        while stop < len(lines) and stop - at < 700 and lines[stop].split("\t", 1)[0] == contig:
+            stop += 1
+        chunk = lines[at:stop]
+        text = np.frombuffer(("\n".join(chunk) + "\n").encode(), dtype=np.uint8)
+        quals = rng.uniform(0, 60, size=len(chunk))
+        res = {"n_records": len(chunk), "recinfo": _recinfo_for(chunk), "low_score": (quals <= 30.0).astype(np.uint8),
+               "qual": quals, "line_start": np.concatenate(([0], np.cumsum([len(x) + 1 for x in chunk]))).astype(np.int64)}
+        sp.write_batch(contig, text, res, with_model=True, overwrite_qual=False, bl_code=None, bl_table=b"", bl_off=None)
+        vf = OracleVariantFile(("\n".join(header) + "\n" + "\n".join(chunk) + "\n").encode())
+        want += [R.write_record(rec, float(quals[i]), 30.0, overwrite_qual=False, blacklist_value=None)[0]
+                 for i, rec in enumerate(vf)]
+        at = stop
+    sp.close(path)
+    body = [ln for ln in gzip.open(path).read().decode().split("\n")[:-1] if not ln.startswith("#")]
+    assert body == want
+    idx = bgzf_io.read_tbi(path + ".tbi")
+    assert list(idx) == ["chr1", "chr2", "chr3"]
+    for c, (vb, ve) in idx.items():
+        got = bgzf_io.inflate(path, vb, ve).tobytes().decode().split("\n")[:-1]
+        assert got == [ln for ln in want if ln.split("\t", 1)[0] == c]
+    assert sp.seconds["deflate"] > 0 and not sp._thread.is_alive()  # noqa: SLF001
+
+    # an error on the writer thread is raised to the caller, and abort() stops the thread
+    bad = fvp._Splicer(str(tmp_path / "no_such_dir" / "x.vcf.gz"), 1)  # noqa: SLF001
+    chunk = lines[:10]
+    text = np.frombuffer(("\n".join(chunk) + "\n").encode(), dtype=np.uint8)
+    res = {"n_records": 10, "recinfo": _recinfo_for(chunk), "low_score": np.zeros(10, np.uint8), "qual": np.ones(10),
+           "line_start": np.concatenate(([0], np.cumsum([len(x) + 1 for x in chunk]))).astype(np.int64)}
+    bad.write_batch("chr1", text, res, with_model=True, overwrite_qual=False, bl_code=None, bl_table=b"", bl_off=None)
+    with pytest.raises(OSError):
+        bad.close(str(tmp_path / "no_such_dir" / "x.vcf.gz"))
+    bad.abort()
+    assert not bad._thread.is_alive()  # noqa: SLF001

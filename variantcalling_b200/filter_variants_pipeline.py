@@ -29,7 +29,11 @@ import ctypes as C
 import logging
 import os.path
 import pickle
+import queue
 import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -100,6 +104,31 @@ class _Splicer:
         self.names: list[str] = []
         self.contig_of, self.beg, self.end, self.u_start, self.u_end = [], [], [], [], []
         self.L = lib.load_library()
+        self.seconds = {"splice": 0.0, "deflate": 0.0}
+        # BGZF compression + index bookkeeping run on their own thread, in submission order, so that
+        # the next batch's GPU pass and splice overlap the previous batch's deflate (zlib releases the GIL)
+        self._queue: "queue.Queue" = queue.Queue(maxsize=3)
+        self._error: BaseException | None = None
+        self._thread = threading.Thread(target=self._drain, name="ugvc-bgzf-writer", daemon=True)
+        self._thread.start()
+
+    def _drain(self):
+        while True:
+            item = self._queue.get()
+            try:
+                if item is None:
+                    return
+                if self._error is None:
+                    self._write_spliced(*item)
+            except BaseException as err:  # noqa: BLE001  (re-raised on the caller's thread)
+                self._error = err
+            finally:
+                self._queue.task_done()
+
+    def _check_writer(self):
+        if self._error is not None:
+            err, self._error = self._error, None
+            raise err
 
     def write_header(self, lines: list[str]):
         self.writer.write(("\n".join(lines) + "\n").encode())
@@ -115,24 +144,46 @@ class _Splicer:
         out_ls = np.empty(n + 1, dtype=np.int64)
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
         table = np.frombuffer(bl_table, dtype=np.uint8) if bl_code is not None and bl_table else None
+        t_splice = time.perf_counter()
         nb = self.L.ugvc_splice_records(
             p(text), p(res["line_start"]), p(res["recinfo"]), p(res.get("low_score")), p(res.get("qual")), n,
             int(overwrite_qual), int(with_model), p(bl_code), p(table), p(bl_off) if table is not None else None,
             p(phreds), 0 if phreds is None else int(phreds.shape[1]), p(out), out.size, p(out_ls), self.threads)
         if nb < 0:
             raise OSError(f"splice failed (ugvc code {nb})")
+        self.seconds["splice"] += time.perf_counter() - t_splice
+        ri = res["recinfo"]
+        beg = ri["pos"].astype(np.int64) - 1
+        self._check_writer()
+        self._queue.put((contig, out[:nb], n, beg, beg + np.maximum(1, (ri["flags"] >> 8).astype(np.int64)), out_ls))
+
+    def _write_spliced(self, contig: str, data: np.ndarray, n: int, beg: np.ndarray, end: np.ndarray, out_ls: np.ndarray):
+        t0 = time.perf_counter()
         base = self.writer.uoffset
-        self.writer.write(out[:nb])
+        self.writer.write(data)
         if not self.names or self.names[-1] != contig:
             self.names.append(contig)
-        ri = res["recinfo"]
         self.contig_of.append(np.full(n, len(self.names) - 1, dtype=np.int32))
-        self.beg.append(ri["pos"].astype(np.int64) - 1)
-        self.end.append(ri["pos"].astype(np.int64) - 1 + np.maximum(1, (ri["flags"] >> 8).astype(np.int64)))
+        self.beg.append(beg)
+        self.end.append(end)
         self.u_start.append(base + out_ls[:-1])
         self.u_end.append(base + out_ls[1:])
+        self.seconds["deflate"] += time.perf_counter() - t0
+
+    def _finish_writer(self):
+        self._queue.put(None)
+        self._thread.join()
+        self._check_writer()
+
+    def abort(self):
+        """Stop the writer thread after a failure on the caller's side (the partial file stays)."""
+        if self._thread.is_alive():
+            self._error = self._error or RuntimeError("aborted")
+            self._queue.put(None)
+            self._thread.join(timeout=30)
 
     def close(self, path: str):
+        self._finish_writer()
         self.writer.close()
         if self.contig_of:
             cat = np.concatenate
@@ -170,6 +221,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
     logging.basicConfig(format="%(asctime)s %(message)s", level=logging.INFO)
     logger = logging.getLogger(__name__)
 
+    out = None
     try:
         model = None
         transformer = None
@@ -224,6 +276,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
 
         out = _Splicer(args.output_file, args.io_threads)
         out.write_header(out_header)
+        seconds = {"inflate_wait": 0.0, "gpu": 0.0}
         totals = {"n_records": 0, "n_low_score": 0, "n_cg": 0, "n_blacklisted": 0}
 
         def blacklist_codes(ri, n, bl_pos):
@@ -252,21 +305,32 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             return (code, b"".join(strings),
                     np.concatenate(([0], np.cumsum([len(x) for x in strings]))).astype(np.int64))
 
-        contigs = list(header.contigs.keys()) if args.limit_to_contigs is None else list(args.limit_to_contigs)
-        for contig in contigs:
-            contig = str(contig)
-            logger.info(f"Filtering variants from {contig}")
+        contigs = [str(c) for c in (header.contigs.keys() if args.limit_to_contigs is None else args.limit_to_contigs)]
+
+        def load_contig(contig: str):
+            """Inflate one contig's records (runs one contig ahead of the loop, on its own thread)."""
             if contig not in index:
-                logger.info(f"No variants found on {contig}")
-                continue
+                return None
             vb, ve = index[contig]
             text = bgzf_io.inflate(args.input_file, vb, ve, n_threads=args.io_threads)
             if text.size == 0:
-                logger.info(f"No variants found on {contig}")
-                continue
+                return None
             if text[-1] != 10:  # noqa: PLR2004
                 text = np.concatenate((text, np.array([10], dtype=np.uint8)))
-            n_contig = int(np.count_nonzero(text == 10))  # noqa: PLR2004
+            return text, int(np.count_nonzero(text == 10))  # noqa: PLR2004
+
+        prefetch = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-bgzf-reader")
+        pending = prefetch.submit(load_contig, contigs[0]) if contigs else None
+        for ci, contig in enumerate(contigs):
+            logger.info(f"Filtering variants from {contig}")
+            t_wait = time.perf_counter()
+            loaded = pending.result()
+            seconds["inflate_wait"] += time.perf_counter() - t_wait
+            pending = prefetch.submit(load_contig, contigs[ci + 1]) if ci + 1 < len(contigs) else None
+            if loaded is None:
+                logger.info(f"No variants found on {contig}")
+                continue
+            text, n_contig = loaded
             logger.info(f"{n_contig} variants found on {contig}")
             if blacklists is not None:
                 logger.info("Applying blacklist")
@@ -325,7 +389,9 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 lane, b, e = item
                 cap = int(np.count_nonzero(text[b:e] == 10)) + 1  # noqa: PLR2004
                 outs = ctx.alloc_outputs(cap, want_recinfo=True)
+                t_gpu = time.perf_counter()
                 n = ctx.collect(lane, outs, cap)
+                seconds["gpu"] += time.perf_counter() - t_gpu
                 res = ctx.trim_outputs(outs, n)
                 phreds = np.ascontiguousarray(ctx.collect_phreds(lane, n)) if recal else None
                 bl_code, bl_table, bl_off = blacklist_codes(res["recinfo"], n, bl_pos)
@@ -347,7 +413,12 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 finish(inflight.pop(0))
             logger.info(f"{contig} done")
 
+        t_close = time.perf_counter()
         out.close(args.output_file)
+        prefetch.shutdown()
+        logger.info("stage seconds (overlapping threads): wait for inflate %.2f, wait for GPU %.2f, splice %.2f, "
+                    "deflate+write %.2f, index %.2f", seconds["inflate_wait"], seconds["gpu"], out.seconds["splice"],
+                    out.seconds["deflate"], time.perf_counter() - t_close)
         ctx.close()
         if idx_ctx is not None:
             idx_ctx.close()
@@ -358,6 +429,8 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         return totals
 
     except Exception as err:
+        if out is not None:
+            out.abort()
         exc_info = sys.exc_info()
         logger.error(exc_info[:2])
         logger.exception(err)
