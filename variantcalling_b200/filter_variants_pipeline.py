@@ -376,18 +376,18 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 continue
 
             ranges = list(_split_batches(text, batch_bytes))
-            need = (max(e - b for b, e in ranges) + 4096,
-                    max(int(np.count_nonzero(text[b:e] == 10)) for b, e in ranges) + 128)  # noqa: PLR2004
+            # records per batch (one scan of the text at most: a contig that fits one batch was counted on load)
+            n_in = [n_contig] if len(ranges) == 1 else [int(np.count_nonzero(text[b:e] == 10)) for b, e in ranges]  # noqa: PLR2004
+            need = (max(e - b for b, e in ranges) + 4096, max(n_in) + 128)
             if need[0] > reserved[0] or need[1] > reserved[1]:
                 reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))
                 ctx.reserve(reserved[0], reserved[1], n_lanes)
 
             logger.info("Writing records")
-            inflight: list[tuple[int, int, int]] = []
+            inflight: list[tuple[int, int, int, int]] = []
 
             def finish(item, contig=contig, text=text, bl_pos=bl_pos):
-                lane, b, e = item
-                cap = int(np.count_nonzero(text[b:e] == 10)) + 1  # noqa: PLR2004
+                lane, b, e, cap = item
                 outs = ctx.alloc_outputs(cap, want_recinfo=True)
                 t_gpu = time.perf_counter()
                 n = ctx.collect(lane, outs, cap)
@@ -408,7 +408,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                     finish(inflight.pop(0))
                 chunk = text[b:e]
                 ctx.submit(lane, chunk, chunk.size, args.decision_threshold)
-                inflight.append((lane, b, e))
+                inflight.append((lane, b, e, n_in[bi] + 1))
             while inflight:
                 finish(inflight.pop(0))
             logger.info(f"{contig} done")
