@@ -477,7 +477,14 @@ void splice_one(const uint8_t* line, size_t len, const ugvc_recinfo& ri, bool wi
                 }
             if (blv.empty()) done_bl = true;
         }
-        if (!(il == 1 && ip[0] == '.')) {
+        // common case: no empty pieces and neither key already present -> the INFO bytes go out in one piece
+        const bool plain = il > 0 && !(il == 1 && ip[0] == '.') && ip[0] != ';' && ip[il - 1] != ';' &&
+                           !memmem(ip, il, ";;", 2) && (done_score || !memmem(ip, il, "TREE_SCORE=", 11)) &&
+                           (done_bl || !memmem(ip, il, "BLACKLST=", 9));
+        if (plain) {
+            out.append(reinterpret_cast<const char*>(ip), il);
+            written = 1;
+        } else if (!(il == 1 && ip[0] == '.')) {
             size_t s = 0;
             for (size_t e = 0; e <= il; ++e) {
                 if (e == il || ip[e] == ';') {
@@ -560,21 +567,29 @@ extern "C" int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_
     work(0);
     for (auto& t : th) t.join();
     size_t total = 0;
-    for (auto& p : parts) total += p.size();
-    if (total > capacity) return UGVC_E_ARG;
-    size_t off = 0;
-    int64_t rec = 0;
+    std::vector<size_t> part_off(n_threads);
     for (int t = 0; t < n_threads; ++t) {
-        memcpy(out + off, parts[t].data(), parts[t].size());
+        part_off[t] = total;
+        total += parts[t].size();
+    }
+    if (total > capacity) return UGVC_E_ARG;
+    // gather: every thread copies its own part (first touch of `out` is spread over the threads too)
+    auto gather = [&](int t) {
+        memcpy(out + part_off[t], parts[t].data(), parts[t].size());
         if (out_line_start) {
-            int64_t o2 = (int64_t)off;
+            int64_t rec = n_records * t / n_threads;
+            int64_t o2 = (int64_t)part_off[t];
             for (int64_t l : lens[t]) {
                 out_line_start[rec++] = o2;
                 o2 += l;
             }
         }
-        off += parts[t].size();
-    }
+        std::string().swap(parts[t]);
+    };
+    th.clear();
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(gather, t);
+    gather(0);
+    for (auto& t : th) t.join();
     if (out_line_start) out_line_start[n_records] = (int64_t)total;
     return (int64_t)total;
 }
