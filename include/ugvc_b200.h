@@ -186,6 +186,8 @@ int64_t ugvc_bgzf_uncompressed_size(const char* path);
 int ugvc_bgzf_deflate_to_file(const char* path, const char* mode, const uint8_t* data, size_t n_bytes,
                               int level, int write_eof, int n_threads, uint64_t* out_compressed_bytes,
                               uint32_t* out_block_csize, size_t block_capacity, size_t* out_n_blocks);
+/* Number of bytes equal to `byte` in data[0, n) (the record count of inflated VCF text), threaded. */
+int64_t ugvc_count_byte(const uint8_t* data, size_t n, int byte, int n_threads);
 /* Build the edited output text of a batch: for each record copy the original
  * line with FILTER rewritten (PASS removed / LOW_SCORE appended / empty -> PASS)
  * and TREE_SCORE (and optionally QUAL, BLACKLST) spliced in, exactly the rules of

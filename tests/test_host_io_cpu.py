@@ -189,3 +189,13 @@ def test_output_pipeline_writer_thread_keeps_order_and_index(tmp_path):
         bad.close(str(tmp_path / "no_such_dir" / "x.vcf.gz"))
     bad.abort()
     assert not bad._thread.is_alive()  # noqa: SLF001
+
+
+def test_count_lines_equals_numpy():
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 5, 1 << 20, (3 << 20) + 17):
+        a = rng.integers(0, 32, size=n, dtype=np.uint8)
+        for threads in (1, 3, 0):
+            assert bgzf_io.count_lines(a, threads) == int(np.count_nonzero(a == 10))
+    assert bgzf_io.count_lines(np.frombuffer(b"a\nb\n\n", dtype=np.uint8)) == 3
+    assert bgzf_io.count_lines(np.arange(100, dtype=np.uint8)[::2]) == 1  # non-contiguous views are copied first

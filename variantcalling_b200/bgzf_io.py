@@ -57,6 +57,15 @@ def inflate(path: str, voff_begin: int = 0, voff_end: int = 0, capacity: int | N
     return out[: n.value]
 
 
+def count_lines(text: np.ndarray, n_threads: int = 0) -> int:
+    """Number of newline bytes in a uint8 array (threaded memchr; NumPy's compare + count is one core)."""
+    buf = np.ascontiguousarray(text)
+    n = _lib.load_library().ugvc_count_byte(buf.ctypes.data_as(C.c_void_p) if buf.size else None, buf.size, 10, n_threads)
+    if n < 0:
+        _check(int(n), "count_lines")
+    return int(n)
+
+
 class BgzfWriter:
     """Append-only BGZF writer that remembers every block's compressed size, so
     virtual offsets of written bytes can be computed for the tabix index."""

@@ -594,6 +594,34 @@ extern "C" int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_
     return (int64_t)total;
 }
 
+// Occurrences of `byte` in data[0, n): the record count of a contig's text (newlines), threaded.
+extern "C" int64_t ugvc_count_byte(const uint8_t* data, size_t n, int byte, int n_threads) {
+    if (!data && n) return UGVC_E_ARG;
+    n_threads = clamp_threads(n_threads);
+    if ((size_t)n_threads > n / (1u << 20) + 1) n_threads = (int)(n / (1u << 20) + 1);
+    std::vector<int64_t> part(n_threads, 0);
+    auto work = [&](int t) {
+        const size_t lo = n * (size_t)t / n_threads, hi = n * (size_t)(t + 1) / n_threads;
+        const uint8_t* p = data + lo;
+        const uint8_t* end = data + hi;
+        int64_t c = 0;
+        while (p < end) {
+            p = static_cast<const uint8_t*>(memchr(p, byte, (size_t)(end - p)));
+            if (!p) break;
+            ++c;
+            ++p;
+        }
+        part[t] = c;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    int64_t total = 0;
+    for (int64_t c : part) total += c;
+    return total;
+}
+
 // The K1 numeric-literal parser compiled for the host (same header as the device code), so
 // the CPU tests can check it against strtod on millions of literals.
 extern "C" int ugvc_test_parse_float(const char* text, float* out_f32, double* out_f64, int* out_consumed) {

@@ -317,7 +317,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 return None
             if text[-1] != 10:  # noqa: PLR2004
                 text = np.concatenate((text, np.array([10], dtype=np.uint8)))
-            return text, int(np.count_nonzero(text == 10))  # noqa: PLR2004
+            return text, bgzf_io.count_lines(text, args.io_threads)
 
         prefetch = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-bgzf-reader")
         pending = prefetch.submit(load_contig, contigs[0]) if contigs else None

@@ -71,6 +71,7 @@ SIGNATURES = {
     "ugvc_bgzf_uncompressed_size": (C.c_int64, [C.c_char_p]),
     "ugvc_bgzf_deflate_to_file": (C.c_int, [C.c_char_p, C.c_char_p, _vp, _sz, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(C.c_uint64), _vp, _sz, C.POINTER(_sz)]),
+    "ugvc_count_byte": (C.c_int64, [_vp, _sz, C.c_int, C.c_int]),
     "ugvc_splice_records": (C.c_int64, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp,
                                         _vp, C.c_int, _vp, _sz, _vp, C.c_int]),
     "ugvc_enable_phreds": (C.c_int, [_vp, C.c_int]),
