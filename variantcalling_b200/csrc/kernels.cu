@@ -25,12 +25,19 @@
 
 #include "numparse.h"
 
+// UGVC_HOST_EMU: tests/host_emu compiles the K1-K3 kernel bodies of this file with g++ (one emulated
+// thread per CTA, TPB = 1) to run the parity tests without a GPU; the product build never defines it.
+#ifndef K1_TPB
 #define K1_TPB 128
+#endif
 #ifndef K1_MIN_CTAS
 #define K1_MIN_CTAS 8  // resident CTAs per SM the register allocation targets (profiled: see DESIGN.md)
 #endif
+#ifndef K2_TPB
 #define K2_TPB 256
+#endif
 
+#ifndef UGVC_HOST_EMU  // K0 (cooperative tile scan, inline PTX): the emulation indexes lines on the host
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------
@@ -185,6 +192,8 @@ void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* scratch, int64_t
                                                   reinterpret_cast<unsigned int*>(scratch), n_tiles, line_start,
                                                   cap_records, d_n_records, d_err);
 }
+
+#endif  // !UGVC_HOST_EMU
 
 // ------------------------------------------------------------------------------------------
 // K1: field parse
@@ -1032,6 +1041,7 @@ __global__ void __launch_bounds__(256) k1_fill(uint32_t* __restrict__ raw, size_
     }
 }
 
+#ifndef UGVC_HOST_EMU
 void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_text, const int64_t* line_start,
                const int64_t* d_n_records,
                uint32_t* raw, size_t row_stride, ugvc_recinfo* recinfo, unsigned long long* d_err,
@@ -1052,6 +1062,8 @@ void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_t
     k1_parse<<<sm_count * per_sm, K1_TPB, smem, st>>>(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo,
                                                       d_err, d_counts);
 }
+
+#endif  // !UGVC_HOST_EMU
 
 // ------------------------------------------------------------------------------------------
 // K2: feature assembly
@@ -1133,10 +1145,12 @@ __global__ void __launch_bounds__(K2_TPB) k2_features(const __grid_constant__ De
     }
 }
 
+#ifndef UGVC_HOST_EMU
 void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, const int64_t* d_n_records, float* feats,
                unsigned long long* d_err, int sm_count, cudaStream_t st) {
     k2_features<<<sm_count * 8, K2_TPB, 0, st>>>(plan, raw, row_stride, d_n_records, feats, d_err);
 }
+#endif  // !UGVC_HOST_EMU
 
 // ------------------------------------------------------------------------------------------
 // K3: inference + score math + FILTER decision
@@ -1441,6 +1455,7 @@ bool k3_plan_fits(const DevPlan& plan) {
     return k3_chunk_nodes(plan) > 0;
 }
 
+#ifndef UGVC_HOST_EMU
 void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const int64_t* d_n_records,
                double threshold, uint8_t* low_score, float* probs, double* qual, double* phreds, int phred_mode,
                long long* d_counts, int sm_count, cudaStream_t st) {
@@ -1464,3 +1479,4 @@ cudaError_t kernels_configure(const DevPlan& plan) {
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k3_infer<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
 }
+#endif  // !UGVC_HOST_EMU
