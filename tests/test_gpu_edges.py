@@ -69,10 +69,12 @@ BAD_ROWS = {
     "unknown_indel_class": ("X_IC=NA", "X_IC=dup"),               # KeyError in ins_del_encode
     "mq0c_single_value": ("MQ0C=0,0", "MQ0C=0"),                  # ragged doublet
     "custom_unknown_value": ("XC=3", "XC=3;LCR=MAYBE"),           # OrdinalEncoder: unknown category
+    "infinite_imputed_value": ("SOR=0.693", "SOR=1e39"),          # float32 overflow -> inf: SimpleImputer's input check
+    "infinite_literal": ("MQ=60.00", "MQ=-inf"),                  # ValueError: Input X contains infinity
 }
 
 
-@pytest.mark.parametrize("case", sorted(BAD_ROWS) + ["pl_too_wide", "alt_missing", "qual_missing"])
+@pytest.mark.parametrize("case", sorted(BAD_ROWS) + ["pl_too_wide", "alt_missing", "qual_missing", "qual_infinite"])
 def test_inputs_the_reference_raises_on_raise_here_too(gpu_ctx, golden, case):
     model = util.fit_model("lr", golden["x"], golden["y"])
     hdr, body, recs = split_text(golden["text"])
@@ -83,6 +85,8 @@ def test_inputs_the_reference_raises_on_raise_here_too(gpu_ctx, golden, case):
         bad = row.replace(a, b, 1)
     elif case == "pl_too_wide":
         bad = row.rsplit(":", 1)[0] + ":100,0,200,300"
+    elif case == "qual_infinite":  # passthrough column: the model's own input check raises on inf
+        cols = row.split("\t"); cols[5] = "1e40"; bad = "\t".join(cols)  # noqa: E702
     elif case == "alt_missing":
         cols = row.split("\t"); cols[4] = "."; bad = "\t".join(cols)  # noqa: E702
     else:

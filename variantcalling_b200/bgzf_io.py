@@ -57,6 +57,11 @@ def inflate(path: str, voff_begin: int = 0, voff_end: int = 0, capacity: int | N
     return out[: n.value]
 
 
+# the empty BGZF block that ends a file (SAM spec 4.1.2)
+BGZF_EOF = bytes([0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0,
+                  0, 0, 0, 0, 0, 0, 0, 0])
+
+
 def count_lines(text: np.ndarray, n_threads: int = 0) -> int:
     """Number of newline bytes in a uint8 array (threaded memchr; NumPy's compare + count is one core)."""
     buf = np.ascontiguousarray(text)

@@ -1079,7 +1079,9 @@ __device__ __forceinline__ float k2_apply(uint32_t bits, const PlanFeature& pf, 
     } else if (bits == RAW_MISSING) {
         if (pf.missing_pol == POL_VALUE) v = pf.missing_val;
         else if (pf.missing_pol == POL_ERROR) atomicMin(err, ugvc_pack_error(rec, f, REASON_NULL_FEATURE));
-    } else if (bits == RAW_ERR) {
+    } else if (bits == RAW_ERR || (bits & 0x7FFFFFFFu) == 0x7F800000u) {
+        // +-inf (an overflowing literal, or "inf" itself): SimpleImputer's / the model's input check
+        // raises "Input X contains infinity" in the reference whatever the column's pipeline is
         atomicMin(err, ugvc_pack_error(rec, f, REASON_BAD_VALUE));
     }
     return v;

@@ -105,6 +105,7 @@ class _Splicer:
         self.contig_of, self.beg, self.end, self.u_start, self.u_end = [], [], [], [], []
         self.L = lib.load_library()
         self.seconds = {"splice": 0.0, "deflate": 0.0}
+        self.ranges: dict[str, tuple[int, int]] = {}  # contig -> [first, last) compressed byte of its blocks
         # BGZF compression + index bookkeeping run on their own thread, in submission order, so that
         # the next batch's GPU pass and splice overlap the previous batch's deflate (zlib releases the GIL)
         self._queue: "queue.Queue" = queue.Queue(maxsize=3)
@@ -160,7 +161,9 @@ class _Splicer:
     def _write_spliced(self, contig: str, data: np.ndarray, n: int, beg: np.ndarray, end: np.ndarray, out_ls: np.ndarray):
         t0 = time.perf_counter()
         base = self.writer.uoffset
+        c_before = self.writer.coffset
         self.writer.write(data)
+        self.ranges[contig] = (self.ranges.get(contig, (c_before, 0))[0], self.writer.coffset)
         if not self.names or self.names[-1] != contig:
             self.names.append(contig)
         self.contig_of.append(np.full(n, len(self.names) - 1, dtype=np.int32))
@@ -182,6 +185,18 @@ class _Splicer:
             self._queue.put(None)
             self._thread.join(timeout=30)
 
+    def finish_part(self) -> dict:
+        """Multi-rank runs: this rank's records are on disk (no header, no EOF block, no index); return
+        what rank 0 needs to place each contig's blocks in the final file and index them."""
+        self._finish_writer()
+        meta = {"names": list(self.names), "ranges": dict(self.ranges), "n_bytes": self.writer.coffset}
+        if self.contig_of:
+            cat = np.concatenate
+            us, ue = cat(self.u_start), cat(self.u_end)
+            meta.update(contig_of=cat(self.contig_of), beg=cat(self.beg), end=cat(self.end),
+                        vs=self.writer.virtual_offsets(us), ve=self.writer.virtual_offsets(ue - 1) + np.uint64(1))
+        return meta
+
     def close(self, path: str):
         self._finish_writer()
         self.writer.close()
@@ -195,6 +210,69 @@ class _Splicer:
             z = np.zeros(0, np.int64)
             payload = bgzf_io.build_tbi([], z, z, z, z.astype(np.uint64), z.astype(np.uint64))
         bgzf_io.write_tbi(path + ".tbi", payload)
+
+
+def _part_path(output_file: str, rank: int) -> str:
+    return f"{output_file}.rank{rank}.part"
+
+
+def _assemble_parts(output_file: str, header_lines: list[str], contigs: list[str], world: int, threads: int):
+    """Rank 0 of a multi-rank run: header + every contig's BGZF blocks (copied verbatim from the rank
+    that owns the contig, in output contig order) + EOF block, and one .tbi over the shifted virtual
+    offsets.  BGZF blocks are self-contained, so concatenating whole blocks is a valid BGZF file
+    (the reference's own precedent: ``bcftools concat --naive``, variant_annotation.py:96-110)."""
+    metas = []
+    for r in range(world):
+        with open(_part_path(output_file, r) + ".meta", "rb") as fh:
+            metas.append(pickle.load(fh))  # noqa: S301  (written by this program a moment ago)
+    w = bgzf_io.BgzfWriter(output_file, n_threads=threads)
+    w.write(("\n".join(header_lines) + "\n").encode())
+    pos = w.coffset
+    names, contig_of, beg, end, vs, ve = [], [], [], [], [], []
+    with open(output_file, "ab") as dst:
+        for contig in contigs:
+            owner = next((r for r, m in enumerate(metas) if contig in m["ranges"]), None)
+            if owner is None or contig in names:
+                continue
+            m = metas[owner]
+            c0, c1 = m["ranges"][contig]
+            with open(_part_path(output_file, owner), "rb") as src:
+                src.seek(c0)
+                left = c1 - c0
+                while left > 0:
+                    chunk = src.read(min(left, 64 << 20))
+                    if not chunk:
+                        raise OSError(f"{_part_path(output_file, owner)} is shorter than its index says")
+                    dst.write(chunk)
+                    left -= len(chunk)
+            sel = np.flatnonzero(m["contig_of"] == m["names"].index(contig))
+            shift = pos - c0
+
+            def moved(v, shift=shift):
+                block = (v >> np.uint64(16)).astype(np.int64) + shift
+                return (block.astype(np.uint64) << np.uint64(16)) | (v & np.uint64(0xFFFF))
+
+            contig_of.append(np.full(sel.size, len(names), dtype=np.int32))
+            names.append(contig)
+            beg.append(m["beg"][sel])
+            end.append(m["end"][sel])
+            vs.append(moved(m["vs"][sel]))
+            ve.append(moved(m["ve"][sel]))
+            pos += c1 - c0
+        dst.write(bgzf_io.BGZF_EOF)
+    cat = np.concatenate
+    if names:
+        payload = bgzf_io.build_tbi(names, cat(contig_of), cat(beg), cat(end), cat(vs), cat(ve))
+    else:
+        z = np.zeros(0, np.int64)
+        payload = bgzf_io.build_tbi([], z, z, z, z.astype(np.uint64), z.astype(np.uint64))
+    bgzf_io.write_tbi(output_file + ".tbi", payload)
+    for r in range(world):
+        for suffix in ("", ".meta"):
+            try:
+                os.remove(_part_path(output_file, r) + suffix)
+            except OSError:
+                pass
 
 
 def _split_batches(text: np.ndarray, limit: int):
@@ -246,6 +324,11 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         with_bl = args.blacklist is not None or args.blacklist_cg_insertions
         out_header = header.edited_lines(with_model=with_model, with_blacklist=with_bl)
         index = bgzf_io.read_tbi(args.input_file + ".tbi")
+        # one process per GPU (torchrun): ranks own whole contigs, no record ever crosses ranks; the only
+        # collective is the SUM of the counters at the end (NCCL on GPUs; gloo when there is no CUDA device,
+        # i.e. in the host-emulation test)
+        world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+        multi = world > 1
 
         device = args.device if args.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
         ctx = lib.Context(device)  # raises without a CUDA device: there is no CPU path
@@ -274,8 +357,9 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         reserved = (0, 0)
         key_order_set = False
 
-        out = _Splicer(args.output_file, args.io_threads)
-        out.write_header(out_header)
+        out = _Splicer(_part_path(args.output_file, rank) if multi else args.output_file, args.io_threads)
+        if not multi:
+            out.write_header(out_header)
         seconds = {"inflate_wait": 0.0, "gpu": 0.0}
         totals = {"n_records": 0, "n_low_score": 0, "n_cg": 0, "n_blacklisted": 0}
 
@@ -306,6 +390,15 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                     np.concatenate(([0], np.cumsum([len(x) for x in strings]))).astype(np.int64))
 
         contigs = [str(c) for c in (header.contigs.keys() if args.limit_to_contigs is None else args.limit_to_contigs)]
+        all_contigs = list(contigs)
+        if multi:
+            from variantcalling_b200 import dist as vdist
+
+            # load = compressed span of the contig in the input (a proxy for its record count that needs no pass)
+            loads = {c: int((index[c][1] >> 16) - (index[c][0] >> 16)) + 1 for c in dict.fromkeys(contigs) if c in index}
+            mine = set(vdist.lpt_partition(loads, world)[rank])
+            contigs = [c for c in contigs if c in mine or (c not in index and rank == 0)]
+            logger.info(f"rank {rank}/{world}: {len(contigs)} of {len(all_contigs)} contigs")
 
         def load_contig(contig: str):
             """Inflate one contig's records (runs one contig ahead of the loop, on its own thread)."""
@@ -414,7 +507,26 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             logger.info(f"{contig} done")
 
         t_close = time.perf_counter()
-        out.close(args.output_file)
+        if multi:
+            import torch
+            import torch.distributed as tdist
+
+            with open(_part_path(args.output_file, rank) + ".meta", "wb") as fh:
+                pickle.dump(out.finish_part(), fh)
+            if not tdist.is_initialized():
+                on_gpu = torch.cuda.is_available()
+                tdist.init_process_group("nccl" if on_gpu else "gloo",
+                                         **({"device_id": torch.device("cuda", device)} if on_gpu else {}))
+            keys = ("n_records", "n_low_score", "n_cg", "n_blacklisted")
+            counts = torch.tensor([totals[k] for k in keys], dtype=torch.int64,
+                                  device=torch.device("cuda", device) if torch.cuda.is_available() else "cpu")
+            vdist.allreduce_counts(counts)  # the single collective of the path; it also orders the parts before rank 0 reads them
+            totals.update({k: int(v) for k, v in zip(keys, counts.tolist())})
+            if rank == 0:
+                _assemble_parts(args.output_file, out_header, all_contigs, world, args.io_threads)
+            tdist.barrier()
+        else:
+            out.close(args.output_file)
         prefetch.shutdown()
         logger.info("stage seconds (overlapping threads): wait for inflate %.2f, wait for GPU %.2f, splice %.2f, "
                     "deflate+write %.2f, index %.2f", seconds["inflate_wait"], seconds["gpu"], out.seconds["splice"],
