@@ -162,10 +162,15 @@ def test_float_literals_match_strtod_float32(gpu_ctx, golden):
         new.append("\t".join(r))
     gpu_ctx.load_plan(MC.compile_plan(VcfHeader(hdr), golden["tr"], model, golden["customs"]).blob)
     gpu_ctx.reserve(4 << 20, 8192, 1)
-    res = gpu_ctx.filter_batch(("\n".join(new) + "\n").encode())
-    qual = gpu_ctx.debug_features(res["n_records"])[21]
     with np.errstate(over="ignore"):
         want = np.array([np.float32(float(s)) for s in lits], dtype=np.float32)
+    # a literal beyond float32 parses to inf, which the batch then refuses like the reference's input checks do
+    # ("Input X contains infinity"); the feature matrix is still there to compare the parse itself
+    with pytest.raises(lib.UgvcDataError):
+        gpu_ctx.filter_batch(("\n".join(new) + "\n").encode())
+    first_inf = int(np.flatnonzero(np.isinf(want))[0])
+    assert gpu_ctx.last_data_error()[0] == first_inf and lits[first_inf] == "17976931348623157e292"
+    qual = gpu_ctx.debug_features(len(lits))[21]
     bad = np.flatnonzero(qual.view(np.uint32) != want.view(np.uint32))
     assert bad.size == 0, f"{bad.size} literals differ, e.g. {lits[bad[0]]!r}: {qual[bad[0]]!r} vs {want[bad[0]]!r}"
 
