@@ -1,6 +1,5 @@
 """CPU: the C-ABI library loads, exports every symbol include/ugvc_b200.h declares, and the
 product path fails loudly (no CPU fallback) when there is no CUDA device."""
-import ctypes as C
 import os
 import re
 

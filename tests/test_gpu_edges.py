@@ -1,6 +1,5 @@
 """GPU: edge cases of the typed decode and of the transformer policies, against the golden
 vectors of the reference's own transformer and against the oracle's error behaviour."""
-import json
 import os
 
 import numpy as np

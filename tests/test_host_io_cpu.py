@@ -2,7 +2,6 @@
 oracle's writer rules (filter_variants_pipeline.py:188-228)."""
 import ctypes as C
 import gzip
-import os
 
 import numpy as np
 import pytest
