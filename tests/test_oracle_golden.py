@@ -178,3 +178,38 @@ def test_mirror_cnv_transformer_matches_reference_golden():
         x = tr.fit_transform(df).to_numpy(dtype=np.float64)
     assert x.shape == feats_ref.shape == (400, 19)
     assert np.array_equal(x, feats_ref)
+
+
+def test_oracle_reader_scalar_versus_tuple_rule_known_answers():
+    """The few facts about pysam's typed decode that the reference's own (in-code) unit tests assert,
+    re-checked on the oracle reader -- they pin the Number=1 -> scalar / otherwise -> tuple rule and the
+    Integer / Float / String typing (everything else about that boundary stays "parity unpinned"):
+      * INFO Integer Number=1 reads back as an int:  ``first_record.info["CNV_TOTAL_READS"] == 2``
+        (ugbio_cnv/tests/unit/test_analyze_cnv_breakpoint_reads.py:232-234; header analyze_cnv_breakpoint_reads.py:443-445)
+      * INFO Integer Number=. reads back as a tuple even with one element: ``record.info["SVLEN"] == (n,)``
+        (tests/unit/test_combine_cnv_vcf_utils.py:656; header cnmops_utils.py:68)
+      * INFO String Number=. -> tuple of str: ``record.info["CNV_SOURCE"] == ("CNVpytor",)``
+        (tests/unit/test_combine_cnv_vcf_utils.py:222,268,349; header cnv_vcf_consts.py:13-19)
+      * INFO Float Number=1 -> float: ``records[0].info["GAP_PERCENTAGE"] == 1.0`` / ``0.5``
+        (tests/unit/test_combine_cnmops_cnvpytor_cnv_calls_unit.py:109-216; header cnv_vcf_consts.py:48-54)
+    """
+    from oracle.vcf_reader import OracleVariantFile
+
+    text = ("##fileformat=VCFv4.2\n"
+            '##INFO=<ID=CNV_TOTAL_READS,Number=1,Type=Integer,Description="x">\n'
+            '##INFO=<ID=CNV_DUP_READS,Number=1,Type=Integer,Description="x">\n'
+            '##INFO=<ID=SVLEN,Number=.,Type=Integer,Description="CNV length">\n'
+            '##INFO=<ID=CNV_SOURCE,Number=.,Type=String,Description="tool">\n'
+            '##INFO=<ID=GAP_PERCENTAGE,Number=1,Type=Float,Description="fraction">\n'
+            "##contig=<ID=chr1,length=1000000>\n"
+            "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n"
+            "chr1\t2500\t.\tN\t<DEL>\t.\tPASS\tCNV_TOTAL_READS=2;CNV_DUP_READS=1;SVLEN=2000;CNV_SOURCE=CNVpytor;GAP_PERCENTAGE=0.5\n"
+            "chr1\t9000\t.\tN\t<DUP>\t.\tPASS\tSVLEN=100,200;CNV_SOURCE=cn.mops,cnvpytor;GAP_PERCENTAGE=1\n")
+    first, second = list(OracleVariantFile(text.encode()))
+    assert first.info["CNV_TOTAL_READS"] == 2 and isinstance(first.info["CNV_TOTAL_READS"], int)
+    assert first.info["CNV_DUP_READS"] == 1
+    assert first.info["SVLEN"] == (2000,)
+    assert first.info["CNV_SOURCE"] == ("CNVpytor",)
+    assert first.info["GAP_PERCENTAGE"] == 0.5 and isinstance(first.info["GAP_PERCENTAGE"], float)
+    assert second.info["SVLEN"] == (100, 200) and second.info["CNV_SOURCE"] == ("cn.mops", "cnvpytor")
+    assert second.info["GAP_PERCENTAGE"] == 1.0
