@@ -8,7 +8,9 @@ party engine behind the reference's loader).  Only ``tests/``,
 PARITY STATUS: *unpinned* for the htslib typed-decode boundary.  pysam/htslib
 are not installed in the build container and every reference test that pins
 this boundary (``ugbio_utils/src/core/tests/unit/vcfbed/test_vcftools.py:110-``)
-runs on git-LFS fixtures that are pointer stubs here.  The behaviour below is
+runs on git-LFS fixtures that are pointer stubs here.  (Only the scalar-versus-tuple rule and the
+Integer / Float / String typing are pinned, by the handful of literal expectations in the reference's
+in-code CNV unit tests -- see tests/test_oracle_golden.py.)  The behaviour below is
 restated from the VCF 4.2 specification plus the documented htslib/pysam rules
 (SURVEY.md Appendix B):
 
