@@ -117,6 +117,15 @@ int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n_bytes, dou
                        uint8_t* d_low_score, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
                        int64_t* d_line_start, size_t capacity_records, int64_t* d_n_records, void* stream);
 
+/* The model-apply step alone (variant_filtering_utils.py:95-125 after the transform; the other
+ * model-apply tools' predict_proba): K3 on a dense row-major float32 matrix x[n][ld] whose first
+ * n_features columns are the features of a plan compiled with model_compiler.compile_plan_model_only
+ * (or any plan with a model).  n <= the max_records of ugvc_reserve; outputs may be NULL; with
+ * ugvc_enable_phreds(ctx, 2) the fp64 class probabilities are fetched with ugvc_collect_phreds(ctx, 0, ...).
+ * A NaN / infinite input value is UGVC_E_DATA (the reference's estimators raise on it). */
+int ugvc_predict_features(ugvc_ctx* ctx, const float* x, size_t n, size_t ld, double threshold,
+                          uint8_t* out_low_score, float* out_probs, double* out_qual);
+
 /* --recalibrate_genotype (filter_variants_pipeline.py:203-215): ask K3 to keep the per-class
  * phreds -10*log10(p + 1e-10) of the host-buffer lanes (takes effect at the next ugvc_reserve)
  * and fetch them (N x n_classes fp64) after ugvc_collect_batch.  on = 2 keeps the fp64 class

@@ -85,6 +85,10 @@ static inline cudaError_t cudaMemcpy2D(void* d, size_t dpitch, const void* s, si
     for (size_t r = 0; r < height; ++r) memmove((char*)d + r * dpitch, (const char*)s + r * spitch, width);
     return cudaSuccess;
 }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height,
+                                            cudaMemcpyKind k, cudaStream_t = nullptr) {
+    return cudaMemcpy2D(d, dpitch, s, spitch, width, height, k);
+}
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = malloc(1); return cudaSuccess; }

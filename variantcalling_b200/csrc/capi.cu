@@ -617,6 +617,57 @@ extern "C" int ugvc_device_status(ugvc_ctx* ctx, void* stream) {
     return decode_error(ctx, e);
 }
 
+// K3 alone on a dense feature matrix assembled by the caller (row-major, n x n_features, leading
+// dimension ld): the model-apply step of variant_filtering_utils.apply_model / the other model-apply
+// tools, without the VCF front end.  Features are staged feature-major in lane 0's K3 input buffer.
+extern "C" int ugvc_predict_features(ugvc_ctx* ctx, const float* x, size_t n, size_t ld, double threshold,
+                                     uint8_t* out_low_score, float* out_probs, double* out_qual) {
+    if (!ctx) return UGVC_E_ARG;
+    if (!ctx->has_plan || ctx->lanes.empty()) return fail(ctx, UGVC_E_STATE, "predict_features: load a plan and reserve first");
+    const DevPlan& p = ctx->plan;
+    const size_t F = p.h.n_features;
+    if (p.h.model_kind == MODEL_NONE || F == 0) return fail(ctx, UGVC_E_STATE, "predict_features: the plan carries no model");
+    if ((n && !x) || ld < F) return fail(ctx, UGVC_E_ARG, "predict_features: bad matrix arguments");
+    if (n > ctx->cap_records) return fail(ctx, UGVC_E_ARG, "predict_features: more rows than the reserved max_records");
+    Lane& l = ctx->lanes[0];
+    if (l.submitted) return fail(ctx, UGVC_E_STATE, "predict_features: lane 0 has a batch in flight");
+    CU(cudaSetDevice(ctx->device));
+    l.last_n = (int64_t)n;
+    if (n == 0) return UGVC_OK;
+    // feature-major staging copy; a non-finite value is refused like the reference's estimators do
+    // ("Input X contains NaN / infinity"; xgboost's missing-value routing is not part of this path)
+    std::vector<float> cols(F * n);
+    for (size_t r0 = 0; r0 < n; r0 += 256) {
+        const size_t r1 = r0 + 256 < n ? r0 + 256 : n;
+        for (size_t f = 0; f < F; ++f)
+            for (size_t r = r0; r < r1; ++r) {
+                const float v = x[r * ld + f];
+                if (!(v - v == 0.0f)) {  // NaN or +-inf
+                    ctx->err_record = (int64_t)r;
+                    ctx->err_column = (int32_t)f;
+                    ctx->err_reason = REASON_NULL_FEATURE;
+                    return fail(ctx, UGVC_E_DATA, "predict_features: non-finite value at row " + std::to_string(r) +
+                                                      ", column " + std::to_string(f));
+                }
+                cols[f * n + r] = v;
+            }
+    }
+    cudaStream_t st = l.stream;
+    CU(cudaMemcpy2DAsync(l.b.feats, l.b.cap_records * sizeof(float), cols.data(), n * sizeof(float), n * sizeof(float), F,
+                         cudaMemcpyHostToDevice, st));
+    const int64_t n64 = (int64_t)n;
+    CU(cudaMemcpyAsync(l.b.n_records, &n64, sizeof(n64), cudaMemcpyHostToDevice, st));
+    launch_k3(p, l.b.feats, l.b.cap_records, l.b.n_records, threshold, l.b.low_score, l.b.probs, l.b.qual,
+              l.b.phreds, ctx->want_phreds, ctx->d_counts, ctx->sm_count, st);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    if (out_low_score) CU(cudaMemcpyAsync(out_low_score, l.b.low_score, n, cudaMemcpyDeviceToHost, st));
+    if (out_probs) CU(cudaMemcpyAsync(out_probs, l.b.probs, n * p.h.n_classes * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out_qual) CU(cudaMemcpyAsync(out_qual, l.b.qual, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // also keeps `cols` and n64 alive until the copies are done
+    return UGVC_OK;
+}
+
 extern "C" int ugvc_enable_phreds(ugvc_ctx* ctx, int on) {
     // takes effect at the next ugvc_reserve
     if (!ctx) return UGVC_E_ARG;

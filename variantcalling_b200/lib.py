@@ -74,6 +74,7 @@ SIGNATURES = {
     "ugvc_count_byte": (C.c_int64, [_vp, _sz, C.c_int, C.c_int]),
     "ugvc_splice_records": (C.c_int64, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp,
                                         _vp, C.c_int, _vp, _sz, _vp, C.c_int]),
+    "ugvc_predict_features": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, _vp, _vp, _vp]),
     "ugvc_enable_phreds": (C.c_int, [_vp, C.c_int]),
     "ugvc_collect_phreds": (C.c_int, [_vp, C.c_int, _vp, _sz]),
     "ugvc_conc_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
@@ -231,6 +232,17 @@ class Context:
                                                 _ptr(out.get("qual")), _ptr(out.get("recinfo")),
                                                 _ptr(out.get("line_start")), capacity, C.byref(n)))
         return n.value
+
+    def predict_features(self, x: np.ndarray, threshold: float = 30.0) -> dict:
+        """K3 on a dense (n, n_features) float32 matrix -> dict(low_score, probs, qual)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.n_features:
+            raise ValueError(f"expected a (n, {self.n_features}) matrix, got {x.shape}")
+        n = x.shape[0]
+        out = self.alloc_outputs(max(1, n), want_recinfo=False)
+        self._check(self.lib.ugvc_predict_features(self.h, _ptr(x) if n else None, n, x.shape[1], threshold,
+                                                   _ptr(out["low_score"]), _ptr(out["probs"]), _ptr(out["qual"])))
+        return self.trim_outputs(out, n)
 
     def enable_phreds(self, on: bool | int = True):
         """1/True: K3 keeps the per-class phreds; 2: the fp64 class likelihoods (--treat_multiallelics)."""

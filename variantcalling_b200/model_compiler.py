@@ -625,6 +625,24 @@ def compile_plan(header: VcfHeader | str | bytes, transformer, model, custom_inf
                 feature_names=b.feature_names, model_kind=m["kind"], classes=m.get("classes", []))
 
 
+def compile_plan_model_only(model, n_features: int) -> Plan:
+    """Plan that carries only the model (for ``ugvc_predict_features``: K3 on a dense feature matrix the
+    caller assembled itself, e.g. ``variant_filtering_utils.apply_model`` with the transformer on the host).
+    The feature table is a placeholder (one fixed slot) -- K1 / K2 never run on this plan."""
+    if n_features < 1 or n_features > MAX_FEATURES:
+        raise PlanError(f"feature count {n_features} out of range")
+    m = _lower_model(model, n_features)
+    slots = [(TAG_FIXED, 0, RED_FIX_QUAL, 0)]
+    feats_packed = b"".join(struct.pack("<HBBff", 0, POL_NULL, POL_NULL, 0.0, 0.0) for _ in range(n_features))
+    hdr = struct.pack("<15I2H4d", PLAN_MAGIC, PLAN_VERSION, 0, len(slots), n_features, 0, 0, m["kind"], m["n_classes"],
+                      m["n_outputs"], m["n_trees"], m["n_nodes"], m["n_leaf_rows"], m["leaf_width"], m["cmp"], 0, 0,
+                      *m["init"])
+    blob = (_pad8(hdr) + _pad8(b"") + _pad8(b"".join(struct.pack("<4B", *x) for x in slots)) + _pad8(b"") + _pad8(b"")
+            + _pad8(feats_packed) + _pad8(b"") + _pad8(b"") + m["section"])
+    return Plan(blob=blob, n_features=n_features, n_classes=m["n_classes"], n_slots=len(slots), tags=[],
+                feature_names=[f"x{i}" for i in range(n_features)], model_kind=m["kind"], classes=m.get("classes", []))
+
+
 def compile_plan_no_model(header: VcfHeader | str | bytes) -> Plan:
     """Plan for runs without ``--model_file``: only K0/K1 run (line index, POS, column
     offsets, CG flag) so the writer can apply the blacklist / PASS-fill rules."""
