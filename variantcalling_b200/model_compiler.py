@@ -476,7 +476,14 @@ def _lower_xgboost_json(doc, n_features: int) -> dict:
     algorithm restated is xgboost's published CPU predictor (fp32 ``x < split_condition`` goes
     left, fp32 margin accumulated in tree order from logit(base_score), fp32 sigmoid/softmax)."""
     if isinstance(doc, (str, bytes)):
-        doc = json.loads(doc)
+        try:
+            doc = json.loads(doc)
+        except (UnicodeDecodeError, json.JSONDecodeError):
+            if isinstance(doc, str):
+                raise
+            from variantcalling_b200 import ubjson  # the binary flavour (save_model("*.ubj"), save_raw("ubj"))
+
+            doc = ubjson.loads(doc)
     learner = doc["learner"]
     objective = learner["objective"]["name"]
     lmp = learner["learner_model_param"]
