@@ -122,3 +122,36 @@ def test_other_vcf_flavours_lower_or_fail_loudly(ds, vtype, extra_info):
         tr.transformers_ = [(n, t, c) for (n, t, c) in tr.transformers]
         with pytest.raises(MC.PlanError):
             MC.compile_plan(VcfHeader(hdr), tr, None, None)
+
+
+def test_real_deepvariant_header_of_the_reference_compiles():
+    """The one real (non-LFS) VCF header in the reference tree, a UG DeepVariant call set with 3366
+    contigs: the header model reads it, the loader whitelist picks its tags, and the ``deep_variant``
+    flavour fitted on records of that schema lowers against it."""
+    import os
+
+    import numpy as np
+    import pandas as pd
+
+    from oracle import ref_pipeline as R
+    from oracle.vcf_reader import OracleVariantFile
+    from tests import dv_data, util
+    from variantcalling_b200 import transformers as T
+    from variantcalling_b200.tprep_constants import VcfType
+
+    path = "/root/reference/ugbio_utils/src/core/tests/resources/header.txt"
+    if not os.path.exists(path):
+        pytest.skip("the reference tree is not mounted here")
+    hdr = VcfHeader(open(path).read())
+    assert len(hdr.contigs) > 3000 and hdr.contigs["chr1"] == 248956422 and hdr.samples
+    cols = hdr.loader_columns(dv_data.CUSTOMS)
+    assert {"ad", "gt", "gq", "pl", "dp", "vaf", "sor", "af", "x_css", "x_gcc", "x_hil", "x_hin", "x_ic", "x_il", "x_lm", "x_rm",
+            "variant_type", "lcr", "ug_hcr"} <= set(cols)
+    ds = dv_data.generate(1500, seed=5)
+    df = R.get_vcf_df(OracleVariantFile(ds["header_text"].encode() + ds["text"]), None, ds["customs"])
+    tr = T.get_transformer(VcfType.DEEP_VARIANT, [c.lower() for c in ds["customs"]])
+    with pd.option_context("future.infer_string", False):
+        x = tr.fit_transform(R.harness_float_columns(df)).to_numpy(dtype=np.float64)
+    plan = MC.compile_plan(hdr, tr, util.fit_model("lr", x, ds["labels"]), ds["customs"])
+    ours = MC.compile_plan(VcfHeader(ds["header_text"]), tr, util.fit_model("lr", x, ds["labels"]), ds["customs"])
+    assert plan.feature_names == ours.feature_names and plan.tags == ours.tags
