@@ -513,7 +513,8 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
 
             with open(_part_path(args.output_file, rank) + ".meta", "wb") as fh:
                 pickle.dump(out.finish_part(), fh)
-            if not tdist.is_initialized():
+            created_group = not tdist.is_initialized()
+            if created_group:
                 on_gpu = torch.cuda.is_available()
                 tdist.init_process_group("nccl" if on_gpu else "gloo",
                                          **({"device_id": torch.device("cuda", device)} if on_gpu else {}))
@@ -525,6 +526,8 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             if rank == 0:
                 _assemble_parts(args.output_file, out_header, all_contigs, world, args.io_threads)
             tdist.barrier()
+            if created_group:
+                tdist.destroy_process_group()
         else:
             out.close(args.output_file)
         prefetch.shutdown()
