@@ -260,7 +260,7 @@ def main():  # noqa: C901, PLR0912, PLR0915
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--records", type=int, default=50_000_000, help="total records of the job (all ranks)")
     ap.add_argument("--batch-records", type=int, default=2_000_000)
-    ap.add_argument("--cpu-sample", type=int, default=50_000, help="records timed on the CPU oracle at N=1")
+    ap.add_argument("--cpu-sample", type=int, default=120_000, help="records timed on the CPU oracle at N=1 (about 15 s)")
     ap.add_argument("--cpu-sample-per-worker", type=int, default=8000)
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (0 = same as --steps)")
     ap.add_argument("--lanes", type=int, default=3)
