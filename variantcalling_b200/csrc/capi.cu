@@ -37,6 +37,10 @@ struct ugvc_ctx {
     uint2* d_nodes = nullptr;
     std::vector<PlanTag> h_tags;   // host copies for name lookups / decode classes
     std::vector<PlanSlot> h_slots;
+#ifdef UGVC_K1_INLINE_DICT1
+    std::vector<PlanDict> h_dicts;
+    std::vector<PlanString> h_strings;
+#endif
     DevSchedule sched{};           // learned key order (empty: generic path only)
     SchedEntry* d_sched = nullptr;
     std::vector<Lane> lanes;
@@ -311,6 +315,14 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     ctx->has_plan = true;
     ctx->h_tags.assign(tags, tags + h.n_tags);
     ctx->h_slots.assign(slots, slots + h.n_slots);
+#ifdef UGVC_K1_INLINE_DICT1
+    {
+        const PlanDict* dd = reinterpret_cast<const PlanDict*>(hb + o_dicts);
+        const PlanString* ss = reinterpret_cast<const PlanString*>(hb + o_strings);
+        ctx->h_dicts.assign(dd, dd + h.n_dicts);
+        ctx->h_strings.assign(ss, ss + h.n_dict_strings);
+    }
+#endif
     cudaFree(ctx->d_sched);  // a key order belongs to a plan
     ctx->d_sched = nullptr;
     ctx->sched = DevSchedule{};
@@ -353,6 +365,22 @@ static void classify(const ugvc_ctx* ctx, int tag, bool format, SchedEntry& se) 
                ctx->h_slots[tg.first_slot].reducer == RED_DICT) {
         se.cls = CLS_DICT1;
         se.dict = ctx->h_slots[tg.first_slot].dict;
+#ifdef UGVC_K1_INLINE_DICT1
+        // a single short category and a key that leaves w1 free: K1 compares the value in the schedule loop itself
+        // (for the default annotation encoder the categories are {FALSE, TRUE} and the file only ever spells TRUE:
+        // the last category is the one compared inline, any other spelling takes the full decoder)
+        if (!format && se.dict < ctx->h_dicts.size() && ctx->h_dicts[se.dict].n_strings >= 1 &&
+            ctx->h_dicts[se.dict].n_strings <= 2) {
+            const int pick = ctx->h_dicts[se.dict].n_strings - 1;
+            const PlanString& ps = ctx->h_strings[ctx->h_dicts[se.dict].first_string + pick];
+            if (ps.len >= 1 && ps.len <= 7) {
+                se.flags |= SCHED_DICT_INLINE | (pick ? SCHED_DICT_INLINE_SECOND : 0u);
+                se.n_elem = ps.len;
+                se.w1 = 0;
+                memcpy(&se.w1, &ps, ps.len);
+            }
+        }
+#endif
     }
 }
 
@@ -382,6 +410,10 @@ extern "C" int ugvc_set_key_order(ugvc_ctx* ctx, const char* info_keys, const ch
             unsigned char buf[16] = {0};
             memcpy(buf, bytes.data(), bytes.size());
             memcpy(&se.w0, buf, 8);
+#ifdef UGVC_K1_INLINE_DICT1
+            if ((se.flags & SCHED_DICT_INLINE) && bytes.size() > 8) se.flags &= ~SCHED_DICT_INLINE;  // w1 is needed for the key
+            if (!(se.flags & SCHED_DICT_INLINE))
+#endif
             memcpy(&se.w1, buf + 8, 8);
             se.m0 = bytes.size() >= 8 ? ~0ull : ((1ull << (8 * bytes.size())) - 1ull);
             entries.push_back(se);

@@ -662,6 +662,25 @@ __device__ __noinline__ Cur decode_sched(RawOut o, unsigned long long meta, Cur 
                     bits = r.st == NUM_OK ? __float_as_uint((float)r.v) : (r.st == NUM_MISSING ? RAW_MISSING : RAW_ERR);
                 }
             } else {
+#ifdef UGVC_K1_NEGFAST
+                // experiment (round 2): "-d.ddd" decoded on the look-ahead too (the rank-sum tags are negative half of the time)
+                if ((x & 0xFFull) == '-') {
+                    const unsigned long long xs = (x >> 8) | (0xFFull << 56);
+                    const int n1 = leading_digits(xs);
+                    if (n1 >= 1 && n1 <= 4 && ((unsigned)(xs >> (8 * n1)) & 0xFFu) == '.') {
+                        const unsigned long long ys = xs >> (8 * (n1 + 1));
+                        const int n2 = leading_digits(ys | (0xFFull << (8 * (7 - n1))));
+                        if (n2 >= 1 && n1 + 1 + n2 <= 6 && is_term((unsigned)(ys >> (8 * n2)) & 0xFFu, vend)) {
+                            unsigned m = 0;
+                            for (int i = 0; i < n1; ++i) m = m * 10u + ((unsigned)(xs >> (8 * i)) & 0xFu);
+                            for (int i = 0; i < n2; ++i) m = m * 10u + ((unsigned)(ys >> (8 * i)) & 0xFu);
+                            bits = __float_as_uint((float)(-((double)m / ugvc_ten(n2))));
+                            c.advance(1 + n1 + 1 + n2);
+                            fast = true;
+                        }
+                    }
+                } else
+#endif
                 if (k1 >= 1 && k1 <= 5 && ((unsigned)(x >> (8 * k1)) & 0xFFu) == '.') {
                     const unsigned long long y = x >> (8 * (k1 + 1));
                     const int k2 = leading_digits(y | (0xFFull << (8 * (7 - k1))));  // bytes past the window: non-digits
@@ -905,6 +924,20 @@ __global__ void __launch_bounds__(K1_TPB, K1_MIN_CTAS) k1_parse(const __grid_con
                                         if (((b.y >> 8) & 0xFFu) != CLS_SKIP) set_tag_missing(o, (int)(short)(b.y >> 48));
                                     }
                                 } else {
+#ifdef UGVC_K1_INLINE_DICT1
+                                    // experiment (round 2): a one-category annotation ("LCR=TRUE") is matched on the
+                                    // look-ahead right here; anything else takes the full decoder
+                                    const unsigned fl = (unsigned)(b.y >> 40) & 0xFFu;
+                                    const int L = (int)((b.y >> 24) & 0xFFu);
+                                    const unsigned long long xv = t.peek8();
+                                    const unsigned nxt = (unsigned)(xv >> (8 * L)) & 0xFFu;
+                                    if ((fl & SCHED_DICT_INLINE) && (xv & ((1ull << (8 * L)) - 1ull)) == b.x &&
+                                        (nxt == ';' || nxt == '\t' || nxt == '\n')) {
+                                        store_slot_f(o, (int)((b.y >> 16) & 0xFFu), (fl & SCHED_DICT_INLINE_SECOND) ? 1.0f : 0.0f);
+                                        t.advance(L);
+                                        c = t;
+                                    } else
+#endif
                                     c = decode_sched(o, b.y, t, ';');
                                 }
                             }

@@ -42,6 +42,8 @@ enum : uint8_t {
 };
 #define SCHED_IS_FLAG 1u
 #define SCHED_COUNT_ALL 2u
+#define SCHED_DICT_INLINE 4u  // UGVC_K1_INLINE_DICT1 builds: one category (<= 7 bytes) of a CLS_DICT1 key held in w1, its length in n_elem
+#define SCHED_DICT_INLINE_SECOND 8u  // ... and it is category 1 of 2 (else category 0)
 struct alignas(8) SchedEntry {   // 32 bytes
     unsigned long long w0, m0;   // first 8 bytes to match ("KEY=", or "KEY" for a valueless key) and their mask
     unsigned long long w1;       // bytes 8..15, zero padded (len > 8)
