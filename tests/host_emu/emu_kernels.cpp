@@ -53,7 +53,13 @@ void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_t
         k1_fill(raw, row_stride, (int)plan.h.n_slots, d_n_records);
     }
     one_thread_grid();
+#ifdef UGVC_K1_SPLIT
+    k1_parse_info(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts);
+    one_thread_grid();
+    k1_parse_frame(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts);
+#else
     k1_parse(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts);
+#endif
 }
 
 void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, const int64_t* d_n_records, float* feats,

@@ -757,306 +757,23 @@ __device__ __noinline__ Cur decode_sched(RawOut o, unsigned long long meta, Cur 
     return c;
 }
 
-__global__ void __launch_bounds__(K1_TPB, K1_MIN_CTAS) k1_parse(const __grid_constant__ DevPlan plan,
-                                                      const __grid_constant__ DevSchedule sched,
-                                                      const uint8_t* __restrict__ text,
-                                                   const int64_t* __restrict__ line_start,
-                                                   const int64_t* __restrict__ n_records_p,
-                                                   uint32_t* __restrict__ raw, size_t row_stride,
-                                                   ugvc_recinfo* __restrict__ recinfo, unsigned long long* err,
-                                                   long long* counts) {
-    // shared-memory copies of the small plan tables
-    const int n_tags = plan.h.n_tags, n_slots = plan.h.n_slots;
-    {
-        const uint32_t* src;
-        uint32_t* dst;
-        src = reinterpret_cast<const uint32_t*>(plan.tags);
-        dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_TAGS);
-        for (int i = threadIdx.x; i < n_tags * 10; i += K1_TPB) dst[i] = src[i];
-        src = reinterpret_cast<const uint32_t*>(plan.strings);
-        dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_STRINGS);
-        for (int i = threadIdx.x; i < (int)plan.h.n_dict_strings * 8; i += K1_TPB) dst[i] = src[i];
-        src = reinterpret_cast<const uint32_t*>(plan.slots);
-        dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_SLOTS);
-        for (int i = threadIdx.x; i < n_slots; i += K1_TPB) dst[i] = src[i];
-        src = reinterpret_cast<const uint32_t*>(plan.dicts);
-        dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_DICTS);
-        for (int i = threadIdx.x; i < (int)plan.h.n_dicts; i += K1_TPB) dst[i] = src[i];
-        for (int i = threadIdx.x; i < 256; i += K1_TPB) k1_smem[K1_OFF_HTAB + i] = plan.htab[i];
-        src = reinterpret_cast<const uint32_t*>(sched.info);
-        dst = reinterpret_cast<uint32_t*>(k1_smem + K1_OFF_SCHED);
-        for (int i = threadIdx.x; i < sched.n_info * 8; i += K1_TPB) dst[i] = src[i];
-    }
-    __syncthreads();
-    const unsigned tab4 = B4('\t');
-    const long long n_rec = *n_records_p;
-    const long long n_tiles = (n_rec + K1_TPB - 1) / K1_TPB;
-    unsigned cg_local = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long rec = tile * K1_TPB + threadIdx.x;
-        if (rec < n_rec) {
-            const uint8_t* const line = text + line_start[rec];
-            RawOut o;
-            o.col = raw + rec;
-            o.stride = row_stride;
-            Cur c;
-            c.init(line);
-            ugvc_recinfo ri;
-            ri.flags = 0;
-            bool malformed = false;
-            // ---- CHROM
-            c = skip_until(c, tab4, tab4);
-            malformed |= (c.peek() != '\t');
-            // ---- POS
-            long long pos = 0;
-            if (!malformed) {
-                c.adv();
-                unsigned ch = c.peek();
-                while (ugvc_is_digit(ch)) {
-                    pos = pos * 10 + (ch - '0');
-                    c.adv();
-                    ch = c.peek();
-                }
-                malformed |= (ch != '\t');
-            }
-            ri.pos = (int32_t)pos;
-            // ---- ID
-            if (!malformed) {
-                c.adv();
-                c = skip_until(c, tab4, tab4);
-                malformed |= (c.peek() != '\t');
-            }
-            // ---- REF / ALT -> allele codes, indel flag, CG flag
-            float a0 = 0.f, a1 = 0.f;
-            bool a1_missing = true, indel = false, cg = false;
-            int n_alleles = 0;
-            if (!malformed) {
-                c.adv();
-                KeyCur r = take_until(c, tab4, tab4);
-                c = r.c;
-                const int ref_len = r.k.len;
-                a0 = ref_len == 1 ? (float)base_code((unsigned)r.k.k0 & 0xFFu) : 0.f;
-                cg |= key_is_cg(r.k);
-                n_alleles = 1;
-                ri.flags |= (unsigned)(ref_len > 0xFFFFFF ? 0xFFFFFF : ref_len) << 8;
-                malformed |= (c.peek() != '\t');
-                if (!malformed) {
-                    c.adv();
-                    for (;;) {
-                        r = take_until(c, B4(','), tab4);
-                        c = r.c;
-                        if (n_alleles == 1 && r.k.len == 1 && (r.k.k0 & 0xFFu) == '.' && c.peek() != ',')
-                            break;  // ALT "." -> alleles == (REF,)
-                        if (n_alleles == 1) {
-                            a1 = r.k.len == 1 ? (float)base_code((unsigned)r.k.k0 & 0xFFu) : 0.f;
-                            a1_missing = false;
-                        }
-                        indel |= (r.k.len != ref_len);
-                        cg |= key_is_cg(r.k);
-                        ++n_alleles;
-                        if (c.peek() != ',') break;
-                        c.adv();
-                    }
-                    malformed |= (c.peek() != '\t');
-                }
-            }
-            // ---- QUAL
-            uint32_t qual_bits = RAW_MISSING;
-            unsigned off = (unsigned)(c.ptr() + 1 - line);
-            ri.qual_off = off > 0xFFFFu ? 0xFFFFu : (uint16_t)off;
-            if (!malformed) {
-                c.adv();
-                const NumCur r = parse_num_cur(c);
-                c = r.c;
-                if (c.peek() != '\t') {
-                    qual_bits = RAW_ERR;
-                    c = skip_until(c, tab4, tab4);
-                } else if (r.st == NUM_OK) {
-                    const float f = (float)r.v;
-                    qual_bits = isnan(f) ? RAW_MISSING : __float_as_uint(f);
-                } else if (r.st == NUM_BAD) {
-                    qual_bits = RAW_ERR;
-                }
-                malformed |= (c.peek() != '\t');
-            }
-            // ---- FILTER (kept as bytes; only its position is reported)
-            off = (unsigned)(c.ptr() + 1 - line);
-            ri.filter_off = off > 0xFFFFu ? 0xFFFFu : (uint16_t)off;
-            if (!malformed) {
-                c.adv();
-                c = skip_until(c, tab4, tab4);
-                malformed |= (c.peek() != '\t');
-            }
-            // ---- INFO
-            off = (unsigned)(c.ptr() + 1 - line);
-            ri.info_off = off > 0xFFFFu ? 0xFFFFu : (uint16_t)off;
-            if (!malformed) {
-                c.adv();
-                const unsigned semi4 = B4(';'), eq4 = B4('=');
-                bool in_info = true;
-                // (1) step through the learned key order: every lane of the warp looks for the same
-                //     key at the same time (one masked 8-byte compare against the cached
-                //     look-ahead), so the lanes that have it decode the same type together
-                unsigned long long x = c.peek8();
-                for (int j = 0; j < sched.n_info; ++j) {
-                    if (in_info) {
-                        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&s_sched()[j]);  // w0, m0
-                        if ((x & a.y) == a.x) {
-                            const ulonglong2 b = *(reinterpret_cast<const ulonglong2*>(&s_sched()[j]) + 1);  // w1, meta
-                            const int len = (int)(b.y & 0xFFu);
-                            Cur t = c;
-                            bool ok = true;
-                            if (len > 8) {
-                                t.advance(8);
-                                const int rem = len - 8;
-                                const unsigned long long mask = rem >= 8 ? ~0ull : ((1ull << (8 * rem)) - 1ull);
-                                ok = (t.peek8() & mask) == b.x;
-                                t.advance(rem);
-                            } else {
-                                t.advance(len);
-                            }
-                            if (ok) {
-                                if ((b.y >> 40) & SCHED_IS_FLAG) {  // valueless key: must end right here
-                                    const unsigned nxt = t.peek();
-                                    ok = nxt == ';' || nxt == '\t' || nxt == '\n';
-                                    if (ok) {
-                                        c = t;
-                                        if (((b.y >> 8) & 0xFFu) != CLS_SKIP) set_tag_missing(o, (int)(short)(b.y >> 48));
-                                    }
-                                } else {
-#ifdef UGVC_K1_INLINE_DICT1
-                                    // experiment (round 2): a one-category annotation ("LCR=TRUE") is matched on the
-                                    // look-ahead right here; anything else takes the full decoder
-                                    const unsigned fl = (unsigned)(b.y >> 40) & 0xFFu;
-                                    const int L = (int)((b.y >> 24) & 0xFFu);
-                                    const unsigned long long xv = t.peek8();
-                                    const unsigned nxt = (unsigned)(xv >> (8 * L)) & 0xFFu;
-                                    if ((fl & SCHED_DICT_INLINE) && (xv & ((1ull << (8 * L)) - 1ull)) == b.x &&
-                                        (nxt == ';' || nxt == '\t' || nxt == '\n')) {
-                                        store_slot_f(o, (int)((b.y >> 16) & 0xFFu), (fl & SCHED_DICT_INLINE_SECOND) ? 1.0f : 0.0f);
-                                        t.advance(L);
-                                        c = t;
-                                    } else
+#define K1_PART 0
+#define K1_KERNEL_NAME k1_parse
+#include "k1_parse_body.inc"
+#undef K1_PART
+#undef K1_KERNEL_NAME
+#ifdef UGVC_K1_SPLIT
+#define K1_PART 1
+#define K1_KERNEL_NAME k1_parse_info
+#include "k1_parse_body.inc"
+#undef K1_PART
+#undef K1_KERNEL_NAME
+#define K1_PART 2
+#define K1_KERNEL_NAME k1_parse_frame
+#include "k1_parse_body.inc"
+#undef K1_PART
+#undef K1_KERNEL_NAME
 #endif
-                                    c = decode_sched(o, b.y, t, ';');
-                                }
-                            }
-                            if (ok) {
-                                if (c.peek() == ';') c.adv();
-                                else in_info = false;  // tab / newline: the INFO column is finished
-                                x = c.peek8();
-                            }
-                        }
-                    }
-                }
-                // (2) whatever is left (keys off the schedule, another order): generic path
-                while (in_info) {
-                    const KeyCur r = take_until(c, eq4, semi4);
-                    c = r.c;
-                    const unsigned ch = c.peek();
-                    const int t = find_tag(r.k);
-                    const unsigned kind = t >= 0 ? s_tags()[t].info_kind : 0u;
-                    if (ch == '=') {
-                        c.adv();
-                        if (kind) c = parse_value(o, t, kind, c, ';');
-                        c = skip_until(c, semi4, semi4);
-                    } else if (kind) {  // key without a value: typed None / ()
-                        set_tag_missing(o, t);
-                    }
-                    if (c.peek() == ';') c.adv();
-                    else in_info = false;
-                }
-            }
-            // ---- FORMAT + first sample (FORMAT values override INFO values of the same
-            //      name: the reference builds its per-record dict from info.items() +
-            //      samples[0].items(), vcftools.py:69-86)
-            off = (unsigned)(c.ptr() + 1 - line);
-            ri.format_off = off > 0xFFFFu ? 0xFFFFu : (uint16_t)off;
-            if (!malformed && c.peek() == '\t') {
-                c.adv();
-                const unsigned col4 = B4(':');
-                Cur sv;
-                bool spec = false;
-                if (sched.n_fmt > 0) {
-                    // the usual FORMAT column, compared as a whole: its sub-fields are then decoded
-                    // in the known order, the same tag in every lane
-                    Cur t = c;
-                    int rem = sched.fmt_len;
-                    spec = true;
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        if (rem > 0) {
-                            const unsigned long long mask = rem >= 8 ? ~0ull : ((1ull << (8 * rem)) - 1ull);
-                            spec &= (t.peek8() & mask) == sched.fmt_w[i];
-                            t.advance(rem >= 8 ? 8 : rem);
-                            rem -= 8;
-                        }
-                    }
-                    spec &= (t.peek() == '\t' || t.peek() == '\n');
-                    sv = t;
-                }
-                if (spec) {
-                    bool have_sample = (sv.peek() == '\t');
-                    if (have_sample) sv.adv();
-                    for (int j = 0; j < sched.n_fmt; ++j) {
-                        const unsigned long long meta = reinterpret_cast<const unsigned long long*>(&sched.fmt[j])[3];
-                        const unsigned cls = (unsigned)(meta >> 8) & 0xFFu;
-                        if (have_sample) {
-                            sv = decode_sched(o, meta, sv, ':');
-                            if (sv.peek() == ':') sv.adv();
-                            else have_sample = false;
-                        } else if (cls != CLS_SKIP) {  // trailing sub-fields dropped: missing
-                            set_tag_missing(o, (int)(short)(meta >> 48));
-                        }
-                    }
-                } else {
-                    sv = skip_until(c, tab4, tab4);
-                    bool have_sample = (sv.peek() == '\t');
-                    if (have_sample) sv.adv();
-                    for (;;) {
-                        const KeyCur r = take_until(c, col4, col4);
-                        c = r.c;
-                        const int t = find_tag(r.k);
-                        const unsigned kind = t >= 0 ? s_tags()[t].fmt_kind : 0u;
-                        if (have_sample) {
-                            if (kind) sv = parse_value(o, t, kind, sv, ':');
-                            sv = skip_until(sv, col4, col4);
-                            if (sv.peek() == ':') sv.adv();
-                            else have_sample = false;
-                        } else if (kind) {  // trailing sub-fields dropped: missing
-                            set_tag_missing(o, t);
-                        }
-                        if (c.peek() == ':') {
-                            c.adv();
-                            continue;
-                        }
-                        break;
-                    }
-                }
-            }
-            // ---- fixed-column slots
-            for (int s = plan.first_fixed_slot; s < n_slots; ++s) {
-                switch (s_slots()[s].reducer) {
-                    case RED_FIX_QUAL: store_slot(o, s, qual_bits); break;
-                    case RED_FIX_ALLELE0: store_slot_f(o, s, a0); break;
-                    case RED_FIX_ALLELE1: store_slot(o, s, a1_missing ? RAW_MISSING : __float_as_uint(a1)); break;
-                    case RED_FIX_INDEL: store_slot_f(o, s, indel ? 1.f : 0.f); break;
-                    case RED_FIX_NALLELES: store_slot_f(o, s, (float)n_alleles); break;
-                    default: break;
-                }
-            }
-            if (malformed) atomicMin(err, ugvc_pack_error(rec, 0xFFFF, REASON_MALFORMED_LINE));
-            if (cg) ri.flags |= 1u;
-            ri.flags |= (unsigned)(n_alleles > 127 ? 127 : n_alleles) << 1;
-            cg_local += cg ? 1u : 0u;
-            if (recinfo) *reinterpret_cast<uint4*>(&recinfo[rec]) = *reinterpret_cast<const uint4*>(&ri);
-        }
-    }
-    // CG-insertion counter: one atomic per warp
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) cg_local += __shfl_xor_sync(0xffffffffu, cg_local, s);
-    if ((threadIdx.x & 31) == 0 && cg_local) atomicAdd((unsigned long long*)&counts[3], (unsigned long long)cg_local);
-}
 
 size_t k1_smem_bytes(const DevPlan&) { return (size_t)K1_SMEM_BYTES; }
 
@@ -1092,8 +809,21 @@ void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_t
         const dim3 fgrid((unsigned)(sm_count * 2), (unsigned)(plan.h.n_slots < 16 ? plan.h.n_slots : 16));
         k1_fill<<<fgrid, 256, 0, st>>>(raw, row_stride, (int)plan.h.n_slots, d_n_records);
     }
+#ifdef UGVC_K1_SPLIT
+    static int occ_i = 0, occ_f = 0;
+    if (occ_i == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, k1_parse_info, K1_TPB, smem) != cudaSuccess || occ_i < 1) occ_i = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k1_parse_frame, K1_TPB, smem) != cudaSuccess || occ_f < 1) occ_f = 1;
+    }
+    k1_parse_info<<<sm_count * occ_i, K1_TPB, smem, st>>>(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo,
+                                                          d_err, d_counts);
+    k1_parse_frame<<<sm_count * occ_f, K1_TPB, smem, st>>>(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo,
+                                                           d_err, d_counts);
+    (void)per_sm;
+#else
     k1_parse<<<sm_count * per_sm, K1_TPB, smem, st>>>(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo,
                                                       d_err, d_counts);
+#endif
 }
 
 #endif  // !UGVC_HOST_EMU
@@ -1510,6 +1240,12 @@ cudaError_t kernels_configure(const DevPlan& plan) {
     cudaError_t e = cudaFuncSetAttribute(k1_parse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)k1_smem_bytes(plan));
     if (e != cudaSuccess) return e;
+#ifdef UGVC_K1_SPLIT
+    e = cudaFuncSetAttribute(k1_parse_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(plan));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k1_parse_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(plan));
+    if (e != cudaSuccess) return e;
+#endif
     e = cudaFuncSetAttribute(k3_infer<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k3_infer<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
