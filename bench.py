@@ -266,6 +266,9 @@ def main():  # noqa: C901, PLR0912, PLR0915
     ap.add_argument("--lanes", type=int, default=3)
     ap.add_argument("--min-presence", type=float, default=None, help="learn_key_order presence threshold (profiling)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-bgzf", action="store_true",
+                    help="also time the e2e pass with BGZF-compressed host buffers inflated on the device "
+                         "(ugvc_submit_bgzf; adds an e2e_bgzf object, off by default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     claim_stdout()
@@ -497,6 +500,54 @@ def main():  # noqa: C901, PLR0912, PLR0915
         # consistency: host path == device path
         assert np.array_equal(o_low, d_low.cpu().numpy()), "host-buffer path differs from the device-resident path"
 
+    # ---- e2e with compressed host buffers (opt-in): the host ships BGZF blocks, the device inflates them
+    e2e_bgzf = None
+    if args.e2e_bgzf and not args.no_e2e:
+        from variantcalling_b200 import bgzf_io
+
+        t0 = time.perf_counter()
+        parts = [bgzf_io.compress_bytes(h_text.array[boff:boff + nbytes], level=6) for boff, nbytes, _nb in batches]
+        len_of = [len(c) for c in parts]  # exact compressed size of each batch (the buffer pads batches to 64 bytes)
+        comp_off = np.concatenate(([0], np.cumsum([(len(c) + 63) // 64 * 64 for c in parts]))).astype(np.int64)
+        h_comp = lib.PinnedBuffer(int(comp_off[-1]) + 64)
+        for c, o in zip(parts, comp_off[:-1]):
+            h_comp.array[o:o + len(c)] = np.frombuffer(c, dtype=np.uint8)
+        comp_bytes = int(sum(len(c) for c in parts))
+        if rank == 0:
+            log(f"[bench] e2e_bgzf: {total_bytes / 1e9:.2f} GB of text -> {comp_bytes / 1e9:.2f} GB of BGZF "
+                f"in {time.perf_counter() - t0:.1f}s on the host (not timed)")
+        del parts
+
+        def bgzf_pass():
+            inflight, got = [], 0
+            for bi in range(len(batches)):
+                lane = bi % n_lanes
+                if len(inflight) == n_lanes:
+                    got += _collect(inflight.pop(0))
+                ctx.submit_bgzf(lane, h_comp.ptr + int(comp_off[bi]), len_of[bi], 30.0)
+                inflight.append((lane, bi))
+            while inflight:
+                got += _collect(inflight.pop(0))
+            return got
+
+        o_low[:] = 0
+        for _ in range(2):
+            assert bgzf_pass() == n_mine
+        assert np.array_equal(o_low, d_low.cpu().numpy()), "compressed-input path differs from the device-resident path"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            bgzf_pass()
+        barrier()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e_bgzf = {"value": args.records * e_steps / float(t_e.item()), "unit": "variants/s",
+                    "h2d_bytes_per_step": comp_bytes, "d2h_bytes_per_step": int(d2h), "steps": e_steps, "lanes": n_lanes,
+                    "compression_ratio": total_bytes / comp_bytes,
+                    "api": "ugvc_submit_bgzf/ugvc_collect_batch (BGZF level 6 in pinned host buffers, inflated on the device)"}
+
     # ---- CPU baseline on a bounded sample of the same input (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -529,6 +580,7 @@ def main():  # noqa: C901, PLR0912, PLR0915
                        "mean_line_bytes": total_bytes / max(1, n_mine), "sharding": "contig LPT",
                        "l2": "inputs larger than L2 (no flush needed)", "threshold": 30.0},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            **({"e2e_bgzf": e2e_bgzf} if e2e_bgzf is not None else {}),
             "counts_last_steps": {"n_records": counts_total[0], "n_low_score": counts_total[1],
                                   "n_pass": counts_total[2], "n_cg": counts_total[3]},
         }

@@ -117,6 +117,17 @@ int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n_bytes, dou
                        uint8_t* d_low_score, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
                        int64_t* d_line_start, size_t capacity_records, int64_t* d_n_records, void* stream);
 
+/* BGZF input, inflated on the device (csrc/inflate.cuh): the host ships the compressed bytes, so the
+ * PCIe traffic of the end-to-end path shrinks by the compression ratio (htslib's BGZF reader behind
+ * pysam.VariantFile, filter_variants_pipeline.py:106,115).  `bgzf` = consecutive whole BGZF blocks in
+ * host memory whose uncompressed bytes are whole VCF data lines (<= the max_bytes of ugvc_reserve).
+ * ugvc_submit_bgzf is ugvc_submit_batch for such input (results through ugvc_collect_batch as usual);
+ * ugvc_bgzf_inflate_device only inflates into lane 0's text buffer and optionally copies the text
+ * back (out_host may be NULL).  A corrupt block is UGVC_E_IO.  CRC32s are not verified on the device. */
+int ugvc_submit_bgzf(ugvc_ctx* ctx, int lane, const uint8_t* bgzf, size_t n_bytes, double threshold);
+int ugvc_bgzf_inflate_device(ugvc_ctx* ctx, const uint8_t* bgzf, size_t n_bytes, uint8_t* out_host, size_t capacity,
+                             size_t* out_n);
+
 /* The model-apply step alone (variant_filtering_utils.py:95-125 after the transform; the other
  * model-apply tools' predict_proba): K3 on a dense row-major float32 matrix x[n][ld] whose first
  * n_features columns are the features of a plan compiled with model_compiler.compile_plan_model_only

@@ -11,6 +11,9 @@ mkdir -p "$out"
 timeout 600 python -m pytest tests -q -m gpu > "$out/tests.log" 2>&1; tail -3 "$out/tests.log"
 # 2. the headline bench line
 timeout 400 python bench.py > "$out/bench_n1.json" 2> "$out/bench_n1.err"; tail -c 600 "$out/bench_n1.json"; echo
+# 2b. end to end with BGZF-compressed host buffers inflated on the device (first GPU timing of csrc/inflate.cuh)
+timeout 600 python bench.py --e2e-bgzf --no-cpu-baseline > "$out/bench_bgzf.json" 2> "$out/bench_bgzf.err"; grep e2e_bgzf "$out/bench_bgzf.err"; python -c "
+import json; d=json.load(open('$out/bench_bgzf.json')); print('e2e', d['e2e']['value']/1e6, 'M/s  e2e_bgzf', d.get('e2e_bgzf'))"
 # 3. A/B of the experimental K1 variants (NEGFAST, INLINE_DICT1, both, SPLIT)
 timeout 900 bash scripts/bench_variants.sh 2>&1 | tee "$out/variants.txt"
 # 4. configs[1] file to file through the CLI

@@ -134,6 +134,8 @@ static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T, class U>
 static inline T atomicAdd(T* p, U v) { T o = *p; *p = o + (T)v; return o; }
 template <class T>
+static inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T>
 static inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
 using std::isnan;
 using std::isinf;

@@ -14,6 +14,7 @@ virtual file offsets ``coffset << 16 | uoffset``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import gzip
 import struct
 
@@ -60,6 +61,32 @@ def inflate(path: str, voff_begin: int = 0, voff_end: int = 0, capacity: int | N
 # the empty BGZF block that ends a file (SAM spec 4.1.2)
 BGZF_EOF = bytes([0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0,
                   0, 0, 0, 0, 0, 0, 0, 0])
+
+
+def compress_bytes(data, level: int = 6, n_threads: int = 0) -> bytes:
+    """BGZF-compress a byte string in memory (whole 0xff00-byte blocks, no EOF block); zlib releases
+    the GIL, so the blocks are deflated on a thread pool.  Used to build compressed host buffers for
+    ``ugvc_submit_bgzf`` (bench, tests); files go through :class:`BgzfWriter`."""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    view = memoryview(data)
+    n = len(view)
+
+    def one(i: int) -> bytes:
+        chunk = bytes(view[i:i + BGZF_BLOCK_DATA])
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 8)
+        payload = c.compress(chunk) + c.flush()
+        if 18 + len(payload) + 8 > 65536:  # incompressible: store
+            c = zlib.compressobj(0, zlib.DEFLATED, -15, 8)
+            payload = c.compress(chunk) + c.flush()
+        bsize = 18 + len(payload) + 8
+        return (b"\x1f\x8b\x08\x04" + b"\0" * 6 + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + payload
+                + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+    with ThreadPoolExecutor(max_workers=n_threads or min(64, (os.cpu_count() or 8))) as pool:
+        return b"".join(pool.map(one, range(0, n, BGZF_BLOCK_DATA), chunksize=16))
 
 
 def count_lines(text: np.ndarray, n_threads: int = 0) -> int:

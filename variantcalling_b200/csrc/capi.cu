@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "inflate.cuh"
 
 #define UGVC_VERSION 100
 #define TEXT_SLACK 64
@@ -24,6 +25,14 @@ struct Lane {
     size_t n_bytes = 0;
     bool submitted = false;
     int64_t last_n = 0;
+    // BGZF input (ugvc_submit_bgzf): compressed bytes + per-block tables on the device, grown on demand
+    uint8_t* d_comp = nullptr;
+    size_t cap_comp = 0;
+    uint64_t* d_blk = nullptr;  // [4][cap_blk]: payload offset, payload bytes, output offset, output bytes
+    size_t cap_blk = 0;
+    int* d_inf_err = nullptr;
+    int* h_inf_err = nullptr;   // pinned
+    std::vector<uint64_t> h_blk;
 };
 
 struct ugvc_ctx {
@@ -109,6 +118,10 @@ static void free_lane(Lane& l) {
     cudaFree(l.b.qual);
     cudaFree(l.b.phreds);
     cudaFree(l.d_err);
+    cudaFree(l.d_comp);
+    cudaFree(l.d_blk);
+    cudaFree(l.d_inf_err);
+    if (l.h_inf_err) cudaFreeHost(l.h_inf_err);
     if (l.h_n) cudaFreeHost(l.h_n);
     if (l.h_err) cudaFreeHost(l.h_err);
     for (auto& ev : l.ev_pool)
@@ -591,6 +604,12 @@ extern "C" int ugvc_collect_batch(ugvc_ctx* ctx, int lane, uint8_t* out_low_scor
     const int64_t n = *l.h_n;
     l.last_n = n;
     if (out_n_records) *out_n_records = n;
+    if (l.h_inf_err && *l.h_inf_err) {
+        const int code = *l.h_inf_err;
+        *l.h_inf_err = 0;
+        return fail(ctx, UGVC_E_IO, "BGZF inflate failed on the device (block " + std::to_string(code >> 8) + ", code " +
+                                        std::to_string(code & 0xFF) + ")");
+    }
     const int rc = decode_error(ctx, *l.h_err);
     if (rc) return rc;
     if ((size_t)n > capacity_records) return fail(ctx, UGVC_E_ARG, "collect: output capacity smaller than the record count");
@@ -647,6 +666,155 @@ extern "C" int ugvc_device_status(ugvc_ctx* ctx, void* stream) {
     unsigned long long e;
     CU(cudaMemcpy(&e, l.d_err, sizeof(e), cudaMemcpyDeviceToHost));
     return decode_error(ctx, e);
+}
+
+// ------------------------------------------------------------------------------------------
+// BGZF input: inflate on the device (inflate.cuh), then K0..K3 as usual
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) bgzf_inflate_blocks(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ blk,
+                                                          size_t cap_blk, int n_blocks, uint8_t* __restrict__ out,
+                                                          int* __restrict__ err) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += gridDim.x * blockDim.x) {
+        const int rc = inf_block(comp + blk[b], (uint32_t)blk[cap_blk + b], out + blk[2 * cap_blk + b],
+                                 (uint32_t)blk[3 * cap_blk + b]);
+        if (rc != INF_OK) atomicMax(err, (b << 8) | rc);
+    }
+}
+
+// walk the BGZF block headers of host bytes: payload offset / size, output offset / size per block
+static int scan_bgzf(ugvc_ctx* ctx, const uint8_t* p, size_t n, std::vector<uint64_t>& coff, std::vector<uint64_t>& clen,
+                     std::vector<uint64_t>& uoff, std::vector<uint64_t>& ulen, size_t* total_out) {
+    size_t at = 0, total = 0;
+    while (at < n) {
+        if (n - at < 18 + 8 || p[at] != 0x1f || p[at + 1] != 0x8b || p[at + 2] != 8 || !(p[at + 3] & 4))
+            return fail(ctx, UGVC_E_IO, "not a BGZF block at byte " + std::to_string(at));
+        const size_t xlen = p[at + 10] | ((size_t)p[at + 11] << 8);
+        size_t bsize = 0, x = at + 12;
+        const size_t xend = x + xlen;
+        if (xend > n) return fail(ctx, UGVC_E_IO, "truncated BGZF header");
+        while (x + 4 <= xend) {
+            const size_t slen = p[x + 2] | ((size_t)p[x + 3] << 8);
+            if (p[x] == 'B' && p[x + 1] == 'C' && slen == 2 && x + 6 <= xend) bsize = (p[x + 4] | ((size_t)p[x + 5] << 8)) + 1;
+            x += 4 + slen;
+        }
+        if (bsize < 12 + xlen + 8 || at + bsize > n) return fail(ctx, UGVC_E_IO, "bad BGZF block size at byte " + std::to_string(at));
+        const uint8_t* tail = p + at + bsize - 4;
+        const size_t isize = tail[0] | ((size_t)tail[1] << 8) | ((size_t)tail[2] << 16) | ((size_t)tail[3] << 24);
+        if (isize > 65536) return fail(ctx, UGVC_E_IO, "BGZF block larger than 64 KiB");
+        if (isize) {  // the empty EOF block carries nothing
+            coff.push_back(at + 12 + xlen);
+            clen.push_back(bsize - 12 - xlen - 8);
+            uoff.push_back(total);
+            ulen.push_back(isize);
+        }
+        total += isize;
+        at += bsize;
+    }
+    *total_out = total;
+    return UGVC_OK;
+}
+
+// compressed bytes -> lane device buffers -> inflate into l.d_text; *n_text = uncompressed size
+static int stage_bgzf(ugvc_ctx* ctx, Lane& l, const uint8_t* bgzf, size_t n_bytes, size_t* n_text) {
+    std::vector<uint64_t> coff, clen, uoff, ulen;
+    size_t total = 0;
+    int rc = scan_bgzf(ctx, bgzf, n_bytes, coff, clen, uoff, ulen, &total);
+    if (rc) return rc;
+    if (total > ctx->cap_bytes) return fail(ctx, UGVC_E_ARG, "bgzf: the inflated batch is larger than the reserved max_bytes");
+    const size_t nb = coff.size();
+    if (n_bytes + 8 > l.cap_comp) {
+        cudaFree(l.d_comp);
+        l.d_comp = nullptr;
+        l.cap_comp = n_bytes + n_bytes / 4 + 4096;
+        CU(cudaMalloc(&l.d_comp, l.cap_comp));
+    }
+    if (nb > l.cap_blk) {
+        cudaFree(l.d_blk);
+        l.d_blk = nullptr;
+        l.cap_blk = nb + nb / 4 + 64;
+        CU(cudaMalloc(&l.d_blk, 4 * l.cap_blk * sizeof(uint64_t)));
+    }
+    if (!l.d_inf_err) {
+        CU(cudaMalloc(&l.d_inf_err, sizeof(int)));
+        CU(cudaHostAlloc(&l.h_inf_err, sizeof(int), cudaHostAllocDefault));
+        *l.h_inf_err = 0;
+    }
+    *n_text = total;
+    cudaStream_t st = l.stream;
+    CU(cudaMemsetAsync(l.d_inf_err, 0, sizeof(int), st));
+    if (nb == 0) return UGVC_OK;
+    l.h_blk.resize(4 * l.cap_blk);  // kept in the lane: the copy below is asynchronous
+    for (size_t i = 0; i < nb; ++i) {
+        l.h_blk[i] = coff[i];
+        l.h_blk[l.cap_blk + i] = clen[i];
+        l.h_blk[2 * l.cap_blk + i] = uoff[i];
+        l.h_blk[3 * l.cap_blk + i] = ulen[i];
+    }
+    CU(cudaMemcpyAsync(l.d_comp, bgzf, n_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(l.d_blk, l.h_blk.data(), 4 * l.cap_blk * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+#ifdef UGVC_HOST_EMU
+    for (size_t i = 0; i < nb; ++i) {
+        const int e = inf_block(l.d_comp + coff[i], (uint32_t)clen[i], l.d_text + uoff[i], (uint32_t)ulen[i]);
+        if (e != INF_OK && *l.d_inf_err < (int)((i << 8) | e)) *l.d_inf_err = (int)((i << 8) | e);
+    }
+#else
+    const int threads = 64;
+    int grid = (int)((nb + threads - 1) / threads);
+    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    bgzf_inflate_blocks<<<grid, threads, 0, st>>>(l.d_comp, l.d_blk, l.cap_blk, (int)nb, l.d_text, l.d_inf_err);
+    CU(cudaGetLastError());
+#endif
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(l.h_inf_err, l.d_inf_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_submit_bgzf(ugvc_ctx* ctx, int lane, const uint8_t* bgzf, size_t n_bytes, double threshold) {
+    if (!ctx) return UGVC_E_ARG;
+    if (!ctx->has_plan || ctx->lanes.empty()) return fail(ctx, UGVC_E_STATE, "submit_bgzf: load a plan and reserve first");
+    if (lane < 0 || lane >= (int)ctx->lanes.size()) return fail(ctx, UGVC_E_ARG, "submit_bgzf: lane out of range");
+    if (n_bytes && !bgzf) return fail(ctx, UGVC_E_ARG, "submit_bgzf: NULL input");
+    CU(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[lane];
+    if (l.submitted) return fail(ctx, UGVC_E_STATE, "submit_bgzf: lane already has a batch in flight");
+    size_t n_text = 0;
+    int rc = stage_bgzf(ctx, l, bgzf, n_bytes, &n_text);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(l.d_text + n_text, '\n', TEXT_SLACK, l.stream));
+    rc = enqueue_kernels(ctx, l, l.d_text, n_text, threshold, l.b.low_score, l.b.probs, l.b.qual, l.b.recinfo,
+                         l.b.line_start, l.b.cap_records, l.b.n_records, l.stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(l.h_n, l.b.n_records, sizeof(int64_t), cudaMemcpyDeviceToHost, l.stream));
+    CU(cudaMemcpyAsync(l.h_err, l.d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
+    l.n_bytes = n_text;
+    l.submitted = true;
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_bgzf_inflate_device(ugvc_ctx* ctx, const uint8_t* bgzf, size_t n_bytes, uint8_t* out_host,
+                                        size_t capacity, size_t* out_n) {
+    if (!ctx) return UGVC_E_ARG;
+    if (ctx->lanes.empty()) return fail(ctx, UGVC_E_STATE, "bgzf_inflate_device: reserve first (the text lands in lane 0)");
+    if (n_bytes && !bgzf) return fail(ctx, UGVC_E_ARG, "bgzf_inflate_device: NULL input");
+    CU(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[0];
+    if (l.submitted) return fail(ctx, UGVC_E_STATE, "bgzf_inflate_device: lane 0 has a batch in flight");
+    size_t n_text = 0;
+    int rc = stage_bgzf(ctx, l, bgzf, n_bytes, &n_text);
+    if (rc) return rc;
+    if (out_n) *out_n = n_text;
+    CU(cudaStreamSynchronize(l.stream));
+    if (l.h_inf_err && *l.h_inf_err) {
+        const int code = *l.h_inf_err;
+        *l.h_inf_err = 0;
+        return fail(ctx, UGVC_E_IO, "BGZF inflate failed on the device (block " + std::to_string(code >> 8) + ", code " +
+                                        std::to_string(code & 0xFF) + ")");
+    }
+    if (out_host) {
+        if (n_text > capacity) return fail(ctx, UGVC_E_ARG, "bgzf_inflate_device: output capacity too small");
+        CU(cudaMemcpy(out_host, l.d_text, n_text, cudaMemcpyDeviceToHost));
+    }
+    return UGVC_OK;
 }
 
 // K3 alone on a dense feature matrix assembled by the caller (row-major, n x n_features, leading

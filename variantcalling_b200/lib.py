@@ -74,6 +74,8 @@ SIGNATURES = {
     "ugvc_count_byte": (C.c_int64, [_vp, _sz, C.c_int, C.c_int]),
     "ugvc_splice_records": (C.c_int64, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp,
                                         _vp, C.c_int, _vp, _sz, _vp, C.c_int]),
+    "ugvc_submit_bgzf": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_double]),
+    "ugvc_bgzf_inflate_device": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "ugvc_predict_features": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, _vp, _vp, _vp]),
     "ugvc_enable_phreds": (C.c_int, [_vp, C.c_int]),
     "ugvc_collect_phreds": (C.c_int, [_vp, C.c_int, _vp, _sz]),
@@ -225,6 +227,19 @@ class Context:
 
     def submit(self, lane: int, text_ptr, n_bytes: int, threshold: float = 30.0):
         self._check(self.lib.ugvc_submit_batch(self.h, lane, _ptr(text_ptr), n_bytes, threshold))
+
+    def submit_bgzf(self, lane: int, bgzf, n_bytes: int, threshold: float = 30.0):
+        """Like :meth:`submit`, for whole BGZF blocks (compressed on the host, inflated on the device)."""
+        self._check(self.lib.ugvc_submit_bgzf(self.h, lane, _ptr(bgzf), n_bytes, threshold))
+
+    def inflate_bgzf(self, bgzf, want_text: bool = True) -> np.ndarray | int:
+        """Inflate whole BGZF blocks on the device; returns the text (uint8 array) or just its size."""
+        buf = np.frombuffer(bgzf, dtype=np.uint8) if isinstance(bgzf, (bytes, bytearray, memoryview)) else bgzf
+        n = C.c_size_t()
+        out = np.empty(self.cap_bytes, dtype=np.uint8) if want_text else None
+        self._check(self.lib.ugvc_bgzf_inflate_device(self.h, _ptr(buf), buf.size, _ptr(out), 0 if out is None else out.size,
+                                                      C.byref(n)))
+        return out[: n.value] if want_text else int(n.value)
 
     def collect(self, lane: int, out: dict, capacity: int) -> int:
         n = C.c_int64()
