@@ -40,16 +40,25 @@ enum : int {
 
 struct InfBits {
     const uint8_t* in;
-    uint32_t n_in, pos;
+    uint32_t n_in, pos;  // pos: next input byte to load
     uint64_t buf;
     int cnt;
+    // Top the buffer up to >= 57 bits.  Whole aligned 32-bit words are loaded once `in + pos` is 4-byte
+    // aligned (the caller guarantees 8 readable bytes after the input, so the last word may reach past n_in:
+    // those bytes are never consumed by a valid stream and an invalid one is caught by the final position check).
     __host__ __device__ inline void refill() {
         while (cnt <= 56) {
-            // past the end zeros are shifted in; the caller checks pos against n_in at the end
-            const uint64_t b = pos < n_in ? in[pos] : 0u;
-            ++pos;
-            buf |= b << cnt;
-            cnt += 8;
+            if (cnt <= 32 && ((reinterpret_cast<uintptr_t>(in) + pos) & 3u) == 0 && pos + 4 <= n_in + 4) {
+                const uint64_t w = *reinterpret_cast<const uint32_t*>(in + pos);
+                buf |= w << cnt;
+                pos += 4;
+                cnt += 32;
+            } else {
+                const uint64_t b = pos < n_in ? in[pos] : 0u;  // past the end zeros are shifted in
+                ++pos;
+                buf |= b << cnt;
+                cnt += 8;
+            }
         }
     }
     __host__ __device__ inline uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1ull)); }
