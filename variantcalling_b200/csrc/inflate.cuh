@@ -247,7 +247,19 @@ __host__ __device__ inline int inf_block(const uint8_t* in, uint32_t n_in, uint8
                 const uint32_t d = DIST_BASE[ds] + b.take(DIST_EXTRA[ds]);
                 if (d > op) return INF_BAD_DISTANCE;
                 if (op + len > n_out) return INF_OUTPUT_OVERRUN;
-                for (uint32_t i = 0; i < len; ++i, ++op) out[op] = out[op - d];
+                // the source bytes were written by this thread a moment ago and come back from L2: when source and
+                // destination cannot overlap within a group, fetch eight bytes before storing them (eight loads in flight)
+                uint32_t i = 0;
+                if (d >= 8) {
+                    for (; i + 8 <= len; i += 8) {
+                        const uint8_t* sp = out + op - d + i;
+                        const uint8_t b0 = sp[0], b1 = sp[1], b2 = sp[2], b3 = sp[3], b4 = sp[4], b5 = sp[5], b6 = sp[6], b7 = sp[7];
+                        uint8_t* dp = out + op + i;
+                        dp[0] = b0, dp[1] = b1, dp[2] = b2, dp[3] = b3, dp[4] = b4, dp[5] = b5, dp[6] = b6, dp[7] = b7;
+                    }
+                }
+                for (; i < len; ++i) out[op + i] = out[op + i - d];
+                op += len;
             }
         } else {
             return INF_BAD_BLOCK_TYPE;
