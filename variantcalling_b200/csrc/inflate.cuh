@@ -247,10 +247,31 @@ __host__ __device__ inline int inf_block(const uint8_t* in, uint32_t n_in, uint8
                 const uint32_t d = DIST_BASE[ds] + b.take(DIST_EXTRA[ds]);
                 if (d > op) return INF_BAD_DISTANCE;
                 if (op + len > n_out) return INF_OUTPUT_OVERRUN;
-                // the source bytes were written by this thread a moment ago and come back from L2: when source and
-                // destination cannot overlap within a group, fetch eight bytes before storing them (eight loads in flight)
+                // The source bytes were written by this thread a moment ago and come back from L2.  A long match far
+                // enough behind is moved as aligned 8-byte words (source words realigned with a funnel shift): one load
+                // and one store per eight bytes instead of sixteen byte transactions; everything else byte by byte,
+                // eight loads in flight where source and destination cannot overlap within a group.
                 uint32_t i = 0;
-                if (d >= 8) {
+                if (d >= 16 && len >= 16) {
+                    while ((reinterpret_cast<uintptr_t>(out + op + i) & 7u) != 0) {  // destination up to an 8-byte boundary
+                        out[op + i] = out[op + i - d];
+                        ++i;
+                    }
+                    const uint8_t* src = out + op + i - d;
+                    const unsigned sm = (unsigned)(reinterpret_cast<uintptr_t>(src) & 7u);
+                    const uint64_t* sw = reinterpret_cast<const uint64_t*>(src - sm);
+                    uint64_t* dw = reinterpret_cast<uint64_t*>(out + op + i);
+                    if (sm == 0) {
+                        for (; i + 8 <= len; i += 8) *dw++ = *sw++;
+                    } else {
+                        uint64_t lo = *sw++;
+                        for (; i + 8 <= len; i += 8) {
+                            const uint64_t hi = *sw++;  // at most 15 bytes past the source position: still behind `op` (d >= 16)
+                            *dw++ = (lo >> (8 * sm)) | (hi << (64 - 8 * sm));
+                            lo = hi;
+                        }
+                    }
+                } else if (d >= 8) {
                     for (; i + 8 <= len; i += 8) {
                         const uint8_t* sp = out + op - d + i;
                         const uint8_t b0 = sp[0], b1 = sp[1], b2 = sp[2], b3 = sp[3], b4 = sp[4], b5 = sp[5], b6 = sp[6], b7 = sp[7];
