@@ -8,10 +8,12 @@
 // blocks).  Each thread keeps a 64-bit bit buffer, decodes stored / fixed / dynamic blocks with a
 // 9-bit look-up table for the literal-length code and a 7-bit one for the distance code (longer
 // codes fall back to a canonical bit-by-bit walk), and writes its output range directly.  The tables
-// live in the thread's local memory (about 1.9 KB).  This first version is written for exactness
-// (byte-identical with zlib, checked on the host emulation and on the GPU); the obvious next steps
-// -- tables in shared memory, word-wide output, warp-cooperative match copies -- are left to the
-// profile.
+// live in the thread's local memory (about 3.9 KB with the code-length scratch).  The bit buffer is
+// refilled with aligned 32-bit loads; long matches far enough behind are moved as aligned 8-byte words
+// (the source realigned with a funnel shift), shorter ones in groups of eight independent byte loads.
+// Written for exactness first (byte-identical with zlib on every block type, checked on the host
+// emulation; first GPU timing pending): literal stores are still byte-wide, and a warp-cooperative
+// decoder (one block per warp, tables in shared memory) is the next step if the profile asks for it.
 #pragma once
 #include <stdint.h>
 
