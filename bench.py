@@ -390,6 +390,7 @@ def main():  # noqa: C901, PLR0912, PLR0915
     elapsed_ms = ev0.elapsed_time(ev1)
     stage_sum, n_calls = ctx.stage_ms()
     ctx.enable_stage_timing(False)
+    slow_last = ctx.slow_records(0)  # records of the last batch that went through the generic parser (-1: tile kernel off)
     launches = ctx.launch_count() - launches0
     counts_total = [int(v) for v in counts_t.tolist()]
     t_el = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
@@ -578,7 +579,8 @@ def main():  # noqa: C901, PLR0912, PLR0915
                                    "(sklearn GradientBoosting, reference XGB hyper-parameters)",
                        "records_total": args.records, "records_rank0": n_mine, "batch_records": B,
                        "mean_line_bytes": total_bytes / max(1, n_mine), "sharding": "contig LPT",
-                       "l2": "inputs larger than L2 (no flush needed)", "threshold": 30.0},
+                       "l2": "inputs larger than L2 (no flush needed)", "threshold": 30.0,
+                       "k1_slow_records_last_batch": slow_last},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             **({"e2e_bgzf": e2e_bgzf} if e2e_bgzf is not None else {}),
             "counts_last_steps": {"n_records": counts_total[0], "n_low_score": counts_total[1],

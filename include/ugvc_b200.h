@@ -171,6 +171,10 @@ int ugvc_debug_features(ugvc_ctx* ctx, int lane, float* out, size_t capacity_flo
  * column (or -1) and a reason code. */
 int ugvc_last_data_error(const ugvc_ctx* ctx, int64_t* record, int32_t* column, int32_t* reason);
 
+/* Records of the last batch on `lane` that K1's tile kernel handed to the generic per-record parser
+ * (unknown INFO key, unusual literal or FORMAT column ...); -1 when the tile kernel is switched off
+ * (UGVC_K1_LEGACY=1).  Blocking; a diagnostic, the results do not depend on it. */
+int64_t ugvc_debug_slow_records(ugvc_ctx* ctx, int lane);
 /* Number of kernel launches issued by this context since ugvc_init. */
 int64_t ugvc_launch_count(const ugvc_ctx* ctx);
 /* Stage timing: while enabled every enqueue brackets K0,K1,K2,K3 with CUDA events on

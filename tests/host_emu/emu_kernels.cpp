@@ -13,10 +13,12 @@
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 alignas(16) uint8_t k1_smem[64 * 1024];
 alignas(16) uint8_t smem3[8 * 1024 * 1024];  // K3: feature tile + the whole forest
+alignas(16) uint8_t kf_smem_emu[128 * 1024];  // K1 tile kernel
 
 #include "../../variantcalling_b200/csrc/kernels.cu"
 
 static_assert(K1_SMEM_BYTES <= sizeof(k1_smem), "k1_smem too small");
+static_assert(KF_SMEM_BYTES <= sizeof(kf_smem_emu), "kf_smem_emu too small");
 
 static void one_thread_grid() {
     threadIdx = dim3(0, 0, 0);
@@ -54,12 +56,35 @@ void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_t
     }
     one_thread_grid();
 #ifdef UGVC_K1_SPLIT
-    k1_parse_info(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts);
+    k1_parse_info(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts, nullptr, nullptr);
     one_thread_grid();
-    k1_parse_frame(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts);
+    k1_parse_frame(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts, nullptr, nullptr);
 #else
-    k1_parse(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts);
+    k1_parse(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts, nullptr, nullptr);
 #endif
+}
+
+// both K1 tiers: the tile kernel's phases run one after the other in the single emulated thread (every phase is a
+// thread-strided loop), then the generic parser takes the slow list.  UGVC_EMU_G=<g> forces g walker lanes per
+// record so that the re-synchronisation on ';' is exercised too.
+void launch_k1_fast(const DevPlan& plan, const DevFast& fast, const DevSchedule& sched, const uint8_t* d_text, size_t n_bytes,
+                    uint32_t* scratch, int64_t* line_start, size_t cap_records, int64_t* d_n_records, uint32_t* raw,
+                    size_t row_stride, ugvc_recinfo* recinfo, uint32_t* slow_list, unsigned long long* d_err,
+                    long long* d_counts, int, cudaStream_t) {
+    const size_t n_tiles = (n_bytes + KF_TILE - 1) / KF_TILE;
+    memset(scratch, 0, 8 + n_tiles * sizeof(unsigned long long));
+    if (n_tiles == 0) {
+        *d_n_records = 0;
+        line_start[0] = 0;
+        return;
+    }
+    const char* g = getenv("UGVC_EMU_G");
+    ugvc_emu_force_g = g ? atoi(g) : 0;
+    one_thread_grid();
+    k1_fast(plan, fast, d_text, n_bytes, reinterpret_cast<unsigned long long*>(scratch) + 1, scratch, scratch + 1, n_tiles,
+            line_start, cap_records, d_n_records, raw, row_stride, recinfo, slow_list, d_err, d_counts);
+    one_thread_grid();
+    k1_parse(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts, slow_list, scratch + 1);
 }
 
 void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, const int64_t* d_n_records, float* feats,

@@ -52,6 +52,11 @@ struct ugvc_ctx {
 #endif
     DevSchedule sched{};           // learned key order (empty: generic path only)
     SchedEntry* d_sched = nullptr;
+    DevFast fast{};                // key table / FORMAT column / slot kinds of the tile kernel (k1_fast)
+    FastKey* d_fast_keys = nullptr;
+    uint8_t* d_fast_htab = nullptr;
+    uint8_t* d_slot_kind = nullptr;
+    std::string learned_info, learned_fmt;  // what ugvc_set_key_order was told
     std::vector<Lane> lanes;
     size_t cap_bytes = 0, cap_records = 0;
     long long* d_counts = nullptr;
@@ -108,6 +113,7 @@ static void free_lane(Lane& l) {
     if (l.stream) cudaStreamSynchronize(l.stream);
     cudaFree(l.d_text);
     cudaFree(l.b.chunk_first);
+    cudaFree(l.b.slow_list);
     cudaFree(l.b.line_start);
     cudaFree(l.b.n_records);
     cudaFree(l.b.raw);
@@ -138,11 +144,151 @@ extern "C" void ugvc_free(ugvc_ctx* ctx) {
     cudaFree(ctx->d_htab);
     cudaFree(ctx->d_nodes);
     cudaFree(ctx->d_sched);
+    cudaFree(ctx->d_fast_keys);
+    cudaFree(ctx->d_fast_htab);
+    cudaFree(ctx->d_slot_kind);
     cudaFree(ctx->d_counts);
     delete ctx;
 }
 
 static size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
+
+static int find_host_tag(const ugvc_ctx* ctx, const std::string& name);
+
+// Tables of the tile kernel (k1_fast): every INFO key it may meet -- the plan's tags declared in ##INFO
+// plus the keys seen in the data (`info_keys`, "KEY;KEY!;..." as for the key order; '!' marks a key that
+// came without a value) -- the usual FORMAT column, the kind bits of every slot, the fixed-column slots.
+static int build_fast(ugvc_ctx* ctx, const std::string& info_keys, const std::string& format_keys) {
+    const PlanHeader& h = ctx->plan.h;
+    DevFast f{};
+    std::vector<int> fmt_tags;
+    // ---- the usual FORMAT column
+    if (!format_keys.empty() && format_keys.size() <= 24) {
+        std::vector<std::string> subs;
+        size_t b = 0;
+        for (;;) {
+            size_t e = format_keys.find(':', b);
+            if (e == std::string::npos) e = format_keys.size();
+            subs.push_back(format_keys.substr(b, e - b));
+            if (e == format_keys.size()) break;
+            b = e + 1;
+        }
+        if (subs.size() <= UGVC_MAX_FMT_KEYS) {
+            f.n_fmt = (int)subs.size();
+            f.fmt_len = (int)format_keys.size();
+            memcpy(f.fmt_w, format_keys.data(), format_keys.size());
+            for (size_t i = 0; i < subs.size(); ++i) {
+                FastMeta m{};
+                m.whole_red = 0xFF;
+                m.tag = 0xFF;
+                const int t = find_host_tag(ctx, subs[i]);
+                if (t >= 0 && ctx->h_tags[t].fmt_kind) {
+                    const PlanTag& tg = ctx->h_tags[t];
+                    const bool has_whole = tg.whole_red != 0xFF;
+                    m.type = tg.fmt_kind & KIND_TYPE_MASK;
+                    m.flags = FK_NEEDED | ((tg.fmt_kind & KIND_SCALAR) ? FK_SCALAR : 0);
+                    m.n_elem = (uint8_t)(tg.n_slots - (has_whole ? 1 : 0));
+                    m.slot0 = tg.first_slot;
+                    m.whole_red = tg.whole_red;
+                    m.whole_slot = tg.whole_slot;
+                    m.tag = (uint8_t)t;
+                    fmt_tags.push_back(t);
+                }
+                f.fmt[i] = m;
+            }
+        }
+    }
+    auto in_fmt = [&](int t) {
+        for (int x : fmt_tags)
+            if (x == t) return true;
+        return false;
+    };
+    // ---- INFO keys
+    std::vector<FastKey> keys;
+    auto add_key = [&](const std::string& name, int t) {
+        if (name.empty() || name.size() > 15 || keys.size() >= KF_MAX_KEYS) return;
+        for (const FastKey& k : keys)
+            if (k.len == name.size() && memcmp(k.name, name.data(), name.size()) == 0) return;
+        FastKey k{};
+        memcpy(k.name, name.data(), name.size());
+        k.len = (uint8_t)name.size();
+        k.m.whole_red = 0xFF;
+        k.m.tag = 0xFF;
+        if (t >= 0 && ctx->h_tags[t].info_kind) {
+            const PlanTag& tg = ctx->h_tags[t];
+            const bool has_whole = tg.whole_red != 0xFF;
+            k.m.type = tg.info_kind & KIND_TYPE_MASK;
+            k.m.flags = FK_NEEDED | ((tg.info_kind & KIND_SCALAR) ? FK_SCALAR : 0) | (in_fmt(t) ? FK_SKIP_FMT : 0);
+            k.m.n_elem = (uint8_t)(tg.n_slots - (has_whole ? 1 : 0));
+            k.m.slot0 = tg.first_slot;
+            k.m.whole_red = tg.whole_red;
+            k.m.whole_slot = tg.whole_slot;
+            k.m.tag = (uint8_t)t;
+        }
+        keys.push_back(k);
+    };
+    for (size_t t = 0; t < ctx->h_tags.size(); ++t)
+        if (ctx->h_tags[t].info_kind) add_key(std::string(ctx->h_tags[t].name, ctx->h_tags[t].len), (int)t);
+    {
+        size_t b = 0;
+        while (b < info_keys.size()) {
+            size_t e = info_keys.find(';', b);
+            if (e == std::string::npos) e = info_keys.size();
+            std::string key = info_keys.substr(b, e - b);
+            b = e + 1;
+            if (!key.empty() && key.back() == '!') key.pop_back();
+            if (!key.empty()) add_key(key, find_host_tag(ctx, key));
+        }
+    }
+    uint8_t htab[256];
+    memset(htab, 0xFF, sizeof(htab));
+    for (size_t i = 0; i < keys.size(); ++i) {
+        uint32_t idx = kf_hash(keys[i].name[0], keys[i].name[1], keys[i].name[2], keys[i].name[3], keys[i].len);
+        while (htab[idx] != 0xFF) idx = (idx + 1) & 255u;
+        htab[idx] = (uint8_t)i;
+    }
+    // ---- per-slot kind bits, fixed-column slots
+    std::vector<uint8_t> kind(h.n_slots ? h.n_slots : 1, 0);
+    memset(f.fix_slot, 0xFF, sizeof(f.fix_slot));
+    for (uint32_t s = 0; s < h.n_slots; ++s) {
+        const PlanSlot& sl = ctx->h_slots[s];
+        if (sl.tag == TAG_FIXED) {
+            const int which = sl.reducer == RED_FIX_QUAL ? FIX_QUAL : sl.reducer == RED_FIX_ALLELE0 ? FIX_ALLELE0
+                              : sl.reducer == RED_FIX_ALLELE1 ? FIX_ALLELE1 : sl.reducer == RED_FIX_INDEL ? FIX_INDEL
+                              : sl.reducer == RED_FIX_NALLELES ? FIX_NALLELES : -1;
+            if (which >= 0 && f.fix_slot[which] == 0xFF) f.fix_slot[which] = (uint8_t)s;
+            continue;
+        }
+        const PlanTag& tg = ctx->h_tags[sl.tag];
+        const unsigned k = (in_fmt(sl.tag) && tg.fmt_kind) ? tg.fmt_kind : (tg.info_kind ? tg.info_kind : tg.fmt_kind);
+        uint8_t bits = 0;
+        if ((k & KIND_TYPE_MASK) == KIND_INT) bits |= SK_INT;
+        if (sl.reducer == RED_STRNUM) bits |= SK_STRNUM;
+        if (k & KIND_SCALAR) bits |= SK_SCALAR;
+        kind[s] = bits;
+    }
+    cudaFree(ctx->d_fast_keys);
+    cudaFree(ctx->d_fast_htab);
+    cudaFree(ctx->d_slot_kind);
+    ctx->d_fast_keys = nullptr;
+    ctx->d_fast_htab = nullptr;
+    ctx->d_slot_kind = nullptr;
+    CU(cudaMalloc(&ctx->d_fast_keys, (keys.size() + 1) * sizeof(FastKey)));
+    if (!keys.empty()) CU(cudaMemcpy(ctx->d_fast_keys, keys.data(), keys.size() * sizeof(FastKey), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_fast_htab, 256));
+    CU(cudaMemcpy(ctx->d_fast_htab, htab, 256, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_slot_kind, kind.size()));
+    CU(cudaMemcpy(ctx->d_slot_kind, kind.data(), kind.size(), cudaMemcpyHostToDevice));
+    f.keys = ctx->d_fast_keys;
+    f.htab = ctx->d_fast_htab;
+    f.slot_kind = ctx->d_slot_kind;
+    f.n_keys = (int)keys.size();
+    const char* legacy = getenv("UGVC_K1_LEGACY");  // profiling / differential tests: the generic parser alone
+    f.enabled = !(legacy && *legacy && *legacy != '0');
+    ctx->fast = f;
+    return UGVC_OK;
+}
+
 
 extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     if (!ctx || !blob) return fail(ctx, UGVC_E_ARG, "null argument");
@@ -339,6 +485,12 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     cudaFree(ctx->d_sched);  // a key order belongs to a plan
     ctx->d_sched = nullptr;
     ctx->sched = DevSchedule{};
+    ctx->learned_info.clear();
+    ctx->learned_fmt.clear();
+    {
+        const int rc = build_fast(ctx, "", "");
+        if (rc) return rc;
+    }
     // a new plan changes the slot/feature counts: lanes must be re-reserved
     for (auto& l : ctx->lanes) free_lane(l);
     ctx->lanes.clear();
@@ -468,7 +620,9 @@ extern "C" int ugvc_set_key_order(ugvc_ctx* ctx, const char* info_keys, const ch
         }
     }
     ctx->sched = sc;
-    return UGVC_OK;
+    ctx->learned_info = info_keys ? info_keys : "";
+    ctx->learned_fmt = format_keys ? format_keys : "";
+    return build_fast(ctx, ctx->learned_info, ctx->learned_fmt);
 }
 
 extern "C" int ugvc_plan_info(const ugvc_ctx* ctx, int32_t* n_features, int32_t* n_classes, int32_t* n_slots) {
@@ -491,7 +645,7 @@ extern "C" int ugvc_reserve(ugvc_ctx* ctx, size_t max_bytes, size_t max_records,
     ctx->cap_bytes = max_bytes;
     ctx->cap_records = max_records;
     ctx->lanes.resize(n_pipeline);
-    const size_t n_chunks = 2 * ((max_bytes + K0_TILE_BYTES_HOST - 1) / K0_TILE_BYTES_HOST + 2);  // uint32 words
+    const size_t n_chunks = 2 * ((max_bytes + K1_TILE_BYTES_HOST - 1) / K1_TILE_BYTES_HOST + 4);  // uint32 words
     const DevPlan& p = ctx->plan;
     for (auto& l : ctx->lanes) {
         CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
@@ -499,6 +653,7 @@ extern "C" int ugvc_reserve(ugvc_ctx* ctx, size_t max_bytes, size_t max_records,
         l.b.cap_bytes = max_bytes;
         l.b.cap_records = max_records;
         CU(cudaMalloc(&l.b.chunk_first, n_chunks * sizeof(uint32_t)));
+        CU(cudaMalloc(&l.b.slow_list, max_records * sizeof(uint32_t)));
         CU(cudaMalloc(&l.b.line_start, (max_records + 1) * sizeof(int64_t)));
         CU(cudaMalloc(&l.b.n_records, sizeof(int64_t)));
         CU(cudaMalloc(&l.b.raw, (size_t)p.h.n_slots * max_records * sizeof(uint32_t)));
@@ -533,10 +688,15 @@ static int enqueue_kernels(ugvc_ctx* ctx, Lane& l, const uint8_t* d_text, size_t
     }
     CU(cudaMemsetAsync(l.d_err, 0xFF, sizeof(unsigned long long), st));
     if (timing) CU(cudaEventRecord(ev[0], st));
-    launch_k0(d_text, n_bytes, l.b.chunk_first, d_line_start, line_cap, d_n_records, l.d_err, ctx->sm_count, st);
+    const bool fast = ctx->fast.enabled && p.h.n_slots <= 250 && line_cap <= 0xFFFFFFFFull;
+    if (!fast) launch_k0(d_text, n_bytes, l.b.chunk_first, d_line_start, line_cap, d_n_records, l.d_err, ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[1], st));
-    launch_k1(p, ctx->sched, d_text, d_line_start, d_n_records, l.b.raw, l.b.cap_records, d_recinfo, l.d_err, ctx->d_counts,
-              ctx->sm_count, st);
+    if (fast)  // line index, field parse and the slow tier in one stage
+        launch_k1_fast(p, ctx->fast, ctx->sched, d_text, n_bytes, l.b.chunk_first, d_line_start, line_cap, d_n_records,
+                       l.b.raw, l.b.cap_records, d_recinfo, l.b.slow_list, l.d_err, ctx->d_counts, ctx->sm_count, st);
+    else
+        launch_k1(p, ctx->sched, d_text, d_line_start, d_n_records, l.b.raw, l.b.cap_records, d_recinfo, l.d_err,
+                  ctx->d_counts, ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[2], st));
     const bool has_model = p.h.model_kind != MODEL_NONE;
     if (has_model) launch_k2(p, l.b.raw, l.b.cap_records, d_n_records, l.b.feats, l.d_err, ctx->sm_count, st);
@@ -545,7 +705,7 @@ static int enqueue_kernels(ugvc_ctx* ctx, Lane& l, const uint8_t* d_text, size_t
         launch_k3(p, l.b.feats, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual,
                   d_low == l.b.low_score ? l.b.phreds : nullptr, ctx->want_phreds, ctx->d_counts, ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[4], st));
-    ctx->launches += (has_model ? 4 : 2) + (p.h.n_slots ? 1 : 0);
+    ctx->launches += (has_model ? 2 : 0) + (fast ? 2 : 2 + (p.h.n_slots ? 1 : 0));
     CU(cudaGetLastError());
     return UGVC_OK;
 }
@@ -943,6 +1103,16 @@ extern "C" int ugvc_last_data_error(const ugvc_ctx* ctx, int64_t* record, int32_
     if (column) *column = ctx->err_column;
     if (reason) *reason = ctx->err_reason;
     return UGVC_OK;
+}
+
+extern "C" int64_t ugvc_debug_slow_records(ugvc_ctx* ctx, int lane) {
+    // records of the lane's last batch that the tile kernel handed to the generic parser (blocking)
+    if (!ctx || lane < 0 || lane >= (int)ctx->lanes.size()) return UGVC_E_ARG;
+    Lane& l = ctx->lanes[lane];
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(l.stream) != cudaSuccess) return UGVC_E_CUDA;
+    uint32_t w[2] = {0, 0};
+    if (cudaMemcpy(w, l.b.chunk_first, sizeof(w), cudaMemcpyDeviceToHost) != cudaSuccess) return UGVC_E_CUDA;
+    return ctx->fast.enabled ? (int64_t)w[1] : -1;
 }
 
 extern "C" int64_t ugvc_launch_count(const ugvc_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -775,6 +775,8 @@ __device__ __noinline__ Cur decode_sched(RawOut o, unsigned long long meta, Cur 
 #undef K1_KERNEL_NAME
 #endif
 
+#include "k1_fast.inc"
+
 size_t k1_smem_bytes(const DevPlan&) { return (size_t)K1_SMEM_BYTES; }
 
 // every slot of every record starts ABSENT (the reference's defaultdict(lambda: None)):
@@ -816,14 +818,37 @@ void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_t
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k1_parse_frame, K1_TPB, smem) != cudaSuccess || occ_f < 1) occ_f = 1;
     }
     k1_parse_info<<<sm_count * occ_i, K1_TPB, smem, st>>>(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo,
-                                                          d_err, d_counts);
+                                                          d_err, d_counts, nullptr, nullptr);
     k1_parse_frame<<<sm_count * occ_f, K1_TPB, smem, st>>>(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo,
-                                                           d_err, d_counts);
+                                                           d_err, d_counts, nullptr, nullptr);
     (void)per_sm;
 #else
     k1_parse<<<sm_count * per_sm, K1_TPB, smem, st>>>(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo,
-                                                      d_err, d_counts);
+                                                      d_err, d_counts, nullptr, nullptr);
 #endif
+}
+
+// K1, both tiers: the tile kernel (line index + parse of the usual records) and the generic parser over
+// the records it put on the slow list.  scratch: [0] tile ticket, [1] slow-record count, then one
+// 64-bit look-back state word per tile.
+void launch_k1_fast(const DevPlan& plan, const DevFast& fast, const DevSchedule& sched, const uint8_t* d_text, size_t n_bytes,
+                    uint32_t* scratch, int64_t* line_start, size_t cap_records, int64_t* d_n_records, uint32_t* raw,
+                    size_t row_stride, ugvc_recinfo* recinfo, uint32_t* slow_list, unsigned long long* d_err,
+                    long long* d_counts, int sm_count, cudaStream_t st) {
+    const size_t n_tiles = (n_bytes + KF_TILE - 1) / KF_TILE;
+    cudaMemsetAsync(scratch, 0, 8 + n_tiles * sizeof(unsigned long long), st);
+    if (n_tiles == 0) {
+        k1_fast_empty<<<1, 1, 0, st>>>(line_start, d_n_records);
+        return;
+    }
+    const size_t blocks = n_tiles < (size_t)sm_count * 2 ? n_tiles : (size_t)sm_count * 2;
+    k1_fast<<<(unsigned)blocks, KF_TPB, KF_SMEM_BYTES, st>>>(plan, fast, d_text, n_bytes,
+                                                             reinterpret_cast<unsigned long long*>(scratch) + 1, scratch,
+                                                             scratch + 1, n_tiles, line_start, cap_records, d_n_records, raw,
+                                                             row_stride, recinfo, slow_list, d_err, d_counts);
+    // the slow tier: usually an empty list (the CTAs leave at once)
+    k1_parse<<<sm_count * 2, K1_TPB, k1_smem_bytes(plan), st>>>(plan, sched, d_text, line_start, d_n_records, raw, row_stride,
+                                                                recinfo, d_err, d_counts, slow_list, scratch + 1);
 }
 
 #endif  // !UGVC_HOST_EMU
@@ -1239,6 +1264,8 @@ void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const
 cudaError_t kernels_configure(const DevPlan& plan) {
     cudaError_t e = cudaFuncSetAttribute(k1_parse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)k1_smem_bytes(plan));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k1_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES);
     if (e != cudaSuccess) return e;
 #ifdef UGVC_K1_SPLIT
     e = cudaFuncSetAttribute(k1_parse_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(plan));

@@ -64,6 +64,59 @@ struct DevSchedule {
     SchedEntry fmt[UGVC_MAX_FMT_KEYS];  // per sub-field: cls / slot0 / n_elem / dict / flags / tag
 };
 
+
+// ---- K1 fast tier (k1_fast.inc) -----------------------------------------------------------
+// The tile kernel identifies INFO keys through a hash table of every key it may meet: the plan's
+// tags declared in ##INFO plus the keys ugvc_set_key_order() saw in the data (keys the plan does
+// not need decode to nothing).  A record that carries anything else -- an unknown key, a literal
+// outside the short decoders, a FORMAT column other than the usual one -- is handed to the
+// generic per-record parser (k1_parse over the slow list), which defines the semantics.
+#define KF_MAX_KEYS 192
+enum : uint8_t {
+    FK_SCALAR = 1,     // Number=1 in this header section
+    FK_IS_FLAG = 2,    // the data carries the key without a value
+    FK_SKIP_FMT = 4,   // the usual FORMAT column has the tag: the sample value overrides the INFO value
+    FK_NEEDED = 8,     // the plan has slots for this tag in this section
+};
+struct alignas(8) FastMeta {   // 8 bytes: how a value of this tag becomes slot words
+    uint8_t type;              // KIND_INT / KIND_FLOAT / KIND_STR / KIND_FLAG of this section
+    uint8_t flags;             // FK_*
+    uint8_t n_elem;            // element slots
+    uint8_t slot0;             // first slot of the tag
+    uint8_t whole_red;         // RED_* of the whole-value slot, 0xFF if none
+    uint8_t whole_slot;
+    uint8_t tag;               // plan tag (duplicate-key bitmap), 0xFF if the plan has no such tag
+    uint8_t pad;
+};
+struct alignas(16) FastKey {   // 32 bytes
+    uint32_t name[4];          // key bytes, zero padded (keys of up to 15 bytes are matched here)
+    FastMeta m;
+    uint8_t len;
+    uint8_t pad[7];
+};
+enum : uint8_t { SK_INT = 1, SK_STRNUM = 2, SK_SCALAR = 4 };  // per-slot bits the decoders need
+enum { FIX_QUAL = 0, FIX_ALLELE0 = 1, FIX_ALLELE1 = 2, FIX_INDEL = 3, FIX_NALLELES = 4 };
+struct DevFast {
+    const FastKey* keys;       // device array
+    const uint8_t* htab;       // 256-entry open-addressing table: key index or 0xFF
+    const uint8_t* slot_kind;  // [n_slots] SK_* bits
+    int n_keys;
+    int enabled;
+    int n_fmt, fmt_len;        // the usual FORMAT column (0: records are expected to end after INFO)
+    uint32_t fmt_w[6];
+    FastMeta fmt[UGVC_MAX_FMT_KEYS];
+    uint8_t fix_slot[8];       // slots of the fixed-column reducers (FIX_*), 0xFF if the plan has none
+};
+#if defined(__CUDACC__) || defined(UGVC_HOST_EMU)
+__host__ __device__
+#endif
+static inline uint32_t kf_hash(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t len) {
+    uint32_t h = (k0 * 0x9E3779B1u) ^ (k1 * 0x85EBCA77u) ^ (k2 * 0xC2B2AE3Du) ^ (k3 * 0x27D4EB2Fu) ^ (len * 0x165667B1u);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    return h >> 24;
+}
+
 // Error word: smaller is earlier.  (record << 24) | (column << 8) | reason
 #define UGVC_NO_ERROR 0xFFFFFFFFFFFFFFFFull
 __host__ __device__ inline unsigned long long ugvc_pack_error(long long rec, int col, int reason) {
@@ -73,8 +126,9 @@ __host__ __device__ inline unsigned long long ugvc_pack_error(long long rec, int
 struct LaneBuffers {
     // sizes
     size_t cap_bytes, cap_records;
-    // K0
-    uint32_t* chunk_first;     // per 4 KiB chunk: records before it
+    // K0 / K1 fast tier scratch: tile ticket, slow-record counter, look-back state words
+    uint32_t* chunk_first;
+    uint32_t* slow_list;       // [cap_records] records handed to the generic parser
     int64_t* line_start;       // [cap_records + 1]
     int64_t* n_records;        // device scalar
     // K1
@@ -90,6 +144,7 @@ struct LaneBuffers {
 };
 
 #define K0_TILE_BYTES_HOST 65536  // one 64-bit look-back state word per 64 KiB tile
+#define K1_TILE_BYTES_HOST 49152  // ... per 48 KiB tile of the K1 tile kernel (more tiles: sizes the scratch)
 
 void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* chunk_first, int64_t* line_start,
                size_t cap_records, int64_t* d_n_records, unsigned long long* d_err, int sm_count,
@@ -102,6 +157,10 @@ void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, cons
 void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const int64_t* d_n_records,
                double threshold, uint8_t* low_score, float* probs, double* qual, double* phreds, int phred_mode,
                long long* d_counts, int sm_count, cudaStream_t st);
+void launch_k1_fast(const DevPlan& plan, const DevFast& fast, const DevSchedule& sched, const uint8_t* d_text, size_t n_bytes,
+                    uint32_t* scratch, int64_t* line_start, size_t cap_records, int64_t* d_n_records, uint32_t* raw,
+                    size_t row_stride, ugvc_recinfo* recinfo, uint32_t* slow_list, unsigned long long* d_err,
+                    long long* d_counts, int sm_count, cudaStream_t st);
 size_t k1_smem_bytes(const DevPlan& plan);
 size_t k3_smem_bytes(const DevPlan& plan);
 bool k3_plan_fits(const DevPlan& plan);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "ugvc_plan_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ugvc_reserve": (C.c_int, [_vp, _sz, _sz, C.c_int]),
     "ugvc_set_key_order": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
+    "ugvc_debug_slow_records": (C.c_int64, [_vp, C.c_int]),
     "ugvc_filter_batch": (C.c_int, [_vp, _vp, _sz, C.c_double, _vp, _vp, _vp, _vp, _vp, _sz, _i64p]),
     "ugvc_submit_batch": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_double]),
     "ugvc_collect_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _i64p]),
@@ -309,6 +310,10 @@ class Context:
         out = np.empty((self.n_slots, max(1, n)), np.uint32)
         self._check(self.lib.ugvc_debug_raw(self.h, lane, _ptr(out), out.size))
         return out[:, :n]
+
+    def slow_records(self, lane: int = 0) -> int:
+        """Records of the lane's last batch that went through the generic parser (diagnostic)."""
+        return int(self.lib.ugvc_debug_slow_records(self.h, lane))
 
     def last_data_error(self) -> tuple[int, int, int]:
         r, c, k = C.c_int64(), C.c_int32(), C.c_int32()
