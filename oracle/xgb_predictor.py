@@ -51,6 +51,12 @@ def sklearn_gb_to_xgb_json(model) -> dict:
                         "gradient_booster": {"name": "gbtree", "model": {"trees": trees, "tree_info": info}}}}
 
 
+def _expf(v: np.ndarray) -> np.ndarray:
+    """libm's expf as xgboost's Sigmoid / Softmax call it: glibc's is correctly rounded for all but about one
+    argument in 10^7, NumPy's SIMD float32 exp is not -- so: float64 exp, rounded once."""
+    return np.exp(np.asarray(v, dtype=np.float32).astype(np.float64)).astype(np.float32)
+
+
 def predict_proba(doc: dict, x: np.ndarray) -> np.ndarray:
     x = np.asarray(x, dtype=np.float32)
     learner = doc["learner"]
@@ -81,9 +87,9 @@ def predict_proba(doc: dict, x: np.ndarray) -> np.ndarray:
         o = model["tree_info"][ti] if n_out > 1 else 0
         margin[:, o] = (margin[:, o] + cond[node]).astype(np.float32)
     if n_out == 1:
-        p1 = (np.float32(1.0) / (np.float32(1.0) + np.exp(-margin[:, 0], dtype=np.float32))).astype(np.float32)
+        p1 = (np.float32(1.0) / (np.float32(1.0) + _expf(-margin[:, 0]))).astype(np.float32)
         return np.stack([np.float32(1.0) - p1, p1], axis=1)
     mx = margin.max(axis=1, keepdims=True)
-    e = np.exp(margin - mx, dtype=np.float32)
+    e = _expf(margin - mx)
     s = e.astype(np.float64).sum(axis=1, keepdims=True)
     return (e / s.astype(np.float32)).astype(np.float32)

@@ -44,6 +44,9 @@ struct ugvc_ctx {
     uint8_t* d_plan = nullptr;
     uint8_t* d_htab = nullptr;
     uint2* d_nodes = nullptr;
+    float* d_heap_thr = nullptr;     // heap form of the forest (k3_heap)
+    uint8_t* d_heap_feat = nullptr;
+    uint16_t* d_heap_leaf = nullptr;
     std::vector<PlanTag> h_tags;   // host copies for name lookups / decode classes
     std::vector<PlanSlot> h_slots;
 #ifdef UGVC_K1_INLINE_DICT1
@@ -143,6 +146,9 @@ extern "C" void ugvc_free(ugvc_ctx* ctx) {
     cudaFree(ctx->d_plan);
     cudaFree(ctx->d_htab);
     cudaFree(ctx->d_nodes);
+    cudaFree(ctx->d_heap_thr);
+    cudaFree(ctx->d_heap_feat);
+    cudaFree(ctx->d_heap_leaf);
     cudaFree(ctx->d_sched);
     cudaFree(ctx->d_fast_keys);
     cudaFree(ctx->d_fast_htab);
@@ -427,9 +433,72 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
             }
         }
     }
+
+    // heap form for k3_heap: every tree padded to a complete binary tree (breadth-first, root at index 1);
+    // below a shallow leaf every node is (+inf, feature 0) and every leaf slot carries its row
+    std::vector<float> heap_thr;
+    std::vector<uint8_t> heap_feat;
+    std::vector<uint16_t> heap_leaf;
+    uint32_t heap_depth = 0;
+    if (!dev_nodes.empty() && max_depth <= 8 && h.n_leaf_rows < 65536 && h.n_features <= 255) {
+        const uint32_t* root = reinterpret_cast<const uint32_t*>(hb + o_root);
+        const PlanNode* nodes = reinterpret_cast<const PlanNode*>(hb + o_nodes);
+        heap_depth = max_depth ? max_depth : 1;
+        const uint32_t H = 1u << heap_depth;
+        const float inf = __builtin_huge_valf();
+        heap_thr.assign((size_t)h.n_trees * H, inf);
+        heap_feat.assign((size_t)h.n_trees * H, 0);
+        heap_leaf.assign((size_t)h.n_trees * H, 0);
+        struct Item { uint32_t node, heap, level; int32_t leaf; };  // leaf >= 0: inside a padded subtree
+        std::vector<Item> stack;
+        for (uint32_t t = 0; t < h.n_trees; ++t) {
+            const uint32_t r0 = root[t];
+            float* thr = heap_thr.data() + (size_t)t * H;
+            uint8_t* ft = heap_feat.data() + (size_t)t * H;
+            uint16_t* lf = heap_leaf.data() + (size_t)t * H;
+            stack.clear();
+            stack.push_back({0, 1, 0, -1});
+            while (!stack.empty()) {
+                const Item it = stack.back();
+                stack.pop_back();
+                int32_t leaf = it.leaf;
+                if (leaf < 0) {
+                    const PlanNode& nd = nodes[r0 + it.node];
+                    if (nd.feature >= 0) {
+                        thr[it.heap] = nd.value;
+                        ft[it.heap] = (uint8_t)nd.feature;
+                        stack.push_back({it.node + 1, 2 * it.heap, it.level + 1, -1});
+                        stack.push_back({nd.right, 2 * it.heap + 1, it.level + 1, -1});
+                        continue;
+                    }
+                    memcpy(&leaf, &nd.value, 4);
+                }
+                if (it.level == heap_depth) {
+                    lf[it.heap - H] = (uint16_t)leaf;
+                } else {  // thr stays +inf, feature 0
+                    stack.push_back({0, 2 * it.heap, it.level + 1, leaf});
+                    stack.push_back({0, 2 * it.heap + 1, it.level + 1, leaf});
+                }
+            }
+        }
+    }
     cudaFree(ctx->d_plan);
     cudaFree(ctx->d_htab);
     cudaFree(ctx->d_nodes);
+    cudaFree(ctx->d_heap_thr);
+    cudaFree(ctx->d_heap_feat);
+    cudaFree(ctx->d_heap_leaf);
+    ctx->d_heap_thr = nullptr;
+    ctx->d_heap_feat = nullptr;
+    ctx->d_heap_leaf = nullptr;
+    if (heap_depth) {
+        CU(cudaMalloc(&ctx->d_heap_thr, heap_thr.size() * sizeof(float)));
+        CU(cudaMemcpy(ctx->d_heap_thr, heap_thr.data(), heap_thr.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&ctx->d_heap_feat, heap_feat.size()));
+        CU(cudaMemcpy(ctx->d_heap_feat, heap_feat.data(), heap_feat.size(), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&ctx->d_heap_leaf, heap_leaf.size() * sizeof(uint16_t)));
+        CU(cudaMemcpy(ctx->d_heap_leaf, heap_leaf.data(), heap_leaf.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
     ctx->d_plan = nullptr;
     ctx->d_htab = nullptr;
     ctx->d_nodes = nullptr;
@@ -458,6 +527,10 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
     p.nodes = reinterpret_cast<const PlanNode*>(d + o_nodes);
     p.dev_nodes = ctx->d_nodes;
     p.max_depth = max_depth;
+    p.heap_thr = ctx->d_heap_thr;
+    p.heap_feat = ctx->d_heap_feat;
+    p.heap_leaf = ctx->d_heap_leaf;
+    p.heap_depth = heap_depth;
     p.leaves = reinterpret_cast<const double*>(d + o_leaves);
     p.htab = ctx->d_htab;
     p.first_fixed_slot = first_fixed;
@@ -699,13 +772,19 @@ static int enqueue_kernels(ugvc_ctx* ctx, Lane& l, const uint8_t* d_text, size_t
                   ctx->d_counts, ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[2], st));
     const bool has_model = p.h.model_kind != MODEL_NONE;
-    if (has_model) launch_k2(p, l.b.raw, l.b.cap_records, d_n_records, l.b.feats, l.d_err, ctx->sm_count, st);
+    static const bool k3_legacy = getenv("UGVC_K3_LEGACY") && *getenv("UGVC_K3_LEGACY") != '0';  // profiling: K2 + preorder K3
+    const bool fused = has_model && !k3_legacy && k3_fused_available(p);
+    if (has_model && !fused) launch_k2(p, l.b.raw, l.b.cap_records, d_n_records, l.b.feats, l.d_err, ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[3], st));
-    if (has_model)
+    if (fused)  // feature assembly happens in the tile load of the inference kernel
+        launch_k3_fused(p, l.b.raw, nullptr, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual,
+                        d_low == l.b.low_score ? l.b.phreds : nullptr, ctx->want_phreds, ctx->d_counts, l.d_err,
+                        ctx->sm_count, st);
+    else if (has_model)
         launch_k3(p, l.b.feats, l.b.cap_records, d_n_records, threshold, d_low, d_probs, d_qual,
                   d_low == l.b.low_score ? l.b.phreds : nullptr, ctx->want_phreds, ctx->d_counts, ctx->sm_count, st);
     if (timing) CU(cudaEventRecord(ev[4], st));
-    ctx->launches += (has_model ? 2 : 0) + (fast ? 2 : 2 + (p.h.n_slots ? 1 : 0));
+    ctx->launches += (has_model ? (fused ? 1 : 2) : 0) + (fast ? 2 : 2 + (p.h.n_slots ? 1 : 0));
     CU(cudaGetLastError());
     return UGVC_OK;
 }
@@ -1017,8 +1096,12 @@ extern "C" int ugvc_predict_features(ugvc_ctx* ctx, const float* x, size_t n, si
                          cudaMemcpyHostToDevice, st));
     const int64_t n64 = (int64_t)n;
     CU(cudaMemcpyAsync(l.b.n_records, &n64, sizeof(n64), cudaMemcpyHostToDevice, st));
-    launch_k3(p, l.b.feats, l.b.cap_records, l.b.n_records, threshold, l.b.low_score, l.b.probs, l.b.qual,
-              l.b.phreds, ctx->want_phreds, ctx->d_counts, ctx->sm_count, st);
+    if (k3_fused_available(p))
+        launch_k3_fused(p, nullptr, l.b.feats, l.b.cap_records, l.b.n_records, threshold, l.b.low_score, l.b.probs, l.b.qual,
+                        l.b.phreds, ctx->want_phreds, ctx->d_counts, l.d_err, ctx->sm_count, st);
+    else
+        launch_k3(p, l.b.feats, l.b.cap_records, l.b.n_records, threshold, l.b.low_score, l.b.probs, l.b.qual,
+                  l.b.phreds, ctx->want_phreds, ctx->d_counts, ctx->sm_count, st);
     ctx->launches += 1;
     CU(cudaGetLastError());
     if (out_low_score) CU(cudaMemcpyAsync(out_low_score, l.b.low_score, n, cudaMemcpyDeviceToHost, st));
@@ -1093,6 +1176,16 @@ extern "C" int ugvc_debug_features(ugvc_ctx* ctx, int lane, float* out, size_t c
     const size_t n = (size_t)l.last_n, F = ctx->plan.h.n_features;
     if (capacity_floats < n * F) return fail(ctx, UGVC_E_ARG, "debug_features: capacity too small");
     CU(cudaStreamSynchronize(l.stream));
+    if (n && F) {
+        // the product path assembles features inside the inference kernel; this diagnostic runs the stand-alone
+        // assembly kernel (same k2_apply) on the lane's raw slots, into the lane's feature buffer
+        unsigned long long* d_scratch_err = nullptr;
+        CU(cudaMalloc(&d_scratch_err, sizeof(unsigned long long)));
+        CU(cudaMemset(d_scratch_err, 0xFF, sizeof(unsigned long long)));
+        launch_k2(ctx->plan, l.b.raw, l.b.cap_records, l.b.n_records, l.b.feats, d_scratch_err, ctx->sm_count, l.stream);
+        CU(cudaStreamSynchronize(l.stream));
+        cudaFree(d_scratch_err);
+    }
     if (n) CU(cudaMemcpy2D(out, n * 4, l.b.feats, l.b.cap_records * 4, n * 4, F, cudaMemcpyDeviceToHost));
     return UGVC_OK;
 }

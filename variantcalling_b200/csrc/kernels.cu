@@ -984,6 +984,131 @@ __device__ __forceinline__ void walk8(const uint2* __restrict__ s_nodes, const u
     for (int j = 0; j < K3_CHAINS; ++j) leaf[j] = (int)(nd[j].x & 0x3FFFFFu);
 }
 
+// Link function, fp64 phred / qual arithmetic and the FILTER decision of one record (shared by the two K3
+// kernels): z / zf are the accumulated raw scores (fp64 for sklearn, fp32 for xgboost), x the record's
+// column of the shared-memory feature tile (stride TPB).  Returns quals <= threshold.
+template <int TPB>
+__device__ __forceinline__ bool k3_finish(const DevPlan& plan, const float* __restrict__ x, double z[UGVC_MAX_CLASSES],
+                                          float zf[UGVC_MAX_CLASSES], long long rec, double threshold,
+                                          uint8_t* __restrict__ low_score, float* __restrict__ probs,
+                                          double* __restrict__ qual_out, double* __restrict__ phred_out, int phred_mode) {
+    const int F = plan.h.n_features, K = plan.h.n_classes, O = plan.h.n_outputs;
+    const unsigned n_trees = plan.h.n_trees;
+    double p[UGVC_MAX_CLASSES] = {0.0, 0.0, 0.0, 0.0};
+    switch (plan.h.model_kind) {
+        case MODEL_LOGISTIC: {
+            // sklearn LogisticRegression: fp64 decision, expit / softmax
+#pragma unroll
+            for (int o = 0; o < UGVC_MAX_CLASSES; ++o) {
+                if (o < O) {
+                    double acc = 0.0;
+                    const double* w = plan.coef + (size_t)o * F;
+                    for (int f = 0; f < F; ++f) acc = fma((double)x[f * TPB], __ldg(&w[f]), acc);
+                    z[o] = acc + plan.intercept[o];
+                }
+            }
+        }
+        // fall through: same link as the fp64 boosting model
+        case MODEL_GB_SKLEARN: {
+            if (O == 1) {
+                p[1] = expit64(z[0]);
+                p[0] = 1.0 - p[1];
+            } else if (plan.h.model_kind == MODEL_LOGISTIC) {
+                double mx = z[0];
+#pragma unroll
+                for (int o = 1; o < UGVC_MAX_CLASSES; ++o)
+                    if (o < O) mx = fmax(mx, z[o]);
+                double s = 0.0;
+#pragma unroll
+                for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                    if (o < O) {
+                        p[o] = exp(z[o] - mx);
+                        s += p[o];
+                    }
+#pragma unroll
+                for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                    if (o < O) p[o] /= s;
+            } else {
+                // sklearn multiclass boosting: exp(raw - logsumexp(raw))
+                double mx = z[0];
+#pragma unroll
+                for (int o = 1; o < UGVC_MAX_CLASSES; ++o)
+                    if (o < O) mx = fmax(mx, z[o]);
+                double s = 0.0;
+#pragma unroll
+                for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                    if (o < O) s += exp(z[o] - mx);
+                const double lse = mx + log(s);
+#pragma unroll
+                for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                    if (o < O) p[o] = exp(z[o] - lse);
+            }
+            break;
+        }
+        case MODEL_RF_SKLEARN: {
+#pragma unroll
+            for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
+                if (k < K) p[k] = z[k] / (double)n_trees;
+            break;
+        }
+        case MODEL_XGB: {
+            // xgboost CPU predictor: fp32 margins, fp32 sigmoid / softmax
+            if (O == 1) {
+                const float p1 = 1.0f / (1.0f + expf(-zf[0]));
+                p[1] = (double)p1;
+                p[0] = (double)(1.0f - p1);
+            } else {
+                float mx = zf[0];
+#pragma unroll
+                for (int o = 1; o < UGVC_MAX_CLASSES; ++o)
+                    if (o < O) mx = fmaxf(mx, zf[o]);
+                double s = 0.0;
+                float e[UGVC_MAX_CLASSES] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                    if (o < O) {
+                        e[o] = expf(zf[o] - mx);
+                        s += (double)e[o];
+                    }
+#pragma unroll
+                for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
+                    if (o < O) p[o] = (double)(e[o] / (float)s);
+            }
+            break;
+        }
+        default:
+            break;
+    }
+    // phred = -10 log10(lik + 1e-10); qual = clip(30 + ph[0] - min(ph[1:]), 0, inf)   (fp64)
+    double ph[UGVC_MAX_CLASSES];
+#pragma unroll
+    for (int k = 0; k < UGVC_MAX_CLASSES; ++k) ph[k] = k < K ? -10.0 * log10(p[k] + 1e-10) : 0.0;
+    const double ph0 = ph[0];
+    double mn = ph[1];
+#pragma unroll
+    for (int k = 2; k < UGVC_MAX_CLASSES; ++k)
+        if (k < K) mn = fmin(mn, ph[k]);
+    if (phred_out) {  // --recalibrate_genotype: PL / GQ come from the per-class phreds;
+                      // mode 2 (--treat_multiallelics): the fp64 likelihoods, merged on the host
+#pragma unroll
+        for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
+            if (k < K) phred_out[(size_t)rec * K + k] = phred_mode == 2 ? p[k] : ph[k];
+    }
+    double q = __dadd_rn(__dadd_rn(30.0, ph0), -mn);
+    q = q < 0.0 ? 0.0 : q;
+    const bool low = q <= threshold;
+    low_score[rec] = low ? 1 : 0;
+    qual_out[rec] = q;
+    if (K == 2) {
+        *reinterpret_cast<float2*>(&probs[(size_t)rec * 2]) = make_float2((float)p[0], (float)p[1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
+            if (k < K) probs[(size_t)rec * K + k] = (float)p[k];
+    }
+    return low;
+}
+
 template <int TPB>
 __global__ void __launch_bounds__(TPB, 1) k3_infer(const __grid_constant__ DevPlan plan,
                                                       const float* __restrict__ feats, size_t row_stride,
@@ -1020,7 +1145,6 @@ __global__ void __launch_bounds__(TPB, 1) k3_infer(const __grid_constant__ DevPl
         }
         __syncthreads();
         const float* x = tile + threadIdx.x;
-        double p[UGVC_MAX_CLASSES] = {0.0, 0.0, 0.0, 0.0};
         double z[UGVC_MAX_CLASSES];   // fp64 accumulators (sklearn) ...
         float zf[UGVC_MAX_CLASSES];   // ... fp32 accumulators (xgboost)
 #pragma unroll
@@ -1082,117 +1206,7 @@ __global__ void __launch_bounds__(TPB, 1) k3_infer(const __grid_constant__ DevPl
             }
         }
         if (!active) continue;
-        switch (plan.h.model_kind) {
-            case MODEL_LOGISTIC: {
-                // sklearn LogisticRegression: fp64 decision, expit / softmax
-#pragma unroll
-                for (int o = 0; o < UGVC_MAX_CLASSES; ++o) {
-                    if (o < O) {
-                        double acc = 0.0;
-                        const double* w = plan.coef + (size_t)o * F;
-                        for (int f = 0; f < F; ++f) acc = fma((double)x[f * TPB], __ldg(&w[f]), acc);
-                        z[o] = acc + plan.intercept[o];
-                    }
-                }
-            }
-            // fall through: same link as the fp64 boosting model
-            case MODEL_GB_SKLEARN: {
-                if (O == 1) {
-                    p[1] = expit64(z[0]);
-                    p[0] = 1.0 - p[1];
-                } else if (plan.h.model_kind == MODEL_LOGISTIC) {
-                    double mx = z[0];
-#pragma unroll
-                    for (int o = 1; o < UGVC_MAX_CLASSES; ++o)
-                        if (o < O) mx = fmax(mx, z[o]);
-                    double s = 0.0;
-#pragma unroll
-                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
-                        if (o < O) {
-                            p[o] = exp(z[o] - mx);
-                            s += p[o];
-                        }
-#pragma unroll
-                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
-                        if (o < O) p[o] /= s;
-                } else {
-                    // sklearn multiclass boosting: exp(raw - logsumexp(raw))
-                    double mx = z[0];
-#pragma unroll
-                    for (int o = 1; o < UGVC_MAX_CLASSES; ++o)
-                        if (o < O) mx = fmax(mx, z[o]);
-                    double s = 0.0;
-#pragma unroll
-                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
-                        if (o < O) s += exp(z[o] - mx);
-                    const double lse = mx + log(s);
-#pragma unroll
-                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
-                        if (o < O) p[o] = exp(z[o] - lse);
-                }
-                break;
-            }
-            case MODEL_RF_SKLEARN: {
-#pragma unroll
-                for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
-                    if (k < K) p[k] = z[k] / (double)n_trees;
-                break;
-            }
-            case MODEL_XGB: {
-                // xgboost CPU predictor: fp32 margins, fp32 sigmoid / softmax
-                if (O == 1) {
-                    const float p1 = 1.0f / (1.0f + expf(-zf[0]));
-                    p[1] = (double)p1;
-                    p[0] = (double)(1.0f - p1);
-                } else {
-                    float mx = zf[0];
-#pragma unroll
-                    for (int o = 1; o < UGVC_MAX_CLASSES; ++o)
-                        if (o < O) mx = fmaxf(mx, zf[o]);
-                    double s = 0.0;
-                    float e[UGVC_MAX_CLASSES] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
-                        if (o < O) {
-                            e[o] = expf(zf[o] - mx);
-                            s += (double)e[o];
-                        }
-#pragma unroll
-                    for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
-                        if (o < O) p[o] = (double)(e[o] / (float)s);
-                }
-                break;
-            }
-            default:
-                break;
-        }
-        // phred = -10 log10(lik + 1e-10); qual = clip(30 + ph[0] - min(ph[1:]), 0, inf)   (fp64)
-        double ph[UGVC_MAX_CLASSES];
-#pragma unroll
-        for (int k = 0; k < UGVC_MAX_CLASSES; ++k) ph[k] = k < K ? -10.0 * log10(p[k] + 1e-10) : 0.0;
-        const double ph0 = ph[0];
-        double mn = ph[1];
-#pragma unroll
-        for (int k = 2; k < UGVC_MAX_CLASSES; ++k)
-            if (k < K) mn = fmin(mn, ph[k]);
-        if (phred_out) {  // --recalibrate_genotype: PL / GQ come from the per-class phreds;
-                          // mode 2 (--treat_multiallelics): the fp64 likelihoods, merged on the host
-#pragma unroll
-            for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
-                if (k < K) phred_out[(size_t)rec * K + k] = phred_mode == 2 ? p[k] : ph[k];
-        }
-        double q = __dadd_rn(__dadd_rn(30.0, ph0), -mn);
-        q = q < 0.0 ? 0.0 : q;
-        const bool low = q <= threshold;
-        low_score[rec] = low ? 1 : 0;
-        qual_out[rec] = q;
-        if (K == 2) {
-            *reinterpret_cast<float2*>(&probs[(size_t)rec * 2]) = make_float2((float)p[0], (float)p[1]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
-                if (k < K) probs[(size_t)rec * K + k] = (float)p[k];
-        }
+        const bool low = k3_finish<TPB>(plan, x, z, zf, rec, threshold, low_score, probs, qual_out, phred_out, phred_mode);
         n_low += low ? 1u : 0u;
         n_seen += 1u;
     }
@@ -1210,6 +1224,245 @@ __global__ void __launch_bounds__(TPB, 1) k3_infer(const __grid_constant__ DevPl
 }
 
 #define K3_SMEM_BUDGET (224u * 1024u)
+
+// ------------------------------------------------------------------------------------------
+// K2 + K3 fused, heap forest
+// ------------------------------------------------------------------------------------------
+// K3 was bound by shared-memory wavefronts: 8-byte preorder nodes gathered by 32 lanes cost 4-5 wavefronts per
+// level.  Here every tree is a complete binary tree in breadth-first order, thresholds / features / leaf rows
+// in separate arrays: the 2^d nodes of level d are 2^d consecutive 4-byte words (d <= 5: distinct banks, equal
+// addresses broadcast), so a level costs three conflict-free wavefronts (feature byte, threshold, x).  The
+// feature tile is assembled straight from K1's raw slots with the fitted transformer's missing / absent
+// policies (what k2_features did in a pass of its own), or copied from a dense matrix (ugvc_predict_features).
+__device__ __forceinline__ void k2_combine_one(const PlanCombine cb, uint32_t bbits, float& a, long long rec, bool live,
+                                               unsigned long long* err) {
+    const bool b_null = bbits == RAW_ABSENT || bbits == RAW_MISSING;
+    if (bbits == RAW_ERR && live) atomicMin(err, ugvc_pack_error(rec, cb.feature, REASON_BAD_VALUE));
+    const float bv = __uint_as_float(bbits);
+    const float r = isnan(a) ? (b_null ? a : bv) : (b_null ? a : fmaxf(a, bv));
+    if (isnan(r) && live) atomicMin(err, ugvc_pack_error(rec, cb.feature, REASON_NULL_FEATURE));
+    a = r;
+}
+
+template <int CMP, int TPB>
+__device__ __forceinline__ void walk8h(const float* __restrict__ s_thr, const uint8_t* __restrict__ s_feat,
+                                       const uint16_t* __restrict__ s_leaf, unsigned H, int depth, unsigned tr,
+                                       unsigned tr_end, const float* __restrict__ x, int leaf[K3_CHAINS]) {
+    unsigned n[K3_CHAINS], base[K3_CHAINS];
+#pragma unroll
+    for (int j = 0; j < K3_CHAINS; ++j) {
+        const unsigned t = tr + j < tr_end ? tr + j : tr;  // pad with a repeat (result ignored)
+        base[j] = t * H;
+        n[j] = 1u;
+    }
+    for (int d = 0; d < depth; ++d) {
+        unsigned f[K3_CHAINS];
+        float th[K3_CHAINS];
+#pragma unroll
+        for (int j = 0; j < K3_CHAINS; ++j) {
+            f[j] = s_feat[base[j] + n[j]];
+            th[j] = s_thr[base[j] + n[j]];
+        }
+#pragma unroll
+        for (int j = 0; j < K3_CHAINS; ++j) {
+            const float xv = x[f[j] * TPB];
+            const bool left = (CMP == CMP_LE) ? (xv <= th[j]) : (xv < th[j]);
+            n[j] = 2u * n[j] + (left ? 0u : 1u);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < K3_CHAINS; ++j) leaf[j] = (int)s_leaf[base[j] + n[j] - H];
+}
+
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 1)
+k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, const float* __restrict__ feats,
+        size_t row_stride, const int64_t* __restrict__ n_records_p, double threshold, uint8_t* __restrict__ low_score,
+        float* __restrict__ probs, double* __restrict__ qual_out, double* __restrict__ phred_out, long long* counts,
+        unsigned chunk_trees, int phred_mode, unsigned long long* err) {
+    extern __shared__ __align__(16) uint8_t smem3[];
+    const int F = plan.h.n_features, K = plan.h.n_classes, O = plan.h.n_outputs;
+    const unsigned n_trees = plan.h.n_trees;
+    const bool forest = plan.h.model_kind != MODEL_LOGISTIC;
+    const int depth = (int)plan.heap_depth;
+    const unsigned H = 1u << depth;
+    float* tile = reinterpret_cast<float*>(smem3);  // [F][TPB]
+    float* s_thr = tile + (size_t)F * TPB;           // [chunk_trees][H]
+    PlanFeature* s_pf = reinterpret_cast<PlanFeature*>(s_thr + (forest ? (size_t)chunk_trees * H : 0));  // [F]
+    uint16_t* s_leaf = reinterpret_cast<uint16_t*>(s_pf + F);                                              // [chunk_trees][H]
+    uint8_t* s_feat = reinterpret_cast<uint8_t*>(s_leaf + (forest ? (size_t)chunk_trees * H : 0));        // [chunk_trees][H]
+    const bool resident = forest && n_trees <= chunk_trees;  // whole forest fits: stage once
+    for (int i = threadIdx.x; i < F; i += TPB) s_pf[i] = plan.feats[i];
+    if (resident) {
+        const unsigned cnt = n_trees * H;
+        for (unsigned i = threadIdx.x; i < cnt; i += TPB) {
+            s_thr[i] = plan.heap_thr[i];
+            s_leaf[i] = plan.heap_leaf[i];
+            s_feat[i] = plan.heap_feat[i];
+        }
+    }
+    const long long n_rec = *n_records_p;
+    const long long n_tiles = (n_rec + TPB - 1) / TPB;
+    unsigned n_low = 0, n_seen = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const long long rec = t * TPB + threadIdx.x;
+        const bool active = rec < n_rec;
+        __syncthreads();
+        if (raw) {
+            // K2: slot -> feature with the missing / absent policies (transformers.py:221-344)
+            const uint32_t* src = raw + rec;
+#pragma unroll 4
+            for (int f = 0; f < F; ++f) {
+                const PlanFeature pf = s_pf[f];
+                tile[f * TPB + threadIdx.x] = active ? k2_apply(__ldg(src + (size_t)pf.slot * row_stride), pf, rec, f, err) : 0.f;
+            }
+            for (unsigned c = 0; c < plan.h.n_combines; ++c) {  // feature = max(feature, slot_b), nulls skipped
+                const PlanCombine cb = plan.combines[c];
+                if (active) k2_combine_one(cb, __ldg(src + (size_t)cb.slot_b * row_stride), tile[cb.feature * TPB + threadIdx.x], rec, true, err);
+            }
+            for (unsigned c = 0; c < plan.h.n_checks; ++c) {
+                const PlanCheck ck = plan.checks[c];
+                if (!active) continue;
+                const uint32_t bits = __ldg(src + (size_t)ck.slot * row_stride);
+                if (bits == RAW_ABSENT || bits == RAW_MISSING) continue;  // handled by the feature policies
+                const float v = __uint_as_float(bits);
+                const bool ok = ck.kind == 0 ? (v <= ck.bound) : (v >= ck.bound);
+                if (!ok) atomicMin(err, ugvc_pack_error(rec, 0xFFFF, ck.kind == 0 ? REASON_TOO_MANY_ELEMS : REASON_BAD_VALUE));
+            }
+        } else {
+            const float* src = feats + rec;
+#pragma unroll 8
+            for (int f = 0; f < F; ++f) tile[f * TPB + threadIdx.x] = active ? __ldg(src + (size_t)f * row_stride) : 0.f;
+        }
+        __syncthreads();
+        const float* x = tile + threadIdx.x;
+        double z[UGVC_MAX_CLASSES];   // fp64 accumulators (sklearn) ...
+        float zf[UGVC_MAX_CLASSES];   // ... fp32 accumulators (xgboost)
+#pragma unroll
+        for (int o = 0; o < UGVC_MAX_CLASSES; ++o) {
+            z[o] = plan.h.model_kind == MODEL_RF_SKLEARN ? 0.0 : plan.h.init[o];
+            zf[o] = (float)plan.h.init[o];
+        }
+        if (forest) {
+            unsigned c0 = 0;
+            while (c0 < n_trees) {
+                unsigned c1 = n_trees;
+                if (!resident) {  // tree chunks [c0, c1) staged in turn
+                    c1 = c0 + chunk_trees < n_trees ? c0 + chunk_trees : n_trees;
+                    __syncthreads();
+                    const unsigned cnt = (c1 - c0) * H;
+                    const size_t off = (size_t)c0 * H;
+                    for (unsigned i = threadIdx.x; i < cnt; i += TPB) {
+                        s_thr[i] = plan.heap_thr[off + i];
+                        s_leaf[i] = plan.heap_leaf[off + i];
+                        s_feat[i] = plan.heap_feat[off + i];
+                    }
+                    __syncthreads();
+                }
+                for (unsigned tr = c0; tr < c1; tr += K3_CHAINS) {
+                    int leaf[K3_CHAINS];
+                    const unsigned lt = resident ? tr : tr - c0, lt_end = resident ? c1 : c1 - c0;
+                    if (plan.h.cmp_mode == CMP_LE) walk8h<CMP_LE, TPB>(s_thr, s_feat, s_leaf, H, depth, lt, lt_end, x, leaf);
+                    else walk8h<CMP_LT, TPB>(s_thr, s_feat, s_leaf, H, depth, lt, lt_end, x, leaf);
+                    if (plan.h.model_kind == MODEL_GB_SKLEARN && O == 1) {
+#pragma unroll
+                        for (int j = 0; j < K3_CHAINS; ++j)
+                            if (tr + j < c1) z[0] = __dadd_rn(z[0], __ldg(&plan.leaves[leaf[j]]));
+                    } else if (plan.h.model_kind == MODEL_RF_SKLEARN) {
+#pragma unroll
+                        for (int j = 0; j < K3_CHAINS; ++j)
+                            if (tr + j < c1) {
+                                const double* lv = plan.leaves + (size_t)leaf[j] * plan.h.leaf_width;
+#pragma unroll
+                                for (int k = 0; k < UGVC_MAX_CLASSES; ++k)
+                                    if (k < K) z[k] = __dadd_rn(z[k], __ldg(&lv[k]));
+                            }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < K3_CHAINS; ++j)
+                            if (tr + j < c1) {
+                                const int o = plan.tree_out[tr + j];
+                                const double add = __ldg(&plan.leaves[leaf[j]]);
+                                const float addf = (float)add;
+#pragma unroll
+                                for (int k = 0; k < UGVC_MAX_CLASSES; ++k) {
+                                    z[k] = o == k ? __dadd_rn(z[k], add) : z[k];
+                                    zf[k] = o == k ? __fadd_rn(zf[k], addf) : zf[k];
+                                }
+                            }
+                    }
+                }
+                c0 = c1;
+            }
+        }
+        if (!active) continue;
+        const bool low = k3_finish<TPB>(plan, x, z, zf, rec, threshold, low_score, probs, qual_out, phred_out, phred_mode);
+        n_low += low ? 1u : 0u;
+        n_seen += 1u;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        n_low += __shfl_xor_sync(0xffffffffu, n_low, s);
+        n_seen += __shfl_xor_sync(0xffffffffu, n_seen, s);
+    }
+    if ((threadIdx.x & 31) == 0 && n_seen) {
+        atomicAdd((unsigned long long*)&counts[0], (unsigned long long)n_seen);
+        atomicAdd((unsigned long long*)&counts[1], (unsigned long long)n_low);
+        atomicAdd((unsigned long long*)&counts[2], (unsigned long long)(n_seen - n_low));
+    }
+}
+
+// shared-memory plan of k3_heap: records per CTA and trees per staged chunk
+static size_t k3h_tree_bytes(const DevPlan& plan) { return (size_t)(1u << plan.heap_depth) * 7u; }
+static size_t k3h_fixed_bytes(const DevPlan& plan, int tpb) {
+    return (size_t)plan.h.n_features * tpb * sizeof(float) + (size_t)plan.h.n_features * sizeof(PlanFeature) + 64;
+}
+static int k3h_tpb(const DevPlan& plan) {
+    static const int force = getenv("UGVC_K3_TPB") ? atoi(getenv("UGVC_K3_TPB")) : 0;  // profiling knob
+    const bool forest = plan.h.model_kind != MODEL_LOGISTIC;
+    const size_t all = forest ? (size_t)plan.h.n_trees * k3h_tree_bytes(plan) : 0;
+    const int cand[3] = {512, 256, 128};
+    for (int c : cand) {
+        if (force && c != force) continue;
+        if (k3h_fixed_bytes(plan, c) + all <= K3_SMEM_BUDGET) return c;
+    }
+    for (int c : cand)  // the forest is staged in chunks: at least 8 trees at a time
+        if (k3h_fixed_bytes(plan, c) + 8 * k3h_tree_bytes(plan) <= K3_SMEM_BUDGET) return c;
+    return 0;
+}
+static unsigned k3h_chunk_trees(const DevPlan& plan, int tpb) {
+    if (plan.h.model_kind == MODEL_LOGISTIC) return 0;
+    const size_t room = K3_SMEM_BUDGET - k3h_fixed_bytes(plan, tpb);
+    size_t n = room / k3h_tree_bytes(plan);
+    if (n > plan.h.n_trees) n = plan.h.n_trees;
+    if (n < plan.h.n_trees) n &= ~(size_t)7;  // whole groups of K3_CHAINS
+    return (unsigned)n;
+}
+bool k3_fused_available(const DevPlan& plan) {
+    if (plan.h.model_kind == MODEL_NONE) return false;
+    if (plan.h.model_kind != MODEL_LOGISTIC && plan.heap_depth == 0) return false;
+    return k3h_tpb(plan) != 0;
+}
+#ifndef UGVC_HOST_EMU
+void launch_k3_fused(const DevPlan& plan, const uint32_t* raw, const float* feats, size_t row_stride,
+                     const int64_t* d_n_records, double threshold, uint8_t* low_score, float* probs, double* qual,
+                     double* phreds, int phred_mode, long long* d_counts, unsigned long long* d_err, int sm_count,
+                     cudaStream_t st) {
+    const int tpb = k3h_tpb(plan);
+    const unsigned chunk = k3h_chunk_trees(plan, tpb);
+    const size_t smem = k3h_fixed_bytes(plan, tpb) + (size_t)chunk * k3h_tree_bytes(plan);
+    int per_sm = (int)((227u * 1024u) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    if (per_sm * tpb > 1536) per_sm = 1536 / tpb;
+#define K3H_LAUNCH(T)                                                                                                   \
+    k3_heap<T><<<sm_count * per_sm, T, smem, st>>>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, \
+                                                   qual, phreds, d_counts, chunk, phred_mode, d_err)
+    if (tpb == 512) K3H_LAUNCH(512);
+    else if (tpb == 256) K3H_LAUNCH(256);
+    else K3H_LAUNCH(128);
+#undef K3H_LAUNCH
+}
+#endif
 static size_t k3_forest_bytes(const DevPlan& plan) {
     if (plan.h.model_kind == MODEL_LOGISTIC || plan.h.model_kind == MODEL_NONE) return 0;
     return (size_t)plan.h.n_nodes * sizeof(uint2);
@@ -1273,6 +1526,12 @@ cudaError_t kernels_configure(const DevPlan& plan) {
     e = cudaFuncSetAttribute(k1_parse_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(plan));
     if (e != cudaSuccess) return e;
 #endif
+    e = cudaFuncSetAttribute(k3_heap<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k3_heap<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k3_heap<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k3_infer<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k3_infer<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));

@@ -24,6 +24,12 @@ struct DevPlan {
     const uint2* dev_nodes;    // device form: x = threshold bits (leaf: quiet NaN | leaf row), y = feature | right_abs << 8
     uint32_t max_depth;        // deepest leaf over all trees
     const double* leaves;
+    // heap form of the forest (k3_heap): every tree padded to a complete binary tree of depth heap_depth,
+    // node i at index i (root 1, children 2i / 2i+1), H = 2^heap_depth entries per tree and array
+    const float* heap_thr;     // [n_trees][H] thresholds (+inf below a shallow leaf: every path ends on its row)
+    const uint8_t* heap_feat;  // [n_trees][H] feature of the node
+    const uint16_t* heap_leaf; // [n_trees][H] leaf row reached from node 2^depth + k
+    uint32_t heap_depth;       // 0: the forest has no heap form (too deep / too many leaf rows): k2 + k3_infer
     const uint8_t* htab;       // 256-entry open-addressing table: tag index or 0xFF
     uint32_t first_fixed_slot; // slots [first_fixed_slot, n_slots) are TAG_FIXED
 };
@@ -157,6 +163,13 @@ void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, cons
 void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const int64_t* d_n_records,
                double threshold, uint8_t* low_score, float* probs, double* qual, double* phreds, int phred_mode,
                long long* d_counts, int sm_count, cudaStream_t st);
+// K2 + K3 in one kernel: the feature tile is assembled from the raw slots (or taken from a dense feature
+// matrix when raw is NULL) while it is staged; false when the plan's model has no heap form (then K2 + launch_k3)
+bool k3_fused_available(const DevPlan& plan);
+void launch_k3_fused(const DevPlan& plan, const uint32_t* raw, const float* feats, size_t row_stride,
+                     const int64_t* d_n_records, double threshold, uint8_t* low_score, float* probs, double* qual,
+                     double* phreds, int phred_mode, long long* d_counts, unsigned long long* d_err, int sm_count,
+                     cudaStream_t st);
 void launch_k1_fast(const DevPlan& plan, const DevFast& fast, const DevSchedule& sched, const uint8_t* d_text, size_t n_bytes,
                     uint32_t* scratch, int64_t* line_start, size_t cap_records, int64_t* d_n_records, uint32_t* raw,
                     size_t row_stride, ugvc_recinfo* recinfo, uint32_t* slow_list, unsigned long long* d_err,
