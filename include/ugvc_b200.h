@@ -117,6 +117,14 @@ int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n_bytes, dou
                        uint8_t* d_low_score, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
                        int64_t* d_line_start, size_t capacity_records, int64_t* d_n_records, void* stream);
 
+/* The same call on lane `lane` (0 <= lane < n_pipeline of ugvc_reserve): every lane has its own scratch (raw slots,
+ * line index, error word), so device-resident batches submitted on different lanes and streams may overlap;
+ * ugvc_filter_device is lane 0.  ugvc_device_status_lane reports the lane's data errors (blocking). */
+int ugvc_filter_device_lane(ugvc_ctx* ctx, int lane, const uint8_t* d_text, size_t n_bytes, double threshold,
+                            uint8_t* d_low_score, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
+                            int64_t* d_line_start, size_t capacity_records, int64_t* d_n_records, void* stream);
+int ugvc_device_status_lane(ugvc_ctx* ctx, int lane, void* stream);
+
 /* BGZF input, inflated on the device (csrc/inflate.cuh): the host ships the compressed bytes, so the
  * PCIe traffic of the end-to-end path shrinks by the compression ratio (htslib's BGZF reader behind
  * pysam.VariantFile, filter_variants_pipeline.py:106,115).  `bgzf` = consecutive whole BGZF blocks in
@@ -160,6 +168,18 @@ int ugvc_counts_get(ugvc_ctx* ctx, ugvc_counts* out);
  * n_cg}: this is the buffer the one NCCL all-reduce of the path sums in place
  * (the host passes it to torch.distributed / ncclAllReduce). */
 int ugvc_counts_device_ptr(ugvc_ctx* ctx, int64_t** d_counts);
+/* The single collective of the path (the reference's only precedent for combining shards is
+ * `bcftools concat` of per-contig parts, ugbio_core/vcfbed/variant_annotation.py:96-110): NCCL sum all-reduce of
+ * that block, in place, on `stream` (NULL: the context's lane-0 stream after a device synchronise).  `nccl_comm`
+ * is an ncclComm_t of this rank -- the host's own, or one made by ugvc_nccl_comm_init (rank 0 draws the 128-byte
+ * id with ugvc_nccl_unique_id and hands it to the other ranks by whatever channel it has).  out_counts (may be
+ * NULL) receives the reduced counters; then the call blocks until the collective is done.  NCCL is bound at run
+ * time (the process's own libnccl if one is loaded, else libnccl.so.2): UGVC_E_STATE when there is none. */
+#define UGVC_NCCL_ID_BYTES 128
+int ugvc_nccl_unique_id(uint8_t id[UGVC_NCCL_ID_BYTES]);
+int ugvc_nccl_comm_init(ugvc_ctx* ctx, const uint8_t id[UGVC_NCCL_ID_BYTES], int world_size, int rank, void** out_comm);
+int ugvc_nccl_comm_destroy(void* nccl_comm);
+int ugvc_counts_allreduce(ugvc_ctx* ctx, void* nccl_comm, int64_t out_counts[4], void* stream);
 
 /* ---- introspection for the parity tests --------------------------------- */
 /* Raw slot columns (K1 output, n_slots x n_records fp32 bit patterns) and the

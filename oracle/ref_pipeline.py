@@ -194,6 +194,11 @@ def edited_header_lines(header_lines: list[str], *, with_model: bool, with_black
     if with_model and "TREE_SCORE" not in hdr.info:
         add.append('##INFO=<ID=TREE_SCORE,Number=1,Type=Float,Description="Filtering score">')
     out = list(header_lines)
+    if not any(ln.startswith("##FILTER=<ID=PASS,") for ln in out):  # (OracleHeader.filters, like pysam's, always lists PASS)
+        # htslib's header always carries the PASS filter (bcf_hdr_parse adds the line first, right after
+        # ##fileformat); pysam.VariantFile(out, "w", header=hdr) writes it even when the input lacked it
+        at = 1 if out and out[0].startswith("##fileformat") else 0
+        out.insert(at, '##FILTER=<ID=PASS,Description="All filters passed">')
     chrom_at = next(i for i, ln in enumerate(out) if ln.startswith("#CHROM"))
     return out[:chrom_at] + add + out[chrom_at:]
 

@@ -47,9 +47,13 @@ def inflate(path: str, voff_begin: int = 0, voff_end: int = 0, capacity: int | N
         if capacity is None:
             capacity = uncompressed_size(path) if voff_end == 0 and voff_begin == 0 else None
         if capacity is None:
-            # a virtual-offset range: bounded by the compressed span * worst ratio is unknown, so
-            # size from the block table (cheap header scan)
-            capacity = uncompressed_size(path)
+            # a virtual-offset range: ask the reader itself -- with no room it only walks the block headers of
+            # [voff_begin, voff_end) and reports the size (one contig of an indexed call set, not the whole file)
+            probe = C.c_size_t()
+            rc = L.ugvc_bgzf_inflate_file(path.encode(), voff_begin, voff_end, None, 0, C.byref(probe), 1)
+            if rc not in (0, _lib.UGVC_E_ARG):
+                _check(rc, f"inflate {path}")
+            capacity = int(probe.value)
         out = np.empty(capacity + 64, dtype=np.uint8)
     n = C.c_size_t()
     rc = L.ugvc_bgzf_inflate_file(path.encode(), voff_begin, voff_end, out.ctypes.data_as(C.c_void_p), out.size,
@@ -232,13 +236,11 @@ def build_tbi(contig_names: list[str], contig_of: np.ndarray, beg: np.ndarray, e
         span = np.flatnonzero(w1 > w0)
         for i in span:  # records crossing window borders are rare (long REF alleles)
             lin[w0[i] + 1: w1[i] + 1] = np.minimum(lin[w0[i] + 1: w1[i] + 1], vs[i])
-        # empty windows inherit the next filled offset (htslib convention: previous value)
+        # empty windows take the offset of the next filled one, as htslib back-fills its linear index
+        # (hts_idx_finish: offset[l] = offset[l + 1] from the end); the last window always holds a record
         filled = lin != np.iinfo(np.uint64).max
-        if not filled[0]:
-            lin[0] = vs[0]
-            filled[0] = True
-        idx = np.maximum.accumulate(np.where(filled, np.arange(n_win), 0))
-        lin = lin[idx]
+        nxt = np.minimum.accumulate(np.where(filled, np.arange(n_win), n_win - 1)[::-1])[::-1]
+        lin = lin[nxt]
         out.append(struct.pack("<i", n_win))
         out.append(lin.astype("<u8").tobytes())
     return b"".join(out)

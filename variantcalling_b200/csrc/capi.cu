@@ -143,6 +143,12 @@ extern "C" void ugvc_free(ugvc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (auto& l : ctx->lanes) free_lane(l);
+    // from here on the previous plan is gone: no plan is loaded until every step below has succeeded, and the
+    // lanes sized for the old slot / feature counts go with it
+    ctx->has_plan = false;
+    for (auto& l : ctx->lanes) free_lane(l);
+    ctx->lanes.clear();
+    ctx->cap_bytes = ctx->cap_records = 0;
     cudaFree(ctx->d_plan);
     cudaFree(ctx->d_htab);
     cudaFree(ctx->d_nodes);
@@ -482,6 +488,12 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
             }
         }
     }
+    // from here on the previous plan is gone: no plan is loaded until every step below has succeeded, and the
+    // lanes sized for the old slot / feature counts go with it
+    ctx->has_plan = false;
+    for (auto& l : ctx->lanes) free_lane(l);
+    ctx->lanes.clear();
+    ctx->cap_bytes = ctx->cap_records = 0;
     cudaFree(ctx->d_plan);
     cudaFree(ctx->d_htab);
     cudaFree(ctx->d_nodes);
@@ -544,7 +556,6 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
                 return fail(ctx, UGVC_E_PLAN, "a single tree does not fit the shared-memory forest buffer");
     }
     CU(kernels_configure(p));
-    ctx->has_plan = true;
     ctx->h_tags.assign(tags, tags + h.n_tags);
     ctx->h_slots.assign(slots, slots + h.n_slots);
 #ifdef UGVC_K1_INLINE_DICT1
@@ -564,6 +575,7 @@ extern "C" int ugvc_load_plan(ugvc_ctx* ctx, const void* blob, size_t n_bytes) {
         const int rc = build_fast(ctx, "", "");
         if (rc) return rc;
     }
+    ctx->has_plan = true;
     // a new plan changes the slot/feature counts: lanes must be re-reserved
     for (auto& l : ctx->lanes) free_lane(l);
     ctx->lanes.clear();
@@ -874,16 +886,17 @@ extern "C" int ugvc_filter_batch(ugvc_ctx* ctx, const uint8_t* vcf_text, size_t 
                               capacity_records, out_n_records);
 }
 
-extern "C" int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n_bytes, double threshold,
-                                  uint8_t* d_low_score, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
-                                  int64_t* d_line_start, size_t capacity_records, int64_t* d_n_records, void* stream) {
+extern "C" int ugvc_filter_device_lane(ugvc_ctx* ctx, int lane, const uint8_t* d_text, size_t n_bytes, double threshold,
+                                       uint8_t* d_low_score, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
+                                       int64_t* d_line_start, size_t capacity_records, int64_t* d_n_records, void* stream) {
     if (!ctx) return UGVC_E_ARG;
     if (!ctx->has_plan || ctx->lanes.empty()) return fail(ctx, UGVC_E_STATE, "filter_device: load a plan and reserve first");
+    if (lane < 0 || lane >= (int)ctx->lanes.size()) return fail(ctx, UGVC_E_ARG, "filter_device: lane out of range");
     if (n_bytes > ctx->cap_bytes) return fail(ctx, UGVC_E_ARG, "filter_device: batch larger than the reserved max_bytes");
     if (!d_text || !d_low_score || !d_probs || !d_qual) return fail(ctx, UGVC_E_ARG, "filter_device: null device pointer");
     if (reinterpret_cast<uintptr_t>(d_text) & 15u) return fail(ctx, UGVC_E_ARG, "filter_device: d_text must be 16-byte aligned");
     CU(cudaSetDevice(ctx->device));
-    Lane& l = ctx->lanes[0];
+    Lane& l = ctx->lanes[lane];
     if (capacity_records == 0 || capacity_records > l.b.cap_records)
         return fail(ctx, UGVC_E_ARG, "filter_device: capacity_records must be in (0, reserved max_records]");
     const size_t line_cap = capacity_records;
@@ -893,6 +906,25 @@ extern "C" int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n
     cudaStream_t st = stream ? (cudaStream_t)stream : l.stream;
     return enqueue_kernels(ctx, l, d_text, n_bytes, threshold, d_low_score, d_probs, d_qual, d_recinfo, d_line_start,
                            line_cap, d_n_records, st);
+}
+
+extern "C" int ugvc_filter_device(ugvc_ctx* ctx, const uint8_t* d_text, size_t n_bytes, double threshold,
+                                  uint8_t* d_low_score, float* d_probs, double* d_qual, ugvc_recinfo* d_recinfo,
+                                  int64_t* d_line_start, size_t capacity_records, int64_t* d_n_records, void* stream) {
+    return ugvc_filter_device_lane(ctx, 0, d_text, n_bytes, threshold, d_low_score, d_probs, d_qual, d_recinfo, d_line_start,
+                                   capacity_records, d_n_records, stream);
+}
+
+extern "C" int ugvc_device_status_lane(ugvc_ctx* ctx, int lane, void* stream) {
+    // blocking: surfaces data errors of the last ugvc_filter_device_lane call on `lane`
+    if (!ctx || lane < 0 || lane >= (int)ctx->lanes.size()) return UGVC_E_STATE;
+    CU(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[lane];
+    cudaStream_t st = stream ? (cudaStream_t)stream : l.stream;
+    CU(cudaStreamSynchronize(st));
+    unsigned long long e;
+    CU(cudaMemcpy(&e, l.d_err, sizeof(e), cudaMemcpyDeviceToHost));
+    return decode_error(ctx, e);
 }
 
 extern "C" int ugvc_device_status(ugvc_ctx* ctx, void* stream) {

@@ -77,8 +77,13 @@ bool inflate_block(const uint8_t* src, uint32_t csize, uint8_t* dst, uint32_t is
     zs.next_out = dst;
     zs.avail_out = isize;
     const int rc = inflate(&zs, Z_FINISH);
-    const bool ok = (rc == Z_STREAM_END) && zs.total_out == isize;
+    bool ok = (rc == Z_STREAM_END) && zs.total_out == isize;
     inflateEnd(&zs);
+    if (ok) {  // the gzip footer's CRC32, as htslib checks it: a corrupted block is refused, not parsed
+        const uint8_t* ft = src + csize - 8;
+        const uint32_t want = (uint32_t)ft[0] | ((uint32_t)ft[1] << 8) | ((uint32_t)ft[2] << 16) | ((uint32_t)ft[3] << 24);
+        ok = (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, isize) == want;
+    }
     return ok;
 }
 

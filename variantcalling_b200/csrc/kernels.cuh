@@ -77,7 +77,7 @@ struct DevSchedule {
 // not need decode to nothing).  A record that carries anything else -- an unknown key, a literal
 // outside the short decoders, a FORMAT column other than the usual one -- is handed to the
 // generic per-record parser (k1_parse over the slow list), which defines the semantics.
-#define KF_MAX_KEYS 192
+#define KF_MAX_KEYS 128
 enum : uint8_t {
     FK_SCALAR = 1,     // Number=1 in this header section
     FK_IS_FLAG = 2,    // the data carries the key without a value
@@ -150,7 +150,7 @@ struct LaneBuffers {
 };
 
 #define K0_TILE_BYTES_HOST 65536  // one 64-bit look-back state word per 64 KiB tile
-#define K1_TILE_BYTES_HOST 49152  // ... per 48 KiB tile of the K1 tile kernel (more tiles: sizes the scratch)
+#define K1_TILE_BYTES_HOST 40960  // ... per 40 KiB tile of the K1 tile kernel (more tiles: sizes the scratch)
 
 void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* chunk_first, int64_t* line_start,
                size_t cap_records, int64_t* d_n_records, unsigned long long* d_err, int sm_count,

@@ -54,6 +54,12 @@ SIGNATURES = {
     "ugvc_collect_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _i64p]),
     "ugvc_filter_device": (C.c_int, [_vp, _vp, _sz, C.c_double, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ugvc_device_status": (C.c_int, [_vp, _vp]),
+    "ugvc_filter_device_lane": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_double, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ugvc_device_status_lane": (C.c_int, [_vp, C.c_int, _vp]),
+    "ugvc_nccl_unique_id": (C.c_int, [_vp]),
+    "ugvc_nccl_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "ugvc_nccl_comm_destroy": (C.c_int, [_vp]),
+    "ugvc_counts_allreduce": (C.c_int, [_vp, _vp, _vp, _vp]),
     "ugvc_host_alloc": (C.c_int, [C.POINTER(_vp), _sz]),
     "ugvc_host_free": (C.c_int, [_vp]),
     "ugvc_counts_reset": (C.c_int, [_vp]),
@@ -272,13 +278,37 @@ class Context:
     # ---- device-resident hot path (pointers are ints, e.g. torch.Tensor.data_ptr())
     def filter_device(self, d_text: int, n_bytes: int, threshold: float, d_low: int, d_probs: int, d_qual: int,
                       capacity: int, d_n_records: int = 0, stream: int = 0, d_recinfo: int = 0,
-                      d_line_start: int = 0):
-        self._check(self.lib.ugvc_filter_device(self.h, d_text, n_bytes, threshold, d_low, d_probs, d_qual,
-                                                d_recinfo or None, d_line_start or None, capacity,
-                                                d_n_records or None, stream or None))
+                      d_line_start: int = 0, lane: int = 0):
+        self._check(self.lib.ugvc_filter_device_lane(self.h, lane, d_text, n_bytes, threshold, d_low, d_probs, d_qual,
+                                                     d_recinfo or None, d_line_start or None, capacity,
+                                                     d_n_records or None, stream or None))
 
-    def device_status(self, stream: int = 0):
-        self._check(self.lib.ugvc_device_status(self.h, stream or None))
+    def device_status(self, stream: int = 0, lane: int = 0):
+        self._check(self.lib.ugvc_device_status_lane(self.h, lane, stream or None))
+
+    # ---- the one collective of the path, through the C ABI (NCCL bound at run time)
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = load_library().ugvc_nccl_unique_id(C.cast(buf, C.c_void_p))
+        if rc:
+            raise UgvcError(rc, load_library().ugvc_last_error(None).decode())
+        return bytes(buf)
+
+    def nccl_comm_init(self, unique_id: bytes, world_size: int, rank: int) -> int:
+        comm = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.ugvc_nccl_comm_init(self.h, C.cast(buf, C.c_void_p), world_size, rank, C.byref(comm)))
+        return comm.value
+
+    def nccl_comm_destroy(self, comm: int):
+        self.lib.ugvc_nccl_comm_destroy(comm)
+
+    def counts_allreduce(self, comm: int, stream: int = 0) -> dict:
+        """Sum the pass / fail counter block over the ranks of `comm` (ncclAllReduce, in place) and read it."""
+        out = (C.c_int64 * 4)()
+        self._check(self.lib.ugvc_counts_allreduce(self.h, comm, C.cast(out, C.c_void_p), stream or None))
+        return {"n_records": out[0], "n_low_score": out[1], "n_pass": out[2], "n_cg": out[3]}
 
     def synth_device(self, seed: int, first: int, n: int, total: int, n_custom: int, d_text: int, capacity: int,
                      stream: int = 0) -> int:

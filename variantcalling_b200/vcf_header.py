@@ -97,5 +97,10 @@ class VcfHeader:
             add.append('##INFO=<ID=BLACKLST,Number=.,Type=String,Description="blacklist">')
         if with_model and "TREE_SCORE" not in self.info:
             add.append('##INFO=<ID=TREE_SCORE,Number=1,Type=Float,Description="Filtering score">')
-        at = next(i for i, ln in enumerate(self.lines) if ln.startswith("#CHROM"))
-        return self.lines[:at] + add + self.lines[at:]
+        lines = list(self.lines)
+        if "PASS" not in self.filters:
+            # pysam / htslib always emit the PASS filter line (first, after ##fileformat); the records written here do carry PASS
+            lines.insert(1 if lines and lines[0].startswith("##fileformat") else 0,
+                         '##FILTER=<ID=PASS,Description="All filters passed">')
+        at = next(i for i, ln in enumerate(lines) if ln.startswith("#CHROM"))
+        return lines[:at] + add + lines[at:]
