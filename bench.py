@@ -217,7 +217,9 @@ def run_reference(args):
                    "sample_records_per_step": n_sample},
         "cpu_baseline": {"value": value, "unit": "variants/s", "cores": cores, "kind": "port",
                          "sample": f"{n_sample} records per step ({per_worker} per worker process), the reference's "
-                                   f"pandas/sklearn path restated in oracle/ (pysam/xgboost absent)"},
+                                   f"pandas/sklearn path restated in oracle/ (pysam/xgboost absent)",
+                         "note": "the parse / write stages are a pure-Python stand-in for htslib's C code (about half of "
+                                 "this arm's time): a baseline beside the GPU number, not the real reference's speed"},
         "e2e": {"value": value, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -235,6 +237,27 @@ def _reference_worker(job):
     return len(res["lines"])
 
 
+def _parity_worker(job):
+    header_text, text, model, tr, customs = job
+    from oracle import ref_pipeline as R
+    from oracle.vcf_reader import OracleVariantFile
+
+    vf = OracleVariantFile((header_text + text.decode()).encode())
+    res = R.filter_variants(vf, model, tr, custom_annotations=customs)
+    low = np.array(["LOW_SCORE" in f.split(";") for f in res["filters"]])
+    return low, np.asarray(res["probs"], dtype=np.float64)
+
+
+def spread_parity(chunks, header_text, model, tr, customs, workers):
+    """FILTER / probabilities of the oracle on record chunks taken all along the input (worker processes: the
+    pandas path does about 10^4 records a second per core)."""
+    import multiprocessing as mp
+
+    jobs = [(header_text, c, model, tr, customs) for c in chunks]
+    with mp.get_context("fork").Pool(workers) as pool:  # the children only run NumPy / pandas / sklearn
+        return pool.map(_parity_worker, jobs)
+
+
 def cpu_baseline_sample(text: bytes, header_text: str, model, tr, customs) -> dict:
     """Oracle timed single-process (like the reference's serial contig loop) on a bounded sample."""
     from oracle import ref_pipeline as R
@@ -248,7 +271,10 @@ def cpu_baseline_sample(text: bytes, header_text: str, model, tr, customs) -> di
     n = len(res["lines"])
     return {"value": n / dt, "unit": "variants/s", "cores": 1, "kind": "port",
             "sample": f"first {n} records of the bench input, single process; stage seconds: "
-                      + ", ".join(f"{k}={v:.2f}" for k, v in tm.items()), "_res": res}
+                      + ", ".join(f"{k}={v:.2f}" for k, v in tm.items()),
+            "note": "pysam / htslib and xgboost are absent from the image: the parse and write stages run a pure-Python "
+                    "stand-in for htslib's C reader / writer (oracle/vcf_reader.py), the model is sklearn's -- the real "
+                    "reference spends less time in those stages", "_res": res}
 
 
 # ------------------------------------------------------------------------------------------
@@ -262,6 +288,8 @@ def main():  # noqa: C901, PLR0912, PLR0915
     ap.add_argument("--batch-records", type=int, default=2_000_000)
     ap.add_argument("--cpu-sample", type=int, default=120_000, help="records timed on the CPU oracle at N=1 (about 15 s)")
     ap.add_argument("--cpu-sample-per-worker", type=int, default=8000)
+    ap.add_argument("--parity-records", type=int, default=1_024_000,
+                    help="records checked against the oracle, in 64 chunks spread over the whole input (N=1, needs the e2e pass)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (0 = same as --steps)")
     ap.add_argument("--lanes", type=int, default=3)
     ap.add_argument("--min-presence", type=float, default=None, help="learn_key_order presence threshold (profiling)")
@@ -413,23 +441,39 @@ def main():  # noqa: C901, PLR0912, PLR0915
         "k0_line_index": text_per_launch + 8 * rec_per_launch,
         "k1_field_parse": text_per_launch + rec_per_launch * (8 + 4 * S + 16),
         "k2_feature_assembly": rec_per_launch * 4 * (S + F),
-        "k3_inference": rec_per_launch * (4 * F + 4 * K + 9),
+        "k3_inference": rec_per_launch * (4 * F + 4 * K + 9),  # fused K2+K3: one 4-byte slot read per feature
     }
     stage_ms = {n: stage_sum[i] / max(1, n_calls) for i, n in enumerate(names)}
     dom = max(names, key=lambda n: stage_ms[n])
     achieved = alg_bytes[dom] / (stage_ms[dom] / 1e3) / 1e9
     path_bytes = total_bytes / max(1, n_mine) + 4 * K + 9  # B_alg per record, SURVEY.md 8d
     kernels_ms_per_step = sum(stage_sum) / args.steps
-    # DRAM bytes per record of each kernel from the committed `ncu --set full` capture
-    # (profiles/r1_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum of one launch over its
-    # 849 481 records -- the record count follows from k1_fill's 278.63 MB = 82 slots x 4 B x records)
-    ncu_traffic_per_record = {"k1_field_parse": 1242.0, "k2_feature_assembly": 743.0, "k3_inference": 411.0}
-    traffic = ncu_traffic_per_record.get(dom)
+    # DRAM bytes per record of each kernel: read from the committed summary of the `ncu --set full` captures
+    # (profiles/ncu_traffic.json, written by scripts/save_profiles_r2.py from the .ncu-rep files: dram__bytes_read.sum +
+    # dram__bytes_write.sum of one launch and the records that launch parsed)
+    traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    ncu_traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    stage_kernel = {"k1_field_parse": "k1_fast", "k3_inference": "k3_heap", "k2_feature_assembly": "k2_features",
+                    "k0_line_index": "k0_index"}
+
+    def traffic_of(stage):
+        t = ncu_traffic.get(stage_kernel.get(stage, ""))
+        return None if not t else t["dram_bytes"] / t["records"] * rec_per_launch
+
+    per_kernel = {}
+    for nme in names:
+        if stage_ms[nme] > 1e-3:  # stages folded into another kernel report no time
+            ach = alg_bytes[nme] / (stage_ms[nme] / 1e3) / 1e9
+            per_kernel[nme] = {"ms_per_launch": stage_ms[nme], "algorithmic_bytes_per_launch": alg_bytes[nme],
+                               "achieved": ach, "frac": ach / peak, "traffic": traffic_of(nme)}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None if traffic is None else traffic * rec_per_launch,
-                "traffic_source": "profiles/r1_ncu_full_summary.csv (ncu --set full, per launch, scaled to this launch size)",
+                "frac": achieved / peak, "traffic": traffic_of(dom),
+                "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram bytes of one launch / its records, "
+                                  "scaled to this launch size)" if traffic_of(dom) is not None else None,
                 "algorithmic_bytes_per_launch": alg_bytes[dom], "peak_source": peak_src,
-                "stage_ms_per_launch": stage_ms, "launches_timed": n_calls,
+                "stage_ms_per_launch": stage_ms, "launches_timed": n_calls, "per_kernel": per_kernel,
+                "stages": "k0 (line index) is folded into k1's tile kernel, k2 (feature assembly) into k3's tile load: "
+                          "their own stages read ~0 ms",
                 "path": {"bytes_per_record": path_bytes,
                          "achieved": path_bytes * n_mine / (kernels_ms_per_step / 1e3) / 1e9,
                          "frac": path_bytes * n_mine / (kernels_ms_per_step / 1e3) / 1e9 / peak}}
@@ -500,6 +544,35 @@ def main():  # noqa: C901, PLR0912, PLR0915
                "api": "ugvc_submit_batch/ugvc_collect_batch (pinned host buffers)"}
         # consistency: host path == device path
         assert np.array_equal(o_low, d_low.cpu().numpy()), "host-buffer path differs from the device-resident path"
+
+    # ---- parity along the whole input (N=1): 64 record chunks, one per stretch of the batch list, oracle in worker processes
+    parity = None
+    if e2e is not None and rank == 0 and world == 1 and not args.no_cpu_baseline and args.parity_records > 0:
+        n_chunks = 64
+        per = max(1, args.parity_records // n_chunks)
+        picks, chunks = [], []
+        for c in range(n_chunks):
+            bi = c * len(batches) // n_chunks
+            boff, _nbytes, nb = batches[bi]
+            r0b = int(rec_starts[bi])
+            n_c = min(per, nb)
+            first = (c * 7919) % max(1, nb - n_c + 1)  # a different place inside every batch
+            ls = o_ls[r0b + bi: r0b + bi + nb + 1]
+            b0, b1 = int(ls[first]), int(ls[first + n_c])
+            chunks.append(bytes(h_text.array[boff + b0: boff + b1]))
+            picks.append((r0b + first, n_c))
+        t0 = time.perf_counter()
+        res = spread_parity(chunks, header_text, model, tr, customs, min(os.cpu_count() or 1, 64))
+        same, worst, n_checked = True, 0.0, 0
+        for (g0, n_c), (low, pr) in zip(picks, res):
+            same &= bool(np.array_equal(low, o_low[g0:g0 + n_c].astype(bool)))
+            worst = max(worst, float(np.abs(pr - o_probs[g0:g0 + n_c]).max()))
+            n_checked += n_c
+        parity = {"records": n_checked, "chunks": n_chunks, "filter_identical": same, "max_abs_prob_diff": worst,
+                  "seconds": time.perf_counter() - t0,
+                  "what": "oracle (reference CPU path restated) vs the e2e results, chunks spread over all batches"}
+        log(f"[bench] parity on {n_checked} records in {n_chunks} chunks: FILTER identical={same}, max |dp|={worst:.2e}")
+        assert same, "FILTER differs from the oracle on the spread sample"
 
     # ---- e2e with compressed host buffers (opt-in): the host ships BGZF blocks, the device inflates them
     e2e_bgzf = None
@@ -582,6 +655,7 @@ def main():  # noqa: C901, PLR0912, PLR0915
                        "l2": "inputs larger than L2 (no flush needed)", "threshold": 30.0,
                        "k1_slow_records_last_batch": slow_last},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "parity": parity,
             **({"e2e_bgzf": e2e_bgzf} if e2e_bgzf is not None else {}),
             "counts_last_steps": {"n_records": counts_total[0], "n_low_score": counts_total[1],
                                   "n_pass": counts_total[2], "n_cg": counts_total[3]},

@@ -24,7 +24,7 @@ fi
 if [ "${SKIP_NCU:-0}" != 1 ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file "$out/launches.csv" \
       python bench.py --records 8000000 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > "$out/ncu_launch.log" 2>&1
-  for k in ${NCU_KERNELS:-k1_fast k3_infer}; do
+  for k in ${NCU_KERNELS:-k1_fast k3_heap}; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o "$out/prof_$k" \
         python bench.py --records 4000000 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > "$out/ncu_$k.log" 2>&1
     ncu -i "$out/prof_$k.ncu-rep" --page raw --csv > "$out/prof_${k}_raw.csv" 2>/dev/null

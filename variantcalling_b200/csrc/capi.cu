@@ -273,9 +273,18 @@ static int build_fast(ugvc_ctx* ctx, const std::string& info_keys, const std::st
         }
         const PlanTag& tg = ctx->h_tags[sl.tag];
         const unsigned k = (in_fmt(sl.tag) && tg.fmt_kind) ? tg.fmt_kind : (tg.info_kind ? tg.info_kind : tg.fmt_kind);
-        uint8_t bits = 0;
-        if ((k & KIND_TYPE_MASK) == KIND_INT) bits |= SK_INT;
-        if (sl.reducer == RED_STRNUM) bits |= SK_STRNUM;
+        const unsigned type = k & KIND_TYPE_MASK;
+        uint8_t bits = SK_CLS_BAD;  // region sets, flags, reducers that do not fit the declared type: the generic parser
+        if (tg.whole_red != RED_REGION && type != KIND_FLAG) {
+            if (sl.reducer == RED_NUM && (type == KIND_INT || type == KIND_FLOAT)) bits = SK_CLS_NUM;
+            else if (sl.reducer == RED_STRNUM) bits = SK_CLS_NUM | SK_STRNUM;
+            else if (sl.reducer == RED_DICT && type == KIND_STR) bits = SK_CLS_DICT;
+            else if ((sl.reducer == RED_INSDEL || sl.reducer == RED_MOTIF_L || sl.reducer == RED_MOTIF_R) && type == KIND_STR) bits = SK_CLS_GEN;
+            else if (sl.reducer == RED_BASE && type == KIND_STR) bits = SK_CLS_GEN | SK_ZERO_LONG;
+            else if (sl.reducer == RED_GT_HOM) bits = SK_CLS_GEN | SK_ZERO_LONG;
+            else if (sl.reducer == RED_LEN) bits = SK_CLS_BAD;  // written directly, never queued
+        }
+        if (type == KIND_INT && sl.reducer != RED_STRNUM) bits |= SK_INT;
         if (k & KIND_SCALAR) bits |= SK_SCALAR;
         kind[s] = bits;
     }

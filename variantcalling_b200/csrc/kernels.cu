@@ -957,6 +957,16 @@ void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, cons
 #endif
 
 __device__ __forceinline__ double expit64(double x) { return 1.0 / (1.0 + exp(-x)); }
+// expf rounded once from the fp64 exponential.  The optimiser would shrink (float)exp((double)x) back to expf(x)
+// (a library-call simplification that is only valid for a correctly rounded expf); the empty asm hides the
+// argument's origin from it.
+__device__ __forceinline__ float k3_expf_cr(float x) {
+    double xd = (double)x;
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+d"(xd));
+#endif
+    return (float)exp(xd);
+}
 
 template <int CMP, int TPB>
 __device__ __forceinline__ void walk8(const uint2* __restrict__ s_nodes, const uint32_t* __restrict__ s_roots,
@@ -1274,7 +1284,11 @@ __device__ __forceinline__ void walk8h(const float* __restrict__ s_thr, const ui
     for (int j = 0; j < K3_CHAINS; ++j) leaf[j] = (int)s_leaf[base[j] + n[j] - H];
 }
 
-template <int TPB>
+// NBUF = 2: the raw rows of the NEXT record tile are fetched by 1-D bulk copies (cp.async.bulk, one per feature row,
+// completion on an mbarrier) while the current tile is walked, so no warp ever waits on HBM; every thread then turns
+// its own column of the landed slot words into feature values in place (K2's policies) -- a thread only ever reads
+// its own column, so the tile needs no barrier between assembly and walk.
+template <int TPB, int NBUF>
 __global__ void __launch_bounds__(TPB, 1)
 k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, const float* __restrict__ feats,
         size_t row_stride, const int64_t* __restrict__ n_records_p, double threshold, uint8_t* __restrict__ low_score,
@@ -1286,8 +1300,8 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
     const bool forest = plan.h.model_kind != MODEL_LOGISTIC;
     const int depth = (int)plan.heap_depth;
     const unsigned H = 1u << depth;
-    float* tile = reinterpret_cast<float*>(smem3);  // [F][TPB]
-    float* s_thr = tile + (size_t)F * TPB;           // [chunk_trees][H]
+    float* tile0 = reinterpret_cast<float*>(smem3);         // [NBUF][F][TPB]
+    float* s_thr = tile0 + (size_t)NBUF * F * TPB;          // [chunk_trees][H]
     PlanFeature* s_pf = reinterpret_cast<PlanFeature*>(s_thr + (forest ? (size_t)chunk_trees * H : 0));  // [F]
     uint16_t* s_leaf = reinterpret_cast<uint16_t*>(s_pf + F);                                              // [chunk_trees][H]
     uint8_t* s_feat = reinterpret_cast<uint8_t*>(s_leaf + (forest ? (size_t)chunk_trees * H : 0));        // [chunk_trees][H]
@@ -1304,17 +1318,68 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
     const long long n_rec = *n_records_p;
     const long long n_tiles = (n_rec + TPB - 1) / TPB;
     unsigned n_low = 0, n_seen = 0;
+#ifndef UGVC_HOST_EMU
+    __shared__ __align__(8) unsigned long long k3_mbar[2];
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NBUF; ++b) {
+            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&k3_mbar[b]);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // rows [t * TPB, ...) of every feature's slot -> tile buffer b (thread 0)
+    auto fetch = [&](long long t, int b) {
+        const size_t rec0 = (size_t)t * TPB;
+        const size_t rows = row_stride - rec0 < (size_t)TPB ? row_stride - rec0 : (size_t)TPB;  // rows are padded to 128 records
+        const uint32_t row_bytes = (uint32_t)rows * 4u;
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&k3_mbar[b]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(row_bytes * (uint32_t)F) : "memory");
+        for (int f = 0; f < F; ++f) {
+            const void* src = raw ? static_cast<const void*>(raw + (size_t)s_pf[f].slot * row_stride + rec0)
+                                  : static_cast<const void*>(feats + (size_t)f * row_stride + rec0);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile0 + ((size_t)b * F + f) * TPB);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(row_bytes), "r"(mb)
+                         : "memory");
+        }
+    };
+    uint32_t phase0 = 0u, phase1 = 0u;
+    if (threadIdx.x == 0 && (long long)blockIdx.x < n_tiles) fetch(blockIdx.x, 0);
+#endif
+    int buf = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const long long rec = t * TPB + threadIdx.x;
         const bool active = rec < n_rec;
-        __syncthreads();
+        float* tile = tile0 + (size_t)buf * F * TPB;
+#ifndef UGVC_HOST_EMU
+        {
+            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&k3_mbar[buf]);
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok)
+                             : "r"(mb), "r"(buf ? phase1 : phase0)
+                             : "memory");
+            if (buf) phase1 ^= 1u;
+            else phase0 ^= 1u;
+            // the other buffer was released by the barrier that ended the previous tile: fetch the next tile into it
+            if (NBUF == 2 && threadIdx.x == 0 && t + gridDim.x < n_tiles) fetch(t + gridDim.x, buf ^ 1);
+        }
+#endif
         if (raw) {
             // K2: slot -> feature with the missing / absent policies (transformers.py:221-344)
             const uint32_t* src = raw + rec;
 #pragma unroll 4
             for (int f = 0; f < F; ++f) {
                 const PlanFeature pf = s_pf[f];
-                tile[f * TPB + threadIdx.x] = active ? k2_apply(__ldg(src + (size_t)pf.slot * row_stride), pf, rec, f, err) : 0.f;
+#ifdef UGVC_HOST_EMU
+                const uint32_t bits = active ? src[(size_t)pf.slot * row_stride] : 0u;
+#else
+                const uint32_t bits = __float_as_uint(tile[f * TPB + threadIdx.x]);
+#endif
+                tile[f * TPB + threadIdx.x] = active ? k2_apply(bits, pf, rec, f, err) : 0.f;
             }
             for (unsigned c = 0; c < plan.h.n_combines; ++c) {  // feature = max(feature, slot_b), nulls skipped
                 const PlanCombine cb = plan.combines[c];
@@ -1330,11 +1395,14 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
                 if (!ok) atomicMin(err, ugvc_pack_error(rec, 0xFFFF, ck.kind == 0 ? REASON_TOO_MANY_ELEMS : REASON_BAD_VALUE));
             }
         } else {
+#ifdef UGVC_HOST_EMU
             const float* src = feats + rec;
-#pragma unroll 8
-            for (int f = 0; f < F; ++f) tile[f * TPB + threadIdx.x] = active ? __ldg(src + (size_t)f * row_stride) : 0.f;
+            for (int f = 0; f < F; ++f) tile[f * TPB + threadIdx.x] = active ? src[(size_t)f * row_stride] : 0.f;
+#else
+            if (!active)
+                for (int f = 0; f < F; ++f) tile[f * TPB + threadIdx.x] = 0.f;
+#endif
         }
-        __syncthreads();
         const float* x = tile + threadIdx.x;
         double z[UGVC_MAX_CLASSES];   // fp64 accumulators (sklearn) ...
         float zf[UGVC_MAX_CLASSES];   // ... fp32 accumulators (xgboost)
@@ -1395,10 +1463,16 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
                 c0 = c1;
             }
         }
-        if (!active) continue;
-        const bool low = k3_finish<TPB>(plan, x, z, zf, rec, threshold, low_score, probs, qual_out, phred_out, phred_mode);
-        n_low += low ? 1u : 0u;
-        n_seen += 1u;
+        if (active) {
+            const bool low = k3_finish<TPB>(plan, x, z, zf, rec, threshold, low_score, probs, qual_out, phred_out, phred_mode);
+            n_low += low ? 1u : 0u;
+            n_seen += 1u;
+        }
+        __syncthreads();  // every thread is done with this tile buffer
+#ifndef UGVC_HOST_EMU
+        if (NBUF == 1 && threadIdx.x == 0 && t + gridDim.x < n_tiles) fetch(t + gridDim.x, 0);
+#endif
+        buf ^= (NBUF == 2) ? 1 : 0;
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
@@ -1412,27 +1486,31 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
     }
 }
 
-// shared-memory plan of k3_heap: records per CTA and trees per staged chunk
+// shared-memory plan of k3_heap: records per CTA, tile buffers, trees per staged chunk
 static size_t k3h_tree_bytes(const DevPlan& plan) { return (size_t)(1u << plan.heap_depth) * 7u; }
-static size_t k3h_fixed_bytes(const DevPlan& plan, int tpb) {
-    return (size_t)plan.h.n_features * tpb * sizeof(float) + (size_t)plan.h.n_features * sizeof(PlanFeature) + 64;
+static size_t k3h_fixed_bytes(const DevPlan& plan, int tpb, int nbuf) {
+    return (size_t)nbuf * plan.h.n_features * tpb * sizeof(float) + (size_t)plan.h.n_features * sizeof(PlanFeature) + 64;
 }
-static int k3h_tpb(const DevPlan& plan) {
-    static const int force = getenv("UGVC_K3_TPB") ? atoi(getenv("UGVC_K3_TPB")) : 0;  // profiling knob
+struct K3hShape {
+    int tpb, nbuf;
+};
+static K3hShape k3h_shape(const DevPlan& plan) {
+    static const int force = getenv("UGVC_K3_TPB") ? atoi(getenv("UGVC_K3_TPB")) : 0;    // profiling knobs
+    static const int force_buf = getenv("UGVC_K3_NBUF") ? atoi(getenv("UGVC_K3_NBUF")) : 0;
     const bool forest = plan.h.model_kind != MODEL_LOGISTIC;
     const size_t all = forest ? (size_t)plan.h.n_trees * k3h_tree_bytes(plan) : 0;
-    const int cand[3] = {512, 256, 128};
-    for (int c : cand) {
-        if (force && c != force) continue;
-        if (k3h_fixed_bytes(plan, c) + all <= K3_SMEM_BUDGET) return c;
+    const K3hShape cand[5] = {{256, 2}, {512, 1}, {128, 2}, {256, 1}, {128, 1}};
+    for (const K3hShape& c : cand) {
+        if ((force && c.tpb != force) || (force_buf && c.nbuf != force_buf)) continue;
+        if (k3h_fixed_bytes(plan, c.tpb, c.nbuf) + all <= K3_SMEM_BUDGET) return c;
     }
-    for (int c : cand)  // the forest is staged in chunks: at least 8 trees at a time
-        if (k3h_fixed_bytes(plan, c) + 8 * k3h_tree_bytes(plan) <= K3_SMEM_BUDGET) return c;
-    return 0;
+    for (const K3hShape& c : cand)  // the forest is staged in chunks: at least 8 trees at a time
+        if (k3h_fixed_bytes(plan, c.tpb, c.nbuf) + 8 * k3h_tree_bytes(plan) <= K3_SMEM_BUDGET) return c;
+    return K3hShape{0, 0};
 }
-static unsigned k3h_chunk_trees(const DevPlan& plan, int tpb) {
+static unsigned k3h_chunk_trees(const DevPlan& plan, K3hShape sh) {
     if (plan.h.model_kind == MODEL_LOGISTIC) return 0;
-    const size_t room = K3_SMEM_BUDGET - k3h_fixed_bytes(plan, tpb);
+    const size_t room = K3_SMEM_BUDGET - k3h_fixed_bytes(plan, sh.tpb, sh.nbuf);
     size_t n = room / k3h_tree_bytes(plan);
     if (n > plan.h.n_trees) n = plan.h.n_trees;
     if (n < plan.h.n_trees) n &= ~(size_t)7;  // whole groups of K3_CHAINS
@@ -1441,25 +1519,27 @@ static unsigned k3h_chunk_trees(const DevPlan& plan, int tpb) {
 bool k3_fused_available(const DevPlan& plan) {
     if (plan.h.model_kind == MODEL_NONE) return false;
     if (plan.h.model_kind != MODEL_LOGISTIC && plan.heap_depth == 0) return false;
-    return k3h_tpb(plan) != 0;
+    return k3h_shape(plan).tpb != 0;
 }
 #ifndef UGVC_HOST_EMU
 void launch_k3_fused(const DevPlan& plan, const uint32_t* raw, const float* feats, size_t row_stride,
                      const int64_t* d_n_records, double threshold, uint8_t* low_score, float* probs, double* qual,
                      double* phreds, int phred_mode, long long* d_counts, unsigned long long* d_err, int sm_count,
                      cudaStream_t st) {
-    const int tpb = k3h_tpb(plan);
-    const unsigned chunk = k3h_chunk_trees(plan, tpb);
-    const size_t smem = k3h_fixed_bytes(plan, tpb) + (size_t)chunk * k3h_tree_bytes(plan);
+    const K3hShape sh = k3h_shape(plan);
+    const unsigned chunk = k3h_chunk_trees(plan, sh);
+    const size_t smem = k3h_fixed_bytes(plan, sh.tpb, sh.nbuf) + (size_t)chunk * k3h_tree_bytes(plan);
     int per_sm = (int)((227u * 1024u) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-    if (per_sm * tpb > 1536) per_sm = 1536 / tpb;
-#define K3H_LAUNCH(T)                                                                                                   \
-    k3_heap<T><<<sm_count * per_sm, T, smem, st>>>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, \
-                                                   qual, phreds, d_counts, chunk, phred_mode, d_err)
-    if (tpb == 512) K3H_LAUNCH(512);
-    else if (tpb == 256) K3H_LAUNCH(256);
-    else K3H_LAUNCH(128);
+    if (per_sm * sh.tpb > 1536) per_sm = 1536 / sh.tpb;
+#define K3H_LAUNCH(T, B)                                                                                                  \
+    k3_heap<T, B><<<sm_count * per_sm, T, smem, st>>>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, \
+                                                      qual, phreds, d_counts, chunk, phred_mode, d_err)
+    if (sh.tpb == 512) K3H_LAUNCH(512, 1);
+    else if (sh.tpb == 256 && sh.nbuf == 2) K3H_LAUNCH(256, 2);
+    else if (sh.tpb == 256) K3H_LAUNCH(256, 1);
+    else if (sh.nbuf == 2) K3H_LAUNCH(128, 2);
+    else K3H_LAUNCH(128, 1);
 #undef K3H_LAUNCH
 }
 #endif
@@ -1526,11 +1606,15 @@ cudaError_t kernels_configure(const DevPlan& plan) {
     e = cudaFuncSetAttribute(k1_parse_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(plan));
     if (e != cudaSuccess) return e;
 #endif
-    e = cudaFuncSetAttribute(k3_heap<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    e = cudaFuncSetAttribute(k3_heap<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    e = cudaFuncSetAttribute(k3_heap<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    e = cudaFuncSetAttribute(k3_heap<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k3_heap<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k3_heap<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k3_infer<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;

@@ -100,7 +100,10 @@ struct alignas(16) FastKey {   // 32 bytes
     uint8_t len;
     uint8_t pad[7];
 };
-enum : uint8_t { SK_INT = 1, SK_STRNUM = 2, SK_SCALAR = 4 };  // per-slot bits the decoders need
+// per-slot byte of the tile kernel: the queue class a value of this slot goes to (bits 0-1: 0 numeric token,
+// 1 not on the fast path, 2 dictionary string, 3 small string reducer) and what the decoders need to know
+enum : uint8_t { SK_CLS_MASK = 3, SK_CLS_NUM = 0, SK_CLS_BAD = 1, SK_CLS_DICT = 2, SK_CLS_GEN = 3,
+                 SK_INT = 4, SK_STRNUM = 8, SK_SCALAR = 16, SK_ZERO_LONG = 32 };
 enum { FIX_QUAL = 0, FIX_ALLELE0 = 1, FIX_ALLELE1 = 2, FIX_INDEL = 3, FIX_NALLELES = 4 };
 struct DevFast {
     const FastKey* keys;       // device array
