@@ -1606,15 +1606,15 @@ cudaError_t kernels_configure(const DevPlan& plan) {
     e = cudaFuncSetAttribute(k1_parse_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(plan));
     if (e != cudaSuccess) return e;
 #endif
-    e = cudaFuncSetAttribute(k3_heap<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    e = cudaFuncSetAttribute(k3_heap<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    e = cudaFuncSetAttribute(k3_heap<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    e = cudaFuncSetAttribute(k3_heap<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    e = cudaFuncSetAttribute(k3_heap<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    e = cudaFuncSetAttribute(k3_heap<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k3_infer<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
