@@ -284,6 +284,9 @@ int ugvc_conc_curve(ugvc_conc* h, int group, double* precision, double* recall, 
 /* K1's numeric-literal parser (csrc/numparse.h) compiled for the host: parses one token of
  * `text` (NUL-terminated); returns 0 ok / 1 missing (".") / 2 not exactly parseable. */
 int ugvc_test_parse_float(const char* text, float* out_f32, double* out_f64, int* out_consumed);
+/* Test hook: the device BGZF encoder (csrc/deflate.cuh) run on the host on one block of at most 57344 bytes (4 readable
+ * bytes after n); out receives a complete BGZF block (<= 65536 bytes), the size is returned. */
+int64_t ugvc_test_deflate_block(const uint8_t* in, uint32_t n, uint8_t* out);
 
 #ifdef __cplusplus
 }

@@ -112,12 +112,12 @@ void launch_k3_fused(const DevPlan& plan, const uint32_t* raw, const float* feat
                      double* phreds, int phred_mode, long long* d_counts, unsigned long long* d_err, int, cudaStream_t) {
     one_thread_grid();
     const size_t need = (size_t)plan.h.n_features * (sizeof(float) + sizeof(PlanFeature)) + 64 +
-                        (size_t)plan.h.n_trees * ((size_t)7 << plan.heap_depth);
+                        (size_t)plan.h.n_trees * ((size_t)10 << plan.heap_depth) + 64;
     if (need > sizeof(smem3)) {
         fprintf(stderr, "host_emu: forest too large for the emulated shared memory\n");
         abort();
     }
-    k3_heap<1, 1>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, qual, phreds, d_counts,
+    k3_heap<1, 1, 8>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, qual, phreds, d_counts,
                plan.h.n_trees, phred_mode, d_err);
 }
 

@@ -17,6 +17,7 @@
 
 #include "../../include/ugvc_b200.h"
 #include "numparse.h"
+#include "deflate.cuh"
 
 namespace {
 
@@ -637,4 +638,20 @@ extern "C" int ugvc_test_parse_float(const char* text, float* out_f32, double* o
     if (out_f32) *out_f32 = (float)v;
     if (out_consumed) *out_consumed = (int)(s.p - reinterpret_cast<const uint8_t*>(text));
     return st;
+}
+
+// The device BGZF encoder (deflate.cuh) compiled for the host -- the same source the GPU runs -- so that the CPU
+// tests can inflate its blocks with zlib.  `in` needs 4 readable bytes after n; out: DEF_BLOCK_STRIDE bytes.
+extern "C" int64_t ugvc_test_deflate_block(const uint8_t* in, uint32_t n, uint8_t* out) {
+    if (!in || !out || n > DEF_CHUNK) return UGVC_E_ARG;
+    static DefTables* tables = [] {
+        DefTables* t = new DefTables();
+        def_build_tables(*t);
+        return t;
+    }();
+    std::vector<uint16_t> head(1u << DEF_HASH_BITS);
+    alignas(16) static thread_local uint8_t buf[DEF_BLOCK_STRIDE];
+    const uint32_t sz = def_block(in, n, buf, head.data(), *tables);
+    memcpy(out, buf, sz);
+    return (int64_t)sz;
 }

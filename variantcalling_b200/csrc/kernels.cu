@@ -1254,41 +1254,43 @@ __device__ __forceinline__ void k2_combine_one(const PlanCombine cb, uint32_t bb
     a = r;
 }
 
-template <int CMP, int TPB>
-__device__ __forceinline__ void walk8h(const float* __restrict__ s_thr, const uint8_t* __restrict__ s_feat,
-                                       const uint16_t* __restrict__ s_leaf, unsigned H, int depth, unsigned tr,
-                                       unsigned tr_end, const float* __restrict__ x, int leaf[K3_CHAINS]) {
-    unsigned n[K3_CHAINS], base[K3_CHAINS];
+// NCH trees at once from the heap form in shared memory: node = (threshold bits, byte offset of the feature's row in
+// the thread's tile column).  All indices are kept as byte offsets so that a level costs six instructions per chain:
+// node load, address add, x load, compare, select, shift-add.
+template <int CMP, int NCH>
+__device__ __forceinline__ void walkh(const uint8_t* __restrict__ s_node, const uint16_t* __restrict__ s_leaf, unsigned H,
+                                      int depth, unsigned tr, unsigned tr_end, const uint8_t* __restrict__ xcol,
+                                      int leaf[NCH]) {
+    unsigned a8[NCH];
+    int go_l[NCH];  // what turns 2 * a8 into the left child's offset (the right one is 8 more)
 #pragma unroll
-    for (int j = 0; j < K3_CHAINS; ++j) {
+    for (int j = 0; j < NCH; ++j) {
         const unsigned t = tr + j < tr_end ? tr + j : tr;  // pad with a repeat (result ignored)
-        base[j] = t * H;
-        n[j] = 1u;
+        const unsigned tb8 = t * H * 8u;
+        a8[j] = tb8 + 8u;  // the root: node 1 of the tree
+        go_l[j] = -(int)tb8;
     }
     for (int d = 0; d < depth; ++d) {
-        unsigned f[K3_CHAINS];
-        float th[K3_CHAINS];
+        uint2 nd[NCH];
 #pragma unroll
-        for (int j = 0; j < K3_CHAINS; ++j) {
-            f[j] = s_feat[base[j] + n[j]];
-            th[j] = s_thr[base[j] + n[j]];
-        }
+        for (int j = 0; j < NCH; ++j) nd[j] = *reinterpret_cast<const uint2*>(s_node + a8[j]);
 #pragma unroll
-        for (int j = 0; j < K3_CHAINS; ++j) {
-            const float xv = x[f[j] * TPB];
-            const bool left = (CMP == CMP_LE) ? (xv <= th[j]) : (xv < th[j]);
-            n[j] = 2u * n[j] + (left ? 0u : 1u);
+        for (int j = 0; j < NCH; ++j) {
+            const float xv = *reinterpret_cast<const float*>(xcol + nd[j].y);
+            const float th = __uint_as_float(nd[j].x);
+            const bool left = (CMP == CMP_LE) ? (xv <= th) : (xv < th);
+            a8[j] = 2u * a8[j] + (unsigned)(left ? go_l[j] : go_l[j] + 8);
         }
     }
 #pragma unroll
-    for (int j = 0; j < K3_CHAINS; ++j) leaf[j] = (int)s_leaf[base[j] + n[j] - H];
+    for (int j = 0; j < NCH; ++j) leaf[j] = (int)s_leaf[(a8[j] >> 3) - H];
 }
 
 // NBUF = 2: the raw rows of the NEXT record tile are fetched by 1-D bulk copies (cp.async.bulk, one per feature row,
 // completion on an mbarrier) while the current tile is walked, so no warp ever waits on HBM; every thread then turns
 // its own column of the landed slot words into feature values in place (K2's policies) -- a thread only ever reads
 // its own column, so the tile needs no barrier between assembly and walk.
-template <int TPB, int NBUF>
+template <int TPB, int NBUF, int NCH>
 __global__ void __launch_bounds__(TPB, 1)
 k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, const float* __restrict__ feats,
         size_t row_stride, const int64_t* __restrict__ n_records_p, double threshold, uint8_t* __restrict__ low_score,
@@ -1301,18 +1303,16 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
     const int depth = (int)plan.heap_depth;
     const unsigned H = 1u << depth;
     float* tile0 = reinterpret_cast<float*>(smem3);         // [NBUF][F][TPB]
-    float* s_thr = tile0 + (size_t)NBUF * F * TPB;          // [chunk_trees][H]
-    PlanFeature* s_pf = reinterpret_cast<PlanFeature*>(s_thr + (forest ? (size_t)chunk_trees * H : 0));  // [F]
+    uint2* s_node = reinterpret_cast<uint2*>(tile0 + (size_t)NBUF * F * TPB);  // [chunk_trees][H]: threshold, row offset
+    PlanFeature* s_pf = reinterpret_cast<PlanFeature*>(s_node + (forest ? (size_t)chunk_trees * H : 0));  // [F]
     uint16_t* s_leaf = reinterpret_cast<uint16_t*>(s_pf + F);                                              // [chunk_trees][H]
-    uint8_t* s_feat = reinterpret_cast<uint8_t*>(s_leaf + (forest ? (size_t)chunk_trees * H : 0));        // [chunk_trees][H]
     const bool resident = forest && n_trees <= chunk_trees;  // whole forest fits: stage once
     for (int i = threadIdx.x; i < F; i += TPB) s_pf[i] = plan.feats[i];
     if (resident) {
         const unsigned cnt = n_trees * H;
         for (unsigned i = threadIdx.x; i < cnt; i += TPB) {
-            s_thr[i] = plan.heap_thr[i];
+            s_node[i] = make_uint2(__float_as_uint(plan.heap_thr[i]), (unsigned)plan.heap_feat[i] * (unsigned)(TPB * sizeof(float)));
             s_leaf[i] = plan.heap_leaf[i];
-            s_feat[i] = plan.heap_feat[i];
         }
     }
     const long long n_rec = *n_records_p;
@@ -1421,24 +1421,33 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
                     const unsigned cnt = (c1 - c0) * H;
                     const size_t off = (size_t)c0 * H;
                     for (unsigned i = threadIdx.x; i < cnt; i += TPB) {
-                        s_thr[i] = plan.heap_thr[off + i];
+                        s_node[i] = make_uint2(__float_as_uint(plan.heap_thr[off + i]),
+                                               (unsigned)plan.heap_feat[off + i] * (unsigned)(TPB * sizeof(float)));
                         s_leaf[i] = plan.heap_leaf[off + i];
-                        s_feat[i] = plan.heap_feat[off + i];
                     }
                     __syncthreads();
                 }
-                for (unsigned tr = c0; tr < c1; tr += K3_CHAINS) {
-                    int leaf[K3_CHAINS];
+                // the leaf values of a group are fetched (global, L1) while the next group is walked and added after
+                // it, still in tree order
+                double pend[NCH];
+                unsigned n_pend = 0;
+                for (unsigned tr = c0; tr < c1; tr += NCH) {
+                    int leaf[NCH];
                     const unsigned lt = resident ? tr : tr - c0, lt_end = resident ? c1 : c1 - c0;
-                    if (plan.h.cmp_mode == CMP_LE) walk8h<CMP_LE, TPB>(s_thr, s_feat, s_leaf, H, depth, lt, lt_end, x, leaf);
-                    else walk8h<CMP_LT, TPB>(s_thr, s_feat, s_leaf, H, depth, lt, lt_end, x, leaf);
+                    const uint8_t* xcol = reinterpret_cast<const uint8_t*>(x);
+                    if (plan.h.cmp_mode == CMP_LE) walkh<CMP_LE, NCH>(reinterpret_cast<const uint8_t*>(s_node), s_leaf, H, depth, lt, lt_end, xcol, leaf);
+                    else walkh<CMP_LT, NCH>(reinterpret_cast<const uint8_t*>(s_node), s_leaf, H, depth, lt, lt_end, xcol, leaf);
                     if (plan.h.model_kind == MODEL_GB_SKLEARN && O == 1) {
+                        // raw += learning_rate * leaf (pre-scaled on the host), fp64, tree order
 #pragma unroll
-                        for (int j = 0; j < K3_CHAINS; ++j)
-                            if (tr + j < c1) z[0] = __dadd_rn(z[0], __ldg(&plan.leaves[leaf[j]]));
+                        for (int j = 0; j < NCH; ++j)
+                            if ((unsigned)j < n_pend) z[0] = __dadd_rn(z[0], pend[j]);
+                        n_pend = c1 - tr < (unsigned)NCH ? c1 - tr : (unsigned)NCH;
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j) pend[j] = __ldg(&plan.leaves[leaf[j]]);
                     } else if (plan.h.model_kind == MODEL_RF_SKLEARN) {
 #pragma unroll
-                        for (int j = 0; j < K3_CHAINS; ++j)
+                        for (int j = 0; j < NCH; ++j)
                             if (tr + j < c1) {
                                 const double* lv = plan.leaves + (size_t)leaf[j] * plan.h.leaf_width;
 #pragma unroll
@@ -1447,7 +1456,7 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
                             }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < K3_CHAINS; ++j)
+                        for (int j = 0; j < NCH; ++j)
                             if (tr + j < c1) {
                                 const int o = plan.tree_out[tr + j];
                                 const double add = __ldg(&plan.leaves[leaf[j]]);
@@ -1460,6 +1469,9 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
                             }
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+                    if ((unsigned)j < n_pend) z[0] = __dadd_rn(z[0], pend[j]);
                 c0 = c1;
             }
         }
@@ -1487,7 +1499,7 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
 }
 
 // shared-memory plan of k3_heap: records per CTA, tile buffers, trees per staged chunk
-static size_t k3h_tree_bytes(const DevPlan& plan) { return (size_t)(1u << plan.heap_depth) * 7u; }
+static size_t k3h_tree_bytes(const DevPlan& plan) { return (size_t)(1u << plan.heap_depth) * 10u; }  // 8-byte nodes + leaf rows
 static size_t k3h_fixed_bytes(const DevPlan& plan, int tpb, int nbuf) {
     return (size_t)nbuf * plan.h.n_features * tpb * sizeof(float) + (size_t)plan.h.n_features * sizeof(PlanFeature) + 64;
 }
@@ -1499,13 +1511,13 @@ static K3hShape k3h_shape(const DevPlan& plan) {
     static const int force_buf = getenv("UGVC_K3_NBUF") ? atoi(getenv("UGVC_K3_NBUF")) : 0;
     const bool forest = plan.h.model_kind != MODEL_LOGISTIC;
     const size_t all = forest ? (size_t)plan.h.n_trees * k3h_tree_bytes(plan) : 0;
-    const K3hShape cand[5] = {{256, 2}, {512, 1}, {128, 2}, {256, 1}, {128, 1}};
+    const K3hShape cand[6] = {{256, 2}, {192, 2}, {128, 2}, {512, 1}, {256, 1}, {128, 1}};
     for (const K3hShape& c : cand) {
         if ((force && c.tpb != force) || (force_buf && c.nbuf != force_buf)) continue;
         if (k3h_fixed_bytes(plan, c.tpb, c.nbuf) + all <= K3_SMEM_BUDGET) return c;
     }
-    for (const K3hShape& c : cand)  // the forest is staged in chunks: at least 8 trees at a time
-        if (k3h_fixed_bytes(plan, c.tpb, c.nbuf) + 8 * k3h_tree_bytes(plan) <= K3_SMEM_BUDGET) return c;
+    for (const K3hShape& c : cand)  // the forest is staged in chunks: at least 16 trees at a time
+        if (k3h_fixed_bytes(plan, c.tpb, c.nbuf) + 16 * k3h_tree_bytes(plan) <= K3_SMEM_BUDGET) return c;
     return K3hShape{0, 0};
 }
 static unsigned k3h_chunk_trees(const DevPlan& plan, K3hShape sh) {
@@ -1513,7 +1525,7 @@ static unsigned k3h_chunk_trees(const DevPlan& plan, K3hShape sh) {
     const size_t room = K3_SMEM_BUDGET - k3h_fixed_bytes(plan, sh.tpb, sh.nbuf);
     size_t n = room / k3h_tree_bytes(plan);
     if (n > plan.h.n_trees) n = plan.h.n_trees;
-    if (n < plan.h.n_trees) n &= ~(size_t)7;  // whole groups of K3_CHAINS
+    if (n < plan.h.n_trees) n &= ~(size_t)15;  // whole groups of chains
     return (unsigned)n;
 }
 bool k3_fused_available(const DevPlan& plan) {
@@ -1532,14 +1544,16 @@ void launch_k3_fused(const DevPlan& plan, const uint32_t* raw, const float* feat
     int per_sm = (int)((227u * 1024u) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
     if (per_sm * sh.tpb > 1536) per_sm = 1536 / sh.tpb;
-#define K3H_LAUNCH(T, B)                                                                                                  \
-    k3_heap<T, B><<<sm_count * per_sm, T, smem, st>>>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, \
-                                                      qual, phreds, d_counts, chunk, phred_mode, d_err)
-    if (sh.tpb == 512) K3H_LAUNCH(512, 1);
-    else if (sh.tpb == 256 && sh.nbuf == 2) K3H_LAUNCH(256, 2);
-    else if (sh.tpb == 256) K3H_LAUNCH(256, 1);
-    else if (sh.nbuf == 2) K3H_LAUNCH(128, 2);
-    else K3H_LAUNCH(128, 1);
+    // few threads per SM (the tiles are large): sixteen trees per thread in flight make up for it
+#define K3H_LAUNCH(T, B, C)                                                                                                  \
+    k3_heap<T, B, C><<<sm_count * per_sm, T, smem, st>>>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, \
+                                                         qual, phreds, d_counts, chunk, phred_mode, d_err)
+    if (sh.tpb == 512) K3H_LAUNCH(512, 1, 8);
+    else if (sh.tpb == 256 && sh.nbuf == 2) K3H_LAUNCH(256, 2, 16);
+    else if (sh.tpb == 256) K3H_LAUNCH(256, 1, 8);
+    else if (sh.tpb == 192) K3H_LAUNCH(192, 2, 16);
+    else if (sh.nbuf == 2) K3H_LAUNCH(128, 2, 16);
+    else K3H_LAUNCH(128, 1, 8);
 #undef K3H_LAUNCH
 }
 #endif
@@ -1606,15 +1620,17 @@ cudaError_t kernels_configure(const DevPlan& plan) {
     e = cudaFuncSetAttribute(k1_parse_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(plan));
     if (e != cudaSuccess) return e;
 #endif
-    e = cudaFuncSetAttribute(k3_heap<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
+    e = cudaFuncSetAttribute(k3_heap<512, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
+    e = cudaFuncSetAttribute(k3_heap<256, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
+    e = cudaFuncSetAttribute(k3_heap<256, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
+    e = cudaFuncSetAttribute(k3_heap<128, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
+    e = cudaFuncSetAttribute(k3_heap<192, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k3_heap<128, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k3_infer<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;

@@ -92,6 +92,7 @@ SIGNATURES = {
     "ugvc_conc_launch_count": (C.c_longlong, [_vp]),
     "ugvc_conc_run": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "ugvc_conc_curve": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz]),
+    "ugvc_test_deflate_block": (C.c_int64, [_vp, C.c_uint32, _vp]),
     "ugvc_test_parse_float": (C.c_int, [C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_double),
                                         C.POINTER(C.c_int)]),
 }
