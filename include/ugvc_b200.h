@@ -250,6 +250,33 @@ int64_t ugvc_splice_records(const uint8_t* text, const int64_t* line_start, cons
                             const double* phreds, int n_classes,
                             uint8_t* out, size_t capacity, int64_t* out_line_start, int n_threads);
 
+/* ---- file to file on the device: compressed bytes in, compressed bytes out ---------------------------------
+ * One range of whole VCF data lines (a contig of an indexed call set) per call: `bgzf` = the consecutive BGZF blocks
+ * that hold it (host memory), `skip_head` = bytes of the first block before the range (the low 16 bits of the tabix
+ * virtual offset), `take_bytes` = uncompressed bytes of the range (0: to the end of the blocks).  The blocks are
+ * inflated on the device, the records filtered and scored (K1..K3 with the loaded plan), the edited records --
+ * FILTER (LOW_SCORE / PASS rules), INFO ";TREE_SCORE=<%g>", with UGVC_FILE_BLACKLIST_CG ";BLACKLST=CG_NON_HMER_INDEL"
+ * on flagged records, with UGVC_FILE_OVERWRITE_QUAL the QUAL column (filter_variants_pipeline.py:188-228) -- are
+ * written and BGZF-compressed there too: out_bgzf receives complete BGZF blocks of 57344 uncompressed bytes each (the
+ * last one shorter), no EOF block.  For the tabix index of the output (the reference runs `bcftools index -t`,
+ * filter_variants_pipeline.py:231): out_block_csize[b] = compressed size of block b, out_line_start[i] =
+ * uncompressed offset of record i in this call's output (n + 1 entries), out_recinfo[i].pos / flags >> 8 = POS and
+ * len(REF).  Returns UGVC_E_FALLBACK (nothing written) when a record needs the general writer of ugvc_splice_records
+ * (an INFO column that is ".", has empty pieces or already carries TREE_SCORE / BLACKLST; a score that prints in
+ * exponent form; a line longer than 64 KiB): the caller then takes the host-buffer path for this range.
+ * Needs a plan with a model and ugvc_reserve() sized for the range.  Replaces htslib's reader / writer either side
+ * of the path (filter_variants_pipeline.py:106,115,228). */
+#define UGVC_E_FALLBACK (-7)
+#define UGVC_FILE_OVERWRITE_QUAL 1
+#define UGVC_FILE_BLACKLIST_CG 2
+int ugvc_filter_bgzf(ugvc_ctx* ctx, int lane, const uint8_t* bgzf, size_t n_bytes, uint32_t skip_head, uint64_t take_bytes,
+                     double threshold, int flags, uint8_t* out_bgzf, size_t out_capacity, size_t* out_bytes,
+                     uint32_t* out_block_csize, size_t block_capacity, size_t* out_n_blocks, ugvc_recinfo* out_recinfo,
+                     int64_t* out_line_start, uint8_t* out_low_score, size_t capacity_records, int64_t* out_n_records);
+/* Stage seconds of the last ugvc_filter_bgzf call on `lane`: H2D + inflate, K1..K3, record writer, deflate + pack,
+ * D2H (device-timed with CUDA events). */
+int ugvc_filter_bgzf_stage_ms(ugvc_ctx* ctx, int lane, float out_ms[5]);
+
 /* ---- concordance metrics (BASELINE configs[4]: evaluate_concordance on the filtered set) ----
  * Precision / recall of calls against truth labels, per variant group, replacing the array work
  * of ugbio_core/concordance/concordance_utils.py:11-188,346-458 and stats_utils.py:141-210 (which

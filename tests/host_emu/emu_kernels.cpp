@@ -117,7 +117,7 @@ void launch_k3_fused(const DevPlan& plan, const uint32_t* raw, const float* feat
         fprintf(stderr, "host_emu: forest too large for the emulated shared memory\n");
         abort();
     }
-    k3_heap<1, 1, 8>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, qual, phreds, d_counts,
+    k3_heap<1, 1, 8, 1>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, qual, phreds, d_counts,
                plan.h.n_trees, phred_mode, d_err);
 }
 

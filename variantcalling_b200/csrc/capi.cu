@@ -9,6 +9,10 @@
 
 #include "kernels.cuh"
 #include "inflate.cuh"
+#include "deflate.cuh"
+#ifndef UGVC_HOST_EMU
+#include "fileio.cuh"
+#endif
 
 #define UGVC_VERSION 100
 #define TEXT_SLACK 64
@@ -33,6 +37,28 @@ struct Lane {
     int* d_inf_err = nullptr;
     int* h_inf_err = nullptr;   // pinned
     std::vector<uint64_t> h_blk;
+    // device-side record writer + BGZF encoder (ugvc_filter_bgzf), allocated at the first call
+    struct FileBufs {
+        uint8_t* d_out_text = nullptr;
+        size_t cap_out = 0;
+        int64_t* d_len = nullptr;     // [cap_records + 1]
+        int64_t* d_out_ls = nullptr;  // [cap_records + 1]
+        uint8_t* d_score = nullptr;   // [cap_records][16]
+        void* d_scan_tmp = nullptr;
+        size_t scan_tmp_bytes = 0;
+        uint8_t* d_blocks = nullptr;  // [cap_blocks][DEF_BLOCK_STRIDE]
+        uint32_t* d_bsize = nullptr;
+        uint64_t *d_bwide = nullptr, *d_boff = nullptr;
+        uint16_t* d_heads = nullptr;
+        size_t cap_blocks = 0;
+        uint8_t* d_packed = nullptr;
+        int* d_fallback = nullptr;
+        int* h_fallback = nullptr;      // pinned
+        int64_t* h_total = nullptr;     // pinned
+        std::vector<uint32_t> h_bsize;
+        cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        float ms[5] = {0, 0, 0, 0, 0};
+    } fb;
 };
 
 struct ugvc_ctx {
@@ -59,6 +85,7 @@ struct ugvc_ctx {
     FastKey* d_fast_keys = nullptr;
     uint8_t* d_fast_htab = nullptr;
     uint8_t* d_slot_kind = nullptr;
+    DefTables* d_def_tables = nullptr;  // BGZF encoder tables (ugvc_filter_bgzf)
     std::string learned_info, learned_fmt;  // what ugvc_set_key_order was told
     std::vector<Lane> lanes;
     size_t cap_bytes = 0, cap_records = 0;
@@ -130,6 +157,22 @@ static void free_lane(Lane& l) {
     cudaFree(l.d_comp);
     cudaFree(l.d_blk);
     cudaFree(l.d_inf_err);
+    cudaFree(l.fb.d_out_text);
+    cudaFree(l.fb.d_len);
+    cudaFree(l.fb.d_out_ls);
+    cudaFree(l.fb.d_score);
+    cudaFree(l.fb.d_scan_tmp);
+    cudaFree(l.fb.d_blocks);
+    cudaFree(l.fb.d_bsize);
+    cudaFree(l.fb.d_bwide);
+    cudaFree(l.fb.d_boff);
+    cudaFree(l.fb.d_heads);
+    cudaFree(l.fb.d_packed);
+    cudaFree(l.fb.d_fallback);
+    if (l.fb.h_fallback) cudaFreeHost(l.fb.h_fallback);
+    if (l.fb.h_total) cudaFreeHost(l.fb.h_total);
+    for (auto& e : l.fb.ev)
+        if (e) cudaEventDestroy(e);
     if (l.h_inf_err) cudaFreeHost(l.h_inf_err);
     if (l.h_n) cudaFreeHost(l.h_n);
     if (l.h_err) cudaFreeHost(l.h_err);
@@ -159,6 +202,7 @@ extern "C" void ugvc_free(ugvc_ctx* ctx) {
     cudaFree(ctx->d_fast_keys);
     cudaFree(ctx->d_fast_htab);
     cudaFree(ctx->d_slot_kind);
+    cudaFree(ctx->d_def_tables);
     cudaFree(ctx->d_counts);
     delete ctx;
 }
@@ -961,6 +1005,23 @@ __global__ void __launch_bounds__(64) bgzf_inflate_blocks(const uint8_t* __restr
     }
 }
 
+#ifndef UGVC_HOST_EMU
+#define INFW_WARPS 16
+__global__ void __launch_bounds__(INFW_WARPS * 32) bgzf_inflate_warps(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ blk,
+                                                                      size_t cap_blk, int n_blocks, uint8_t* __restrict__ out,
+                                                                      int* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t infw_smem[];
+    InfWarpTables& T = reinterpret_cast<InfWarpTables*>(infw_smem)[threadIdx.x >> 5];
+    const int warp = (int)(blockIdx.x * INFW_WARPS + (threadIdx.x >> 5)), n_warps = (int)(gridDim.x * INFW_WARPS);
+    for (int b = warp; b < n_blocks; b += n_warps) {
+        const int rc = inf_block_warp(comp + blk[b], (uint32_t)blk[cap_blk + b], out + blk[2 * cap_blk + b],
+                                      (uint32_t)blk[3 * cap_blk + b], T);
+        if (rc != INF_OK && (threadIdx.x & 31) == 0) atomicMax(err, (b << 8) | rc);
+        __syncwarp();
+    }
+}
+#endif
+
 // walk the BGZF block headers of host bytes: payload offset / size, output offset / size per block
 static int scan_bgzf(ugvc_ctx* ctx, const uint8_t* p, size_t n, std::vector<uint64_t>& coff, std::vector<uint64_t>& clen,
                      std::vector<uint64_t>& uoff, std::vector<uint64_t>& ulen, size_t* total_out) {
@@ -995,12 +1056,13 @@ static int scan_bgzf(ugvc_ctx* ctx, const uint8_t* p, size_t n, std::vector<uint
 }
 
 // compressed bytes -> lane device buffers -> inflate into l.d_text; *n_text = uncompressed size
-static int stage_bgzf(ugvc_ctx* ctx, Lane& l, const uint8_t* bgzf, size_t n_bytes, size_t* n_text) {
+static int stage_bgzf(ugvc_ctx* ctx, Lane& l, const uint8_t* bgzf, size_t n_bytes, size_t* n_text, size_t out_shift = 0) {
     std::vector<uint64_t> coff, clen, uoff, ulen;
     size_t total = 0;
     int rc = scan_bgzf(ctx, bgzf, n_bytes, coff, clen, uoff, ulen, &total);
     if (rc) return rc;
-    if (total > ctx->cap_bytes) return fail(ctx, UGVC_E_ARG, "bgzf: the inflated batch is larger than the reserved max_bytes");
+    if (total + out_shift > ctx->cap_bytes) return fail(ctx, UGVC_E_ARG, "bgzf: the inflated batch is larger than the reserved max_bytes");
+    for (auto& u : uoff) u += out_shift;
     const size_t nb = coff.size();
     if (n_bytes + 8 > l.cap_comp) {
         cudaFree(l.d_comp);
@@ -1038,10 +1100,23 @@ static int stage_bgzf(ugvc_ctx* ctx, Lane& l, const uint8_t* bgzf, size_t n_byte
         if (e != INF_OK && *l.d_inf_err < (int)((i << 8) | e)) *l.d_inf_err = (int)((i << 8) | e);
     }
 #else
-    const int threads = 64;
-    int grid = (int)((nb + threads - 1) / threads);
-    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
-    bgzf_inflate_blocks<<<grid, threads, 0, st>>>(l.d_comp, l.d_blk, l.cap_blk, (int)nb, l.d_text, l.d_inf_err);
+    static const bool per_thread = getenv("UGVC_INFLATE_THREADS") && *getenv("UGVC_INFLATE_THREADS") != '0';  // A/B: one thread per block
+    if (per_thread) {
+        const int threads = 64;
+        int grid = (int)((nb + threads - 1) / threads);
+        if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+        bgzf_inflate_blocks<<<grid, threads, 0, st>>>(l.d_comp, l.d_blk, l.cap_blk, (int)nb, l.d_text, l.d_inf_err);
+    } else {  // one warp per block, tables in shared memory
+        const size_t smem = INFW_WARPS * sizeof(InfWarpTables);
+        static bool configured = false;
+        if (!configured) {
+            CU(cudaFuncSetAttribute(bgzf_inflate_warps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        int grid = (int)((nb + INFW_WARPS - 1) / INFW_WARPS);
+        if (grid > ctx->sm_count * 3) grid = ctx->sm_count * 3;
+        bgzf_inflate_warps<<<grid, INFW_WARPS * 32, smem, st>>>(l.d_comp, l.d_blk, l.cap_blk, (int)nb, l.d_text, l.d_inf_err);
+    }
     CU(cudaGetLastError());
 #endif
     ctx->launches += 1;
@@ -1096,6 +1171,157 @@ extern "C" int ugvc_bgzf_inflate_device(ugvc_ctx* ctx, const uint8_t* bgzf, size
     }
     return UGVC_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// file to file on the device: inflate -> K1..K3 -> record writer -> deflate (fileio.cu)
+// ------------------------------------------------------------------------------------------
+#ifdef UGVC_HOST_EMU
+extern "C" int ugvc_filter_bgzf(ugvc_ctx* ctx, int, const uint8_t*, size_t, uint32_t, uint64_t, double, int, uint8_t*, size_t, size_t*,
+                                uint32_t*, size_t, size_t*, ugvc_recinfo*, int64_t*, uint8_t*, size_t, int64_t*) {
+    return fail(ctx, UGVC_E_FALLBACK, "the device-side record writer is not part of the host emulation");
+}
+extern "C" int ugvc_filter_bgzf_stage_ms(ugvc_ctx*, int, float*) { return UGVC_E_STATE; }
+#else
+static int file_bufs(ugvc_ctx* ctx, Lane& l) {
+    Lane::FileBufs& f = l.fb;
+    if (f.d_out_text) return UGVC_OK;
+    const size_t cap_rec = l.b.cap_records;
+    f.cap_out = ctx->cap_bytes + cap_rec * 64 + 4096;
+    f.cap_blocks = f.cap_out / DEF_CHUNK + 2;
+    CU(cudaMalloc(&f.d_out_text, f.cap_out + 64));
+    CU(cudaMalloc(&f.d_len, (cap_rec + 1) * sizeof(int64_t)));
+    CU(cudaMalloc(&f.d_out_ls, (cap_rec + 1) * sizeof(int64_t)));
+    CU(cudaMalloc(&f.d_score, cap_rec * 16));
+    size_t t1 = 0, t2 = 0;
+    CU(fio_scan_i64(nullptr, t1, f.d_len, f.d_out_ls, (int64_t)cap_rec + 1, nullptr));
+    CU(fio_scan_u64(nullptr, t2, nullptr, nullptr, (int)f.cap_blocks + 1, nullptr));
+    f.scan_tmp_bytes = (t1 > t2 ? t1 : t2) + 256;
+    CU(cudaMalloc(&f.d_scan_tmp, f.scan_tmp_bytes));
+    CU(cudaMalloc(&f.d_blocks, f.cap_blocks * (size_t)DEF_BLOCK_STRIDE));
+    CU(cudaMalloc(&f.d_bsize, (f.cap_blocks + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&f.d_bwide, (f.cap_blocks + 1) * sizeof(uint64_t)));
+    CU(cudaMalloc(&f.d_boff, (f.cap_blocks + 1) * sizeof(uint64_t)));
+    CU(cudaMalloc(&f.d_heads, (f.cap_blocks << DEF_HASH_BITS) * sizeof(uint16_t)));
+    CU(cudaMalloc(&f.d_packed, f.cap_blocks * (size_t)DEF_BLOCK_STRIDE));
+    CU(cudaMalloc(&f.d_fallback, sizeof(int)));
+    CU(cudaHostAlloc(&f.h_fallback, sizeof(int), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&f.h_total, sizeof(int64_t), cudaHostAllocDefault));
+    for (auto& e : f.ev) CU(cudaEventCreate(&e));
+    if (!ctx->d_def_tables) {
+        DefTables* t = new DefTables();
+        def_build_tables(*t);
+        CU(cudaMalloc(&ctx->d_def_tables, sizeof(DefTables)));
+        CU(cudaMemcpy(ctx->d_def_tables, t, sizeof(DefTables), cudaMemcpyHostToDevice));
+        delete t;
+    }
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_filter_bgzf(ugvc_ctx* ctx, int lane, const uint8_t* bgzf, size_t n_bytes, uint32_t skip_head, uint64_t take_bytes,
+                                double threshold, int flags, uint8_t* out_bgzf, size_t out_capacity, size_t* out_bytes,
+                                uint32_t* out_block_csize, size_t block_capacity, size_t* out_n_blocks, ugvc_recinfo* out_recinfo,
+                                int64_t* out_line_start, uint8_t* out_low_score, size_t capacity_records, int64_t* out_n_records) {
+    if (!ctx) return UGVC_E_ARG;
+    if (!ctx->has_plan || ctx->lanes.empty()) return fail(ctx, UGVC_E_STATE, "filter_bgzf: load a plan and reserve first");
+    if (ctx->plan.h.model_kind == MODEL_NONE) return fail(ctx, UGVC_E_STATE, "filter_bgzf: the plan carries no model");
+    if (lane < 0 || lane >= (int)ctx->lanes.size()) return fail(ctx, UGVC_E_ARG, "filter_bgzf: lane out of range");
+    if (!bgzf || !n_bytes || !out_bgzf || !out_bytes || !out_n_records) return fail(ctx, UGVC_E_ARG, "filter_bgzf: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[lane];
+    if (l.submitted) return fail(ctx, UGVC_E_STATE, "filter_bgzf: lane already has a batch in flight");
+    int rc = file_bufs(ctx, l);
+    if (rc) return rc;
+    Lane::FileBufs& f = l.fb;
+    cudaStream_t st = l.stream;
+    CU(cudaEventRecord(f.ev[0], st));
+    // ---- compressed blocks -> text on the device, the range's first byte 16-byte aligned
+    const size_t shift = (16 - (skip_head & 15u)) & 15u;
+    size_t total = 0;
+    rc = stage_bgzf(ctx, l, bgzf, n_bytes, &total, shift);
+    if (rc) return rc;
+    if (skip_head > total) return fail(ctx, UGVC_E_ARG, "filter_bgzf: skip_head beyond the inflated blocks");
+    const size_t n_text = take_bytes ? (size_t)take_bytes : total - skip_head;
+    if (skip_head + n_text > total) return fail(ctx, UGVC_E_ARG, "filter_bgzf: the range is longer than the inflated blocks");
+    const uint8_t* d_text = l.d_text + shift + skip_head;
+    CU(cudaEventRecord(f.ev[1], st));
+    // ---- K1..K3
+    rc = enqueue_kernels(ctx, l, d_text, n_text, threshold, l.b.low_score, l.b.probs, l.b.qual, l.b.recinfo, l.b.line_start,
+                         l.b.cap_records, l.b.n_records, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(l.h_n, l.b.n_records, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(l.h_err, l.d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(f.ev[2], st));
+    CU(cudaStreamSynchronize(st));
+    if (l.h_inf_err && *l.h_inf_err) {
+        const int code = *l.h_inf_err;
+        *l.h_inf_err = 0;
+        return fail(ctx, UGVC_E_IO, "BGZF inflate failed on the device (block " + std::to_string(code >> 8) + ", code " +
+                                        std::to_string(code & 0xFF) + ")");
+    }
+    rc = decode_error(ctx, *l.h_err);
+    if (rc) return rc;
+    const int64_t n = *l.h_n;
+    l.last_n = n;
+    *out_n_records = n;
+    if ((size_t)n > capacity_records) return fail(ctx, UGVC_E_ARG, "filter_bgzf: output capacity smaller than the record count");
+    // ---- record writer
+    CU(cudaMemsetAsync(f.d_fallback, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(f.d_len + n, 0, sizeof(int64_t), st));
+    fio_launch_splice_len(d_text, l.b.line_start, l.b.recinfo, l.b.low_score, l.b.qual, n, flags, f.d_len, f.d_score, f.d_fallback,
+                          ctx->sm_count, st);
+    size_t tmp = f.scan_tmp_bytes;
+    CU(fio_scan_i64(f.d_scan_tmp, tmp, f.d_len, f.d_out_ls, n + 1, st));
+    CU(cudaMemcpyAsync(f.h_total, f.d_out_ls + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(f.h_fallback, f.d_fallback, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (*f.h_fallback) return UGVC_E_FALLBACK;
+    const size_t out_text = (size_t)*f.h_total;
+    if (out_text > f.cap_out) return fail(ctx, UGVC_E_ARG, "filter_bgzf: the edited text exceeds the writer's buffer");
+    fio_launch_splice_copy(d_text, l.b.line_start, l.b.recinfo, l.b.low_score, n, flags, f.d_out_ls, f.d_score, f.d_out_text,
+                           f.d_fallback, ctx->sm_count, st);
+    CU(cudaMemsetAsync(f.d_out_text + out_text, 0, 16, st));  // the encoder reads whole words
+    CU(cudaMemcpyAsync(f.h_fallback, f.d_fallback, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(f.ev[3], st));
+    // ---- deflate, pack
+    const int n_blocks = (int)((out_text + DEF_CHUNK - 1) / DEF_CHUNK);
+    if ((size_t)n_blocks > f.cap_blocks || (out_block_csize && (size_t)n_blocks > block_capacity))
+        return fail(ctx, UGVC_E_ARG, "filter_bgzf: more output blocks than room for them");
+    fio_launch_deflate(f.d_out_text, out_text, ctx->d_def_tables, f.d_blocks, f.d_bsize, f.d_heads, n_blocks, st);
+    fio_launch_widen(f.d_bsize, f.d_bwide, n_blocks, st);
+    CU(cudaMemsetAsync(f.d_bwide + n_blocks, 0, sizeof(uint64_t), st));
+    tmp = f.scan_tmp_bytes;
+    CU(fio_scan_u64(f.d_scan_tmp, tmp, f.d_bwide, f.d_boff, n_blocks + 1, st));
+    fio_launch_pack(f.d_blocks, f.d_bsize, f.d_bwide, f.d_boff, n_blocks, f.d_packed, ctx->sm_count, st);
+    f.h_bsize.resize((size_t)n_blocks + 1);
+    if (n_blocks) CU(cudaMemcpyAsync(f.h_bsize.data(), f.d_bsize, (size_t)n_blocks * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(f.ev[4], st));
+    CU(cudaStreamSynchronize(st));
+    if (*f.h_fallback) return UGVC_E_FALLBACK;
+    size_t packed = 0;
+    for (int b = 0; b < n_blocks; ++b) packed += f.h_bsize[b];
+    if (packed > out_capacity) return fail(ctx, UGVC_E_ARG, "filter_bgzf: out_capacity smaller than the compressed output");
+    ctx->launches += 6;
+    // ---- results to the host
+    if (packed) CU(cudaMemcpyAsync(out_bgzf, f.d_packed, packed, cudaMemcpyDeviceToHost, st));
+    if (out_block_csize && n_blocks) memcpy(out_block_csize, f.h_bsize.data(), (size_t)n_blocks * sizeof(uint32_t));
+    if (out_recinfo && n) CU(cudaMemcpyAsync(out_recinfo, l.b.recinfo, (size_t)n * sizeof(ugvc_recinfo), cudaMemcpyDeviceToHost, st));
+    if (out_line_start) CU(cudaMemcpyAsync(out_line_start, f.d_out_ls, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (out_low_score && n) CU(cudaMemcpyAsync(out_low_score, l.b.low_score, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(f.ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    *out_bytes = packed;
+    if (out_n_blocks) *out_n_blocks = (size_t)n_blocks;
+    for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&f.ms[k], f.ev[k], f.ev[k + 1]);
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_filter_bgzf_stage_ms(ugvc_ctx* ctx, int lane, float out_ms[5]) {
+    if (!ctx || !out_ms || lane < 0 || lane >= (int)ctx->lanes.size()) return UGVC_E_ARG;
+    for (int k = 0; k < 5; ++k) out_ms[k] = ctx->lanes[lane].fb.ms[k];
+    return UGVC_OK;
+}
+#endif  // !UGVC_HOST_EMU
 
 // K3 alone on a dense feature matrix assembled by the caller (row-major, n x n_features, leading
 // dimension ld): the model-apply step of variant_filtering_utils.apply_model / the other model-apply

@@ -292,3 +292,162 @@ __host__ __device__ inline int inf_block(const uint8_t* in, uint32_t n_in, uint8
     if (b.pos - (uint32_t)(b.cnt >> 3) > n_in) return INF_INPUT_OVERRUN;
     return op == n_out ? INF_OK : INF_SIZE_MISMATCH;
 }
+
+#if defined(__CUDACC__) && !defined(UGVC_HOST_EMU)
+// ---------------------------------------------------------------------------------------------------
+// One WARP per BGZF block.  The thread-per-block decoder above diverges 32 ways inside a warp and keeps its
+// tables in local memory (measured: 7 GB/s of output on a B200).  Here the serial part -- bit buffer, table
+// look-up, symbol decode -- runs warp-uniformly (every lane holds the same state, the tables are in shared
+// memory, the input word is a broadcast load), so nothing diverges, and the byte moves of the matches are spread
+// over the lanes (lane k copies byte k; an overlapping match repeats with period d).  Literals are stored by
+// one lane.  The output window lives in global memory: a match reads bytes the warp wrote a moment ago, so the
+// source loads bypass L1 (ld.volatile) and are ordered behind the stores by __syncwarp().
+#define INFW_LIT_BITS 10
+#define INFW_DIST_BITS 8
+struct InfWarpTables {
+    uint16_t lit_lut[1 << INFW_LIT_BITS];
+    uint16_t dist_lut[1 << INFW_DIST_BITS];
+    InfCode lit, dist;
+    uint8_t lens[320];
+    uint8_t cl[32];
+};
+
+// the symbol -> base / extra-bit tables: warp-uniform indices, so the constant cache serves them
+__constant__ uint16_t INFW_LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t INFW_LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t INFW_DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t INFW_DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t INFW_CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+__device__ __forceinline__ int inf_block_warp(const uint8_t* __restrict__ in, uint32_t n_in, uint8_t* out, uint32_t n_out,
+                                              InfWarpTables& T) {
+    const unsigned lane = threadIdx.x & 31u;
+    const volatile uint8_t* vout = out;
+    InfBits b;
+    b.in = in;
+    b.n_in = n_in;
+    b.pos = 0;
+    b.buf = 0;
+    b.cnt = 0;
+    uint32_t op = 0;
+    for (;;) {
+        b.refill();
+        const uint32_t last = b.take(1);
+        const uint32_t type = b.take(2);
+        if (type == 0) {  // stored: the lanes share the copy
+            b.drop(b.cnt & 7);
+            b.refill();
+            const uint32_t len = b.take(16), nlen = b.take(16);
+            if ((len ^ 0xFFFFu) != nlen) return INF_BAD_STORED_LEN;
+            if (op + len > n_out) return INF_OUTPUT_OVERRUN;
+            const uint32_t p = b.pos - (uint32_t)(b.cnt >> 3);
+            if (p + len > n_in) return INF_INPUT_OVERRUN;
+            for (uint32_t i = lane; i < len; i += 32u) out[op + i] = in[p + i];
+            op += len;
+            b.pos = p + len;
+            b.buf = 0;
+            b.cnt = 0;
+        } else if (type == 1 || type == 2) {
+            int err = INF_OK;
+            if (type == 1) {  // fixed code
+                if (lane == 0) {
+                    for (int i = 0; i < 144; ++i) T.lens[i] = 8;
+                    for (int i = 144; i < 256; ++i) T.lens[i] = 9;
+                    for (int i = 256; i < 280; ++i) T.lens[i] = 7;
+                    for (int i = 280; i < 288; ++i) T.lens[i] = 8;
+                    inf_build(T.lit, T.lens, 288, T.lit_lut, INFW_LIT_BITS);
+                    for (int i = 0; i < 30; ++i) T.lens[i] = 5;
+                    inf_build(T.dist, T.lens, 30, T.dist_lut, INFW_DIST_BITS);
+                }
+            } else {  // dynamic code: the header is decoded by every lane (uniform), the tables are built by lane 0
+                const int hlit = (int)b.take(5) + 257, hdist = (int)b.take(5) + 1, hclen = (int)b.take(4) + 4;
+                if (hlit > 286 || hdist > 30) return INF_BAD_CODE_LENGTHS;
+                b.refill();
+                uint32_t cl3[19];
+                for (int i = 0; i < 19; ++i) cl3[i] = 0;
+                for (int i = 0; i < hclen; ++i) {
+                    if (b.cnt < 3) b.refill();
+                    cl3[i] = b.take(3);
+                }
+                if (lane == 0) {
+                    uint8_t cl[19];
+                    for (int i = 0; i < 19; ++i) cl[i] = 0;
+                    for (int i = 0; i < hclen; ++i) cl[INFW_CL_ORDER[i]] = (uint8_t)cl3[i];
+                    // the code-length code shares the distance tables' storage until they are built
+                    if (!inf_build(T.dist, cl, 19, T.dist_lut, 7)) err = INF_BAD_CODE_LENGTHS;
+                }
+                __syncwarp();
+                err = __shfl_sync(0xffffffffu, err, 0);
+                if (err) return err;
+                int i = 0;
+                while (i < hlit + hdist) {
+                    b.refill();
+                    const int sym = inf_decode(b, T.dist, T.dist_lut, 7);
+                    if (sym < 0) return INF_BAD_SYMBOL;
+                    if (sym < 16) {
+                        if (lane == 0) T.lens[i] = (uint8_t)sym;
+                        ++i;
+                    } else {
+                        int rep, val = 0;
+                        if (sym == 16) {
+                            if (i == 0) return INF_BAD_CODE_LENGTHS;
+                            __syncwarp();
+                            val = T.lens[i - 1];
+                            rep = 3 + (int)b.take(2);
+                        } else if (sym == 17) {
+                            rep = 3 + (int)b.take(3);
+                        } else {
+                            rep = 11 + (int)b.take(7);
+                        }
+                        if (i + rep > hlit + hdist) return INF_BAD_CODE_LENGTHS;
+                        if (lane == 0)
+                            for (int r = 0; r < rep; ++r) T.lens[i + r] = (uint8_t)val;
+                        i += rep;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if (T.lens[256] == 0) err = INF_BAD_CODE_LENGTHS;  // no end-of-block code
+                    else if (!inf_build(T.lit, T.lens, hlit, T.lit_lut, INFW_LIT_BITS)) err = INF_BAD_CODE_LENGTHS;
+                    else if (!inf_build(T.dist, T.lens + hlit, hdist, T.dist_lut, INFW_DIST_BITS)) err = INF_BAD_CODE_LENGTHS;
+                }
+            }
+            __syncwarp();
+            err = __shfl_sync(0xffffffffu, err, 0);
+            if (err) return err;
+            for (;;) {
+                b.refill();  // >= 57 bits: a literal-length code (15) + extra (5) + distance code (15) + extra (13)
+                int sym = inf_decode(b, T.lit, T.lit_lut, INFW_LIT_BITS);
+                if (sym < 0) return INF_BAD_SYMBOL;
+                if (sym < 256) {
+                    if (op >= n_out) return INF_OUTPUT_OVERRUN;
+                    if (lane == 0) out[op] = (uint8_t)sym;
+                    ++op;
+                    continue;
+                }
+                if (sym == 256) break;
+                sym -= 257;
+                if (sym >= 29) return INF_BAD_SYMBOL;
+                const uint32_t len = INFW_LEN_BASE[sym] + b.take(INFW_LEN_EXTRA[sym]);
+                const int ds = inf_decode(b, T.dist, T.dist_lut, INFW_DIST_BITS);
+                if (ds < 0 || ds >= 30) return INF_BAD_DISTANCE;
+                const uint32_t d = INFW_DIST_BASE[ds] + b.take(INFW_DIST_EXTRA[ds]);
+                if (d > op) return INF_BAD_DISTANCE;
+                if (op + len > n_out) return INF_OUTPUT_OVERRUN;
+                __syncwarp();  // the bytes this match reads are in memory
+                if (d >= len) {
+                    for (uint32_t k = lane; k < len; k += 32u) out[op + k] = vout[op - d + k];
+                } else {  // overlapping: the match repeats its first d bytes
+                    for (uint32_t k = lane; k < len; k += 32u) out[op + k] = vout[op - d + k % d];
+                }
+                op += len;
+            }
+        } else {
+            return INF_BAD_BLOCK_TYPE;
+        }
+        if (last) break;
+    }
+    if (b.pos - (uint32_t)(b.cnt >> 3) > n_in) return INF_INPUT_OVERRUN;
+    return op == n_out ? INF_OK : INF_SIZE_MISMATCH;
+}
+#endif

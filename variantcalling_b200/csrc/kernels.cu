@@ -861,16 +861,15 @@ void launch_k1_fast(const DevPlan& plan, const DevFast& fast, const DevSchedule&
 __device__ __forceinline__ float k2_apply(uint32_t bits, const PlanFeature& pf, long long rec, int f,
                                           unsigned long long* err) {
     float v = __uint_as_float(bits);
-    if (bits == RAW_ABSENT) {
-        if (pf.absent_pol == POL_VALUE) v = pf.absent_val;
-        else if (pf.absent_pol == POL_ERROR) atomicMin(err, ugvc_pack_error(rec, f, REASON_BAD_VALUE));
-    } else if (bits == RAW_MISSING) {
-        if (pf.missing_pol == POL_VALUE) v = pf.missing_val;
-        else if (pf.missing_pol == POL_ERROR) atomicMin(err, ugvc_pack_error(rec, f, REASON_NULL_FEATURE));
-    } else if (bits == RAW_ERR || (bits & 0x7FFFFFFFu) == 0x7F800000u) {
-        // +-inf (an overflowing literal, or "inf" itself): SimpleImputer's / the model's input check
-        // raises "Input X contains infinity" in the reference whatever the column's pipeline is
-        atomicMin(err, ugvc_pack_error(rec, f, REASON_BAD_VALUE));
+    if ((bits & 0x7F800000u) == 0x7F800000u) {  // the three sentinels are NaNs; the infinities share the exponent
+        const bool ab = bits == RAW_ABSENT, mi = bits == RAW_MISSING;
+        v = ab && pf.absent_pol == POL_VALUE ? pf.absent_val : v;
+        v = mi && pf.missing_pol == POL_VALUE ? pf.missing_val : v;
+        // +-inf (an overflowing literal, or "inf" itself): SimpleImputer's / the model's input check raises
+        // "Input X contains infinity" in the reference whatever the column's pipeline is
+        const bool bad_value = (ab && pf.absent_pol == POL_ERROR) || (!ab && !mi && (bits == RAW_ERR || (bits & 0x7FFFFFFFu) == 0x7F800000u));
+        if (bad_value) atomicMin(err, ugvc_pack_error(rec, f, REASON_BAD_VALUE));
+        else if (mi && pf.missing_pol == POL_ERROR) atomicMin(err, ugvc_pack_error(rec, f, REASON_NULL_FEATURE));
     }
     return v;
 }
@@ -957,15 +956,15 @@ void launch_k2(const DevPlan& plan, const uint32_t* raw, size_t row_stride, cons
 #endif
 
 __device__ __forceinline__ double expit64(double x) { return 1.0 / (1.0 + exp(-x)); }
-// expf rounded once from the fp64 exponential.  The optimiser would shrink (float)exp((double)x) back to expf(x)
-// (a library-call simplification that is only valid for a correctly rounded expf); the empty asm hides the
-// argument's origin from it.
+// expf rounded once from the fp64 exponential.  The optimiser shrinks (float)exp((double)x) back to expf(x) (a
+// library-call simplification that is only valid for a correctly rounded expf: seen on the GPU as 1-ulp differences
+// in a sixth of the probabilities); the rounding therefore goes through the conversion intrinsic.
 __device__ __forceinline__ float k3_expf_cr(float x) {
-    double xd = (double)x;
 #ifdef __CUDA_ARCH__
-    asm volatile("" : "+d"(xd));
+    return __double2float_rn(exp((double)x));  // an intrinsic, not an fptrunc: the call is not shrunk
+#else
+    return (float)exp((double)x);
 #endif
-    return (float)exp(xd);
 }
 
 template <int CMP, int TPB>
@@ -1279,7 +1278,8 @@ __device__ __forceinline__ void walkh(const uint8_t* __restrict__ s_node, const 
             const float xv = *reinterpret_cast<const float*>(xcol + nd[j].y);
             const float th = __uint_as_float(nd[j].x);
             const bool left = (CMP == CMP_LE) ? (xv <= th) : (xv < th);
-            a8[j] = 2u * a8[j] + (unsigned)(left ? go_l[j] : go_l[j] + 8);
+            const unsigned l8 = 2u * a8[j] + (unsigned)go_l[j];  // off the critical path: ready before the compare
+            a8[j] = left ? l8 : l8 + 8u;
         }
     }
 #pragma unroll
@@ -1290,7 +1290,7 @@ __device__ __forceinline__ void walkh(const uint8_t* __restrict__ s_node, const 
 // completion on an mbarrier) while the current tile is walked, so no warp ever waits on HBM; every thread then turns
 // its own column of the landed slot words into feature values in place (K2's policies) -- a thread only ever reads
 // its own column, so the tile needs no barrier between assembly and walk.
-template <int TPB, int NBUF, int NCH>
+template <int TPB, int NBUF, int NCH, int GROUPS>
 __global__ void __launch_bounds__(TPB, 1)
 k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, const float* __restrict__ feats,
         size_t row_stride, const int64_t* __restrict__ n_records_p, double threshold, uint8_t* __restrict__ low_score,
@@ -1302,8 +1302,12 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
     const bool forest = plan.h.model_kind != MODEL_LOGISTIC;
     const int depth = (int)plan.heap_depth;
     const unsigned H = 1u << depth;
-    float* tile0 = reinterpret_cast<float*>(smem3);         // [NBUF][F][TPB]
-    uint2* s_node = reinterpret_cast<uint2*>(tile0 + (size_t)NBUF * F * TPB);  // [chunk_trees][H]: threshold, row offset
+    // GROUPS = 2: the CTA is two independent halves (own tile, own mbarrier, named barrier): while one half waits for
+    // its next tile the other one walks -- the forest in shared memory is paid for once
+    constexpr int GS = TPB / GROUPS;                        // threads = records of one group's tile
+    const int gid = GROUPS == 1 ? 0 : (int)threadIdx.x / GS, gtid = GROUPS == 1 ? (int)threadIdx.x : (int)threadIdx.x % GS;
+    float* tile0 = reinterpret_cast<float*>(smem3) + (size_t)gid * NBUF * F * GS;  // this group's [NBUF][F][GS]
+    uint2* s_node = reinterpret_cast<uint2*>(reinterpret_cast<float*>(smem3) + (size_t)GROUPS * NBUF * F * GS);  // [chunk_trees][H]
     PlanFeature* s_pf = reinterpret_cast<PlanFeature*>(s_node + (forest ? (size_t)chunk_trees * H : 0));  // [F]
     uint16_t* s_leaf = reinterpret_cast<uint16_t*>(s_pf + F);                                              // [chunk_trees][H]
     const bool resident = forest && n_trees <= chunk_trees;  // whole forest fits: stage once
@@ -1311,18 +1315,20 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
     if (resident) {
         const unsigned cnt = n_trees * H;
         for (unsigned i = threadIdx.x; i < cnt; i += TPB) {
-            s_node[i] = make_uint2(__float_as_uint(plan.heap_thr[i]), (unsigned)plan.heap_feat[i] * (unsigned)(TPB * sizeof(float)));
+            s_node[i] = make_uint2(__float_as_uint(plan.heap_thr[i]), (unsigned)plan.heap_feat[i] * (unsigned)(GS * sizeof(float)));
             s_leaf[i] = plan.heap_leaf[i];
         }
     }
     const long long n_rec = *n_records_p;
-    const long long n_tiles = (n_rec + TPB - 1) / TPB;
+    const long long n_tiles = (n_rec + GS - 1) / GS;
+    const long long tile_first = (long long)blockIdx.x * GROUPS + gid, tile_step = (long long)gridDim.x * GROUPS;
     unsigned n_low = 0, n_seen = 0;
 #ifndef UGVC_HOST_EMU
-    __shared__ __align__(8) unsigned long long k3_mbar[2];
+    __shared__ __align__(8) unsigned long long k3_mbar_all[4];
+    unsigned long long* k3_mbar = k3_mbar_all + 2 * gid;
     if (threadIdx.x == 0) {
-        for (int b = 0; b < NBUF; ++b) {
-            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&k3_mbar[b]);
+        for (int b = 0; b < 2 * GROUPS; ++b) {
+            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&k3_mbar_all[b]);
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1330,8 +1336,8 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
     __syncthreads();
     // rows [t * TPB, ...) of every feature's slot -> tile buffer b (thread 0)
     auto fetch = [&](long long t, int b) {
-        const size_t rec0 = (size_t)t * TPB;
-        const size_t rows = row_stride - rec0 < (size_t)TPB ? row_stride - rec0 : (size_t)TPB;  // rows are padded to 128 records
+        const size_t rec0 = (size_t)t * GS;
+        const size_t rows = row_stride - rec0 < (size_t)GS ? row_stride - rec0 : (size_t)GS;  // rows are padded to 128 records
         const uint32_t row_bytes = (uint32_t)rows * 4u;
         const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&k3_mbar[b]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1339,20 +1345,26 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
         for (int f = 0; f < F; ++f) {
             const void* src = raw ? static_cast<const void*>(raw + (size_t)s_pf[f].slot * row_stride + rec0)
                                   : static_cast<const void*>(feats + (size_t)f * row_stride + rec0);
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile0 + ((size_t)b * F + f) * TPB);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile0 + ((size_t)b * F + f) * GS);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(dst), "l"(src), "r"(row_bytes), "r"(mb)
                          : "memory");
         }
     };
     uint32_t phase0 = 0u, phase1 = 0u;
-    if (threadIdx.x == 0 && (long long)blockIdx.x < n_tiles) fetch(blockIdx.x, 0);
+    if (gtid == 0 && tile_first < n_tiles) fetch(tile_first, 0);
 #endif
     int buf = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const long long rec = t * TPB + threadIdx.x;
+    auto group_sync = [&]() {
+#ifndef UGVC_HOST_EMU
+        if (GROUPS == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(GS) : "memory");
+#endif
+    };
+    for (long long t = tile_first; t < n_tiles; t += tile_step) {
+        const long long rec = t * GS + gtid;
         const bool active = rec < n_rec;
-        float* tile = tile0 + (size_t)buf * F * TPB;
+        float* tile = tile0 + (size_t)buf * F * GS;
 #ifndef UGVC_HOST_EMU
         {
             const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&k3_mbar[buf]);
@@ -1365,7 +1377,7 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
             if (buf) phase1 ^= 1u;
             else phase0 ^= 1u;
             // the other buffer was released by the barrier that ended the previous tile: fetch the next tile into it
-            if (NBUF == 2 && threadIdx.x == 0 && t + gridDim.x < n_tiles) fetch(t + gridDim.x, buf ^ 1);
+            if (NBUF == 2 && gtid == 0 && t + tile_step < n_tiles) fetch(t + tile_step, buf ^ 1);
         }
 #endif
         if (raw) {
@@ -1377,13 +1389,13 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
 #ifdef UGVC_HOST_EMU
                 const uint32_t bits = active ? src[(size_t)pf.slot * row_stride] : 0u;
 #else
-                const uint32_t bits = __float_as_uint(tile[f * TPB + threadIdx.x]);
+                const uint32_t bits = __float_as_uint(tile[f * GS + gtid]);
 #endif
-                tile[f * TPB + threadIdx.x] = active ? k2_apply(bits, pf, rec, f, err) : 0.f;
+                tile[f * GS + gtid] = active ? k2_apply(bits, pf, rec, f, err) : 0.f;
             }
             for (unsigned c = 0; c < plan.h.n_combines; ++c) {  // feature = max(feature, slot_b), nulls skipped
                 const PlanCombine cb = plan.combines[c];
-                if (active) k2_combine_one(cb, __ldg(src + (size_t)cb.slot_b * row_stride), tile[cb.feature * TPB + threadIdx.x], rec, true, err);
+                if (active) k2_combine_one(cb, __ldg(src + (size_t)cb.slot_b * row_stride), tile[cb.feature * GS + gtid], rec, true, err);
             }
             for (unsigned c = 0; c < plan.h.n_checks; ++c) {
                 const PlanCheck ck = plan.checks[c];
@@ -1397,13 +1409,13 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
         } else {
 #ifdef UGVC_HOST_EMU
             const float* src = feats + rec;
-            for (int f = 0; f < F; ++f) tile[f * TPB + threadIdx.x] = active ? src[(size_t)f * row_stride] : 0.f;
+            for (int f = 0; f < F; ++f) tile[f * GS + gtid] = active ? src[(size_t)f * row_stride] : 0.f;
 #else
             if (!active)
-                for (int f = 0; f < F; ++f) tile[f * TPB + threadIdx.x] = 0.f;
+                for (int f = 0; f < F; ++f) tile[f * GS + gtid] = 0.f;
 #endif
         }
-        const float* x = tile + threadIdx.x;
+        const float* x = tile + gtid;
         double z[UGVC_MAX_CLASSES];   // fp64 accumulators (sklearn) ...
         float zf[UGVC_MAX_CLASSES];   // ... fp32 accumulators (xgboost)
 #pragma unroll
@@ -1422,7 +1434,7 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
                     const size_t off = (size_t)c0 * H;
                     for (unsigned i = threadIdx.x; i < cnt; i += TPB) {
                         s_node[i] = make_uint2(__float_as_uint(plan.heap_thr[off + i]),
-                                               (unsigned)plan.heap_feat[off + i] * (unsigned)(TPB * sizeof(float)));
+                                               (unsigned)plan.heap_feat[off + i] * (unsigned)(GS * sizeof(float)));
                         s_leaf[i] = plan.heap_leaf[off + i];
                     }
                     __syncthreads();
@@ -1476,13 +1488,13 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
             }
         }
         if (active) {
-            const bool low = k3_finish<TPB>(plan, x, z, zf, rec, threshold, low_score, probs, qual_out, phred_out, phred_mode);
+            const bool low = k3_finish<GS>(plan, x, z, zf, rec, threshold, low_score, probs, qual_out, phred_out, phred_mode);
             n_low += low ? 1u : 0u;
             n_seen += 1u;
         }
-        __syncthreads();  // every thread is done with this tile buffer
+        group_sync();  // every thread of the group is done with this tile buffer
 #ifndef UGVC_HOST_EMU
-        if (NBUF == 1 && threadIdx.x == 0 && t + gridDim.x < n_tiles) fetch(t + gridDim.x, 0);
+        if (NBUF == 1 && gtid == 0 && t + tile_step < n_tiles) fetch(t + tile_step, 0);
 #endif
         buf ^= (NBUF == 2) ? 1 : 0;
     }
@@ -1500,29 +1512,29 @@ k3_heap(const __grid_constant__ DevPlan plan, const uint32_t* __restrict__ raw, 
 
 // shared-memory plan of k3_heap: records per CTA, tile buffers, trees per staged chunk
 static size_t k3h_tree_bytes(const DevPlan& plan) { return (size_t)(1u << plan.heap_depth) * 10u; }  // 8-byte nodes + leaf rows
-static size_t k3h_fixed_bytes(const DevPlan& plan, int tpb, int nbuf) {
-    return (size_t)nbuf * plan.h.n_features * tpb * sizeof(float) + (size_t)plan.h.n_features * sizeof(PlanFeature) + 64;
-}
 struct K3hShape {
-    int tpb, nbuf;
+    int tpb, nbuf, groups;
 };
+static size_t k3h_tile_bytes(const DevPlan& plan, K3hShape c) {  // all tile buffers of the CTA + the policy table
+    return (size_t)c.nbuf * plan.h.n_features * c.tpb * sizeof(float) + (size_t)plan.h.n_features * sizeof(PlanFeature) + 64;
+}
 static K3hShape k3h_shape(const DevPlan& plan) {
-    static const int force = getenv("UGVC_K3_TPB") ? atoi(getenv("UGVC_K3_TPB")) : 0;    // profiling knobs
-    static const int force_buf = getenv("UGVC_K3_NBUF") ? atoi(getenv("UGVC_K3_NBUF")) : 0;
+    static const int force = getenv("UGVC_K3_SHAPE") ? atoi(getenv("UGVC_K3_SHAPE")) : -1;  // profiling knob: index below
     const bool forest = plan.h.model_kind != MODEL_LOGISTIC;
     const size_t all = forest ? (size_t)plan.h.n_trees * k3h_tree_bytes(plan) : 0;
-    const K3hShape cand[6] = {{256, 2}, {192, 2}, {128, 2}, {512, 1}, {256, 1}, {128, 1}};
-    for (const K3hShape& c : cand) {
-        if ((force && c.tpb != force) || (force_buf && c.nbuf != force_buf)) continue;
-        if (k3h_fixed_bytes(plan, c.tpb, c.nbuf) + all <= K3_SMEM_BUDGET) return c;
+    // two half-CTAs with one tile each first (most warps for the shared memory), then double-buffered single groups
+    const K3hShape cand[7] = {{512, 1, 2}, {384, 1, 2}, {256, 2, 1}, {192, 2, 1}, {128, 2, 1}, {256, 1, 1}, {128, 1, 1}};
+    for (int i = 0; i < 7; ++i) {
+        if (force >= 0 && i != force) continue;
+        if (k3h_tile_bytes(plan, cand[i]) + all <= K3_SMEM_BUDGET) return cand[i];
     }
-    for (const K3hShape& c : cand)  // the forest is staged in chunks: at least 16 trees at a time
-        if (k3h_fixed_bytes(plan, c.tpb, c.nbuf) + 16 * k3h_tree_bytes(plan) <= K3_SMEM_BUDGET) return c;
-    return K3hShape{0, 0};
+    for (int i = 2; i < 7; ++i)  // the forest is staged in chunks (single group: the chunks need whole-CTA barriers)
+        if (k3h_tile_bytes(plan, cand[i]) + 16 * k3h_tree_bytes(plan) <= K3_SMEM_BUDGET) return cand[i];
+    return K3hShape{0, 0, 0};
 }
 static unsigned k3h_chunk_trees(const DevPlan& plan, K3hShape sh) {
     if (plan.h.model_kind == MODEL_LOGISTIC) return 0;
-    const size_t room = K3_SMEM_BUDGET - k3h_fixed_bytes(plan, sh.tpb, sh.nbuf);
+    const size_t room = K3_SMEM_BUDGET - k3h_tile_bytes(plan, sh);
     size_t n = room / k3h_tree_bytes(plan);
     if (n > plan.h.n_trees) n = plan.h.n_trees;
     if (n < plan.h.n_trees) n &= ~(size_t)15;  // whole groups of chains
@@ -1540,20 +1552,21 @@ void launch_k3_fused(const DevPlan& plan, const uint32_t* raw, const float* feat
                      cudaStream_t st) {
     const K3hShape sh = k3h_shape(plan);
     const unsigned chunk = k3h_chunk_trees(plan, sh);
-    const size_t smem = k3h_fixed_bytes(plan, sh.tpb, sh.nbuf) + (size_t)chunk * k3h_tree_bytes(plan);
+    const size_t smem = k3h_tile_bytes(plan, sh) + (size_t)chunk * k3h_tree_bytes(plan);
     int per_sm = (int)((227u * 1024u) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
     if (per_sm * sh.tpb > 1536) per_sm = 1536 / sh.tpb;
     // few threads per SM (the tiles are large): sixteen trees per thread in flight make up for it
-#define K3H_LAUNCH(T, B, C)                                                                                                  \
-    k3_heap<T, B, C><<<sm_count * per_sm, T, smem, st>>>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, \
-                                                         qual, phreds, d_counts, chunk, phred_mode, d_err)
-    if (sh.tpb == 512) K3H_LAUNCH(512, 1, 8);
-    else if (sh.tpb == 256 && sh.nbuf == 2) K3H_LAUNCH(256, 2, 16);
-    else if (sh.tpb == 256) K3H_LAUNCH(256, 1, 8);
-    else if (sh.tpb == 192) K3H_LAUNCH(192, 2, 16);
-    else if (sh.nbuf == 2) K3H_LAUNCH(128, 2, 16);
-    else K3H_LAUNCH(128, 1, 8);
+#define K3H_LAUNCH(T, B, C, G)                                                                                                  \
+    k3_heap<T, B, C, G><<<sm_count * per_sm, T, smem, st>>>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, \
+                                                            qual, phreds, d_counts, chunk, phred_mode, d_err)
+    if (sh.groups == 2 && sh.tpb == 512) K3H_LAUNCH(512, 1, 8, 2);
+    else if (sh.groups == 2) K3H_LAUNCH(384, 1, 16, 2);
+    else if (sh.tpb == 256 && sh.nbuf == 2) K3H_LAUNCH(256, 2, 16, 1);
+    else if (sh.tpb == 192) K3H_LAUNCH(192, 2, 16, 1);
+    else if (sh.tpb == 256) K3H_LAUNCH(256, 1, 8, 1);
+    else if (sh.nbuf == 2) K3H_LAUNCH(128, 2, 16, 1);
+    else K3H_LAUNCH(128, 1, 8, 1);
 #undef K3H_LAUNCH
 }
 #endif
@@ -1620,18 +1633,16 @@ cudaError_t kernels_configure(const DevPlan& plan) {
     e = cudaFuncSetAttribute(k1_parse_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(plan));
     if (e != cudaSuccess) return e;
 #endif
-    e = cudaFuncSetAttribute(k3_heap<512, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<256, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<256, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<128, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<192, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k3_heap<128, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));  // 16 bytes are static
-    if (e != cudaSuccess) return e;
+    {
+        const int lim = 226 * 1024;  // a few static bytes (the mbarrier words) come on top of the dynamic part
+        if ((e = cudaFuncSetAttribute(k3_heap<512, 1, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k3_heap<384, 1, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k3_heap<256, 2, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k3_heap<192, 2, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k3_heap<256, 1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k3_heap<128, 2, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k3_heap<128, 1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
+    }
     e = cudaFuncSetAttribute(k3_infer<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k3_infer<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));

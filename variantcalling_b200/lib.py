@@ -14,6 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("UGVC_LIB_PATH") or os.path.join(_HERE, "libugvc_b200.so")  # env: profiling builds
 
 UGVC_OK, UGVC_E_CUDA, UGVC_E_ARG, UGVC_E_PLAN, UGVC_E_DATA, UGVC_E_IO, UGVC_E_STATE = 0, -1, -2, -3, -4, -5, -6
+UGVC_E_FALLBACK = -7  # ugvc_filter_bgzf: a record needs the general host writer
+FILE_OVERWRITE_QUAL, FILE_BLACKLIST_CG = 1, 2
+DEF_CHUNK = 57344     # uncompressed bytes per BGZF block written by the device encoder
 
 
 class UgvcError(RuntimeError):
@@ -93,6 +96,9 @@ SIGNATURES = {
     "ugvc_conc_run": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "ugvc_conc_curve": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz]),
     "ugvc_test_deflate_block": (C.c_int64, [_vp, C.c_uint32, _vp]),
+    "ugvc_filter_bgzf": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_uint32, C.c_uint64, C.c_double, C.c_int, _vp, _sz, C.POINTER(_sz),
+                                   _vp, _sz, C.POINTER(_sz), _vp, _vp, _vp, _sz, C.POINTER(C.c_int64)]),
+    "ugvc_filter_bgzf_stage_ms": (C.c_int, [_vp, C.c_int, _vp]),
     "ugvc_test_parse_float": (C.c_int, [C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_double),
                                         C.POINTER(C.c_int)]),
 }
@@ -286,6 +292,34 @@ class Context:
 
     def device_status(self, stream: int = 0, lane: int = 0):
         self._check(self.lib.ugvc_device_status_lane(self.h, lane, stream or None))
+
+    # ---- file to file on the device
+    def filter_bgzf(self, bgzf: np.ndarray, skip_head: int, take_bytes: int, threshold: float, flags: int, max_records: int,
+                    lane: int = 0) -> dict | None:
+        """One range of whole lines: compressed blocks in, filtered + scored + edited records out as BGZF blocks
+        (see ugvc_filter_bgzf).  Returns None when the range needs the general host writer."""
+        comp = np.ascontiguousarray(bgzf, dtype=np.uint8)
+        n_text_max = (take_bytes or comp.size * 64) + max_records * 64 + 65536
+        out = np.empty(n_text_max // DEF_CHUNK * 65536 + 65536 if take_bytes else comp.size * 8 + (1 << 20), dtype=np.uint8)
+        blocks = np.empty(out.size // 65536 + 8, dtype=np.uint32)
+        ri = np.empty(max_records, dtype=RECINFO_DTYPE)
+        ls = np.empty(max_records + 1, dtype=np.int64)
+        low = np.empty(max_records, dtype=np.uint8)
+        nb, nblk, n = C.c_size_t(), C.c_size_t(), C.c_int64()
+        rc = self.lib.ugvc_filter_bgzf(self.h, lane, _ptr(comp), comp.size, skip_head, take_bytes, threshold, flags, _ptr(out),
+                                       out.size, C.byref(nb), _ptr(blocks), blocks.size, C.byref(nblk), _ptr(ri), _ptr(ls),
+                                       _ptr(low), max_records, C.byref(n))
+        if rc == UGVC_E_FALLBACK:
+            return None
+        self._check(rc)
+        k = n.value
+        return {"n_records": k, "bgzf": out[: nb.value], "block_csize": blocks[: nblk.value], "recinfo": ri[:k],
+                "line_start": ls[: k + 1], "low_score": low[:k]}
+
+    def filter_bgzf_stage_ms(self, lane: int = 0) -> list[float]:
+        ms = (C.c_float * 5)()
+        self._check(self.lib.ugvc_filter_bgzf_stage_ms(self.h, lane, C.cast(ms, C.c_void_p)))
+        return list(ms)
 
     # ---- the one collective of the path, through the C ABI (NCCL bound at run time)
     @staticmethod
