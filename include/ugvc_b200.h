@@ -221,6 +221,11 @@ int64_t ugvc_synth_header(int n_custom, char* out, size_t capacity);
 int ugvc_bgzf_inflate_file(const char* path, uint64_t voff_begin, uint64_t voff_end, uint8_t* out,
                            size_t capacity, size_t* out_bytes, int n_threads);
 int64_t ugvc_bgzf_uncompressed_size(const char* path);
+/* The blocks that hold the virtual-offset range [voff_begin, voff_end) of a BGZF file: their compressed byte range
+ * [c_begin, c_end), the bytes of the first block before the range and the range's uncompressed length -- the
+ * arguments of ugvc_filter_bgzf for one contig of a tabix-indexed call set. */
+int ugvc_bgzf_range_info(const char* path, uint64_t voff_begin, uint64_t voff_end, uint64_t* c_begin, uint64_t* c_end,
+                         uint32_t* skip_head, uint64_t* take_bytes);
 /* Append `n_bytes` as BGZF blocks to `path` (mode 'w' truncates, 'a' appends;
  * write_eof != 0 adds the 28-byte EOF block).  Every block but the last holds
  * 0xff00 bytes of input; out_block_csize (may be NULL) receives the compressed

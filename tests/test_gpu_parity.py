@@ -84,6 +84,13 @@ def test_xgboost_json_model_path(gpu_ctx, ds, n_class):
     res = gpu_ctx.filter_batch(ds["text"], 30.0)
     want = XP.predict_proba(doc, ds["x"].astype(np.float32))
     bad = np.argwhere(res["probs"] != want)
+    if bad.size:  # diagnostics: are the features the same, and what does the restatement give on the device's features?
+        feats = gpu_ctx.debug_features(res["n_records"]).T
+        same_feats = bool(np.array_equal(feats, ds["x"].astype(np.float32)))
+        again = XP.predict_proba(doc, feats)
+        print(f"features identical: {same_feats}; restatement on device features == device probs: "
+              f"{bool(np.array_equal(again, res['probs']))}; margins (logit of p1) device vs oracle at the first bad rows: "
+              f"{[(float(np.log(res['probs'][b[0], 1] / res['probs'][b[0], 0])), float(np.log(want[b[0], 1] / want[b[0], 0]))) for b in bad[:3]]}")
     assert bad.size == 0, (  # bit for bit
         f"fp32 probabilities differ from the xgboost restatement at {len(bad)} places, first {bad[:4].tolist()}: "
         f"{[(res['probs'][tuple(b)].view(np.uint32), want[tuple(b)].view(np.uint32)) for b in bad[:4]]}")

@@ -62,6 +62,26 @@ def inflate(path: str, voff_begin: int = 0, voff_end: int = 0, capacity: int | N
     return out[: n.value]
 
 
+def range_info(path: str, voff_begin: int, voff_end: int) -> tuple[int, int, int, int]:
+    """(c_begin, c_end, skip_head, take_bytes) of the blocks holding a virtual-offset range (ugvc_bgzf_range_info)."""
+    c0, c1, skip, take = C.c_uint64(), C.c_uint64(), C.c_uint32(), C.c_uint64()
+    rc = _lib.load_library().ugvc_bgzf_range_info(path.encode(), voff_begin, voff_end, C.byref(c0), C.byref(c1), C.byref(skip),
+                                                  C.byref(take))
+    _check(rc, f"range of {path}")
+    return int(c0.value), int(c1.value), int(skip.value), int(take.value)
+
+
+def first_block_text(comp: np.ndarray, skip_head: int) -> bytes:
+    """The uncompressed bytes of the first BGZF block of `comp` from skip_head on (a sample of the records that follow)."""
+    import struct
+    import zlib
+
+    raw = memoryview(comp)
+    xlen = struct.unpack_from("<H", raw, 10)[0]
+    bsize = struct.unpack_from("<H", raw, 16)[0] + 1
+    return zlib.decompress(bytes(raw[12 + xlen: bsize - 8]), -15)[skip_head:]
+
+
 # the empty BGZF block that ends a file (SAM spec 4.1.2)
 BGZF_EOF = bytes([0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0,
                   0, 0, 0, 0, 0, 0, 0, 0])
@@ -135,6 +155,20 @@ class BgzfWriter:
             self.block_u.append(u_start)
         self.coffset += int(total.value)
         self.uoffset += int(buf.size)
+
+    def write_compressed(self, blocks: np.ndarray, block_csize: np.ndarray, n_uncompressed: int, chunk: int):
+        """Append BGZF blocks compressed elsewhere (the device encoder: `chunk` uncompressed bytes per block, the last
+        one shorter) and keep the offset map the index needs."""
+        with open(self.path, "ab" if self._started else "wb") as fh:
+            fh.write(memoryview(np.ascontiguousarray(blocks)))
+        self._started = True
+        n_blocks = int(block_csize.size)
+        if n_blocks:
+            cs = block_csize.astype(np.int64)
+            self.block_c.append(self.coffset + np.concatenate(([0], np.cumsum(cs)[:-1])))
+            self.block_u.append(self.uoffset + np.arange(n_blocks, dtype=np.int64) * chunk)
+            self.coffset += int(cs.sum())
+        self.uoffset += int(n_uncompressed)
 
     def close(self):
         if not self._started:

@@ -113,6 +113,42 @@ extern "C" int64_t ugvc_bgzf_uncompressed_size(const char* path) {
     return blocks.empty() ? 0 : (int64_t)(blocks.back().uoff + blocks.back().isize);
 }
 
+// The compressed byte range [c_begin, c_end) of the blocks that hold the virtual-offset range, the bytes of the first
+// block before it and its uncompressed length: what ugvc_filter_bgzf wants to know about a contig of an indexed file.
+extern "C" int ugvc_bgzf_range_info(const char* path, uint64_t voff_begin, uint64_t voff_end, uint64_t* c_begin, uint64_t* c_end,
+                                    uint32_t* skip_head, uint64_t* take_bytes) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return UGVC_E_IO;
+    fseeko(f, 0, SEEK_END);
+    const uint64_t fs = (uint64_t)ftello(f);
+    const uint64_t cb = voff_begin >> 16, ub = voff_begin & 0xffff;
+    const bool to_eof = (voff_end == 0 || voff_end == ~0ull);
+    const uint64_t ce = to_eof ? fs : (voff_end >> 16), ue = to_eof ? 0 : (voff_end & 0xffff);
+    std::vector<Block> blocks;
+    const int rc = scan_blocks(f, fs, cb, ue ? ce + 1 : ce, blocks);
+    fclose(f);
+    if (rc) return rc;
+    while (!blocks.empty() && blocks.back().isize == 0) blocks.pop_back();  // the EOF block carries nothing
+    if (blocks.empty()) {
+        *c_begin = *c_end = cb;
+        *skip_head = 0;
+        *take_bytes = 0;
+        return UGVC_OK;
+    }
+    const uint64_t total_u = blocks.back().uoff + blocks.back().isize;
+    uint64_t last_cut = 0;
+    if (ue && blocks.back().coff == ce) {
+        if (ue > blocks.back().isize) return UGVC_E_IO;
+        last_cut = blocks.back().isize - ue;
+    }
+    if (ub > blocks.front().isize || ub + last_cut > total_u) return UGVC_E_IO;
+    *c_begin = blocks.front().coff;
+    *c_end = blocks.back().coff + blocks.back().csize;
+    *skip_head = (uint32_t)ub;
+    *take_bytes = total_u - ub - last_cut;
+    return UGVC_OK;
+}
+
 extern "C" int ugvc_bgzf_inflate_file(const char* path, uint64_t voff_begin, uint64_t voff_end, uint8_t* out,
                                       size_t capacity, size_t* out_bytes, int n_threads) {
     FILE* f = fopen(path, "rb");

@@ -69,6 +69,8 @@ def parse_args(argv: list[str]) -> argparse.Namespace:
                         default=None)
     # B200 host knobs (not in the reference; defaults need no tuning)
     ap_var.add_argument("--device", help="CUDA device index (default: LOCAL_RANK or 0)", type=int, default=None)
+    ap_var.add_argument("--host_io", help="Inflate, edit and deflate the records on host threads even when the device-side "
+                        "file path applies", action="store_true")
     ap_var.add_argument("--batch_mb", help="VCF text per GPU batch, MiB", type=int, default=256)
     ap_var.add_argument("--io_threads", help="Host threads for BGZF inflate/deflate/splice (0 = all)", type=int,
                         default=0)
@@ -158,11 +160,25 @@ class _Splicer:
         self._check_writer()
         self._queue.put((contig, out[:nb], n, beg, beg + np.maximum(1, (ri["flags"] >> 8).astype(np.int64)), out_ls))
 
-    def _write_spliced(self, contig: str, data: np.ndarray, n: int, beg: np.ndarray, end: np.ndarray, out_ls: np.ndarray):
+    def write_device_batch(self, contig: str, res: dict):
+        """Records edited and BGZF-compressed on the device (lib.Context.filter_bgzf): only file and index work is left."""
+        n = res["n_records"]
+        if n == 0:
+            return
+        ri = res["recinfo"]
+        beg = ri["pos"].astype(np.int64) - 1
+        self._check_writer()
+        self._queue.put((contig, (res["bgzf"], res["block_csize"]), n, beg,
+                         beg + np.maximum(1, (ri["flags"] >> 8).astype(np.int64)), res["line_start"]))
+
+    def _write_spliced(self, contig: str, data, n: int, beg: np.ndarray, end: np.ndarray, out_ls: np.ndarray):
         t0 = time.perf_counter()
         base = self.writer.uoffset
         c_before = self.writer.coffset
-        self.writer.write(data)
+        if isinstance(data, tuple):  # compressed on the device
+            self.writer.write_compressed(data[0], data[1], int(out_ls[-1]), lib.DEF_CHUNK)
+        else:
+            self.writer.write(data)
         self.ranges[contig] = (self.ranges.get(contig, (c_before, 0))[0], self.writer.coffset)
         if not self.names or self.names[-1] != contig:
             self.names.append(contig)
@@ -400,11 +416,23 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             contigs = [c for c in contigs if c in mine or (c not in index and rank == 0)]
             logger.info(f"rank {rank}/{world}: {len(contigs)} of {len(all_contigs)} contigs")
 
-        def load_contig(contig: str):
-            """Inflate one contig's records (runs one contig ahead of the loop, on its own thread)."""
+        # compressed bytes both ways: the contig's BGZF blocks go to the device as they are, come back filtered, edited
+        # and compressed again (ugvc_filter_bgzf); what that path does not cover keeps the host readers / writers
+        device_io = bool(with_model and not split_sites and not recal and blacklists is None and not args.host_io)
+        file_flags = (lib.FILE_OVERWRITE_QUAL if args.overwrite_qual_tag else 0) | \
+                     (lib.FILE_BLACKLIST_CG if args.blacklist_cg_insertions else 0)
+
+        def load_contig(contig: str, on_device: bool = False):
+            """Inflate one contig's records (runs one contig ahead of the loop, on its own thread) -- or, for the
+            device-side file path, just read its compressed blocks."""
             if contig not in index:
                 return None
             vb, ve = index[contig]
+            if on_device:
+                c0, c1, skip, take = bgzf_io.range_info(args.input_file, vb, ve)
+                if take == 0:
+                    return None
+                return "device", np.fromfile(args.input_file, dtype=np.uint8, count=c1 - c0, offset=c0), skip, take
             text = bgzf_io.inflate(args.input_file, vb, ve, n_threads=args.io_threads)
             if text.size == 0:
                 return None
@@ -413,16 +441,47 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             return text, bgzf_io.count_lines(text, args.io_threads)
 
         prefetch = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-bgzf-reader")
-        pending = prefetch.submit(load_contig, contigs[0]) if contigs else None
+        pending = prefetch.submit(load_contig, contigs[0], device_io) if contigs else None
         for ci, contig in enumerate(contigs):
             logger.info(f"Filtering variants from {contig}")
             t_wait = time.perf_counter()
             loaded = pending.result()
             seconds["inflate_wait"] += time.perf_counter() - t_wait
-            pending = prefetch.submit(load_contig, contigs[ci + 1]) if ci + 1 < len(contigs) else None
+            pending = prefetch.submit(load_contig, contigs[ci + 1], device_io) if ci + 1 < len(contigs) else None
             if loaded is None:
                 logger.info(f"No variants found on {contig}")
                 continue
+            if isinstance(loaded[0], str):  # ("device", compressed blocks, skip, take)
+                _tag, comp, skip, take = loaded
+                if args.blacklist_cg_insertions:
+                    logger.info("Marking CG insertions")
+                if not key_order_set:
+                    head = bgzf_io.first_block_text(comp, skip)
+                    ctx.set_key_order(*lib.learn_key_order(head[: head.rfind(b"\n") + 1]))
+                    key_order_set = True
+                need = (take + 4096, take // 32 + 1024)
+                if need[0] > reserved[0] or need[1] > reserved[1]:
+                    reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))
+                    ctx.reserve(reserved[0], reserved[1], n_lanes)
+                t_gpu = time.perf_counter()
+                res = ctx.filter_bgzf(comp, skip, take, args.decision_threshold, file_flags, reserved[1])
+                seconds["gpu"] += time.perf_counter() - t_gpu
+                if res is not None:
+                    logger.info(f"{res['n_records']} variants found on {contig}")
+                    logger.info("Writing records")
+                    out.write_device_batch(contig, res)
+                    totals["n_records"] += res["n_records"]
+                    totals["n_low_score"] += int(res["low_score"].sum())
+                    if args.blacklist_cg_insertions:
+                        n_cg = int(np.count_nonzero(res["recinfo"]["flags"] & 1))
+                        totals["n_cg"] += n_cg
+                        totals["n_blacklisted"] += n_cg
+                    logger.info(f"{contig} done")
+                    continue
+                logger.info(f"{contig}: records that need the general writer, taking the host path")
+                loaded = load_contig(contig)
+                if loaded is None:
+                    continue
             text, n_contig = loaded
             logger.info(f"{n_contig} variants found on {contig}")
             if blacklists is not None:
