@@ -114,6 +114,18 @@ def contig_record_ranges(total: int):
     return out
 
 
+def range_partition(ranges, world: int):
+    """Equal record ranges in genome order: rank r owns records [r N / W, (r + 1) N / W), cut into (contig, first, last)
+    pieces at the contig borders (a piece never spans contigs: a batch is lines of one contig, as in the tool).  Whole
+    contigs by LPT left rank 0 three per cent above the mean at eight ranks; ranges are exact."""
+    total = ranges[-1][2]
+    bins = []
+    for r in range(world):
+        lo, hi = total * r // world, total * (r + 1) // world
+        bins.append([(c, max(r0, lo), min(r1, hi)) for c, r0, r1 in ranges if min(r1, hi) > max(r0, lo)])
+    return bins
+
+
 def lpt_partition(ranges, world: int):
     """Longest-processing-time bin packing of contigs onto ranks."""
     bins = [[] for _ in range(world)]
@@ -316,6 +328,9 @@ def main():  # noqa: C901, PLR0912, PLR0915
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the hot path)")
+    from variantcalling_b200 import dist as vdist
+
+    numa = vdist.bind_to_gpu_numa_node(local_rank) if world > 1 else {"gpu": local_rank, "node": None, "cpus": None}
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -337,7 +352,7 @@ def main():  # noqa: C901, PLR0912, PLR0915
 
     # ---- this rank's records: contigs by LPT, generated straight into HBM in batches
     ranges = contig_record_ranges(args.records)
-    mine = lpt_partition(ranges, world)[rank]
+    mine = range_partition(ranges, world)[rank]
     n_mine = sum(r1 - r0 for _, r0, r1 in mine)
     B = min(args.batch_records, max(1, n_mine))
     bytes_guess = int(n_mine * 470 * 1.05) + (64 << 20)
@@ -651,9 +666,10 @@ def main():  # noqa: C901, PLR0912, PLR0915
             "config": {"workload": "cfg3: synthetic WGS VCF, 81 features, 100x depth-6 tree ensemble "
                                    "(sklearn GradientBoosting, reference XGB hyper-parameters)",
                        "records_total": args.records, "records_rank0": n_mine, "batch_records": B,
-                       "mean_line_bytes": total_bytes / max(1, n_mine), "sharding": "contig LPT",
+                       "mean_line_bytes": total_bytes / max(1, n_mine),
+                       "sharding": "equal record ranges in genome order, pieces cut at contig borders",
                        "l2": "inputs larger than L2 (no flush needed)", "threshold": 30.0,
-                       "k1_slow_records_last_batch": slow_last},
+                       "k1_slow_records_last_batch": slow_last, "numa_binding": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity,
             **({"e2e_bgzf": e2e_bgzf} if e2e_bgzf is not None else {}),

@@ -309,12 +309,21 @@ int ugvc_conc_run(ugvc_conc* h, int64_t n, const double* scores, const uint8_t* 
                   const uint8_t* indel, const int32_t* hmer_len, const int8_t* group, int inputs_on_device,
                   int want_curves, int64_t* out_counts, int64_t* out_curve_len, double* out_cutoff,
                   int64_t* out_selected);
+/* The per-record rules that produce the `classify` / `classify_gt` columns the metrics consume (vcf2concordance,
+ * ugbio_comparison/comparison_utils.py:153-229): gt_ultima / gt_truth hold two int8 per record (allele index, -1 for
+ * None, -2 when the genotype tuple has a single element), base_fn (may be NULL) is 1 where vcfeval's BASE is FN or
+ * FN_CA.  Outputs: 0 = tp, 1 = fp, 2 = fn. */
+int ugvc_conc_classify(ugvc_conc* h, int64_t n, const int8_t* gt_ultima, const int8_t* gt_truth, const uint8_t* base_fn,
+                       uint8_t* out_classify, uint8_t* out_classify_gt);
 int ugvc_conc_curve(ugvc_conc* h, int group, double* precision, double* recall, double* thresholds,
                     size_t capacity);
 
 /* ---- test hook ------------------------------------------------------------ */
 /* K1's numeric-literal parser (csrc/numparse.h) compiled for the host: parses one token of
  * `text` (NUL-terminated); returns 0 ok / 1 missing (".") / 2 not exactly parseable. */
+/* Test hook: K3's xgboost-flavoured fp32 sigmoid evaluated on the device for an array of margins (p1 and the
+ * exponential it used). */
+int ugvc_test_device_sigmoid(ugvc_ctx* ctx, const float* margins, int n, float* out_p1, float* out_e);
 int ugvc_test_parse_float(const char* text, float* out_f32, double* out_f64, int* out_consumed);
 /* Test hook: the device BGZF encoder (csrc/deflate.cuh) run on the host on one block of at most 57344 bytes (4 readable
  * bytes after n); out receives a complete BGZF block (<= 65536 bytes), the size is returned. */

@@ -18,4 +18,5 @@ extern "C" const char* ugvc_conc_last_error(const ugvc_conc*) { return NOT_EMULA
 extern "C" long long ugvc_conc_launch_count(const ugvc_conc*) { return 0; }
 extern "C" int ugvc_conc_run(ugvc_conc*, int64_t, const double*, const uint8_t*, const uint8_t*, const uint8_t*, const int32_t*,
                              const int8_t*, int, int, int64_t*, int64_t*, double*, int64_t*) { return UGVC_E_CUDA; }
+extern "C" int ugvc_conc_classify(ugvc_conc*, int64_t, const int8_t*, const int8_t*, const uint8_t*, uint8_t*, uint8_t*) { return UGVC_E_CUDA; }
 extern "C" int ugvc_conc_curve(ugvc_conc*, int, double*, double*, double*, size_t) { return UGVC_E_CUDA; }

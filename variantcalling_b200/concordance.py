@@ -122,6 +122,30 @@ class ConcordanceContext:
             raise lib.UgvcError(rc, self.lib.ugvc_conc_last_error(self.h).decode())
         return {"counts": counts, "curve_len": curve_len, "cutoff": cutoff, "selected": selected}
 
+    def classify(self, gt_ultima, gt_truth, base=None) -> tuple[np.ndarray, np.ndarray]:
+        """The `classify` / `classify_gt` columns of vcf2concordance (comparison_utils.py:153-229) for genotype tuples
+        (None alleles allowed, one or two alleles) and vcfeval's BASE column; string arrays "tp" / "fp" / "fn"."""
+        n = len(gt_ultima)
+
+        def pack(gts):
+            out = np.full((n, 2), -2, dtype=np.int8)
+            for i, g in enumerate(gts):
+                g = tuple(g)
+                if len(g) > 2:  # noqa: PLR2004
+                    raise ValueError("genotypes of more than two alleles are not lowered")
+                for k, a in enumerate(g):
+                    out[i, k] = -1 if a is None else int(a)
+            return np.ascontiguousarray(out)
+
+        gu, gt = pack(gt_ultima), pack(gt_truth)
+        bfn = None if base is None else np.ascontiguousarray(np.isin(np.asarray(base, dtype=object), ["FN", "FN_CA"]).astype(np.uint8))
+        c, g = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint8)
+        rc = self.lib.ugvc_conc_classify(self.h, n, lib._ptr(gu), lib._ptr(gt), lib._ptr(bfn), lib._ptr(c), lib._ptr(g))  # noqa: SLF001
+        if rc:
+            raise lib.UgvcError(rc, self.lib.ugvc_conc_last_error(self.h).decode())
+        names = np.array(["tp", "fp", "fn"], dtype=object)
+        return names[c], names[g]
+
     def curve(self, g: int, n: int):
         """Raw curve of group g: (precision, recall, thresholds), increasing thresholds."""
         out = [np.empty(max(1, n), dtype=np.float64) for _ in range(3)]

@@ -1475,6 +1475,29 @@ extern "C" int64_t ugvc_debug_slow_records(ugvc_ctx* ctx, int lane) {
     return ctx->fast.enabled ? (int64_t)w[1] : -1;
 }
 
+#ifndef UGVC_HOST_EMU
+void launch_test_sigmoid(const float* d_m, int n, float* d_p1, float* d_e, cudaStream_t st);
+extern "C" int ugvc_test_device_sigmoid(ugvc_ctx* ctx, const float* margins, int n, float* out_p1, float* out_e) {
+    // test hook: K3's fp32 sigmoid (xgboost flavour) on the device, for comparison with the restatement
+    if (!ctx || !margins || !out_p1 || !out_e || n <= 0) return UGVC_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    float *d_m = nullptr, *d_p = nullptr, *d_e = nullptr;
+    CU(cudaMalloc(&d_m, n * sizeof(float)));
+    CU(cudaMalloc(&d_p, n * sizeof(float)));
+    CU(cudaMalloc(&d_e, n * sizeof(float)));
+    CU(cudaMemcpy(d_m, margins, n * sizeof(float), cudaMemcpyHostToDevice));
+    launch_test_sigmoid(d_m, n, d_p, d_e, nullptr);
+    CU(cudaMemcpy(out_p1, d_p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_e, d_e, n * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d_m);
+    cudaFree(d_p);
+    cudaFree(d_e);
+    return UGVC_OK;
+}
+#else
+extern "C" int ugvc_test_device_sigmoid(ugvc_ctx*, const float*, int, float*, float*) { return UGVC_E_CUDA; }
+#endif
+
 extern "C" int64_t ugvc_launch_count(const ugvc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int ugvc_enable_stage_timing(ugvc_ctx* ctx, int on) {

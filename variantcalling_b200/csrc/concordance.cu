@@ -362,3 +362,76 @@ extern "C" int ugvc_conc_curve(ugvc_conc* h, int group, double* precision, doubl
         if (dst[a]) CCU(cudaMemcpy(dst[a], h->curve[group][a], (size_t)d * sizeof(double), cudaMemcpyDeviceToHost));
     return UGVC_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// per-record classification of a comparison frame (vcf2concordance, comparison_utils.py:153-229)
+// ------------------------------------------------------------------------------------------
+// Genotypes arrive as two int8 per record: allele index, -1 for None, -2 when the tuple has one element.
+// classify (allele match): :153-182; classify_gt (allele + genotype match): :186-213; fix-ups :214-229.
+__device__ __forceinline__ bool conc_gt_none(int a, int b) { return a == -1 && (b == -1 || b == -2); }
+__global__ void __launch_bounds__(CONC_TPB) conc_classify_gt(int64_t n, const int8_t* __restrict__ gu, const int8_t* __restrict__ gt,
+                                                             const uint8_t* __restrict__ base_fn, uint8_t* __restrict__ cls,
+                                                             uint8_t* __restrict__ cls_gt) {
+    enum { TP = 0, FP = 1, FN = 2 };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int u0 = gu[2 * i], u1 = gu[2 * i + 1], t0 = gt[2 * i], t1 = gt[2 * i + 1];
+        int c, g;
+        if (conc_gt_none(u0, u1)) {
+            c = g = FN;
+        } else if (conc_gt_none(t0, t1)) {
+            c = g = FP;
+        } else {
+            // sets of non-reference alleles (None is an element like any other)
+            const bool u0_in = u0 != 0, u1_in = u1 != 0 && u1 != -2, t0_in = t0 != 0, t1_in = t1 != 0 && t1 != -2;
+            const bool u0_hit = u0_in && ((t0_in && u0 == t0) || (t1_in && u0 == t1));
+            const bool u1_hit = u1_in && ((t0_in && u1 == t0) || (t1_in && u1 == t1));
+            if (u0_hit || u1_hit) c = TP;
+            else if (u0_in || u1_in) c = FP;  // an allele of the call that the truth does not have
+            else c = FN;
+            const int nref_t = (t0 == 0) + (t1 == 0), nref_u = (u0 == 0) + (u1 == 0);
+            if (nref_t < nref_u) g = FN;
+            else if (nref_t > nref_u) g = FP;
+            else if (u0 != t0 || u1 != t1) g = FP;  // tuples differ (order and length count)
+            else g = TP;
+        }
+        if (g == TP && c == FP) g = FP;
+        if (base_fn && base_fn[i]) {  // vcfeval's BASE says FN / FN_CA: a wrong call that was filtered is a miss
+            if (c == FP) c = FN;
+            if (g == FP) g = FN;
+        }
+        cls[i] = (uint8_t)c;
+        cls_gt[i] = (uint8_t)g;
+    }
+}
+
+extern "C" int ugvc_conc_classify(ugvc_conc* h, int64_t n, const int8_t* gt_ultima, const int8_t* gt_truth, const uint8_t* base_fn,
+                                  uint8_t* out_classify, uint8_t* out_classify_gt) {
+    if (!h || n < 0 || (n && (!gt_ultima || !gt_truth || !out_classify || !out_classify_gt))) return conc_fail(h, UGVC_E_ARG, "conc_classify: bad arguments");
+    if (n == 0) return UGVC_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return conc_fail(h, UGVC_E_CUDA, "cudaSetDevice failed");
+    int8_t *d_u = nullptr, *d_t = nullptr;
+    uint8_t *d_b = nullptr, *d_c = nullptr, *d_g = nullptr;
+    cudaError_t e = cudaMalloc(&d_u, 2 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_t, 2 * n);
+    if (e == cudaSuccess && base_fn) e = cudaMalloc(&d_b, n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_c, n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_g, n);
+    if (e == cudaSuccess) e = cudaMemcpy(d_u, gt_ultima, 2 * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_t, gt_truth, 2 * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && base_fn) e = cudaMemcpy(d_b, base_fn, n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        int64_t blocks = (n + CONC_TPB - 1) / CONC_TPB;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        conc_classify_gt<<<(unsigned)blocks, CONC_TPB>>>(n, d_u, d_t, d_b, d_c, d_g);
+        h->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_classify, d_c, n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_classify_gt, d_g, n, cudaMemcpyDeviceToHost);
+    cudaFree(d_u);
+    cudaFree(d_t);
+    cudaFree(d_b);
+    cudaFree(d_c);
+    cudaFree(d_g);
+    return e == cudaSuccess ? UGVC_OK : conc_fail(h, UGVC_E_CUDA, cudaGetErrorString(e));
+}

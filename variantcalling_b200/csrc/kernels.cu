@@ -993,6 +993,20 @@ __device__ __forceinline__ void walk8(const uint2* __restrict__ s_nodes, const u
     for (int j = 0; j < K3_CHAINS; ++j) leaf[j] = (int)(nd[j].x & 0x3FFFFFu);
 }
 
+#ifndef UGVC_HOST_EMU
+// test hook: the xgboost-flavoured fp32 sigmoid exactly as k3_finish evaluates it, on an array of margins
+__global__ void k3_test_sigmoid(const float* __restrict__ m, int n, float* __restrict__ p1, float* __restrict__ e_out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float e = k3_expf_cr(-m[i]);
+        e_out[i] = e;
+        p1[i] = 1.0f / (1.0f + e);
+    }
+}
+void launch_test_sigmoid(const float* d_m, int n, float* d_p1, float* d_e, cudaStream_t st) {
+    k3_test_sigmoid<<<(n + 255) / 256, 256, 0, st>>>(d_m, n, d_p1, d_e);
+}
+#endif
+
 // Link function, fp64 phred / qual arithmetic and the FILTER decision of one record (shared by the two K3
 // kernels): z / zf are the accumulated raw scores (fp64 for sklearn, fp32 for xgboost), x the record's
 // column of the shared-memory feature tile (stride TPB).  Returns quals <= threshold.

@@ -44,3 +44,35 @@ def allreduce_counts(counts_tensor, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(counts_tensor, op=dist.ReduceOp.SUM, group=group)
     return counts_tensor
+
+
+def bind_to_gpu_numa_node(gpu_index: int) -> dict:
+    """Pin this process (and the threads it starts later) to the CPUs of the NUMA node the GPU hangs off, BEFORE any
+    pinned host buffer is allocated: first-touch then places those buffers on that node, so the H2D / D2H copies of
+    several ranks do not all cross the same memory controller / PCIe root (round 1 measured 54 -> 36 GB/s per GPU at
+    four and eight ranks without it).  Best effort: returns what was done, never raises."""
+    import os
+    import subprocess
+
+    info = {"gpu": gpu_index, "node": None, "cpus": None}
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return info
+        if len(bus.split(":")[0]) == 8:  # 00000000:1B:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(node=node, cpus=len(allowed))
+    except (OSError, ValueError, subprocess.SubprocessError):
+        pass
+    return info

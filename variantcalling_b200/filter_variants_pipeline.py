@@ -347,6 +347,10 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         multi = world > 1
 
         device = args.device if args.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
+        if multi:
+            from variantcalling_b200 import dist as vdist0
+
+            logger.info(f"rank {rank}: NUMA binding {vdist0.bind_to_gpu_numa_node(device)}")
         ctx = lib.Context(device)  # raises without a CUDA device: there is no CPU path
         plan = None
         if with_model:
@@ -459,7 +463,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                     head = bgzf_io.first_block_text(comp, skip)
                     ctx.set_key_order(*lib.learn_key_order(head[: head.rfind(b"\n") + 1]))
                     key_order_set = True
-                need = (take + 4096, take // 32 + 1024)
+                need = (take + (1 << 17) + 4096, take // 32 + 1024)  # whole blocks are inflated: up to 64 KiB either side of the range
                 if need[0] > reserved[0] or need[1] > reserved[1]:
                     reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))
                     ctx.reserve(reserved[0], reserved[1], n_lanes)
