@@ -157,6 +157,9 @@ int ugvc_collect_phreds(ugvc_ctx* ctx, int lane, double* out, size_t capacity_re
  * ugvc_filter_device call. */
 int ugvc_device_status(ugvc_ctx* ctx, void* stream);
 
+/* Make the context's device current on the calling host thread (a helper thread that is about to allocate pinned
+ * memory with ugvc_host_alloc: the allocation belongs to the current device's context). */
+int ugvc_bind_thread(ugvc_ctx* ctx);
 /* Pinned host memory for the host-buffer API (full-rate PCIe copies). */
 int ugvc_host_alloc(void** out, size_t n_bytes);
 int ugvc_host_free(void* p);

@@ -218,6 +218,66 @@ def reg2bin(beg: np.ndarray, end: np.ndarray) -> np.ndarray:
     return out
 
 
+def tbi_section(beg: np.ndarray, end: np.ndarray, voff_start: np.ndarray, voff_end: np.ndarray) -> bytes:
+    """The binning index + linear index of ONE reference sequence (records sorted by position): the bytes that follow
+    the names in a ``.tbi``.  beg/end are 0-based half-open; voff_* the virtual offsets of each record's first byte
+    and one past its last byte."""
+    if len(beg) == 0:
+        return struct.pack("<i", 0) + struct.pack("<i", 0)
+    b, e = np.asarray(beg, dtype=np.int64), np.asarray(end, dtype=np.int64)
+    vs, ve = np.asarray(voff_start, dtype=np.uint64), np.asarray(voff_end, dtype=np.uint64)
+    out = []
+    bins = reg2bin(b, np.maximum(e, b + 1))
+    # chunks: runs of consecutive records with the same bin
+    change = np.flatnonzero(np.concatenate(([True], bins[1:] != bins[:-1])))
+    run_bin = bins[change]
+    run_beg = vs[change]
+    run_end = ve[np.concatenate((change[1:] - 1, [bins.size - 1]))]
+    order = np.argsort(run_bin, kind="stable")
+    run_bin, run_beg, run_end = run_bin[order], run_beg[order], run_end[order]
+    uniq, first = np.unique(run_bin, return_index=True)
+    counts = np.diff(np.concatenate((first, [run_bin.size])))
+    out.append(struct.pack("<i", uniq.size))
+    # every bin is (u32 bin, i32 n_chunks, n_chunks x (u64 begin, u64 end)): lay all of them out at once.
+    # Bin k's header starts at 8-byte word k + 2 * first[k]; run r (of bin k) follows at word (k + 1) + 2 r.
+    words = np.zeros(uniq.size + 2 * run_bin.size, dtype="<u8")
+    halves = words.view("<u4")
+    head = np.arange(uniq.size, dtype=np.int64) + 2 * first
+    halves[2 * head] = uniq.astype(np.uint32)
+    halves[2 * head + 1] = counts.astype(np.uint32)
+    at = np.repeat(np.arange(uniq.size, dtype=np.int64), counts) + 1 + 2 * np.arange(run_bin.size, dtype=np.int64)
+    words[at] = run_beg
+    words[at + 1] = run_end
+    out.append(words.tobytes())
+    # linear index: smallest virtual offset of any record overlapping each 16 kb window
+    n_win = int((np.maximum(e, b + 1).max() - 1) >> TBI_SHIFT) + 1
+    lin = np.full(n_win, np.iinfo(np.uint64).max, dtype=np.uint64)
+    w0 = b >> TBI_SHIFT
+    w1 = (np.maximum(e, b + 1) - 1) >> TBI_SHIFT
+    if np.all(w0[1:] >= w0[:-1]) and np.all(vs[1:] >= vs[:-1]):  # sorted file: the first record of a window is its minimum
+        win, first_rec = np.unique(w0, return_index=True)
+        lin[win] = vs[first_rec]
+    else:
+        np.minimum.at(lin, w0, vs)
+    span = np.flatnonzero(w1 > w0)
+    for i in span:  # records crossing window borders are rare (long REF alleles)
+        lin[w0[i] + 1: w1[i] + 1] = np.minimum(lin[w0[i] + 1: w1[i] + 1], vs[i])
+    # empty windows take the offset of the next filled one, as htslib back-fills its linear index
+    # (hts_idx_finish: offset[l] = offset[l + 1] from the end); the last window always holds a record
+    filled = lin != np.iinfo(np.uint64).max
+    nxt = np.minimum.accumulate(np.where(filled, np.arange(n_win), n_win - 1)[::-1])[::-1]
+    lin = lin[nxt]
+    out.append(struct.pack("<i", n_win))
+    out.append(lin.astype("<u8").tobytes())
+    return b"".join(out)
+
+
+def tbi_assemble(contig_names: list[str], sections: list[bytes]) -> bytes:
+    """Uncompressed ``.tbi`` payload from the per-sequence sections (tbi_section), in file order."""
+    names = b"".join(n.encode() + b"\0" for n in contig_names)
+    return b"".join([b"TBI\x01", struct.pack("<8i", len(contig_names), 2, 1, 2, 0, ord("#"), 0, len(names)), names, *sections])
+
+
 def build_tbi(contig_names: list[str], contig_of: np.ndarray, beg: np.ndarray, end: np.ndarray,
               voff_start: np.ndarray, voff_end: np.ndarray) -> bytes:
     """Uncompressed ``.tbi`` payload for records sorted by (contig block, position).
@@ -225,59 +285,11 @@ def build_tbi(contig_names: list[str], contig_of: np.ndarray, beg: np.ndarray, e
     contig_of[i] indexes contig_names; beg/end are 0-based half-open; voff_* are the
     virtual offsets of each record's first byte and one past its last byte.
     """
-    names = b"".join(n.encode() + b"\0" for n in contig_names)
-    out = [b"TBI\x01", struct.pack("<8i", len(contig_names), 2, 1, 2, 0, ord("#"), 0, len(names)), names]
+    sections = []
     for ci in range(len(contig_names)):
         sel = np.flatnonzero(contig_of == ci)
-        if sel.size == 0:
-            out.append(struct.pack("<i", 0))
-            out.append(struct.pack("<i", 0))
-            continue
-        b, e = beg[sel].astype(np.int64), end[sel].astype(np.int64)
-        vs, ve = voff_start[sel].astype(np.uint64), voff_end[sel].astype(np.uint64)
-        bins = reg2bin(b, np.maximum(e, b + 1))
-        # chunks: runs of consecutive records with the same bin
-        change = np.flatnonzero(np.concatenate(([True], bins[1:] != bins[:-1])))
-        run_bin = bins[change]
-        run_beg = vs[change]
-        run_end = ve[np.concatenate((change[1:] - 1, [bins.size - 1]))]
-        order = np.argsort(run_bin, kind="stable")
-        run_bin, run_beg, run_end = run_bin[order], run_beg[order], run_end[order]
-        uniq, first = np.unique(run_bin, return_index=True)
-        counts = np.diff(np.concatenate((first, [run_bin.size])))
-        out.append(struct.pack("<i", uniq.size))
-        # every bin is (u32 bin, i32 n_chunks, n_chunks x (u64 begin, u64 end)): lay all of them out at once.
-        # Bin k's header starts at 8-byte word k + 2 * first[k]; run r (of bin k) follows at word (k + 1) + 2 r.
-        words = np.zeros(uniq.size + 2 * run_bin.size, dtype="<u8")
-        halves = words.view("<u4")
-        head = np.arange(uniq.size, dtype=np.int64) + 2 * first
-        halves[2 * head] = uniq.astype(np.uint32)
-        halves[2 * head + 1] = counts.astype(np.uint32)
-        at = np.repeat(np.arange(uniq.size, dtype=np.int64), counts) + 1 + 2 * np.arange(run_bin.size, dtype=np.int64)
-        words[at] = run_beg
-        words[at + 1] = run_end
-        out.append(words.tobytes())
-        # linear index: smallest virtual offset of any record overlapping each 16 kb window
-        n_win = int((np.maximum(e, b + 1).max() - 1) >> TBI_SHIFT) + 1
-        lin = np.full(n_win, np.iinfo(np.uint64).max, dtype=np.uint64)
-        w0 = b >> TBI_SHIFT
-        w1 = (np.maximum(e, b + 1) - 1) >> TBI_SHIFT
-        if np.all(w0[1:] >= w0[:-1]) and np.all(vs[1:] >= vs[:-1]):  # sorted file: the first record of a window is its minimum
-            win, first_rec = np.unique(w0, return_index=True)
-            lin[win] = vs[first_rec]
-        else:
-            np.minimum.at(lin, w0, vs)
-        span = np.flatnonzero(w1 > w0)
-        for i in span:  # records crossing window borders are rare (long REF alleles)
-            lin[w0[i] + 1: w1[i] + 1] = np.minimum(lin[w0[i] + 1: w1[i] + 1], vs[i])
-        # empty windows take the offset of the next filled one, as htslib back-fills its linear index
-        # (hts_idx_finish: offset[l] = offset[l + 1] from the end); the last window always holds a record
-        filled = lin != np.iinfo(np.uint64).max
-        nxt = np.minimum.accumulate(np.where(filled, np.arange(n_win), n_win - 1)[::-1])[::-1]
-        lin = lin[nxt]
-        out.append(struct.pack("<i", n_win))
-        out.append(lin.astype("<u8").tobytes())
-    return b"".join(out)
+        sections.append(tbi_section(beg[sel], end[sel], voff_start[sel], voff_end[sel]))
+    return tbi_assemble(contig_names, sections)
 
 
 def write_tbi(path: str, payload: bytes):

@@ -1530,6 +1530,13 @@ extern "C" int ugvc_stage_ms(ugvc_ctx* ctx, float out_ms[4], int64_t* out_n_call
     return UGVC_OK;
 }
 
+extern "C" int ugvc_bind_thread(ugvc_ctx* ctx) {
+    // make the context's device current on the calling host thread (helper threads that allocate pinned memory)
+    if (!ctx) return UGVC_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    return UGVC_OK;
+}
+
 extern "C" int ugvc_host_alloc(void** out, size_t n_bytes) {
     // pinned host memory for the host-buffer API (H2D/D2H at full PCIe rate)
     ugvc_ctx* ctx = nullptr;

@@ -105,6 +105,10 @@ class _Splicer:
         self.threads = threads
         self.names: list[str] = []
         self.contig_of, self.beg, self.end, self.u_start, self.u_end = [], [], [], [], []
+        # tabix sections are built contig by contig on the writer thread (single-process runs), beside the GPU passes
+        self.sections: list[bytes] = []
+        self._cur: list[tuple] = []
+        self.keep_arrays = False  # multi-rank runs: rank 0 shifts the virtual offsets, so the arrays travel instead
         self.L = lib.load_library()
         self.seconds = {"splice": 0.0, "deflate": 0.0}
         self.ranges: dict[str, tuple[int, int]] = {}  # contig -> [first, last) compressed byte of its blocks
@@ -160,15 +164,18 @@ class _Splicer:
         self._check_writer()
         self._queue.put((contig, out[:nb], n, beg, beg + np.maximum(1, (ri["flags"] >> 8).astype(np.int64)), out_ls))
 
-    def write_device_batch(self, contig: str, res: dict):
-        """Records edited and BGZF-compressed on the device (lib.Context.filter_bgzf): only file and index work is left."""
+    def write_device_batch(self, contig: str, res: dict, release=None):
+        """Records edited and BGZF-compressed on the device (lib.Context.filter_bgzf): only file and index work is left.
+        `release` is called once the buffers of `res` are no longer needed."""
         n = res["n_records"]
         if n == 0:
+            if release:
+                release()
             return
         ri = res["recinfo"]
         beg = ri["pos"].astype(np.int64) - 1
         self._check_writer()
-        self._queue.put((contig, (res["bgzf"], res["block_csize"]), n, beg,
+        self._queue.put((contig, (res["bgzf"], res["block_csize"], release), n, beg,
                          beg + np.maximum(1, (ri["flags"] >> 8).astype(np.int64)), res["line_start"]))
 
     def _write_spliced(self, contig: str, data, n: int, beg: np.ndarray, end: np.ndarray, out_ls: np.ndarray):
@@ -181,13 +188,31 @@ class _Splicer:
             self.writer.write(data)
         self.ranges[contig] = (self.ranges.get(contig, (c_before, 0))[0], self.writer.coffset)
         if not self.names or self.names[-1] != contig:
+            self._close_section()
             self.names.append(contig)
-        self.contig_of.append(np.full(n, len(self.names) - 1, dtype=np.int32))
-        self.beg.append(beg)
-        self.end.append(end)
-        self.u_start.append(base + out_ls[:-1])
-        self.u_end.append(base + out_ls[1:])
+        if self.keep_arrays:
+            self.contig_of.append(np.full(n, len(self.names) - 1, dtype=np.int32))
+            self.beg.append(beg)
+            self.end.append(end)
+            self.u_start.append(base + out_ls[:-1])
+            self.u_end.append(base + out_ls[1:])
+        else:
+            vs = self.writer.virtual_offsets(base + out_ls[:-1])
+            ve = self.writer.virtual_offsets(base + out_ls[1:] - 1) + np.uint64(1)
+            self._cur.append((beg, end, vs, ve))
         self.seconds["deflate"] += time.perf_counter() - t0
+        if isinstance(data, tuple) and data[2] is not None:
+            data[2]()  # the device batch's buffers may be reused
+
+    def _close_section(self):
+        if self.keep_arrays or not self.names:
+            return
+        t0 = time.perf_counter()
+        cat = np.concatenate
+        cols = [cat([c[k] for c in self._cur]) if self._cur else np.zeros(0, np.int64) for k in range(4)]
+        self.sections.append(bgzf_io.tbi_section(cols[0], cols[1], cols[2].astype(np.uint64), cols[3].astype(np.uint64)))
+        self._cur = []
+        self.seconds["index"] = self.seconds.get("index", 0.0) + time.perf_counter() - t0
 
     def _finish_writer(self):
         self._queue.put(None)
@@ -216,16 +241,35 @@ class _Splicer:
     def close(self, path: str):
         self._finish_writer()
         self.writer.close()
-        if self.contig_of:
-            cat = np.concatenate
-            us, ue = cat(self.u_start), cat(self.u_end)
-            vs = self.writer.virtual_offsets(us)
-            ve = self.writer.virtual_offsets(ue - 1) + np.uint64(1)
-            payload = bgzf_io.build_tbi(self.names, cat(self.contig_of), cat(self.beg), cat(self.end), vs, ve)
-        else:
-            z = np.zeros(0, np.int64)
-            payload = bgzf_io.build_tbi([], z, z, z, z.astype(np.uint64), z.astype(np.uint64))
-        bgzf_io.write_tbi(path + ".tbi", payload)
+        self._close_section()
+        bgzf_io.write_tbi(path + ".tbi", bgzf_io.tbi_assemble(self.names, self.sections))
+
+
+class _PinnedPool:
+    """A few reusable sets of pinned host buffers (page-locked once, not page-faulted per contig): the compressed
+    input of a contig, and what comes back from ugvc_filter_bgzf.  acquire() blocks until a set is free."""
+
+    def __init__(self, n_sets: int):
+        self._free: "queue.Queue" = queue.Queue()
+        for _ in range(n_sets):
+            self._free.put({})
+
+    def acquire(self, sizes: dict) -> dict:
+        bufs = self._free.get()
+        for key, (n_items, dtype) in sizes.items():
+            need = int(n_items) * np.dtype(dtype).itemsize
+            have = bufs.get(key)
+            if have is None or have[0].array.size < need:
+                if have is not None:
+                    have[0].free()
+                pb = lib.PinnedBuffer(need + need // 4 + 4096)
+                bufs[key] = (pb, None)
+            pb = bufs[key][0]
+            bufs[key] = (pb, pb.array[: need].view(dtype))
+        return bufs
+
+    def release(self, bufs: dict):
+        self._free.put(bufs)
 
 
 def _part_path(output_file: str, rank: int) -> str:
@@ -378,6 +422,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         key_order_set = False
 
         out = _Splicer(_part_path(args.output_file, rank) if multi else args.output_file, args.io_threads)
+        out.keep_arrays = multi
         if not multi:
             out.write_header(out_header)
         seconds = {"inflate_wait": 0.0, "gpu": 0.0}
@@ -436,7 +481,15 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 c0, c1, skip, take = bgzf_io.range_info(args.input_file, vb, ve)
                 if take == 0:
                     return None
-                return "device", np.fromfile(args.input_file, dtype=np.uint8, count=c1 - c0, offset=c0), skip, take
+                ctx.bind_thread()  # the reader thread pins memory for this rank's device
+                bufs = in_pool.acquire({"comp": (c1 - c0, np.uint8)})
+                comp = bufs["comp"][1]
+                with open(args.input_file, "rb") as fh:
+                    fh.seek(c0)
+                    got = fh.readinto(memoryview(comp))
+                if got != c1 - c0:
+                    raise OSError(f"{args.input_file}: short read of {contig}")
+                return "device", comp, skip, take, bufs
             text = bgzf_io.inflate(args.input_file, vb, ve, n_threads=args.io_threads)
             if text.size == 0:
                 return None
@@ -444,6 +497,8 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 text = np.concatenate((text, np.array([10], dtype=np.uint8)))
             return text, bgzf_io.count_lines(text, args.io_threads)
 
+        in_pool, out_pool = _PinnedPool(2), _PinnedPool(3)
+        dev_ms = np.zeros(5)
         prefetch = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-bgzf-reader")
         pending = prefetch.submit(load_contig, contigs[0], device_io) if contigs else None
         for ci, contig in enumerate(contigs):
@@ -456,7 +511,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 logger.info(f"No variants found on {contig}")
                 continue
             if isinstance(loaded[0], str):  # ("device", compressed blocks, skip, take)
-                _tag, comp, skip, take = loaded
+                _tag, comp, skip, take, in_bufs = loaded
                 if args.blacklist_cg_insertions:
                     logger.info("Marking CG insertions")
                 if not key_order_set:
@@ -468,12 +523,21 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                     reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))
                     ctx.reserve(reserved[0], reserved[1], n_lanes)
                 t_gpu = time.perf_counter()
-                res = ctx.filter_bgzf(comp, skip, take, args.decision_threshold, file_flags, reserved[1])
+                n_max = take // 32 + 1024
+                out_bufs = out_pool.acquire({"out": ((take + n_max * 64) // lib.DEF_CHUNK * 65536 + (1 << 17), np.uint8),
+                                             "blocks": ((take + n_max * 64) // lib.DEF_CHUNK + 16, np.uint32),
+                                             "ri": (n_max, lib.RECINFO_DTYPE), "ls": (n_max + 1, np.int64), "low": (n_max, np.uint8)})
+                res = ctx.filter_bgzf(comp, skip, take, args.decision_threshold, file_flags, n_max,
+                                      bufs={k: v[1] for k, v in out_bufs.items()})
                 seconds["gpu"] += time.perf_counter() - t_gpu
-                if res is not None:
+                in_pool.release(in_bufs)
+                if res is None:
+                    out_pool.release(out_bufs)
+                else:
+                    dev_ms += np.array(ctx.filter_bgzf_stage_ms())
                     logger.info(f"{res['n_records']} variants found on {contig}")
                     logger.info("Writing records")
-                    out.write_device_batch(contig, res)
+                    out.write_device_batch(contig, res, release=lambda b=out_bufs: out_pool.release(b))
                     totals["n_records"] += res["n_records"]
                     totals["n_low_score"] += int(res["low_score"].sum())
                     if args.blacklist_cg_insertions:
@@ -595,8 +659,11 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             out.close(args.output_file)
         prefetch.shutdown()
         logger.info("stage seconds (overlapping threads): wait for inflate %.2f, wait for GPU %.2f, splice %.2f, "
-                    "deflate+write %.2f, index %.2f", seconds["inflate_wait"], seconds["gpu"], out.seconds["splice"],
-                    out.seconds["deflate"], time.perf_counter() - t_close)
+                    "deflate+write %.2f, index %.2f (+ %.2f at close)", seconds["inflate_wait"], seconds["gpu"],
+                    out.seconds["splice"], out.seconds["deflate"], out.seconds.get("index", 0.0), time.perf_counter() - t_close)
+        if device_io:
+            logger.info("device file path, ms on the GPU: H2D + inflate %.0f, K1..K3 %.0f, record writer %.0f, deflate + pack %.0f, "
+                        "D2H %.0f", *dev_ms)
         ctx.close()
         if idx_ctx is not None:
             idx_ctx.close()

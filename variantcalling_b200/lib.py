@@ -63,6 +63,7 @@ SIGNATURES = {
     "ugvc_nccl_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "ugvc_nccl_comm_destroy": (C.c_int, [_vp]),
     "ugvc_counts_allreduce": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "ugvc_bind_thread": (C.c_int, [_vp]),
     "ugvc_host_alloc": (C.c_int, [C.POINTER(_vp), _sz]),
     "ugvc_host_free": (C.c_int, [_vp]),
     "ugvc_counts_reset": (C.c_int, [_vp]),
@@ -201,6 +202,10 @@ class Context:
             pass
 
     # ---- setup
+    def bind_thread(self):
+        """Make this context's device current on the calling thread (before it allocates pinned memory)."""
+        self._check(self.lib.ugvc_bind_thread(self.h))
+
     def load_plan(self, blob: bytes):
         buf = np.frombuffer(blob, dtype=np.uint8)
         self._check(self.lib.ugvc_load_plan(self.h, _ptr(buf), buf.size))
@@ -299,16 +304,19 @@ class Context:
 
     # ---- file to file on the device
     def filter_bgzf(self, bgzf: np.ndarray, skip_head: int, take_bytes: int, threshold: float, flags: int, max_records: int,
-                    lane: int = 0) -> dict | None:
+                    lane: int = 0, bufs: dict | None = None) -> dict | None:
         """One range of whole lines: compressed blocks in, filtered + scored + edited records out as BGZF blocks
         (see ugvc_filter_bgzf).  Returns None when the range needs the general host writer."""
         comp = np.ascontiguousarray(bgzf, dtype=np.uint8)
-        n_text_max = (take_bytes or comp.size * 64) + max_records * 64 + 65536
-        out = np.empty(n_text_max // DEF_CHUNK * 65536 + 65536 if take_bytes else comp.size * 8 + (1 << 20), dtype=np.uint8)
-        blocks = np.empty(out.size // 65536 + 8, dtype=np.uint32)
-        ri = np.empty(max_records, dtype=RECINFO_DTYPE)
-        ls = np.empty(max_records + 1, dtype=np.int64)
-        low = np.empty(max_records, dtype=np.uint8)
+        if bufs is not None:  # the caller's (pinned, reused) buffers: out, blocks, ri, ls, low
+            out, blocks, ri, ls, low = bufs["out"], bufs["blocks"], bufs["ri"], bufs["ls"], bufs["low"]
+        else:
+            n_text_max = (take_bytes or comp.size * 64) + max_records * 64 + 65536
+            out = np.empty(n_text_max // DEF_CHUNK * 65536 + 65536 if take_bytes else comp.size * 8 + (1 << 20), dtype=np.uint8)
+            blocks = np.empty(out.size // 65536 + 8, dtype=np.uint32)
+            ri = np.empty(max_records, dtype=RECINFO_DTYPE)
+            ls = np.empty(max_records + 1, dtype=np.int64)
+            low = np.empty(max_records, dtype=np.uint8)
         nb, nblk, n = C.c_size_t(), C.c_size_t(), C.c_int64()
         rc = self.lib.ugvc_filter_bgzf(self.h, lane, _ptr(comp), comp.size, skip_head, take_bytes, threshold, flags, _ptr(out),
                                        out.size, C.byref(nb), _ptr(blocks), blocks.size, C.byref(nblk), _ptr(ri), _ptr(ls),
