@@ -67,6 +67,24 @@ def test_filter_batch_matches_oracle(gpu_ctx, ds, kind, order):
         assert ds["text"][ls[i]:ls[i + 1] - 1].decode() == line
 
 
+def test_device_sigmoid_equals_the_restatement(gpu_ctx):
+    """K3's fp32 sigmoid (exponential rounded once from fp64) == the restatement's, bit for bit, on a margin sweep."""
+    from oracle import xgb_predictor as XP
+
+    rng = np.random.default_rng(5)
+    m = np.concatenate([rng.normal(scale=3.0, size=200_000), np.linspace(-20, 20, 4001)]).astype(np.float32)
+    p1, e = np.empty_like(m), np.empty_like(m)
+    rc = gpu_ctx.lib.ugvc_test_device_sigmoid(gpu_ctx.h, lib._ptr(m), m.size, lib._ptr(p1), lib._ptr(e))  # noqa: SLF001
+    assert rc == 0
+    want_e = XP._expf(-m)  # noqa: SLF001
+    bad_e = np.flatnonzero(e != want_e)
+    want_p = (np.float32(1.0) / (np.float32(1.0) + want_e)).astype(np.float32)
+    bad_p = np.flatnonzero(p1 != want_p)
+    assert bad_e.size == 0 and bad_p.size == 0, (
+        f"exp differs at {bad_e.size} margins (first {[(float(m[i]), e[i].view(np.uint32), want_e[i].view(np.uint32)) for i in bad_e[:3]]}), "
+        f"sigmoid at {bad_p.size} (first {[(float(m[i]), p1[i].view(np.uint32), want_p[i].view(np.uint32)) for i in bad_p[:3]]})")
+
+
 @pytest.mark.parametrize("n_class", [2, 3])
 def test_xgboost_json_model_path(gpu_ctx, ds, n_class):
     """MODEL_XGB (x < t, fp32 margins in tree order, fp32 sigmoid / softmax) against the NumPy
@@ -100,24 +118,6 @@ def test_xgboost_json_model_path(gpu_ctx, ds, n_class):
     assert np.array_equal(res["low_score"].astype(bool), quals <= 30.0)
     if n_class == 2:  # same trees, same prior: sklearn's fp64 evaluation agrees to fp32 accuracy
         assert np.abs(gb.predict_proba(ds["x"]) - want).max() < 1e-5
-
-
-def test_device_sigmoid_equals_the_restatement(gpu_ctx):
-    """K3's fp32 sigmoid (exponential rounded once from fp64) == the restatement's, bit for bit, on a margin sweep."""
-    from oracle import xgb_predictor as XP
-
-    rng = np.random.default_rng(5)
-    m = np.concatenate([rng.normal(scale=3.0, size=200_000), np.linspace(-20, 20, 4001)]).astype(np.float32)
-    p1, e = np.empty_like(m), np.empty_like(m)
-    rc = gpu_ctx.lib.ugvc_test_device_sigmoid(gpu_ctx.h, lib._ptr(m), m.size, lib._ptr(p1), lib._ptr(e))  # noqa: SLF001
-    assert rc == 0
-    want_e = XP._expf(-m)  # noqa: SLF001
-    bad_e = np.flatnonzero(e != want_e)
-    want_p = (np.float32(1.0) / (np.float32(1.0) + want_e)).astype(np.float32)
-    bad_p = np.flatnonzero(p1 != want_p)
-    assert bad_e.size == 0 and bad_p.size == 0, (
-        f"exp differs at {bad_e.size} margins (first {[(float(m[i]), e[i].view(np.uint32), want_e[i].view(np.uint32)) for i in bad_e[:3]]}), "
-        f"sigmoid at {bad_p.size} (first {[(float(m[i]), p1[i].view(np.uint32), want_p[i].view(np.uint32)) for i in bad_p[:3]]})")
 
 
 def test_multinomial_logistic_regression(gpu_ctx, ds):

@@ -52,6 +52,29 @@ def test_features_filter_and_scores(gpu_ctx, dv, kind):
         np.testing.assert_allclose(res["probs"], exp["probs"], atol=1e-5, rtol=0)
 
 
+def test_joint_callset_flavour(gpu_ctx, dv):
+    """VcfType.JOINT: the common transform list alone (transformers.py:278; no `vaf`, no `qual`) on the same records --
+    features, FILTER and scores against the oracle, with and without a learned key order."""
+    tr = T.get_transformer(VcfType.JOINT, [c.lower() for c in dv["customs"]])
+    with pd.option_context("future.infer_string", False):
+        x = tr.fit_transform(R.harness_float_columns(dv["df"])).to_numpy(dtype=np.float64)
+    model = util.fit_model("gb_small", x, dv["labels"])
+    plan = MC.compile_plan(VcfHeader(dv["header_text"]), tr, model, dv["customs"])
+    assert "vaf" not in plan.feature_names and "qual" not in plan.feature_names and x.shape[1] == plan.n_features
+    gpu_ctx.load_plan(plan.blob)
+    gpu_ctx.reserve(len(dv["text"]) + 1024, len(dv["lines"]) + 16, 1)
+    exp = R.filter_variants(dv["vf"], model, tr, custom_annotations=dv["customs"])
+    want_low = np.array(["LOW_SCORE" in f.split(";") for f in exp["filters"]])
+    for mode in ("generic", "learned"):
+        gpu_ctx.set_key_order(*(lib.learn_key_order(dv["text"]) if mode == "learned" else ("", "")))
+        res = gpu_ctx.filter_batch(dv["text"], 30.0)
+        feats = gpu_ctx.debug_features(res["n_records"]).T
+        bad = np.argwhere(feats != x.astype(np.float32))
+        assert bad.size == 0, f"[{mode}] first mismatch {bad[0]} ({plan.feature_names[bad[0][1]]})"
+        assert np.array_equal(res["low_score"].astype(bool), want_low)
+        np.testing.assert_allclose(res["probs"], exp["probs"], atol=1e-5, rtol=0)
+
+
 def test_cli_on_a_deepvariant_file(dv, tmp_path):
     model = util.fit_model("rf", dv["x"], dv["labels"])
     vcf, mpath, out = str(tmp_path / "dv.vcf.gz"), str(tmp_path / "m.pkl"), str(tmp_path / "o.vcf.gz")

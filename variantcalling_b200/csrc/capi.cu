@@ -49,7 +49,6 @@ struct Lane {
         uint8_t* d_blocks = nullptr;  // [cap_blocks][DEF_BLOCK_STRIDE]
         uint32_t* d_bsize = nullptr;
         uint64_t *d_bwide = nullptr, *d_boff = nullptr;
-        uint16_t* d_heads = nullptr;
         size_t cap_blocks = 0;
         uint8_t* d_packed = nullptr;
         int* d_fallback = nullptr;
@@ -166,7 +165,6 @@ static void free_lane(Lane& l) {
     cudaFree(l.fb.d_bsize);
     cudaFree(l.fb.d_bwide);
     cudaFree(l.fb.d_boff);
-    cudaFree(l.fb.d_heads);
     cudaFree(l.fb.d_packed);
     cudaFree(l.fb.d_fallback);
     if (l.fb.h_fallback) cudaFreeHost(l.fb.h_fallback);
@@ -1202,7 +1200,6 @@ static int file_bufs(ugvc_ctx* ctx, Lane& l) {
     CU(cudaMalloc(&f.d_bsize, (f.cap_blocks + 1) * sizeof(uint32_t)));
     CU(cudaMalloc(&f.d_bwide, (f.cap_blocks + 1) * sizeof(uint64_t)));
     CU(cudaMalloc(&f.d_boff, (f.cap_blocks + 1) * sizeof(uint64_t)));
-    CU(cudaMalloc(&f.d_heads, (f.cap_blocks << DEF_HASH_BITS) * sizeof(uint16_t)));
     CU(cudaMalloc(&f.d_packed, f.cap_blocks * (size_t)DEF_BLOCK_STRIDE));
     CU(cudaMalloc(&f.d_fallback, sizeof(int)));
     CU(cudaHostAlloc(&f.h_fallback, sizeof(int), cudaHostAllocDefault));
@@ -1287,7 +1284,7 @@ extern "C" int ugvc_filter_bgzf(ugvc_ctx* ctx, int lane, const uint8_t* bgzf, si
     const int n_blocks = (int)((out_text + DEF_CHUNK - 1) / DEF_CHUNK);
     if ((size_t)n_blocks > f.cap_blocks || (out_block_csize && (size_t)n_blocks > block_capacity))
         return fail(ctx, UGVC_E_ARG, "filter_bgzf: more output blocks than room for them");
-    fio_launch_deflate(f.d_out_text, out_text, ctx->d_def_tables, f.d_blocks, f.d_bsize, f.d_heads, n_blocks, st);
+    fio_launch_deflate(f.d_out_text, out_text, ctx->d_def_tables, f.d_blocks, f.d_bsize, n_blocks, st);
     fio_launch_widen(f.d_bsize, f.d_bwide, n_blocks, st);
     CU(cudaMemsetAsync(f.d_bwide + n_blocks, 0, sizeof(uint64_t), st));
     tmp = f.scan_tmp_bytes;
@@ -1300,7 +1297,8 @@ extern "C" int ugvc_filter_bgzf(ugvc_ctx* ctx, int lane, const uint8_t* bgzf, si
     if (*f.h_fallback) return UGVC_E_FALLBACK;
     size_t packed = 0;
     for (int b = 0; b < n_blocks; ++b) packed += f.h_bsize[b];
-    if (packed > out_capacity) return fail(ctx, UGVC_E_ARG, "filter_bgzf: out_capacity smaller than the compressed output");
+    if (packed > out_capacity)  // the caller sized out_bgzf for text that compresses; it can take its host writer instead
+        return fail(ctx, UGVC_E_FALLBACK, "filter_bgzf: out_capacity smaller than the compressed output");
     ctx->launches += 6;
     // ---- results to the host
     if (packed) CU(cudaMemcpyAsync(out_bgzf, f.d_packed, packed, cudaMemcpyDeviceToHost, st));

@@ -267,14 +267,16 @@ __global__ void __launch_bounds__(256) splice_copy(const uint8_t* __restrict__ t
 }
 
 // ---- deflate: one thread per block of DEF_CHUNK output-text bytes
-__global__ void __launch_bounds__(64) fio_deflate(const uint8_t* __restrict__ text, size_t n_bytes, const DefTables* __restrict__ T,
-                                                  uint8_t* __restrict__ blocks, uint32_t* __restrict__ bsize,
-                                                  uint16_t* __restrict__ heads, int n_blocks) {
+#define FIO_DEF_TPB 32
+__global__ void __launch_bounds__(FIO_DEF_TPB) fio_deflate(const uint8_t* __restrict__ text, size_t n_bytes,
+                                                           const DefTables* __restrict__ T, uint8_t* __restrict__ blocks,
+                                                           uint32_t* __restrict__ bsize, int n_blocks) {
+    extern __shared__ __align__(16) uint16_t fio_heads[];  // [FIO_DEF_TPB][1 << DEF_HASH_BITS]
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
     const size_t off = (size_t)b * DEF_CHUNK;
     const uint32_t n = (uint32_t)(n_bytes - off < DEF_CHUNK ? n_bytes - off : DEF_CHUNK);
-    bsize[b] = def_block(text + off, n, blocks + (size_t)b * DEF_BLOCK_STRIDE, heads + ((size_t)b << DEF_HASH_BITS), *T);
+    bsize[b] = def_block(text + off, n, blocks + (size_t)b * DEF_BLOCK_STRIDE, fio_heads + ((size_t)threadIdx.x << DEF_HASH_BITS), *T);
 }
 
 __global__ void __launch_bounds__(256) fio_pack(const uint8_t* __restrict__ blocks, const uint32_t* __restrict__ bsize,
@@ -316,9 +318,15 @@ void fio_launch_splice_copy(const uint8_t* text, const int64_t* line_start, cons
     splice_copy<<<(unsigned)blocks, 256, 0, st>>>(text, line_start, recinfo, low, n, flags, out_start, score_txt, out, fallback);
 }
 void fio_launch_deflate(const uint8_t* text, size_t n_bytes, const DefTables* tables, uint8_t* blocks, uint32_t* bsize,
-                        uint16_t* heads, int n_blocks, cudaStream_t st) {
+                        int n_blocks, cudaStream_t st) {
     if (n_blocks <= 0) return;
-    fio_deflate<<<(n_blocks + 63) / 64, 64, 0, st>>>(text, n_bytes, tables, blocks, bsize, heads, n_blocks);
+    const size_t smem = (size_t)FIO_DEF_TPB * sizeof(uint16_t) << DEF_HASH_BITS;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(fio_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    fio_deflate<<<(n_blocks + FIO_DEF_TPB - 1) / FIO_DEF_TPB, FIO_DEF_TPB, smem, st>>>(text, n_bytes, tables, blocks, bsize, n_blocks);
 }
 void fio_launch_pack(const uint8_t* blocks, const uint32_t* bsize, uint64_t* wide, const uint64_t* boff, int n_blocks,
                      uint8_t* packed, int sm_count, cudaStream_t st) {

@@ -262,7 +262,7 @@ class _PinnedPool:
             if have is None or have[0].array.size < need:
                 if have is not None:
                     have[0].free()
-                pb = lib.PinnedBuffer(need + need // 4 + 4096)
+                pb = lib.PinnedBuffer(need + need // 16 + 4096)
                 bufs[key] = (pb, None)
             pb = bufs[key][0]
             bufs[key] = (pb, pb.array[: need].view(dtype))
@@ -425,7 +425,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         out.keep_arrays = multi
         if not multi:
             out.write_header(out_header)
-        seconds = {"inflate_wait": 0.0, "gpu": 0.0}
+        seconds = {"inflate_wait": 0.0, "gpu": 0.0, "alloc": 0.0}
         totals = {"n_records": 0, "n_low_score": 0, "n_cg": 0, "n_blacklisted": 0}
 
         def blacklist_codes(ri, n, bl_pos):
@@ -519,14 +519,17 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                     ctx.set_key_order(*lib.learn_key_order(head[: head.rfind(b"\n") + 1]))
                     key_order_set = True
                 need = (take + (1 << 17) + 4096, take // 32 + 1024)  # whole blocks are inflated: up to 64 KiB either side of the range
+                t_alloc = time.perf_counter()
                 if need[0] > reserved[0] or need[1] > reserved[1]:
                     reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))
                     ctx.reserve(reserved[0], reserved[1], n_lanes)
-                t_gpu = time.perf_counter()
                 n_max = take // 32 + 1024
-                out_bufs = out_pool.acquire({"out": ((take + n_max * 64) // lib.DEF_CHUNK * 65536 + (1 << 17), np.uint8),
+                # VCF text deflates to well under half its size; text that does not comes back as UGVC_E_FALLBACK
+                out_bufs = out_pool.acquire({"out": (take * 5 // 8 + (1 << 20), np.uint8),
                                              "blocks": ((take + n_max * 64) // lib.DEF_CHUNK + 16, np.uint32),
                                              "ri": (n_max, lib.RECINFO_DTYPE), "ls": (n_max + 1, np.int64), "low": (n_max, np.uint8)})
+                seconds["alloc"] += time.perf_counter() - t_alloc
+                t_gpu = time.perf_counter()
                 res = ctx.filter_bgzf(comp, skip, take, args.decision_threshold, file_flags, n_max,
                                       bufs={k: v[1] for k, v in out_bufs.items()})
                 seconds["gpu"] += time.perf_counter() - t_gpu
@@ -658,8 +661,8 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         else:
             out.close(args.output_file)
         prefetch.shutdown()
-        logger.info("stage seconds (overlapping threads): wait for inflate %.2f, wait for GPU %.2f, splice %.2f, "
-                    "deflate+write %.2f, index %.2f (+ %.2f at close)", seconds["inflate_wait"], seconds["gpu"],
+        logger.info("stage seconds (overlapping threads): wait for inflate %.2f, buffers %.2f, wait for GPU %.2f, splice %.2f, "
+                    "deflate+write %.2f, index %.2f (+ %.2f at close)", seconds["inflate_wait"], seconds["alloc"], seconds["gpu"],
                     out.seconds["splice"], out.seconds["deflate"], out.seconds.get("index", 0.0), time.perf_counter() - t_close)
         if device_io:
             logger.info("device file path, ms on the GPU: H2D + inflate %.0f, K1..K3 %.0f, record writer %.0f, deflate + pack %.0f, "
