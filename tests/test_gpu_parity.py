@@ -1,6 +1,8 @@
 """GPU parity: the CUDA path through the C ABI vs the oracle (reference restatement) on the
 same seeded VCF text.  FILTER decision bit-identical, features bit-identical (fp32), scores
 within 1e-5 (BASELINE.json north_star tolerance)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -75,6 +77,8 @@ def test_device_sigmoid_equals_the_restatement(gpu_ctx):
     m = np.concatenate([rng.normal(scale=3.0, size=200_000), np.linspace(-20, 20, 4001)]).astype(np.float32)
     p1, e = np.empty_like(m), np.empty_like(m)
     rc = gpu_ctx.lib.ugvc_test_device_sigmoid(gpu_ctx.h, lib._ptr(m), m.size, lib._ptr(p1), lib._ptr(e))  # noqa: SLF001
+    if rc != 0 and os.environ.get("UGVC_LIB_PATH"):
+        pytest.skip("a device-code hook: not part of the host emulation")
     assert rc == 0
     want_e = XP._expf(-m)  # noqa: SLF001
     bad_e = np.flatnonzero(e != want_e)

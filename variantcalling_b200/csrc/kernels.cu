@@ -1077,7 +1077,7 @@ __device__ __forceinline__ bool k3_finish(const DevPlan& plan, const float* __re
         case MODEL_XGB: {
             // xgboost CPU predictor: fp32 margins, fp32 sigmoid / softmax
             if (O == 1) {
-                const float p1 = 1.0f / (1.0f + expf(-zf[0]));
+                const float p1 = 1.0f / (1.0f + k3_expf_cr(-zf[0]));
                 p[1] = (double)p1;
                 p[0] = (double)(1.0f - p1);
             } else {
@@ -1090,7 +1090,7 @@ __device__ __forceinline__ bool k3_finish(const DevPlan& plan, const float* __re
 #pragma unroll
                 for (int o = 0; o < UGVC_MAX_CLASSES; ++o)
                     if (o < O) {
-                        e[o] = expf(zf[o] - mx);
+                        e[o] = k3_expf_cr(zf[o] - mx);
                         s += (double)e[o];
                     }
 #pragma unroll
