@@ -284,6 +284,11 @@ int ugvc_filter_bgzf(ugvc_ctx* ctx, int lane, const uint8_t* bgzf, size_t n_byte
 /* Stage seconds of the last ugvc_filter_bgzf call on `lane`: H2D + inflate, K1..K3, record writer, deflate + pack,
  * D2H (device-timed with CUDA events). */
 int ugvc_filter_bgzf_stage_ms(ugvc_ctx* ctx, int lane, float out_ms[5]);
+/* After ugvc_filter_bgzf on `lane`: for each of `n` byte offsets into the range's text (0 = its first byte), the index of the
+ * first record that starts at or after it.  A caller that hands several contigs to one call (adjacent in the file) gives
+ * the offsets where each contig's text begins and gets back where its records begin: what the per-contig tabix
+ * bookkeeping of the writer (filter_variants_pipeline.py:231, `bcftools index -t`) needs. */
+int ugvc_filter_bgzf_first_records(ugvc_ctx* ctx, int lane, const uint64_t* text_offsets, int n, int64_t* out_first_record);
 
 /* ---- concordance metrics (BASELINE configs[4]: evaluate_concordance on the filtered set) ----
  * Precision / recall of calls against truth labels, per variant group, replacing the array work
@@ -331,6 +336,9 @@ int ugvc_test_parse_float(const char* text, float* out_f32, double* out_f64, int
 /* Test hook: the device BGZF encoder (csrc/deflate.cuh) run on the host on one block of at most 57344 bytes (4 readable
  * bytes after n); out receives a complete BGZF block (<= 65536 bytes), the size is returned. */
 int64_t ugvc_test_deflate_block(const uint8_t* in, uint32_t n, uint8_t* out);
+/* Test hook: the host model of the warp-per-block encoder (fileio.cu: fio_deflate_warp) -- same windows, candidate
+ * rule, token bits and slice-wise CRC, the 32 lanes as a loop.  Same contract as ugvc_test_deflate_block. */
+int64_t ugvc_test_deflate_block_lanes(const uint8_t* in, uint32_t n, uint8_t* out);
 
 #ifdef __cplusplus
 }

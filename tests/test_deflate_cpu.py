@@ -13,10 +13,24 @@ from variantcalling_b200 import lib
 CHUNK = 57344
 
 
+import pytest
+
+
+@pytest.fixture(params=["ugvc_test_deflate_block", "ugvc_test_deflate_block_lanes"], autouse=True)
+def encoder(request):
+    """Both encoders: one thread per block (deflate.cuh: def_block) and the host model of the warp-per-block kernel."""
+    global ENCODER
+    ENCODER = request.param
+    return request.param
+
+
+ENCODER = "ugvc_test_deflate_block"
+
+
 def encode(L, data: bytes) -> bytes:
     src = np.frombuffer(data + b"\0" * 8, dtype=np.uint8).copy()
     out = np.zeros(65536, dtype=np.uint8)
-    n = L.ugvc_test_deflate_block(src.ctypes.data_as(C.c_void_p), len(data), out.ctypes.data_as(C.c_void_p))
+    n = getattr(L, ENCODER)(src.ctypes.data_as(C.c_void_p), len(data), out.ctypes.data_as(C.c_void_p))
     assert n > 0, n
     return out[:n].tobytes()
 
@@ -42,6 +56,7 @@ def test_vcf_text_round_trip_and_ratio():
         check_block(blk, part)
         total_in += len(part)
         total_out += len(blk)
+    print(ENCODER, "ratio", total_in / total_out)
     assert total_out < 0.6 * total_in, (total_in, total_out)  # greedy LZ + fixed codes still shrinks VCF text well
 
 

@@ -1180,6 +1180,7 @@ extern "C" int ugvc_filter_bgzf(ugvc_ctx* ctx, int, const uint8_t*, size_t, uint
     return fail(ctx, UGVC_E_FALLBACK, "the device-side record writer is not part of the host emulation");
 }
 extern "C" int ugvc_filter_bgzf_stage_ms(ugvc_ctx*, int, float*) { return UGVC_E_STATE; }
+extern "C" int ugvc_filter_bgzf_first_records(ugvc_ctx*, int, const uint64_t*, int, int64_t*) { return UGVC_E_STATE; }
 #else
 static int file_bufs(ugvc_ctx* ctx, Lane& l) {
     Lane::FileBufs& f = l.fb;
@@ -1317,6 +1318,22 @@ extern "C" int ugvc_filter_bgzf(ugvc_ctx* ctx, int lane, const uint8_t* bgzf, si
 extern "C" int ugvc_filter_bgzf_stage_ms(ugvc_ctx* ctx, int lane, float out_ms[5]) {
     if (!ctx || !out_ms || lane < 0 || lane >= (int)ctx->lanes.size()) return UGVC_E_ARG;
     for (int k = 0; k < 5; ++k) out_ms[k] = ctx->lanes[lane].fb.ms[k];
+    return UGVC_OK;
+}
+
+extern "C" int ugvc_filter_bgzf_first_records(ugvc_ctx* ctx, int lane, const uint64_t* text_offsets, int n, int64_t* out_first_record) {
+    if (!ctx || lane < 0 || lane >= (int)ctx->lanes.size() || n < 0 || (n && (!text_offsets || !out_first_record))) return UGVC_E_ARG;
+    Lane& l = ctx->lanes[lane];
+    if (!l.fb.d_out_text || l.last_n < 0) return fail(ctx, UGVC_E_STATE, "filter_bgzf_first_records: no ugvc_filter_bgzf call on this lane yet");
+    if (n == 0) return UGVC_OK;
+    if ((size_t)n * 16 > l.fb.scan_tmp_bytes) return fail(ctx, UGVC_E_ARG, "filter_bgzf_first_records: too many offsets");
+    CU(cudaSetDevice(ctx->device));
+    uint64_t* d_off = reinterpret_cast<uint64_t*>(l.fb.d_scan_tmp);
+    int64_t* d_out = reinterpret_cast<int64_t*>(d_off + n);
+    CU(cudaMemcpyAsync(d_off, text_offsets, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
+    fio_launch_first_records(l.b.line_start, l.last_n, d_off, n, d_out, l.stream);
+    CU(cudaMemcpyAsync(out_first_record, d_out, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, l.stream));
+    CU(cudaStreamSynchronize(l.stream));
     return UGVC_OK;
 }
 #endif  // !UGVC_HOST_EMU

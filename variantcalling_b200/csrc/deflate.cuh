@@ -36,7 +36,18 @@ struct DefTables {
     uint8_t dist_code[512]; // zlib's d_code table
     uint16_t dist_base[30];
     uint8_t dist_extra[30];
+    uint32_t x2n[32];       // x^(2^k) mod the CRC polynomial (reflected): the CRC32 of a concatenation from its parts
 };
+
+// a * b mod the CRC-32 polynomial, both in the reflected representation (bit 31 = x^0)
+__host__ __device__ inline uint32_t def_multmodp(uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+    for (int i = 31; i >= 0; --i) {
+        p ^= b & (0u - ((a >> i) & 1u));
+        b = (b >> 1) ^ (0xEDB88320u & (0u - (b & 1u)));
+    }
+    return p;
+}
 
 // host: fill the tables (uploaded once per context)
 static inline void def_build_tables(DefTables& t) {
@@ -50,6 +61,8 @@ static inline void def_build_tables(DefTables& t) {
         t.crc[2][i] = (t.crc[1][i] >> 8) ^ t.crc[0][t.crc[1][i] & 0xFF];
         t.crc[3][i] = (t.crc[2][i] >> 8) ^ t.crc[0][t.crc[2][i] & 0xFF];
     }
+    t.x2n[0] = 0x40000000u;  // x^1
+    for (int k = 1; k < 32; ++k) t.x2n[k] = def_multmodp(t.x2n[k - 1], t.x2n[k - 1]);
     static const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
     uint32_t len = 3;
     for (int c = 0; c < 29; ++c) {
@@ -216,3 +229,78 @@ __host__ __device__ inline uint32_t def_block(const uint8_t* in, uint32_t n, uin
     out[17] = (uint8_t)((bsize - 1) >> 8);
     return bsize;
 }
+
+// ------------------------------------------------------------------------------------------
+// pieces of the warp-per-block encoder (fileio.cu: fio_deflate_warp), shared with its host model
+// (hostio.cpp: ugvc_test_deflate_block_lanes) so that everything but the shuffles is exercised on the CPU
+// ------------------------------------------------------------------------------------------
+// CRC32 (the usual pre / post inversion) of p[0, n)
+__host__ __device__ inline uint32_t def_crc_slice(const DefTables& T, const uint8_t* p, uint32_t n) {
+    uint32_t crc = 0xFFFFFFFFu, i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t w = def_ld4(p + i) ^ crc;
+        crc = T.crc[3][w & 0xFF] ^ T.crc[2][(w >> 8) & 0xFF] ^ T.crc[1][(w >> 16) & 0xFF] ^ T.crc[0][w >> 24];
+    }
+    for (; i < n; ++i) crc = (crc >> 8) ^ T.crc[0][(crc ^ p[i]) & 0xFF];
+    return ~crc;
+}
+// crc(A || B) from crc(A), crc(B) and |B|: crc(A) * x^(8 |B|) + crc(B)
+__host__ __device__ inline uint32_t def_crc_combine(const DefTables& T, uint32_t crc_a, uint32_t crc_b, uint32_t len_b) {
+    uint32_t p = 0x80000000u;  // x^0
+    for (uint32_t n = len_b, k = 3; n; n >>= 1, ++k)
+        if (n & 1u) p = def_multmodp(T.x2n[k & 31u], p);
+    return def_multmodp(p, crc_a) ^ crc_b;
+}
+// the bits of one token, LSB first: a literal (len == 0) or a match of len bytes dist back; at most 31 bits
+__host__ __device__ inline uint32_t def_token(const DefTables& T, uint32_t lit, uint32_t len, uint32_t dist, uint32_t& nbits) {
+    if (len == 0) {
+        if (lit < 144) {
+            nbits = 8;
+            return def_rev(0x30 + lit, 8);
+        }
+        nbits = 9;
+        return def_rev(0x190 + (lit - 144), 9);
+    }
+    const uint32_t lc = T.len_code[len], lsym = lc & 31u, lx = lc >> 8;
+    uint32_t bits, n;
+    if (lsym < 23) {  // symbols 257..279: seven bits
+        bits = def_rev(lsym + 1, 7);
+        n = 7;
+    } else {
+        bits = def_rev(0xC0 + (lsym - 23), 8);
+        n = 8;
+    }
+    if (lx) {
+        bits |= (len - T.len_base[lsym]) << n;
+        n += lx;
+    }
+    const uint32_t d0 = dist - 1;
+    const uint32_t dc = d0 < 256 ? T.dist_code[d0] : T.dist_code[256 + (d0 >> 7)];
+    bits |= def_rev(dc, 5) << n;
+    n += 5;
+    const uint32_t dx = T.dist_extra[dc];
+    if (dx) {
+        bits |= (dist - T.dist_base[dc]) << n;
+        n += dx;
+    }
+    nbits = n;
+    return bits;
+}
+// the longest match of in[pos..] against in[cand..] given that the first four bytes agree; at most maxlen
+__host__ __device__ inline uint32_t def_extend(const uint8_t* in, uint32_t cand, uint32_t pos, uint32_t maxlen) {
+    uint32_t l = 4;
+    while (l + 4 <= maxlen) {
+        const uint32_t x = def_ld4(in + cand + l) ^ def_ld4(in + pos + l);
+        if (x) {
+#if defined(__CUDA_ARCH__)
+            return l + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+#else
+            return l + ((uint32_t)__builtin_ctz(x) >> 3);
+#endif
+        }
+        l += 4;
+    }
+    while (l < maxlen && in[cand + l] == in[pos + l]) ++l;
+    return l;
+}
+#define DEFW_HASH(w) (((w) * 2654435761u) >> (32 - DEF_HASH_BITS))

@@ -14,6 +14,7 @@
 // Same text as the host writer produces (tests compare the two), so the output contract is unchanged.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <cub/device/device_scan.cuh>
 
@@ -279,6 +280,148 @@ __global__ void __launch_bounds__(FIO_DEF_TPB) fio_deflate(const uint8_t* __rest
     bsize[b] = def_block(text + off, n, blocks + (size_t)b * DEF_BLOCK_STRIDE, fio_heads + ((size_t)threadIdx.x << DEF_HASH_BITS), *T);
 }
 
+// ---- deflate, one warp per block (the default).  A thread per block is bound by its own dependent chain (about
+// 2000 clocks a token: 0.7 s for a 5 M-record file); here the 32 lanes take 32 consecutive positions at a time:
+//   every lane hashes its four bytes and reads the candidate BEFORE any lane of the window inserts (so a match
+//   starts at least one window back), verifies and extends it on its own;
+//   the token starts are then picked greedily from the left with one shuffle per token (uniform loop);
+//   the token bits (def_token, <= 31 each) go to their bit offsets (warp scan) in a 32-word ring in shared memory
+//   with atomicOr, and the words that became complete are stored to the block coalesced;
+//   the CRC32 is computed as 32 slices combined pairwise (crc(A||B) = crc(A) x^(8|B|) + crc(B)).
+// hostio.cpp: ugvc_test_deflate_block_lanes is the same algorithm with the lanes as a loop (CPU tests).
+#define FIO_DEFW_WARPS 16
+#define FIO_DEFW_SMEM (FIO_DEFW_WARPS * ((2u << DEF_HASH_BITS) + 128u))
+__global__ void __launch_bounds__(FIO_DEFW_WARPS * 32) fio_deflate_warp(const uint8_t* __restrict__ text, size_t n_bytes,
+                                                                        const DefTables* __restrict__ Tp,
+                                                                        uint8_t* __restrict__ blocks,
+                                                                        uint32_t* __restrict__ bsize, int n_blocks) {
+    extern __shared__ __align__(16) uint32_t fio_sm[];
+    const unsigned FULL = 0xffffffffu;
+    const int wib = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int b = blockIdx.x * FIO_DEFW_WARPS + wib;
+    if (b >= n_blocks) return;  // warps are independent: no CTA-wide barrier below
+    uint16_t* head = reinterpret_cast<uint16_t*>(fio_sm) + ((size_t)wib << DEF_HASH_BITS);
+    uint32_t* ring = fio_sm + ((FIO_DEFW_WARPS << DEF_HASH_BITS) >> 1) + wib * 32;
+    const DefTables& T = *Tp;
+    const size_t off0 = (size_t)b * DEF_CHUNK;
+    const uint32_t n = (uint32_t)(n_bytes - off0 < DEF_CHUNK ? n_bytes - off0 : DEF_CHUNK);
+    const uint8_t* in = text + off0;
+    uint8_t* out = blocks + (size_t)b * DEF_BLOCK_STRIDE;
+    uint32_t* outw = reinterpret_cast<uint32_t*>(out + 16);  // the bit stream starts with the two BSIZE bytes
+    if (lane == 0) {  // 1f 8b 08 04 | mtime 0 | xfl 0, os ff | xlen 6 | 'B' 'C' 2 0
+        reinterpret_cast<uint64_t*>(out)[0] = 0x0000000004088b1full;
+        reinterpret_cast<uint64_t*>(out)[1] = 0x000243420006ff00ull;
+    }
+    // ---- CRC32: a slice per lane, then five pairwise combines
+    uint32_t crc;
+    {
+        const uint32_t L = (((n + 31u) >> 5) + 3u) & ~3u;
+        const uint32_t s0 = lane * L;
+        uint32_t cov = s0 < n ? (n - s0 < L ? n - s0 : L) : 0u;
+        crc = def_crc_slice(T, in + (cov ? s0 : 0u), cov);
+#pragma unroll 1
+        for (uint32_t s = 1; s < 32; s <<= 1) {
+            const uint32_t pc = __shfl_down_sync(FULL, crc, s), pl = __shfl_down_sync(FULL, cov, s);
+            if ((lane & (2u * s - 1u)) == 0u) {
+                if (pl) crc = def_crc_combine(T, crc, pc, pl);
+                cov += pl;
+            }
+        }
+    }
+    // ---- LZ77 + fixed Huffman codes
+    for (uint32_t i = lane; i < ((1u << DEF_HASH_BITS) >> 1); i += 32) reinterpret_cast<uint32_t*>(head)[i] = 0xFFFFFFFFu;
+    ring[lane] = lane == 0 ? (3u << 16) : 0u;  // BFINAL = 1, BTYPE = 01 after the 16 BSIZE bits
+    __syncwarp();
+    uint32_t bp = 19, flushed = 0, carry = 0;
+#pragma unroll 1
+    for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+        const uint32_t pos = p0 + lane;
+        const bool can = pos + DEF_MIN_MATCH <= n;
+        const uint32_t w = can ? def_ld4(in + pos) : 0u;
+        const uint32_t h = DEFW_HASH(w);
+        const uint32_t cand = can ? head[h] : 0xFFFFu;
+        __syncwarp();
+        if (can) head[h] = (uint16_t)pos;
+        __syncwarp();
+        if (carry >= 32) {  // the whole window lies inside the last match
+            carry -= 32;
+            continue;
+        }
+        uint32_t len = 0, dist = 0;
+        if (cand != 0xFFFFu && pos - cand <= 32768u && def_ld4(in + cand) == w) {
+            const uint32_t maxlen = n - pos < DEF_MAX_MATCH ? n - pos : DEF_MAX_MATCH;
+            len = def_extend(in, cand, pos, maxlen);
+            dist = pos - cand;
+        }
+        // token starts: follow "next" from the first position the last window left uncovered
+        const uint32_t nxt = lane + (len ? len : 1u);
+        const uint32_t lim = n - p0 < 32u ? n - p0 : 32u;
+        uint32_t mask = 0, cur = carry;
+        while (cur < lim) {
+            mask |= 1u << cur;
+            cur = __shfl_sync(FULL, nxt, (int)cur);
+        }
+        carry = cur >= 32u ? cur - 32u : 0u;
+        uint32_t nb = 0, bits = 0;
+        if ((mask >> lane) & 1u) bits = def_token(T, can ? (w & 0xFFu) : (uint32_t)in[pos], len, dist, nb);
+        uint32_t incl = nb;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, s);
+            if ((int)lane >= s) incl += t;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        if (nb) {
+            const uint32_t o = bp + incl - nb, wi = o >> 5, sh = o & 31u;
+            atomicOr(&ring[wi & 31u], bits << sh);
+            if (sh + nb > 32u) atomicOr(&ring[(wi + 1u) & 31u], bits >> (32u - sh));
+        }
+        bp += total;
+        __syncwarp();
+        const uint32_t full = bp >> 5;
+        if (lane < full - flushed) {  // at most ten words a window
+            const uint32_t wi = flushed + lane;
+            outw[wi] = ring[wi & 31u];
+            ring[wi & 31u] = 0u;
+        }
+        flushed = full;
+        __syncwarp();
+    }
+    bp += 7;  // end of block: seven zero bits
+    {
+        const uint32_t endw = (bp + 31u) >> 5;
+        if (flushed + lane < endw) outw[flushed + lane] = ring[(flushed + lane) & 31u];
+    }
+    __syncwarp();
+    uint32_t payload = ((bp + 7u) >> 3) - 2u;
+    if (payload >= n + 5u) {  // did not shrink: one stored block
+        if (lane == 0) {
+            uint8_t* p = out + 18;
+            p[0] = 1;
+            p[1] = (uint8_t)n;
+            p[2] = (uint8_t)(n >> 8);
+            p[3] = (uint8_t)~n;
+            p[4] = (uint8_t)(~n >> 8);
+        }
+        for (uint32_t k = lane; k < n; k += 32) out[23 + k] = in[k];
+        payload = n + 5u;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        uint8_t* ft = out + 18 + payload;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ft[k] = (uint8_t)(crc >> (8 * k));
+            ft[4 + k] = (uint8_t)(n >> (8 * k));
+        }
+        const uint32_t bs = 18u + payload + 8u;
+        out[16] = (uint8_t)(bs - 1u);
+        out[17] = (uint8_t)((bs - 1u) >> 8);
+        bsize[b] = bs;
+    }
+}
+
 __global__ void __launch_bounds__(256) fio_pack(const uint8_t* __restrict__ blocks, const uint32_t* __restrict__ bsize,
                                                 const uint64_t* __restrict__ boff, int n_blocks, uint8_t* __restrict__ packed) {
     for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
@@ -288,6 +431,25 @@ __global__ void __launch_bounds__(256) fio_pack(const uint8_t* __restrict__ bloc
         // blocks start 64 KiB apart (16-byte aligned); the packed position is arbitrary: words where both agree
         for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
     }
+}
+
+// first record starting at or after each text offset (lower bound on line_start[0, n])
+__global__ void fio_first_records(const int64_t* __restrict__ line_start, int64_t n, const uint64_t* __restrict__ offsets, int m,
+                                  int64_t* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const int64_t want = (int64_t)offsets[k];
+    int64_t lo = 0, hi = n;  // answer in [0, n]
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (line_start[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    out[k] = lo;
+}
+void fio_launch_first_records(const int64_t* line_start, int64_t n, const uint64_t* offsets, int m, int64_t* out, cudaStream_t st) {
+    if (m <= 0) return;
+    fio_first_records<<<(m + 63) / 64, 64, 0, st>>>(line_start, n, offsets, m, out);
 }
 
 __global__ void fio_widen(const uint32_t* __restrict__ bsize, uint64_t* __restrict__ wide, int n) {
@@ -321,10 +483,17 @@ void fio_launch_deflate(const uint8_t* text, size_t n_bytes, const DefTables* ta
                         int n_blocks, cudaStream_t st) {
     if (n_blocks <= 0) return;
     const size_t smem = (size_t)FIO_DEF_TPB * sizeof(uint16_t) << DEF_HASH_BITS;
-    static bool configured = false;
-    if (!configured) {
+    static int thread_per_block = -1;  // UGVC_DEFLATE_THREADS=1: the thread-per-block encoder (A/B)
+    if (thread_per_block < 0) {
+        const char* e = getenv("UGVC_DEFLATE_THREADS");
+        thread_per_block = e && e[0] == '1' ? 1 : 0;
         cudaFuncSetAttribute(fio_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        cudaFuncSetAttribute(fio_deflate_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIO_DEFW_SMEM);
+    }
+    if (!thread_per_block) {
+        fio_deflate_warp<<<(n_blocks + FIO_DEFW_WARPS - 1) / FIO_DEFW_WARPS, FIO_DEFW_WARPS * 32, FIO_DEFW_SMEM, st>>>(
+            text, n_bytes, tables, blocks, bsize, n_blocks);
+        return;
     }
     fio_deflate<<<(n_blocks + FIO_DEF_TPB - 1) / FIO_DEF_TPB, FIO_DEF_TPB, smem, st>>>(text, n_bytes, tables, blocks, bsize, n_blocks);
 }

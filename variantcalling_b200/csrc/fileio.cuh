@@ -19,3 +19,4 @@ void fio_launch_deflate(const uint8_t* text, size_t n_bytes, const DefTables* ta
 void fio_launch_pack(const uint8_t* blocks, const uint32_t* bsize, uint64_t* wide, const uint64_t* boff, int n_blocks,
                      uint8_t* packed, int sm_count, cudaStream_t st);
 void fio_launch_widen(const uint32_t* bsize, uint64_t* wide, int n, cudaStream_t st);
+void fio_launch_first_records(const int64_t* line_start, int64_t n, const uint64_t* offsets, int m, int64_t* out, cudaStream_t st);

@@ -691,3 +691,92 @@ extern "C" int64_t ugvc_test_deflate_block(const uint8_t* in, uint32_t n, uint8_
     memcpy(out, buf, sz);
     return (int64_t)sz;
 }
+
+// Host model of fio_deflate_warp (fileio.cu): the same windows of 32 positions, the same candidate rule (the hash
+// table is read by all 32 positions before any of them is inserted), the same token selection, bit layout and
+// slice-wise CRC -- with the lanes as a loop.  Test hook: the CPU suite inflates its output with zlib.
+extern "C" int64_t ugvc_test_deflate_block_lanes(const uint8_t* in_, uint32_t n, uint8_t* out) {
+    if (!in_ || !out || n > DEF_CHUNK) return UGVC_E_ARG;
+    static DefTables* T = [] {
+        DefTables* t = new DefTables();
+        def_build_tables(*t);
+        return t;
+    }();
+    std::vector<uint8_t> inbuf((size_t)n + 64, 0);  // the encoder reads whole words past the end
+    memcpy(inbuf.data() + 16, in_, n);
+    const uint8_t* in = inbuf.data() + 16;
+    std::vector<uint16_t> head(1u << DEF_HASH_BITS, 0xFFFFu);
+    std::vector<uint32_t> words((DEF_BLOCK_STRIDE >> 2), 0u);  // the bit stream from byte 16 of the block
+    const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    memcpy(out, hdr, 16);
+    // CRC: 32 slices, combined pairwise
+    const uint32_t L = (((n + 31u) / 32u) + 3u) & ~3u;
+    uint32_t crc[32], cov[32];
+    for (uint32_t lane = 0; lane < 32; ++lane) {
+        const uint32_t s0 = lane * L, len = s0 < n ? (n - s0 < L ? n - s0 : L) : 0;
+        crc[lane] = def_crc_slice(*T, in + (len ? s0 : 0), len);
+        cov[lane] = len;
+    }
+    for (uint32_t s = 1; s < 32; s <<= 1)
+        for (uint32_t lane = 0; lane < 32; lane += 2 * s) {
+            crc[lane] = def_crc_combine(*T, crc[lane], crc[lane + s], cov[lane + s]);
+            cov[lane] += cov[lane + s];
+        }
+    words[0] = 3u << 16;
+    uint32_t bp = 19, carry = 0;
+    for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+        uint32_t w[32], cand[32], len[32], dist[32];
+        bool can[32];
+        for (uint32_t lane = 0; lane < 32; ++lane) {
+            const uint32_t pos = p0 + lane;
+            can[lane] = pos + 4 <= n;
+            w[lane] = can[lane] ? def_ld4(in + pos) : 0;
+            cand[lane] = can[lane] ? head[DEFW_HASH(w[lane])] : 0xFFFFu;
+        }
+        for (uint32_t lane = 0; lane < 32; ++lane)
+            if (can[lane]) head[DEFW_HASH(w[lane])] = (uint16_t)(p0 + lane);  // the highest lane wins, like the last store
+        for (uint32_t lane = 0; lane < 32; ++lane) {
+            const uint32_t pos = p0 + lane;
+            len[lane] = dist[lane] = 0;
+            if (carry < 32 && cand[lane] != 0xFFFFu && pos - cand[lane] <= 32768u && def_ld4(in + cand[lane]) == w[lane]) {
+                const uint32_t maxlen = n - pos < DEF_MAX_MATCH ? n - pos : DEF_MAX_MATCH;
+                len[lane] = def_extend(in, cand[lane], pos, maxlen);
+                dist[lane] = pos - cand[lane];
+            }
+        }
+        const uint32_t lim = n - p0 < 32 ? n - p0 : 32;
+        uint32_t cur = carry;
+        while (cur < lim) {
+            uint32_t nb = 0;
+            const uint32_t bits = def_token(*T, in[p0 + cur], len[cur], dist[cur], nb);
+            const uint32_t wi = bp >> 5, sh = bp & 31u;
+            words[wi] |= bits << sh;
+            if (sh + nb > 32) words[wi + 1] |= bits >> (32 - sh);
+            bp += nb;
+            cur += len[cur] ? len[cur] : 1;
+        }
+        carry = cur >= 32 ? cur - 32 : 0;
+    }
+    bp += 7;  // end of block: seven zero bits
+    uint32_t payload = ((bp + 7) >> 3) - 2;
+    memcpy(out + 16, words.data(), (size_t)payload + 2);
+    if (payload >= n + 5) {
+        uint8_t* p = out + 18;
+        p[0] = 1;
+        p[1] = (uint8_t)n;
+        p[2] = (uint8_t)(n >> 8);
+        p[3] = (uint8_t)~n;
+        p[4] = (uint8_t)(~n >> 8);
+        memcpy(p + 5, in, n);
+        payload = n + 5;
+    }
+    uint8_t* ft = out + 18 + payload;
+    for (int k = 0; k < 4; ++k) {
+        ft[k] = (uint8_t)(crc[0] >> (8 * k));
+        ft[4 + k] = (uint8_t)(n >> (8 * k));
+    }
+    const uint32_t bsize = 18 + payload + 8;
+    out[16] = (uint8_t)(bsize - 1);
+    out[17] = (uint8_t)((bsize - 1) >> 8);
+    return (int64_t)bsize;
+}

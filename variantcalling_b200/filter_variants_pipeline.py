@@ -164,9 +164,10 @@ class _Splicer:
         self._check_writer()
         self._queue.put((contig, out[:nb], n, beg, beg + np.maximum(1, (ri["flags"] >> 8).astype(np.int64)), out_ls))
 
-    def write_device_batch(self, contig: str, res: dict, release=None):
+    def write_device_batch(self, contigs: list[str], bounds: np.ndarray, res: dict, release=None):
         """Records edited and BGZF-compressed on the device (lib.Context.filter_bgzf): only file and index work is left.
-        `release` is called once the buffers of `res` are no longer needed."""
+        The batch holds the records of `contigs` in order, contig k in [bounds[k], bounds[k + 1]).  `release` is called
+        once the buffers of `res` are no longer needed."""
         n = res["n_records"]
         if n == 0:
             if release:
@@ -175,10 +176,10 @@ class _Splicer:
         ri = res["recinfo"]
         beg = ri["pos"].astype(np.int64) - 1
         self._check_writer()
-        self._queue.put((contig, (res["bgzf"], res["block_csize"], release), n, beg,
+        self._queue.put(((list(contigs), np.asarray(bounds, dtype=np.int64)), (res["bgzf"], res["block_csize"], release), n, beg,
                          beg + np.maximum(1, (ri["flags"] >> 8).astype(np.int64)), res["line_start"]))
 
-    def _write_spliced(self, contig: str, data, n: int, beg: np.ndarray, end: np.ndarray, out_ls: np.ndarray):
+    def _write_spliced(self, contig, data, n: int, beg: np.ndarray, end: np.ndarray, out_ls: np.ndarray):
         t0 = time.perf_counter()
         base = self.writer.uoffset
         c_before = self.writer.coffset
@@ -186,20 +187,27 @@ class _Splicer:
             self.writer.write_compressed(data[0], data[1], int(out_ls[-1]), lib.DEF_CHUNK)
         else:
             self.writer.write(data)
-        self.ranges[contig] = (self.ranges.get(contig, (c_before, 0))[0], self.writer.coffset)
-        if not self.names or self.names[-1] != contig:
-            self._close_section()
-            self.names.append(contig)
-        if self.keep_arrays:
-            self.contig_of.append(np.full(n, len(self.names) - 1, dtype=np.int32))
-            self.beg.append(beg)
-            self.end.append(end)
-            self.u_start.append(base + out_ls[:-1])
-            self.u_end.append(base + out_ls[1:])
-        else:
+        contigs, bounds = contig if isinstance(contig, tuple) else ([contig], np.array([0, n], dtype=np.int64))
+        if len(contigs) == 1:  # (multi-rank runs: always; rank 0 copies the contig's blocks as they are)
+            self.ranges[contigs[0]] = (self.ranges.get(contigs[0], (c_before, 0))[0], self.writer.coffset)
+        if not self.keep_arrays:
             vs = self.writer.virtual_offsets(base + out_ls[:-1])
             ve = self.writer.virtual_offsets(base + out_ls[1:] - 1) + np.uint64(1)
-            self._cur.append((beg, end, vs, ve))
+        for k, name in enumerate(contigs):
+            r0, r1 = int(bounds[k]), int(bounds[k + 1])
+            if r1 <= r0:
+                continue
+            if not self.names or self.names[-1] != name:
+                self._close_section()
+                self.names.append(name)
+            if self.keep_arrays:
+                self.contig_of.append(np.full(r1 - r0, len(self.names) - 1, dtype=np.int32))
+                self.beg.append(beg[r0:r1])
+                self.end.append(end[r0:r1])
+                self.u_start.append(base + out_ls[r0:r1])
+                self.u_end.append(base + out_ls[r0 + 1:r1 + 1])
+            else:
+                self._cur.append((beg[r0:r1], end[r0:r1], vs[r0:r1], ve[r0:r1]))
         self.seconds["deflate"] += time.perf_counter() - t0
         if isinstance(data, tuple) and data[2] is not None:
             data[2]()  # the device batch's buffers may be reused
@@ -365,6 +373,19 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         transformer = None
         blacklists = None
 
+        # the CUDA context comes up on its own thread (the driver calls release the GIL) while this one unpickles the
+        # model, which imports the estimator's library: the two longest start-up steps of a run side by side
+        world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+        multi = world > 1
+        device = args.device if args.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
+        numa = None
+        if multi:
+            from variantcalling_b200 import dist as vdist0
+
+            numa = vdist0.bind_to_gpu_numa_node(device)
+        ctx_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-cuda-init")
+        ctx_future = ctx_pool.submit(lib.Context, device)
+
         if args.model_file is not None:
             logger.info(f"Loading model from {args.model_file}")
             mf = _load_pickle(args.model_file)
@@ -387,15 +408,10 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         # one process per GPU (torchrun): ranks own whole contigs, no record ever crosses ranks; the only
         # collective is the SUM of the counters at the end (NCCL on GPUs; gloo when there is no CUDA device,
         # i.e. in the host-emulation test)
-        world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
-        multi = world > 1
-
-        device = args.device if args.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
         if multi:
-            from variantcalling_b200 import dist as vdist0
-
-            logger.info(f"rank {rank}: NUMA binding {vdist0.bind_to_gpu_numa_node(device)}")
-        ctx = lib.Context(device)  # raises without a CUDA device: there is no CPU path
+            logger.info(f"rank {rank}: NUMA binding {numa}")
+        ctx = ctx_future.result()  # raises without a CUDA device: there is no CPU path
+        ctx_pool.shutdown(wait=False)
         plan = None
         if with_model:
             if model is None or transformer is None:
@@ -471,25 +487,11 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         file_flags = (lib.FILE_OVERWRITE_QUAL if args.overwrite_qual_tag else 0) | \
                      (lib.FILE_BLACKLIST_CG if args.blacklist_cg_insertions else 0)
 
-        def load_contig(contig: str, on_device: bool = False):
-            """Inflate one contig's records (runs one contig ahead of the loop, on its own thread) -- or, for the
-            device-side file path, just read its compressed blocks."""
+        def load_contig(contig: str):
+            """Inflate one contig's records (runs one contig ahead of the loop, on its own thread)."""
             if contig not in index:
                 return None
             vb, ve = index[contig]
-            if on_device:
-                c0, c1, skip, take = bgzf_io.range_info(args.input_file, vb, ve)
-                if take == 0:
-                    return None
-                ctx.bind_thread()  # the reader thread pins memory for this rank's device
-                bufs = in_pool.acquire({"comp": (c1 - c0, np.uint8)})
-                comp = bufs["comp"][1]
-                with open(args.input_file, "rb") as fh:
-                    fh.seek(c0)
-                    got = fh.readinto(memoryview(comp))
-                if got != c1 - c0:
-                    raise OSError(f"{args.input_file}: short read of {contig}")
-                return "device", comp, skip, take, bufs
             text = bgzf_io.inflate(args.input_file, vb, ve, n_threads=args.io_threads)
             if text.size == 0:
                 return None
@@ -497,62 +499,12 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 text = np.concatenate((text, np.array([10], dtype=np.uint8)))
             return text, bgzf_io.count_lines(text, args.io_threads)
 
-        in_pool, out_pool = _PinnedPool(2), _PinnedPool(3)
+        in_pool, out_pool = _PinnedPool(2), _PinnedPool(2)
         dev_ms = np.zeros(5)
-        prefetch = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-bgzf-reader")
-        pending = prefetch.submit(load_contig, contigs[0], device_io) if contigs else None
-        for ci, contig in enumerate(contigs):
-            logger.info(f"Filtering variants from {contig}")
-            t_wait = time.perf_counter()
-            loaded = pending.result()
-            seconds["inflate_wait"] += time.perf_counter() - t_wait
-            pending = prefetch.submit(load_contig, contigs[ci + 1], device_io) if ci + 1 < len(contigs) else None
-            if loaded is None:
-                logger.info(f"No variants found on {contig}")
-                continue
-            if isinstance(loaded[0], str):  # ("device", compressed blocks, skip, take)
-                _tag, comp, skip, take, in_bufs = loaded
-                if args.blacklist_cg_insertions:
-                    logger.info("Marking CG insertions")
-                if not key_order_set:
-                    head = bgzf_io.first_block_text(comp, skip)
-                    ctx.set_key_order(*lib.learn_key_order(head[: head.rfind(b"\n") + 1]))
-                    key_order_set = True
-                need = (take + (1 << 17) + 4096, take // 32 + 1024)  # whole blocks are inflated: up to 64 KiB either side of the range
-                t_alloc = time.perf_counter()
-                if need[0] > reserved[0] or need[1] > reserved[1]:
-                    reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))
-                    ctx.reserve(reserved[0], reserved[1], n_lanes)
-                n_max = take // 32 + 1024
-                # VCF text deflates to well under half its size; text that does not comes back as UGVC_E_FALLBACK
-                out_bufs = out_pool.acquire({"out": (take * 5 // 8 + (1 << 20), np.uint8),
-                                             "blocks": ((take + n_max * 64) // lib.DEF_CHUNK + 16, np.uint32),
-                                             "ri": (n_max, lib.RECINFO_DTYPE), "ls": (n_max + 1, np.int64), "low": (n_max, np.uint8)})
-                seconds["alloc"] += time.perf_counter() - t_alloc
-                t_gpu = time.perf_counter()
-                res = ctx.filter_bgzf(comp, skip, take, args.decision_threshold, file_flags, n_max,
-                                      bufs={k: v[1] for k, v in out_bufs.items()})
-                seconds["gpu"] += time.perf_counter() - t_gpu
-                in_pool.release(in_bufs)
-                if res is None:
-                    out_pool.release(out_bufs)
-                else:
-                    dev_ms += np.array(ctx.filter_bgzf_stage_ms())
-                    logger.info(f"{res['n_records']} variants found on {contig}")
-                    logger.info("Writing records")
-                    out.write_device_batch(contig, res, release=lambda b=out_bufs: out_pool.release(b))
-                    totals["n_records"] += res["n_records"]
-                    totals["n_low_score"] += int(res["low_score"].sum())
-                    if args.blacklist_cg_insertions:
-                        n_cg = int(np.count_nonzero(res["recinfo"]["flags"] & 1))
-                        totals["n_cg"] += n_cg
-                        totals["n_blacklisted"] += n_cg
-                    logger.info(f"{contig} done")
-                    continue
-                logger.info(f"{contig}: records that need the general writer, taking the host path")
-                loaded = load_contig(contig)
-                if loaded is None:
-                    continue
+
+        def host_contig(contig: str, loaded):
+            """One contig through the host readers / writers (text inflated on the host, records spliced on host threads)."""
+            nonlocal reserved, idx_reserved, key_order_set
             text, n_contig = loaded
             logger.info(f"{n_contig} variants found on {contig}")
             if blacklists is not None:
@@ -596,7 +548,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 totals["n_records"] += n
                 totals["n_low_score"] += int(low.sum())
                 logger.info(f"{contig} done")
-                continue
+                return
 
             ranges = list(_split_batches(text, batch_bytes))
             # records per batch (one scan of the text at most: a contig that fits one batch was counted on load)
@@ -635,6 +587,122 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             while inflight:
                 finish(inflight.pop(0))
             logger.info(f"{contig} done")
+
+
+        # ---- work list: the host path takes a contig at a time; the device-side file path takes runs of contigs that are
+        # adjacent in the file, so that a call inflates / encodes tens of thousands of BGZF blocks at once (a block is a
+        # warp's work: small contigs alone leave most of the GPU idle).  Multi-rank runs keep whole contigs per call: rank 0
+        # copies each contig's blocks verbatim, which needs them to start on a block boundary.
+        def device_groups():
+            groups, cur, cur_bytes, last_ve = [], [], 0, None
+            for c in contigs:
+                if c not in index:
+                    continue
+                vb, ve = index[c]
+                span = int(ve >> 16) - int(vb >> 16)
+                if cur and (multi or vb != last_ve or cur_bytes + span > group_bytes):
+                    groups.append(cur)
+                    cur, cur_bytes = [], 0
+                cur.append(c)
+                cur_bytes += span
+                last_ve = ve
+            if cur:
+                groups.append(cur)
+            return groups
+
+        group_bytes = max(1, args.batch_mb) << 18  # compressed bytes a call: about batch_mb of text at the usual ratio of 4
+        work = device_groups() if device_io else [[c] for c in contigs]
+        for c in contigs if device_io else []:
+            if c not in index:
+                logger.info(f"Filtering variants from {c}")
+                logger.info(f"No variants found on {c}")
+
+        def load_group(group: list[str]):
+            """The compressed blocks of a run of adjacent contigs and where each contig's text begins in them."""
+            infos = [bgzf_io.range_info(args.input_file, *index[c]) for c in group]
+            live = [(c, i) for c, i in zip(group, infos) if i[3] > 0]
+            if not live:
+                return None
+            c0, c1, skip = live[0][1][0], live[-1][1][1], live[0][1][2]
+            starts, take = [], 0
+            for _c, i in live:
+                starts.append(take)
+                take += i[3]
+            ctx.bind_thread()  # the reader thread pins memory for this rank's device
+            bufs = in_pool.acquire({"comp": (c1 - c0, np.uint8)})
+            comp = bufs["comp"][1]
+            with open(args.input_file, "rb") as fh:
+                fh.seek(c0)
+                got = fh.readinto(memoryview(comp))
+            if got != c1 - c0:
+                raise OSError(f"{args.input_file}: short read of {group[0]}..{group[-1]}")
+            return "device", comp, skip, take, bufs, [c for c, _ in live], np.array(starts, dtype=np.uint64)
+
+        def load_work(group: list[str]):
+            return load_group(group) if device_io else load_contig(group[0])
+
+        prefetch = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-bgzf-reader")
+        pending = prefetch.submit(load_work, work[0]) if work else None
+        for gi, group in enumerate(work):
+            for c in group:
+                logger.info(f"Filtering variants from {c}")
+            t_wait = time.perf_counter()
+            loaded = pending.result()
+            seconds["inflate_wait"] += time.perf_counter() - t_wait
+            pending = prefetch.submit(load_work, work[gi + 1]) if gi + 1 < len(work) else None
+            if loaded is None:
+                for c in group:
+                    logger.info(f"No variants found on {c}")
+                continue
+            if not isinstance(loaded[0], str):
+                host_contig(group[0], loaded)
+                continue
+            _tag, comp, skip, take, in_bufs, live, starts = loaded  # ("device", compressed blocks, ...)
+            if args.blacklist_cg_insertions:
+                logger.info("Marking CG insertions")
+            if not key_order_set:
+                head = bgzf_io.first_block_text(comp, skip)
+                ctx.set_key_order(*lib.learn_key_order(head[: head.rfind(b"\n") + 1]))
+                key_order_set = True
+            need = (take + (1 << 17) + 4096, take // 32 + 1024)  # whole blocks are inflated: up to 64 KiB either side of the range
+            t_alloc = time.perf_counter()
+            if need[0] > reserved[0] or need[1] > reserved[1]:
+                reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))
+                ctx.reserve(reserved[0], reserved[1], n_lanes)
+            n_max = take // 32 + 1024
+            # VCF text deflates to well under half its size; text that does not comes back as UGVC_E_FALLBACK
+            out_bufs = out_pool.acquire({"out": (take * 5 // 8 + (1 << 20), np.uint8),
+                                         "blocks": ((take + n_max * 64) // lib.DEF_CHUNK + 16, np.uint32),
+                                         "ri": (n_max, lib.RECINFO_DTYPE), "ls": (n_max + 1, np.int64), "low": (n_max, np.uint8)})
+            seconds["alloc"] += time.perf_counter() - t_alloc
+            t_gpu = time.perf_counter()
+            res = ctx.filter_bgzf(comp, skip, take, args.decision_threshold, file_flags, n_max,
+                                  bufs={k: v[1] for k, v in out_bufs.items()})
+            first = ctx.filter_bgzf_first_records(starts) if res is not None else None
+            seconds["gpu"] += time.perf_counter() - t_gpu
+            in_pool.release(in_bufs)
+            if res is None:
+                out_pool.release(out_bufs)
+                logger.info(f"{live[0]}..{live[-1]}: records that need the general writer, taking the host path")
+                for c in live:
+                    again = load_contig(c)
+                    if again is not None:
+                        host_contig(c, again)
+                continue
+            dev_ms += np.array(ctx.filter_bgzf_stage_ms())
+            bounds = np.concatenate((first, [res["n_records"]])).astype(np.int64)
+            for k, c in enumerate(live):
+                logger.info(f"{int(bounds[k + 1] - bounds[k])} variants found on {c}")
+            logger.info("Writing records")
+            out.write_device_batch(live, bounds, res, release=lambda b=out_bufs: out_pool.release(b))
+            totals["n_records"] += res["n_records"]
+            totals["n_low_score"] += int(res["low_score"].sum())
+            if args.blacklist_cg_insertions:
+                n_cg = int(np.count_nonzero(res["recinfo"]["flags"] & 1))
+                totals["n_cg"] += n_cg
+                totals["n_blacklisted"] += n_cg
+            for c in live:
+                logger.info(f"{c} done")
 
         t_close = time.perf_counter()
         if multi:

@@ -98,12 +98,14 @@ SIGNATURES = {
     "ugvc_conc_classify": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "ugvc_conc_curve": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz]),
     "ugvc_test_deflate_block": (C.c_int64, [_vp, C.c_uint32, _vp]),
+    "ugvc_test_deflate_block_lanes": (C.c_int64, [_vp, C.c_uint32, _vp]),
     "ugvc_test_device_sigmoid": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "ugvc_bgzf_range_info": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "ugvc_filter_bgzf": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_uint32, C.c_uint64, C.c_double, C.c_int, _vp, _sz, C.POINTER(_sz),
                                    _vp, _sz, C.POINTER(_sz), _vp, _vp, _vp, _sz, C.POINTER(C.c_int64)]),
     "ugvc_filter_bgzf_stage_ms": (C.c_int, [_vp, C.c_int, _vp]),
+    "ugvc_filter_bgzf_first_records": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
     "ugvc_test_parse_float": (C.c_int, [C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_double),
                                         C.POINTER(C.c_int)]),
 }
@@ -327,6 +329,13 @@ class Context:
         k = n.value
         return {"n_records": k, "bgzf": out[: nb.value], "block_csize": blocks[: nblk.value], "recinfo": ri[:k],
                 "line_start": ls[: k + 1], "low_score": low[:k]}
+
+    def filter_bgzf_first_records(self, text_offsets, lane: int = 0) -> np.ndarray:
+        """Index of the first record at or after each byte offset of the last filter_bgzf range's text."""
+        off = np.ascontiguousarray(text_offsets, dtype=np.uint64)
+        out = np.empty(off.size, dtype=np.int64)
+        self._check(self.lib.ugvc_filter_bgzf_first_records(self.h, lane, _ptr(off), off.size, _ptr(out)))
+        return out
 
     def filter_bgzf_stage_ms(self, lane: int = 0) -> list[float]:
         ms = (C.c_float * 5)()
