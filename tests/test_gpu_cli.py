@@ -192,3 +192,27 @@ def test_cli_small_batches_long_lines_and_rescoring(job):
     assert all(r.count("TREE_SCORE=") == 1 for r in recs2)
     assert any(r.split("\t")[6] == "LOW_SCORE" for r in recs1) and sum("LOW_SCORE" in r.split("\t")[6] for r in recs2) >= \
         sum("LOW_SCORE" in r.split("\t")[6] for r in recs1)
+
+
+def test_cli_device_groups_cut_contigs_at_index_entries(job):
+    """--batch_mb 1: the device-side file path takes pieces of about 128 KiB of compressed input -- chr1 is cut at entries
+    of the input's tabix linear index, chr2 and chr3 share a call -- and the output (records, index) is what one call
+    per contig and the host writers produce."""
+    ds = job["ds"]
+    base = ["--input_file", job["vcf"], "--model_file", job["model"]] + [a for c in ds["customs"] for a in ("--custom_annotations", c)]
+    outs = {}
+    for tag, extra in (("pieces", ["--batch_mb", "1"]), ("whole", []), ("host", ["--host_io"])):
+        outs[tag] = str(job["dir"] / f"out_groups_{tag}.vcf.gz")
+        fvp.run(base + ["--output_file", outs[tag]] + extra)
+    exp = R.filter_variants(ds["vf"], job["model_obj"], job["tr"], custom_annotations=ds["customs"])
+    for tag, path in outs.items():
+        hdr, recs = read_out(path)
+        assert hdr == exp["header"] and recs == exp["lines"], tag
+        idx = bgzf_io.read_tbi(path + ".tbi")
+        assert list(idx) == ["chr1", "chr2", "chr3"], tag
+        for contig, (vb, ve) in idx.items():
+            got = bgzf_io.inflate(path, vb, ve).tobytes().decode().split("\n")[:-1]
+            assert got == [l for l in exp["lines"] if l.split("\t", 1)[0] == contig], (tag, contig)
+    # the pieces really were pieces: the linear index of the input offers cut points inside chr1
+    _, lin = bgzf_io.read_tbi(job["vcf"] + ".tbi", linear=True)
+    assert lin["chr1"].size > 4

@@ -297,8 +297,10 @@ def write_tbi(path: str, payload: bytes):
     w.write(payload, last=True)
 
 
-def read_tbi(path: str) -> dict:
-    """{contig: (min chunk begin voff, max chunk end voff)} in file order, from a ``.tbi``."""
+def read_tbi(path: str, linear: bool = False):
+    """{contig: (min chunk begin voff, max chunk end voff)} in file order, from a ``.tbi``.  linear=True: also
+    {contig: the distinct virtual offsets of its linear index, ascending} -- each is where a record starts, so a
+    contig can be cut there into pieces that are read (and filtered) independently."""
     with gzip.open(path, "rb") as fh:
         data = fh.read()
     if data[:4] != b"TBI\x01":
@@ -307,7 +309,7 @@ def read_tbi(path: str) -> dict:
     p = 36
     names = data[p:p + l_nm].split(b"\0")[:n_ref]
     p += l_nm
-    out = {}
+    out, lin = {}, {}
     for r in range(n_ref):
         (n_bin,) = struct.unpack_from("<i", data, p)
         p += 4
@@ -323,10 +325,13 @@ def read_tbi(path: str) -> dict:
             lo = b if lo is None else min(lo, b)
             hi = e if hi is None else max(hi, e)
         (n_intv,) = struct.unpack_from("<i", data, p)
+        if linear and lo is not None:
+            io = np.unique(np.frombuffer(data, dtype="<u8", count=n_intv, offset=p + 4))
+            lin[names[r].decode()] = io[(io > lo) & (io < hi)]
         p += 4 + 8 * n_intv
         if lo is not None:
             out[names[r].decode()] = (lo, hi)
-    return out
+    return (out, lin) if linear else out
 
 
 def write_vcf_gz(path: str, header_lines: list[str], record_lines: list[str], n_threads: int = 0):

@@ -118,6 +118,7 @@ class _Splicer:
         self._error: BaseException | None = None
         self._thread = threading.Thread(target=self._drain, name="ugvc-bgzf-writer", daemon=True)
         self._thread.start()
+        self._index_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-tabix")  # sections, in contig order
 
     def _drain(self):
         while True:
@@ -215,12 +216,17 @@ class _Splicer:
     def _close_section(self):
         if self.keep_arrays or not self.names:
             return
-        t0 = time.perf_counter()
-        cat = np.concatenate
-        cols = [cat([c[k] for c in self._cur]) if self._cur else np.zeros(0, np.int64) for k in range(4)]
-        self.sections.append(bgzf_io.tbi_section(cols[0], cols[1], cols[2].astype(np.uint64), cols[3].astype(np.uint64)))
-        self._cur = []
-        self.seconds["index"] = self.seconds.get("index", 0.0) + time.perf_counter() - t0
+        cur, self._cur = self._cur, []
+
+        def section():
+            t0 = time.perf_counter()
+            cat = np.concatenate
+            cols = [cat([c[k] for c in cur]) if cur else np.zeros(0, np.int64) for k in range(4)]
+            sec = bgzf_io.tbi_section(cols[0], cols[1], cols[2].astype(np.uint64), cols[3].astype(np.uint64))
+            self.seconds["index"] = self.seconds.get("index", 0.0) + time.perf_counter() - t0
+            return sec
+
+        self.sections.append(self._index_pool.submit(section))
 
     def _finish_writer(self):
         self._queue.put(None)
@@ -250,7 +256,8 @@ class _Splicer:
         self._finish_writer()
         self.writer.close()
         self._close_section()
-        bgzf_io.write_tbi(path + ".tbi", bgzf_io.tbi_assemble(self.names, self.sections))
+        bgzf_io.write_tbi(path + ".tbi", bgzf_io.tbi_assemble(self.names, [f.result() for f in self.sections]))
+        self._index_pool.shutdown()
 
 
 class _PinnedPool:
@@ -262,7 +269,9 @@ class _PinnedPool:
         for _ in range(n_sets):
             self._free.put({})
 
-    def acquire(self, sizes: dict) -> dict:
+    def acquire(self, sizes: dict, grow: float = 1.0) -> dict:
+        """`grow`: how much larger than this request the largest one is expected to be (buffers are sized for that when
+        they have to be page-locked, so that they are page-locked once)."""
         bufs = self._free.get()
         for key, (n_items, dtype) in sizes.items():
             need = int(n_items) * np.dtype(dtype).itemsize
@@ -270,7 +279,7 @@ class _PinnedPool:
             if have is None or have[0].array.size < need:
                 if have is not None:
                     have[0].free()
-                pb = lib.PinnedBuffer(need + need // 16 + 4096)
+                pb = lib.PinnedBuffer(int(need * max(1.0, grow)) + need // 16 + 4096)
                 bufs[key] = (pb, None)
             pb = bufs[key][0]
             bufs[key] = (pb, pb.array[: need].view(dtype))
@@ -404,7 +413,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         with_model = args.model_file is not None
         with_bl = args.blacklist is not None or args.blacklist_cg_insertions
         out_header = header.edited_lines(with_model=with_model, with_blacklist=with_bl)
-        index = bgzf_io.read_tbi(args.input_file + ".tbi")
+        index, linear_index = bgzf_io.read_tbi(args.input_file + ".tbi", linear=True)
         # one process per GPU (torchrun): ranks own whole contigs, no record ever crosses ranks; the only
         # collective is the SUM of the counters at the end (NCCL on GPUs; gloo when there is no CUDA device,
         # i.e. in the host-emulation test)
@@ -487,11 +496,12 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         file_flags = (lib.FILE_OVERWRITE_QUAL if args.overwrite_qual_tag else 0) | \
                      (lib.FILE_BLACKLIST_CG if args.blacklist_cg_insertions else 0)
 
-        def load_contig(contig: str):
-            """Inflate one contig's records (runs one contig ahead of the loop, on its own thread)."""
+        def load_contig(contig: str, piece: tuple | None = None):
+            """Inflate one contig's records, or the piece of it between two virtual offsets (runs one contig ahead of
+            the loop, on its own thread)."""
             if contig not in index:
                 return None
-            vb, ve = index[contig]
+            vb, ve = piece if piece is not None else index[contig]
             text = bgzf_io.inflate(args.input_file, vb, ve, n_threads=args.io_threads)
             if text.size == 0:
                 return None
@@ -594,68 +604,81 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         # warp's work: small contigs alone leave most of the GPU idle).  Multi-rank runs keep whole contigs per call: rank 0
         # copies each contig's blocks verbatim, which needs them to start on a block boundary.
         def device_groups():
-            groups, cur, cur_bytes, last_ve = [], [], 0, None
+            """[[(contig, begin voff, end voff), ...], ...]: pieces adjacent in the file, about group_bytes compressed a group.
+            Contigs longer than that are cut at entries of the tabix linear index (record starts)."""
+            pieces = []
             for c in contigs:
                 if c not in index:
                     continue
                 vb, ve = index[c]
-                span = int(ve >> 16) - int(vb >> 16)
-                if cur and (multi or vb != last_ve or cur_bytes + span > group_bytes):
+                cuts = [vb]
+                if not multi:
+                    for v in linear_index.get(c, ()):
+                        if (int(v) >> 16) - (cuts[-1] >> 16) >= group_bytes and (ve >> 16) - (int(v) >> 16) >= group_bytes // 4:
+                            cuts.append(int(v))
+                cuts.append(ve)
+                pieces += [(c, cuts[k], cuts[k + 1]) for k in range(len(cuts) - 1)]
+            groups, cur, cur_bytes = [], [], 0
+            for c, vb, ve in pieces:
+                span = (ve >> 16) - (vb >> 16)
+                if cur and (multi or vb != cur[-1][2] or cur_bytes + span > group_bytes + group_bytes // 4):
                     groups.append(cur)
                     cur, cur_bytes = [], 0
-                cur.append(c)
+                cur.append((c, vb, ve))
                 cur_bytes += span
-                last_ve = ve
             if cur:
                 groups.append(cur)
             return groups
 
-        group_bytes = max(1, args.batch_mb) << 18  # compressed bytes a call: about batch_mb of text at the usual ratio of 4
-        work = device_groups() if device_io else [[c] for c in contigs]
+        # compressed bytes a call: about batch_mb / 2 of text at the usual ratio of 4 -- thousands of BGZF blocks in flight
+        # (a block is a warp's work), buffers small enough that page-locking them does not cost more than the copies save
+        group_bytes = max(1, args.batch_mb) << 17
+        work = device_groups() if device_io else [[(c, 0, 0)] for c in contigs]
+        max_span = max([(g[-1][2] >> 16) - (g[0][1] >> 16) + (1 << 16) for g in work], default=0) if device_io else 0
         for c in contigs if device_io else []:
             if c not in index:
                 logger.info(f"Filtering variants from {c}")
                 logger.info(f"No variants found on {c}")
 
-        def load_group(group: list[str]):
-            """The compressed blocks of a run of adjacent contigs and where each contig's text begins in them."""
-            infos = [bgzf_io.range_info(args.input_file, *index[c]) for c in group]
-            live = [(c, i) for c, i in zip(group, infos) if i[3] > 0]
+        def load_group(group: list[tuple]):
+            """The compressed blocks of a run of adjacent pieces and where each piece's text begins in them."""
+            infos = [bgzf_io.range_info(args.input_file, vb, ve) for _c, vb, ve in group]
+            live = [(g, i) for g, i in zip(group, infos) if i[3] > 0]
             if not live:
                 return None
             c0, c1, skip = live[0][1][0], live[-1][1][1], live[0][1][2]
             starts, take = [], 0
-            for _c, i in live:
+            for _g, i in live:
                 starts.append(take)
                 take += i[3]
             ctx.bind_thread()  # the reader thread pins memory for this rank's device
-            bufs = in_pool.acquire({"comp": (c1 - c0, np.uint8)})
+            bufs = in_pool.acquire({"comp": (c1 - c0, np.uint8)}, grow=max_span / max(1, c1 - c0))
             comp = bufs["comp"][1]
             with open(args.input_file, "rb") as fh:
                 fh.seek(c0)
                 got = fh.readinto(memoryview(comp))
             if got != c1 - c0:
-                raise OSError(f"{args.input_file}: short read of {group[0]}..{group[-1]}")
-            return "device", comp, skip, take, bufs, [c for c, _ in live], np.array(starts, dtype=np.uint64)
+                raise OSError(f"{args.input_file}: short read of {group[0][0]}..{group[-1][0]}")
+            return "device", comp, skip, take, bufs, [g for g, _ in live], np.array(starts, dtype=np.uint64)
 
-        def load_work(group: list[str]):
-            return load_group(group) if device_io else load_contig(group[0])
+        def load_work(group: list[tuple]):
+            return load_group(group) if device_io else load_contig(group[0][0])
 
         prefetch = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-bgzf-reader")
         pending = prefetch.submit(load_work, work[0]) if work else None
         for gi, group in enumerate(work):
-            for c in group:
+            for c in dict.fromkeys(g[0] for g in group):
                 logger.info(f"Filtering variants from {c}")
             t_wait = time.perf_counter()
             loaded = pending.result()
             seconds["inflate_wait"] += time.perf_counter() - t_wait
             pending = prefetch.submit(load_work, work[gi + 1]) if gi + 1 < len(work) else None
             if loaded is None:
-                for c in group:
+                for c in dict.fromkeys(g[0] for g in group):
                     logger.info(f"No variants found on {c}")
                 continue
             if not isinstance(loaded[0], str):
-                host_contig(group[0], loaded)
+                host_contig(group[0][0], loaded)
                 continue
             _tag, comp, skip, take, in_bufs, live, starts = loaded  # ("device", compressed blocks, ...)
             if args.blacklist_cg_insertions:
@@ -667,13 +690,15 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             need = (take + (1 << 17) + 4096, take // 32 + 1024)  # whole blocks are inflated: up to 64 KiB either side of the range
             t_alloc = time.perf_counter()
             if need[0] > reserved[0] or need[1] > reserved[1]:
-                reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))
+                ahead = max(1.0, max_span / max(1, comp.size)) * 1.05  # the largest group, at this one's compression ratio
+                reserved = (max(int(need[0] * ahead), reserved[0]), max(int(need[1] * ahead), reserved[1]))
                 ctx.reserve(reserved[0], reserved[1], n_lanes)
             n_max = take // 32 + 1024
             # VCF text deflates to well under half its size; text that does not comes back as UGVC_E_FALLBACK
             out_bufs = out_pool.acquire({"out": (take * 5 // 8 + (1 << 20), np.uint8),
                                          "blocks": ((take + n_max * 64) // lib.DEF_CHUNK + 16, np.uint32),
-                                         "ri": (n_max, lib.RECINFO_DTYPE), "ls": (n_max + 1, np.int64), "low": (n_max, np.uint8)})
+                                         "ri": (n_max, lib.RECINFO_DTYPE), "ls": (n_max + 1, np.int64), "low": (n_max, np.uint8)},
+                                        grow=max_span / max(1, comp.size))
             seconds["alloc"] += time.perf_counter() - t_alloc
             t_gpu = time.perf_counter()
             res = ctx.filter_bgzf(comp, skip, take, args.decision_threshold, file_flags, n_max,
@@ -683,25 +708,25 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             in_pool.release(in_bufs)
             if res is None:
                 out_pool.release(out_bufs)
-                logger.info(f"{live[0]}..{live[-1]}: records that need the general writer, taking the host path")
-                for c in live:
-                    again = load_contig(c)
+                logger.info(f"{live[0][0]}..{live[-1][0]}: records that need the general writer, taking the host path")
+                for c, vb, ve in live:
+                    again = load_contig(c, (vb, ve))
                     if again is not None:
                         host_contig(c, again)
                 continue
             dev_ms += np.array(ctx.filter_bgzf_stage_ms())
             bounds = np.concatenate((first, [res["n_records"]])).astype(np.int64)
-            for k, c in enumerate(live):
+            for k, (c, _vb, _ve) in enumerate(live):
                 logger.info(f"{int(bounds[k + 1] - bounds[k])} variants found on {c}")
             logger.info("Writing records")
-            out.write_device_batch(live, bounds, res, release=lambda b=out_bufs: out_pool.release(b))
+            out.write_device_batch([g[0] for g in live], bounds, res, release=lambda b=out_bufs: out_pool.release(b))
             totals["n_records"] += res["n_records"]
             totals["n_low_score"] += int(res["low_score"].sum())
             if args.blacklist_cg_insertions:
                 n_cg = int(np.count_nonzero(res["recinfo"]["flags"] & 1))
                 totals["n_cg"] += n_cg
                 totals["n_blacklisted"] += n_cg
-            for c in live:
+            for c in dict.fromkeys(g[0] for g in live):
                 logger.info(f"{c} done")
 
         t_close = time.perf_counter()
