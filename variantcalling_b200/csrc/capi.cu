@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1206,6 +1207,8 @@ static int file_bufs(ugvc_ctx* ctx, Lane& l) {
     CU(cudaHostAlloc(&f.h_fallback, sizeof(int), cudaHostAllocDefault));
     CU(cudaHostAlloc(&f.h_total, sizeof(int64_t), cudaHostAllocDefault));
     for (auto& e : f.ev) CU(cudaEventCreate(&e));
+    static std::mutex tables_mu;  // lanes may take their first file-path call on different host threads
+    std::lock_guard<std::mutex> lock(tables_mu);
     if (!ctx->d_def_tables) {
         DefTables* t = new DefTables();
         def_build_tables(*t);

@@ -394,6 +394,8 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             numa = vdist0.bind_to_gpu_numa_node(device)
         ctx_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-cuda-init")
         ctx_future = ctx_pool.submit(lib.Context, device)
+        t_start = time.perf_counter()
+        startup = {}
 
         if args.model_file is not None:
             logger.info(f"Loading model from {args.model_file}")
@@ -403,6 +405,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         if args.blacklist is not None:
             logger.info(f"Loading blacklist from {args.blacklist}")
             blacklists = _load_pickle(args.blacklist)
+        startup["pickles"] = time.perf_counter() - t_start
         if args.treat_multiallelics and args.ref_fasta is None:
             raise ValueError("Reference FASTA file is required for multiallelic treatment")
         if not os.path.exists(args.input_file):
@@ -419,8 +422,12 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         # i.e. in the host-emulation test)
         if multi:
             logger.info(f"rank {rank}: NUMA binding {numa}")
+        startup["header+index"] = time.perf_counter() - t_start - startup["pickles"]
+        t0 = time.perf_counter()
         ctx = ctx_future.result()  # raises without a CUDA device: there is no CPU path
         ctx_pool.shutdown(wait=False)
+        startup["wait for CUDA"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
         plan = None
         if with_model:
             if model is None or transformer is None:
@@ -446,6 +453,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         reserved = (0, 0)
         key_order_set = False
 
+        startup["plan"] = time.perf_counter() - t0
         out = _Splicer(_part_path(args.output_file, rank) if multi else args.output_file, args.io_threads)
         out.keep_arrays = multi
         if not multi:
@@ -509,7 +517,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 text = np.concatenate((text, np.array([10], dtype=np.uint8)))
             return text, bgzf_io.count_lines(text, args.io_threads)
 
-        in_pool, out_pool = _PinnedPool(2), _PinnedPool(2)
+        in_pool, out_pool = _PinnedPool(3), _PinnedPool(3)  # two device calls in flight + the reader / the writer
         dev_ms = np.zeros(5)
 
         def host_contig(contig: str, loaded):
@@ -664,6 +672,66 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         def load_work(group: list[tuple]):
             return load_group(group) if device_io else load_contig(group[0][0])
 
+        # device-side file path: two calls in flight (one lane and stream each, issued from two host threads), so that one
+        # piece's copies and host-side waits overlap the other's kernels; results are written in submission order
+        gpu_pool = ThreadPoolExecutor(max_workers=n_lanes, thread_name_prefix="ugvc-device")
+        flying: list[tuple] = []
+        n_calls = 0
+
+        def device_call(lane: int, comp, skip: int, take: int, in_bufs: dict, starts):
+            ctx.bind_thread()
+            n_max = take // 32 + 1024
+            # VCF text deflates to well under half its size; text that does not comes back as UGVC_E_FALLBACK
+            out_bufs = out_pool.acquire({"out": (take * 5 // 8 + (1 << 20), np.uint8),
+                                         "blocks": ((take + n_max * 64) // lib.DEF_CHUNK + 16, np.uint32),
+                                         "ri": (n_max, lib.RECINFO_DTYPE), "ls": (n_max + 1, np.int64), "low": (n_max, np.uint8)},
+                                        grow=max_span / max(1, comp.size))
+            try:
+                res = ctx.filter_bgzf(comp, skip, take, args.decision_threshold, file_flags, n_max, lane=lane,
+                                      bufs={k: v[1] for k, v in out_bufs.items()})
+                first = ctx.filter_bgzf_first_records(starts, lane=lane) if res is not None else None
+                ms = ctx.filter_bgzf_stage_ms(lane) if res is not None else None
+            except BaseException:
+                out_pool.release(out_bufs)
+                raise
+            finally:
+                in_pool.release(in_bufs)
+            if res is None:
+                out_pool.release(out_bufs)
+            return res, first, ms, out_bufs
+
+        def drain_device(leave: int):
+            """Take finished device calls (oldest first) until `leave` are in flight; write their records."""
+            nonlocal dev_ms
+            while len(flying) > leave:
+                live, fut = flying.pop(0)
+                t_gpu = time.perf_counter()
+                res, first, ms, out_bufs = fut.result()
+                seconds["gpu"] += time.perf_counter() - t_gpu
+                if res is None:
+                    logger.info(f"{live[0][0]}..{live[-1][0]}: records that need the general writer, taking the host path")
+                    for _l, f in flying:
+                        f.exception()  # the host path uses the same lanes: newer calls finish first (written after these records)
+                    for c, vb, ve in live:
+                        again = load_contig(c, (vb, ve))
+                        if again is not None:
+                            host_contig(c, again)
+                    continue
+                dev_ms += np.array(ms)
+                bounds = np.concatenate((first, [res["n_records"]])).astype(np.int64)
+                for k, (c, _vb, _ve) in enumerate(live):
+                    logger.info(f"{int(bounds[k + 1] - bounds[k])} variants found on {c}")
+                logger.info("Writing records")
+                out.write_device_batch([g[0] for g in live], bounds, res, release=lambda b=out_bufs: out_pool.release(b))
+                totals["n_records"] += res["n_records"]
+                totals["n_low_score"] += int(res["low_score"].sum())
+                if args.blacklist_cg_insertions:
+                    n_cg = int(np.count_nonzero(res["recinfo"]["flags"] & 1))
+                    totals["n_cg"] += n_cg
+                    totals["n_blacklisted"] += n_cg
+                for c in dict.fromkeys(g[0] for g in live):
+                    logger.info(f"{c} done")
+
         prefetch = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-bgzf-reader")
         pending = prefetch.submit(load_work, work[0]) if work else None
         for gi, group in enumerate(work):
@@ -690,44 +758,16 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             need = (take + (1 << 17) + 4096, take // 32 + 1024)  # whole blocks are inflated: up to 64 KiB either side of the range
             t_alloc = time.perf_counter()
             if need[0] > reserved[0] or need[1] > reserved[1]:
+                drain_device(0)  # the lanes' buffers are about to move
                 ahead = max(1.0, max_span / max(1, comp.size)) * 1.05  # the largest group, at this one's compression ratio
                 reserved = (max(int(need[0] * ahead), reserved[0]), max(int(need[1] * ahead), reserved[1]))
                 ctx.reserve(reserved[0], reserved[1], n_lanes)
-            n_max = take // 32 + 1024
-            # VCF text deflates to well under half its size; text that does not comes back as UGVC_E_FALLBACK
-            out_bufs = out_pool.acquire({"out": (take * 5 // 8 + (1 << 20), np.uint8),
-                                         "blocks": ((take + n_max * 64) // lib.DEF_CHUNK + 16, np.uint32),
-                                         "ri": (n_max, lib.RECINFO_DTYPE), "ls": (n_max + 1, np.int64), "low": (n_max, np.uint8)},
-                                        grow=max_span / max(1, comp.size))
             seconds["alloc"] += time.perf_counter() - t_alloc
-            t_gpu = time.perf_counter()
-            res = ctx.filter_bgzf(comp, skip, take, args.decision_threshold, file_flags, n_max,
-                                  bufs={k: v[1] for k, v in out_bufs.items()})
-            first = ctx.filter_bgzf_first_records(starts) if res is not None else None
-            seconds["gpu"] += time.perf_counter() - t_gpu
-            in_pool.release(in_bufs)
-            if res is None:
-                out_pool.release(out_bufs)
-                logger.info(f"{live[0][0]}..{live[-1][0]}: records that need the general writer, taking the host path")
-                for c, vb, ve in live:
-                    again = load_contig(c, (vb, ve))
-                    if again is not None:
-                        host_contig(c, again)
-                continue
-            dev_ms += np.array(ctx.filter_bgzf_stage_ms())
-            bounds = np.concatenate((first, [res["n_records"]])).astype(np.int64)
-            for k, (c, _vb, _ve) in enumerate(live):
-                logger.info(f"{int(bounds[k + 1] - bounds[k])} variants found on {c}")
-            logger.info("Writing records")
-            out.write_device_batch([g[0] for g in live], bounds, res, release=lambda b=out_bufs: out_pool.release(b))
-            totals["n_records"] += res["n_records"]
-            totals["n_low_score"] += int(res["low_score"].sum())
-            if args.blacklist_cg_insertions:
-                n_cg = int(np.count_nonzero(res["recinfo"]["flags"] & 1))
-                totals["n_cg"] += n_cg
-                totals["n_blacklisted"] += n_cg
-            for c in dict.fromkeys(g[0] for g in live):
-                logger.info(f"{c} done")
+            drain_device(n_lanes - 1)  # at most n_lanes calls in flight, each on its own lane and stream
+            flying.append((live, gpu_pool.submit(device_call, n_calls % n_lanes, comp, skip, take, in_bufs, starts)))
+            n_calls += 1
+        drain_device(0)
+        gpu_pool.shutdown()
 
         t_close = time.perf_counter()
         if multi:
@@ -757,6 +797,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         logger.info("stage seconds (overlapping threads): wait for inflate %.2f, buffers %.2f, wait for GPU %.2f, splice %.2f, "
                     "deflate+write %.2f, index %.2f (+ %.2f at close)", seconds["inflate_wait"], seconds["alloc"], seconds["gpu"],
                     out.seconds["splice"], out.seconds["deflate"], out.seconds.get("index", 0.0), time.perf_counter() - t_close)
+        logger.info("start-up seconds: " + ", ".join(f"{k} {v:.2f}" for k, v in startup.items()))
         if device_io:
             logger.info("device file path, ms on the GPU: H2D + inflate %.0f, K1..K3 %.0f, record writer %.0f, deflate + pack %.0f, "
                         "D2H %.0f", *dev_ms)
