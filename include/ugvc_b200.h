@@ -229,6 +229,13 @@ int64_t ugvc_bgzf_uncompressed_size(const char* path);
  * arguments of ugvc_filter_bgzf for one contig of a tabix-indexed call set. */
 int ugvc_bgzf_range_info(const char* path, uint64_t voff_begin, uint64_t voff_end, uint64_t* c_begin, uint64_t* c_end,
                          uint32_t* skip_head, uint64_t* take_bytes);
+/* Per-contig summary of a tabix index (`data`: the inflated .tbi): out_lo / out_hi = smallest chunk begin / largest chunk
+ * end over the contig's bins (~0 / 0 when it has none), out_linear_offset / out_linear_count = where its linear index
+ * (uint64 virtual offsets) sits in `data`; the contig names are the NUL-separated bytes at out_names_offset.  What
+ * pysam's fetch(contig) (filter_variants_pipeline.py:130) gets from htslib's index loader. */
+int ugvc_tbi_summary(const uint8_t* data, size_t n, int32_t n_ref_capacity, uint64_t* out_lo, uint64_t* out_hi,
+                     int64_t* out_linear_offset, int32_t* out_linear_count, int32_t* out_n_ref, int64_t* out_names_offset,
+                     int32_t* out_names_bytes);
 /* Append `n_bytes` as BGZF blocks to `path` (mode 'w' truncates, 'a' appends;
  * write_eof != 0 adds the 28-byte EOF block).  Every block but the last holds
  * 0xff00 bytes of input; out_block_csize (may be NULL) receives the compressed

@@ -305,32 +305,26 @@ def read_tbi(path: str, linear: bool = False):
         data = fh.read()
     if data[:4] != b"TBI\x01":
         raise OSError(f"{path}: not a tabix index")
-    n_ref, _fmt, _cs, _cb, _ce, _meta, _skip, l_nm = struct.unpack_from("<8i", data, 4)
-    p = 36
-    names = data[p:p + l_nm].split(b"\0")[:n_ref]
-    p += l_nm
+    (n_ref,) = struct.unpack_from("<i", data, 4)
+    n_ref = max(0, n_ref)
+    L = _lib.load_library()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    lo, hi = np.empty(n_ref, np.uint64), np.empty(n_ref, np.uint64)
+    l_off, l_cnt = np.empty(n_ref, np.int64), np.empty(n_ref, np.int32)
+    got, nm_off, nm_len = C.c_int32(), C.c_int64(), C.c_int32()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    _check(L.ugvc_tbi_summary(p(buf), buf.size, n_ref, p(lo), p(hi), p(l_off), p(l_cnt), C.byref(got), C.byref(nm_off),
+                               C.byref(nm_len)), f"{path}: malformed tabix index")
+    names = data[nm_off.value:nm_off.value + nm_len.value].split(b"\0")[:n_ref]
     out, lin = {}, {}
     for r in range(n_ref):
-        (n_bin,) = struct.unpack_from("<i", data, p)
-        p += 4
-        lo, hi = None, None
-        for _ in range(n_bin):
-            bn, n_chunk = struct.unpack_from("<Ii", data, p)
-            p += 8
-            ch = np.frombuffer(data, dtype="<u8", count=2 * n_chunk, offset=p)
-            p += 16 * n_chunk
-            if bn == 37450 or n_chunk == 0:  # noqa: PLR2004  (htslib pseudo-bin: metadata)
-                continue
-            b, e = int(ch[0::2].min()), int(ch[1::2].max())
-            lo = b if lo is None else min(lo, b)
-            hi = e if hi is None else max(hi, e)
-        (n_intv,) = struct.unpack_from("<i", data, p)
-        if linear and lo is not None:
-            io = np.unique(np.frombuffer(data, dtype="<u8", count=n_intv, offset=p + 4))
-            lin[names[r].decode()] = io[(io > lo) & (io < hi)]
-        p += 4 + 8 * n_intv
-        if lo is not None:
-            out[names[r].decode()] = (lo, hi)
+        if int(hi[r]) == 0 and int(lo[r]) == 0xFFFFFFFFFFFFFFFF:
+            continue  # no records on this contig
+        name = names[r].decode()
+        out[name] = (int(lo[r]), int(hi[r]))
+        if linear:
+            io = np.unique(np.frombuffer(data, dtype="<u8", count=int(l_cnt[r]), offset=int(l_off[r])))
+            lin[name] = io[(io > lo[r]) & (io < hi[r])]
     return (out, lin) if linear else out
 
 

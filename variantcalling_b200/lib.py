@@ -97,6 +97,7 @@ SIGNATURES = {
     "ugvc_conc_run": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "ugvc_conc_classify": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "ugvc_conc_curve": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz]),
+    "ugvc_tbi_summary": (C.c_int, [_vp, C.c_size_t, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ugvc_test_deflate_block": (C.c_int64, [_vp, C.c_uint32, _vp]),
     "ugvc_test_deflate_block_lanes": (C.c_int64, [_vp, C.c_uint32, _vp]),
     "ugvc_test_device_sigmoid": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
