@@ -1107,11 +1107,8 @@ static int stage_bgzf(ugvc_ctx* ctx, Lane& l, const uint8_t* bgzf, size_t n_byte
         bgzf_inflate_blocks<<<grid, threads, 0, st>>>(l.d_comp, l.d_blk, l.cap_blk, (int)nb, l.d_text, l.d_inf_err);
     } else {  // one warp per block, tables in shared memory
         const size_t smem = INFW_WARPS * sizeof(InfWarpTables);
-        static bool configured = false;
-        if (!configured) {
-            CU(cudaFuncSetAttribute(bgzf_inflate_warps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
+        // per call: a function attribute belongs to the current device, and lanes are driven from several host threads
+        CU(cudaFuncSetAttribute(bgzf_inflate_warps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = (int)((nb + INFW_WARPS - 1) / INFW_WARPS);
         if (grid > ctx->sm_count * 3) grid = ctx->sm_count * 3;
         bgzf_inflate_warps<<<grid, INFW_WARPS * 32, smem, st>>>(l.d_comp, l.d_blk, l.cap_blk, (int)nb, l.d_text, l.d_inf_err);
@@ -1235,6 +1232,7 @@ extern "C" int ugvc_filter_bgzf(ugvc_ctx* ctx, int lane, const uint8_t* bgzf, si
     if (rc) return rc;
     Lane::FileBufs& f = l.fb;
     cudaStream_t st = l.stream;
+    (void)cudaGetLastError();  // nothing stale from this host thread's earlier calls
     CU(cudaEventRecord(f.ev[0], st));
     // ---- compressed blocks -> text on the device, the range's first byte 16-byte aligned
     const size_t shift = (16 - (skip_head & 15u)) & 15u;
@@ -1288,12 +1286,15 @@ extern "C" int ugvc_filter_bgzf(ugvc_ctx* ctx, int lane, const uint8_t* bgzf, si
     const int n_blocks = (int)((out_text + DEF_CHUNK - 1) / DEF_CHUNK);
     if ((size_t)n_blocks > f.cap_blocks || (out_block_csize && (size_t)n_blocks > block_capacity))
         return fail(ctx, UGVC_E_ARG, "filter_bgzf: more output blocks than room for them");
-    fio_launch_deflate(f.d_out_text, out_text, ctx->d_def_tables, f.d_blocks, f.d_bsize, n_blocks, st);
+    CU(cudaGetLastError());
+    CU(fio_launch_deflate(f.d_out_text, out_text, ctx->d_def_tables, f.d_blocks, f.d_bsize, n_blocks, st));
     fio_launch_widen(f.d_bsize, f.d_bwide, n_blocks, st);
+    CU(cudaGetLastError());
     CU(cudaMemsetAsync(f.d_bwide + n_blocks, 0, sizeof(uint64_t), st));
     tmp = f.scan_tmp_bytes;
     CU(fio_scan_u64(f.d_scan_tmp, tmp, f.d_bwide, f.d_boff, n_blocks + 1, st));
     fio_launch_pack(f.d_blocks, f.d_bsize, f.d_bwide, f.d_boff, n_blocks, f.d_packed, ctx->sm_count, st);
+    CU(cudaGetLastError());
     f.h_bsize.resize((size_t)n_blocks + 1);
     if (n_blocks) CU(cudaMemcpyAsync(f.h_bsize.data(), f.d_bsize, (size_t)n_blocks * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(f.ev[4], st));

@@ -479,23 +479,26 @@ void fio_launch_splice_copy(const uint8_t* text, const int64_t* line_start, cons
     if (blocks > (int64_t)sm_count * 32) blocks = (int64_t)sm_count * 32;
     splice_copy<<<(unsigned)blocks, 256, 0, st>>>(text, line_start, recinfo, low, n, flags, out_start, score_txt, out, fallback);
 }
-void fio_launch_deflate(const uint8_t* text, size_t n_bytes, const DefTables* tables, uint8_t* blocks, uint32_t* bsize,
-                        int n_blocks, cudaStream_t st) {
-    if (n_blocks <= 0) return;
-    const size_t smem = (size_t)FIO_DEF_TPB * sizeof(uint16_t) << DEF_HASH_BITS;
-    static int thread_per_block = -1;  // UGVC_DEFLATE_THREADS=1: the thread-per-block encoder (A/B)
-    if (thread_per_block < 0) {
+cudaError_t fio_launch_deflate(const uint8_t* text, size_t n_bytes, const DefTables* tables, uint8_t* blocks, uint32_t* bsize,
+                               int n_blocks, cudaStream_t st) {
+    if (n_blocks <= 0) return cudaSuccess;
+    static const bool thread_per_block = [] {  // UGVC_DEFLATE_THREADS=1: the thread-per-block encoder (A/B)
         const char* e = getenv("UGVC_DEFLATE_THREADS");
-        thread_per_block = e && e[0] == '1' ? 1 : 0;
-        cudaFuncSetAttribute(fio_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(fio_deflate_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIO_DEFW_SMEM);
-    }
+        return e && e[0] == '1';
+    }();
+    cudaError_t e;
+    // the attribute is set per call: it belongs to the current device, and lanes are driven from several host threads
     if (!thread_per_block) {
+        if ((e = cudaFuncSetAttribute(fio_deflate_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIO_DEFW_SMEM)) != cudaSuccess)
+            return e;
         fio_deflate_warp<<<(n_blocks + FIO_DEFW_WARPS - 1) / FIO_DEFW_WARPS, FIO_DEFW_WARPS * 32, FIO_DEFW_SMEM, st>>>(
             text, n_bytes, tables, blocks, bsize, n_blocks);
-        return;
+        return cudaGetLastError();
     }
+    const size_t smem = (size_t)FIO_DEF_TPB * sizeof(uint16_t) << DEF_HASH_BITS;
+    if ((e = cudaFuncSetAttribute(fio_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     fio_deflate<<<(n_blocks + FIO_DEF_TPB - 1) / FIO_DEF_TPB, FIO_DEF_TPB, smem, st>>>(text, n_bytes, tables, blocks, bsize, n_blocks);
+    return cudaGetLastError();
 }
 void fio_launch_pack(const uint8_t* blocks, const uint32_t* bsize, uint64_t* wide, const uint64_t* boff, int n_blocks,
                      uint8_t* packed, int sm_count, cudaStream_t st) {

@@ -14,7 +14,7 @@ void fio_launch_splice_len(const uint8_t* text, const int64_t* line_start, const
 void fio_launch_splice_copy(const uint8_t* text, const int64_t* line_start, const ugvc_recinfo* recinfo, const uint8_t* low,
                             int64_t n, int flags, const int64_t* out_start, const uint8_t* score_txt, uint8_t* out,
                             int* fallback, int sm_count, cudaStream_t st);
-void fio_launch_deflate(const uint8_t* text, size_t n_bytes, const DefTables* tables, uint8_t* blocks, uint32_t* bsize,
+cudaError_t fio_launch_deflate(const uint8_t* text, size_t n_bytes, const DefTables* tables, uint8_t* blocks, uint32_t* bsize,
                         int n_blocks, cudaStream_t st);
 void fio_launch_pack(const uint8_t* blocks, const uint32_t* bsize, uint64_t* wide, const uint64_t* boff, int n_blocks,
                      uint8_t* packed, int sm_count, cudaStream_t st);
