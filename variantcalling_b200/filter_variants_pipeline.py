@@ -392,8 +392,24 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             from variantcalling_b200 import dist as vdist0
 
             numa = vdist0.bind_to_gpu_numa_node(device)
-        ctx_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ugvc-cuda-init")
+        ctx_pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="ugvc-cuda-init")
         ctx_future = ctx_pool.submit(lib.Context, device)
+
+        def init_group():
+            """The process group of a multi-rank run (NCCL on GPUs; gloo without a CUDA device, i.e. the host-emulation
+            test) comes up in the background: importing torch and building the communicator take seconds, the ranks need
+            it only for the SUM of the counters at the end."""
+            import torch
+            import torch.distributed as tdist
+
+            if tdist.is_initialized():
+                return False
+            on_gpu = torch.cuda.is_available()
+            tdist.init_process_group("nccl" if on_gpu else "gloo",
+                                     **({"device_id": torch.device("cuda", device)} if on_gpu else {}))
+            return True
+
+        group_future = ctx_pool.submit(init_group) if multi else None
         t_start = time.perf_counter()
         startup = {}
 
@@ -778,18 +794,16 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
 
             with open(_part_path(args.output_file, rank) + ".meta", "wb") as fh:
                 pickle.dump(out.finish_part(), fh)
-            created_group = not tdist.is_initialized()
-            if created_group:
-                on_gpu = torch.cuda.is_available()
-                tdist.init_process_group("nccl" if on_gpu else "gloo",
-                                         **({"device_id": torch.device("cuda", device)} if on_gpu else {}))
+            created_group = group_future.result()
             keys = ("n_records", "n_low_score", "n_cg", "n_blacklisted")
             counts = torch.tensor([totals[k] for k in keys], dtype=torch.int64,
                                   device=torch.device("cuda", device) if torch.cuda.is_available() else "cpu")
             vdist.allreduce_counts(counts)  # the single collective of the path; it also orders the parts before rank 0 reads them
             totals.update({k: int(v) for k, v in zip(keys, counts.tolist())})
             if rank == 0:
+                t_asm = time.perf_counter()
                 _assemble_parts(args.output_file, out_header, all_contigs, world, args.io_threads)
+                logger.info("parts assembled and indexed in %.2f s", time.perf_counter() - t_asm)
             tdist.barrier()
             if created_group:
                 tdist.destroy_process_group()
