@@ -10,7 +10,7 @@ mkdir -p gpurun_out/variants
 for lib in default variantcalling_b200/variants/*.so; do
     name=$(basename "$lib" .so)
     if [ "$lib" = default ]; then unset UGVC_LIB_PATH; else export UGVC_LIB_PATH="$PWD/$lib"; fi
-    if timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edges.py tests/test_gpu_fuzz.py -x -q -m gpu \
+    if timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -x -q -m gpu \
          > "gpurun_out/variants/$name.tests.log" 2>&1; then
         timeout 300 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline \
             > "gpurun_out/variants/$name.json" 2> "gpurun_out/variants/$name.err"

@@ -841,7 +841,7 @@ void launch_k1_fast(const DevPlan& plan, const DevFast& fast, const DevSchedule&
         k1_fast_empty<<<1, 1, 0, st>>>(line_start, d_n_records);
         return;
     }
-    const size_t blocks = n_tiles < (size_t)sm_count * 2 ? n_tiles : (size_t)sm_count * 2;
+    const size_t blocks = n_tiles < (size_t)sm_count * KF_MIN_CTAS ? n_tiles : (size_t)sm_count * KF_MIN_CTAS;
     k1_fast<<<(unsigned)blocks, KF_TPB, KF_SMEM_BYTES, st>>>(plan, fast, d_text, n_bytes,
                                                              reinterpret_cast<unsigned long long*>(scratch) + 1, scratch,
                                                              scratch + 1, n_tiles, line_start, cap_records, d_n_records, raw,
