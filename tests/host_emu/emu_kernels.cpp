@@ -13,12 +13,14 @@
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 alignas(16) uint8_t k1_smem[64 * 1024];
 alignas(16) uint8_t smem3[8 * 1024 * 1024];  // K3: feature tile + the whole forest
-alignas(16) uint8_t kf_smem_emu[128 * 1024];  // K1 tile kernel
+alignas(16) uint8_t kf_smem_emu[128 * 1024];  // K1 tile kernel (queue form)
+alignas(16) uint8_t kt_smem_emu[128 * 1024];  // K1 tile kernel (token form)
 
 #include "../../variantcalling_b200/csrc/kernels.cu"
 
 static_assert(K1_SMEM_BYTES <= sizeof(k1_smem), "k1_smem too small");
 static_assert(KF_SMEM_BYTES <= sizeof(kf_smem_emu), "kf_smem_emu too small");
+static_assert(KT_SMEM_BYTES <= sizeof(kt_smem_emu), "kt_smem_emu too small");
 
 static void one_thread_grid() {
     threadIdx = dim3(0, 0, 0);
@@ -81,8 +83,16 @@ void launch_k1_fast(const DevPlan& plan, const DevFast& fast, const DevSchedule&
     const char* g = getenv("UGVC_EMU_G");
     ugvc_emu_force_g = g ? atoi(g) : 0;
     one_thread_grid();
-    k1_fast(plan, fast, d_text, n_bytes, reinterpret_cast<unsigned long long*>(scratch) + 1, scratch, scratch + 1, n_tiles,
-            line_start, cap_records, d_n_records, raw, row_stride, recinfo, slow_list, d_err, d_counts);
+    // the token form emulates all 512 threads of its CTA phase by phase (KT_FOR_THREADS); UGVC_K1_TILE_KERNEL=fast: the queue form
+    const char* which = getenv("UGVC_K1_TILE_KERNEL");
+    uint32_t wcap = kt_window_records(plan.h.n_slots);
+    if (const char* w = getenv("UGVC_EMU_WCAP")) wcap = (uint32_t)atoi(w) < wcap ? (uint32_t)atoi(w) : wcap;  // tests: small windows
+    if (wcap >= 16u && !(which && which[0] == 'f'))
+        k1_tok(plan, fast, d_text, n_bytes, reinterpret_cast<unsigned long long*>(scratch) + 1, scratch, scratch + 1, n_tiles,
+               line_start, cap_records, d_n_records, raw, row_stride, recinfo, slow_list, d_err, d_counts, wcap);
+    else
+        k1_fast(plan, fast, d_text, n_bytes, reinterpret_cast<unsigned long long*>(scratch) + 1, scratch, scratch + 1, n_tiles,
+                line_start, cap_records, d_n_records, raw, row_stride, recinfo, slow_list, d_err, d_counts);
     one_thread_grid();
     k1_parse(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts, slow_list, scratch + 1);
 }

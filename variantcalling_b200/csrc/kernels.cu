@@ -776,6 +776,7 @@ __device__ __noinline__ Cur decode_sched(RawOut o, unsigned long long meta, Cur 
 #endif
 
 #include "k1_fast.inc"
+#include "k1_tok.inc"
 
 size_t k1_smem_bytes(const DevPlan&) { return (size_t)K1_SMEM_BYTES; }
 
@@ -842,10 +843,20 @@ void launch_k1_fast(const DevPlan& plan, const DevFast& fast, const DevSchedule&
         return;
     }
     const size_t blocks = n_tiles < (size_t)sm_count * KF_MIN_CTAS ? n_tiles : (size_t)sm_count * KF_MIN_CTAS;
-    k1_fast<<<(unsigned)blocks, KF_TPB, KF_SMEM_BYTES, st>>>(plan, fast, d_text, n_bytes,
-                                                             reinterpret_cast<unsigned long long*>(scratch) + 1, scratch,
-                                                             scratch + 1, n_tiles, line_start, cap_records, d_n_records, raw,
-                                                             row_stride, recinfo, slow_list, d_err, d_counts);
+    // the token form (k1_tok) unless the plan has so many slots that a window would hold under sixteen records;
+    // UGVC_K1_TILE_KERNEL=fast selects the queue form (differential tests, profiling)
+    static const char* which = getenv("UGVC_K1_TILE_KERNEL");
+    const uint32_t wcap = kt_window_records(plan.h.n_slots);
+    if (wcap >= 16u && !(which && which[0] == 'f'))
+        k1_tok<<<(unsigned)blocks, KT_TPB, KT_SMEM_BYTES, st>>>(plan, fast, d_text, n_bytes,
+                                                                reinterpret_cast<unsigned long long*>(scratch) + 1, scratch,
+                                                                scratch + 1, n_tiles, line_start, cap_records, d_n_records, raw,
+                                                                row_stride, recinfo, slow_list, d_err, d_counts, wcap);
+    else
+        k1_fast<<<(unsigned)blocks, KF_TPB, KF_SMEM_BYTES, st>>>(plan, fast, d_text, n_bytes,
+                                                                 reinterpret_cast<unsigned long long*>(scratch) + 1, scratch,
+                                                                 scratch + 1, n_tiles, line_start, cap_records, d_n_records, raw,
+                                                                 row_stride, recinfo, slow_list, d_err, d_counts);
     // the slow tier: usually an empty list (the CTAs leave at once)
     k1_parse<<<sm_count * 2, K1_TPB, k1_smem_bytes(plan), st>>>(plan, sched, d_text, line_start, d_n_records, raw, row_stride,
                                                                 recinfo, d_err, d_counts, slow_list, scratch + 1);
@@ -1640,6 +1651,8 @@ cudaError_t kernels_configure(const DevPlan& plan) {
                                          (int)k1_smem_bytes(plan));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k1_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k1_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT_SMEM_BYTES);
     if (e != cudaSuccess) return e;
 #ifdef UGVC_K1_SPLIT
     e = cudaFuncSetAttribute(k1_parse_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(plan));

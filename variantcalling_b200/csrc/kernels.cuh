@@ -154,9 +154,9 @@ struct LaneBuffers {
 
 #define K0_TILE_BYTES_HOST 65536  // one 64-bit look-back state word per 64 KiB tile
 #ifndef K1_TILE_BYTES_HOST
-#define K1_TILE_BYTES_HOST 40960u
+#define K1_TILE_BYTES_HOST 32768u
 #endif
-// ... per tile of the K1 tile kernel (40 KiB; more tiles than K0: sizes the scratch)
+// ... per tile of the K1 tile kernel (32 KiB; more tiles than K0: sizes the scratch)
 
 void launch_k0(const uint8_t* d_text, size_t n_bytes, uint32_t* chunk_first, int64_t* line_start,
                size_t cap_records, int64_t* d_n_records, unsigned long long* d_err, int sm_count,
