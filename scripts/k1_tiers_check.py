@@ -9,12 +9,12 @@ _, tr, x = util.fit_transformer(ds)
 model = util.fit_model("gb_small", x, ds["labels"])
 plan = MC.compile_plan(VcfHeader(ds["header_text"]), tr, model, ds["customs"])
 ctx = lib.Context(0); ctx.load_plan(plan.blob); ctx.reserve(len(ds["text"])+1024, 4096, 1)
-for mode in ["nolearn","learn"]:
+for mode in (["learn"] if os.environ.get("MODE") == "learn" else ["nolearn","learn"]):
     if mode=="learn": ctx.set_key_order(*lib.learn_key_order(ds["text"]))
     out = ctx.filter_batch(ds["text"])
     n = out["n_records"]
     raw = ctx.debug_raw(n)
     print(mode, "n", n, "slow", ctx.slow_records(0))
-    if mode=="nolearn": raw0=raw.copy()
+    if mode=="nolearn" or os.environ.get("MODE") == "learn": raw0=raw.copy()
 print("raw equal", np.array_equal(raw0, raw))
 np.save("/tmp/raw_%s.npy" % os.environ.get("TAG","x"), raw)

@@ -1548,9 +1548,10 @@ static K3hShape k3h_shape(const DevPlan& plan) {
     const bool forest = plan.h.model_kind != MODEL_LOGISTIC;
     const size_t all = forest ? (size_t)plan.h.n_trees * k3h_tree_bytes(plan) : 0;
     // two half-CTAs with one tile each first (most warps for the shared memory), then double-buffered single groups
-    const K3hShape cand[7] = {{512, 1, 2}, {384, 1, 2}, {256, 2, 1}, {192, 2, 1}, {128, 2, 1}, {256, 1, 1}, {128, 1, 1}};
-    for (int i = 0; i < 7; ++i) {
-        if (force >= 0 && i != force) continue;
+    // (the last entry is only taken when UGVC_K3_SHAPE=7 asks for it: not yet the winner of an A/B)
+    const K3hShape cand[8] = {{512, 1, 2}, {384, 1, 2}, {256, 2, 1}, {192, 2, 1}, {128, 2, 1}, {256, 1, 1}, {128, 1, 1}, {448, 1, 2}};
+    for (int i = 0; i < 8; ++i) {
+        if (force >= 0 ? i != force : i == 7) continue;
         if (k3h_tile_bytes(plan, cand[i]) + all <= K3_SMEM_BUDGET) return cand[i];
     }
     for (int i = 2; i < 7; ++i)  // the forest is staged in chunks (single group: the chunks need whole-CTA barriers)
@@ -1585,7 +1586,10 @@ void launch_k3_fused(const DevPlan& plan, const uint32_t* raw, const float* feat
 #define K3H_LAUNCH(T, B, C, G)                                                                                                  \
     k3_heap<T, B, C, G><<<sm_count * per_sm, T, smem, st>>>(plan, raw, feats, row_stride, d_n_records, threshold, low_score, probs, \
                                                             qual, phreds, d_counts, chunk, phred_mode, d_err)
+    static const int nch448 = getenv("UGVC_K3_NCH448") ? atoi(getenv("UGVC_K3_NCH448")) : 8;  // profiling knob
     if (sh.groups == 2 && sh.tpb == 512) K3H_LAUNCH(512, 1, 8, 2);
+    else if (sh.groups == 2 && sh.tpb == 448 && nch448 == 12) K3H_LAUNCH(448, 1, 12, 2);
+    else if (sh.groups == 2 && sh.tpb == 448) K3H_LAUNCH(448, 1, 8, 2);
     else if (sh.groups == 2) K3H_LAUNCH(384, 1, 16, 2);
     else if (sh.tpb == 256 && sh.nbuf == 2) K3H_LAUNCH(256, 2, 16, 1);
     else if (sh.tpb == 192) K3H_LAUNCH(192, 2, 16, 1);
@@ -1654,6 +1658,8 @@ cudaError_t kernels_configure(const DevPlan& plan) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k1_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT_SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k1_tok, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // two CTAs per SM need all of it
+    if (e != cudaSuccess) return e;
 #ifdef UGVC_K1_SPLIT
     e = cudaFuncSetAttribute(k1_parse_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(plan));
     if (e != cudaSuccess) return e;
@@ -1664,6 +1670,8 @@ cudaError_t kernels_configure(const DevPlan& plan) {
         const int lim = 226 * 1024;  // a few static bytes (the mbarrier words) come on top of the dynamic part
         if ((e = cudaFuncSetAttribute(k3_heap<512, 1, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k3_heap<384, 1, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k3_heap<448, 1, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k3_heap<448, 1, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k3_heap<256, 2, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k3_heap<192, 2, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k3_heap<256, 1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)) != cudaSuccess) return e;
