@@ -7,10 +7,10 @@ tag=${1:-r2n}
 out=gpurun_out/$tag
 mkdir -p "$out"
 nvidia-smi --query-gpu=name,clocks.max.sm --format=csv > "$out/box.txt" 2>&1
-timeout 600 python -m pytest tests/test_gpu_y_tiletok.py tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_edges.py tests/test_gpu_y_lanes.py -q -m gpu --maxfail=8 > "$out/tests.log" 2>&1; tail -4 "$out/tests.log"
+timeout 600 python -m pytest ${TESTS:-tests/test_gpu_y_tiletok.py tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_edges.py tests/test_gpu_y_lanes.py} -q -m gpu --maxfail=8 > "$out/tests.log" 2>&1; tail -4 "$out/tests.log"
 if [ "${SKIP_SANITIZER:-0}" != 1 ]; then
-  timeout 300 compute-sanitizer --tool racecheck --racecheck-report all python scripts/k1_tiers_check.py > "$out/racecheck.log" 2>&1; grep -c "Race reported\|hazard" "$out/racecheck.log"; tail -3 "$out/racecheck.log"
-  timeout 300 compute-sanitizer --tool memcheck python scripts/k1_tiers_check.py > "$out/memcheck.log" 2>&1; tail -3 "$out/memcheck.log"
+  timeout 300 MODE=learn compute-sanitizer --tool racecheck --racecheck-report all python scripts/k1_tiers_check.py > "$out/racecheck.log" 2>&1; grep -c "Race reported\|hazard" "$out/racecheck.log"; tail -3 "$out/racecheck.log"
+  grep -A2 "hazard detected" "$out/racecheck.log" | grep "Thread" | sed -E 's/Thread \([0-9]+,0,0\)//; s/\+0x[0-9a-f]+//' | sort | uniq -c | sort -rn | head -12
 fi
 run_bench() {  # name, env...
   local name=$1; shift
@@ -25,9 +25,6 @@ except Exception as e:
 PY
 }
 run_bench tok A=1
-run_bench fast UGVC_K1_TILE_KERNEL=fast
-run_bench k3_448x8 UGVC_K3_SHAPE=7
-run_bench k3_448x12 UGVC_K3_SHAPE=7 UGVC_K3_NCH448=12
 for k in ${NCU_KERNELS:-k1_tok}; do
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o "$out/prof_$k" \
       python bench.py --records 4000000 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > "$out/ncu_$k.log" 2>&1

@@ -1548,13 +1548,13 @@ static K3hShape k3h_shape(const DevPlan& plan) {
     const bool forest = plan.h.model_kind != MODEL_LOGISTIC;
     const size_t all = forest ? (size_t)plan.h.n_trees * k3h_tree_bytes(plan) : 0;
     // two half-CTAs with one tile each first (most warps for the shared memory), then double-buffered single groups
-    // (the last entry is only taken when UGVC_K3_SHAPE=7 asks for it: not yet the winner of an A/B)
-    const K3hShape cand[8] = {{512, 1, 2}, {384, 1, 2}, {256, 2, 1}, {192, 2, 1}, {128, 2, 1}, {256, 1, 1}, {128, 1, 1}, {448, 1, 2}};
+    // (measured on cfg 3: 448 threads x 8 trees in flight 0.372 ms per launch, 384 x 16 0.406 ms, 448 x 12 0.381 ms)
+    const K3hShape cand[8] = {{512, 1, 2}, {448, 1, 2}, {384, 1, 2}, {256, 2, 1}, {192, 2, 1}, {128, 2, 1}, {256, 1, 1}, {128, 1, 1}};
     for (int i = 0; i < 8; ++i) {
-        if (force >= 0 ? i != force : i == 7) continue;
+        if (force >= 0 && i != force) continue;
         if (k3h_tile_bytes(plan, cand[i]) + all <= K3_SMEM_BUDGET) return cand[i];
     }
-    for (int i = 2; i < 7; ++i)  // the forest is staged in chunks (single group: the chunks need whole-CTA barriers)
+    for (int i = 3; i < 8; ++i)  // the forest is staged in chunks (single group: the chunks need whole-CTA barriers)
         if (k3h_tile_bytes(plan, cand[i]) + 16 * k3h_tree_bytes(plan) <= K3_SMEM_BUDGET) return cand[i];
     return K3hShape{0, 0, 0};
 }
