@@ -9,7 +9,7 @@ mkdir -p "$out"
 nvidia-smi --query-gpu=name,clocks.max.sm --format=csv > "$out/box.txt" 2>&1
 timeout 600 python -m pytest ${TESTS:-tests/test_gpu_y_tiletok.py tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_edges.py tests/test_gpu_y_lanes.py} -q -m gpu --maxfail=8 > "$out/tests.log" 2>&1; tail -4 "$out/tests.log"
 if [ "${SKIP_SANITIZER:-0}" != 1 ]; then
-  timeout 300 MODE=learn compute-sanitizer --tool racecheck --racecheck-report all python scripts/k1_tiers_check.py > "$out/racecheck.log" 2>&1; grep -c "Race reported\|hazard" "$out/racecheck.log"; tail -3 "$out/racecheck.log"
+  MODE=learn timeout 300 compute-sanitizer --tool racecheck --racecheck-report all python scripts/k1_tiers_check.py > "$out/racecheck.log" 2>&1; grep -c "Race reported\|hazard" "$out/racecheck.log"; tail -3 "$out/racecheck.log"
   grep -A2 "hazard detected" "$out/racecheck.log" | grep "Thread" | sed -E 's/Thread \([0-9]+,0,0\)//; s/\+0x[0-9a-f]+//' | sort | uniq -c | sort -rn | head -12
 fi
 run_bench() {  # name, env...
