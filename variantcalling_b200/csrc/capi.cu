@@ -331,6 +331,29 @@ static int build_fast(ugvc_ctx* ctx, const std::string& info_keys, const std::st
         if (k & KIND_SCALAR) bits |= SK_SCALAR;
         kind[s] = bits;
     }
+    // ---- k1_tok: where the values of a tag are decoded.  Numbers and string reducers get a column of the window's
+    // value table (same key, same spelling: the lanes of a warp run one path), single categories go through the
+    // dictionary queue (mostly sparse annotation flags), everything else is decoded where it is met.
+    {
+        unsigned next_col = 0;
+        auto place = [&](FastMeta& m) {
+            m.col = KF_COL_NONE;
+            if (!(m.flags & FK_NEEDED) || (m.flags & FK_SKIP_FMT)) return;
+            const bool special = m.whole_red != 0xFF && m.whole_red != RED_LEN;
+            if (!special && m.n_elem == 0) {  // only the element count is wanted
+                if (next_col < KF_COLS) m.col = (uint8_t)next_col++;
+                return;
+            }
+            const unsigned slot = special ? m.whole_slot : m.slot0;
+            if (slot >= kind.size()) return;
+            const unsigned c = kind[slot] & SK_CLS_MASK;
+            if (c == SK_CLS_DICT && (special || m.n_elem == 1)) m.col = KF_COL_DICT;
+            else if ((c == SK_CLS_NUM || c == SK_CLS_GEN) && next_col < KF_COLS) m.col = (uint8_t)next_col++;
+        };
+        for (FastKey& k : keys) place(k.m);
+        for (int i = 0; i < f.n_fmt; ++i) place(f.fmt[i]);
+        f.n_cols = (int)next_col;
+    }
     cudaFree(ctx->d_fast_keys);
     cudaFree(ctx->d_fast_htab);
     cudaFree(ctx->d_slot_kind);

@@ -92,8 +92,12 @@ struct alignas(8) FastMeta {   // 8 bytes: how a value of this tag becomes slot 
     uint8_t whole_red;         // RED_* of the whole-value slot, 0xFF if none
     uint8_t whole_slot;
     uint8_t tag;               // plan tag (duplicate-key bitmap), 0xFF if the plan has no such tag
-    uint8_t pad;
+    uint8_t col;               // k1_tok: < KF_COLS column of the window's value table (the tag's values are decoded side by
+                               // side for consecutive records), KF_COL_DICT the dictionary queue, KF_COL_NONE decoded where met
 };
+#define KF_COLS 64
+#define KF_COL_DICT 0xFEu
+#define KF_COL_NONE 0xFFu
 struct alignas(16) FastKey {   // 32 bytes
     uint32_t name[4];          // key bytes, zero padded (keys of up to 15 bytes are matched here)
     FastMeta m;
@@ -111,6 +115,7 @@ struct DevFast {
     const uint8_t* slot_kind;  // [n_slots] SK_* bits
     int n_keys;
     int enabled;
+    int n_cols;                // columns of the value table in use (FastMeta.col)
     int n_fmt, fmt_len;        // the usual FORMAT column (0: records are expected to end after INFO)
     uint32_t fmt_w[6];
     FastMeta fmt[UGVC_MAX_FMT_KEYS];
