@@ -308,9 +308,15 @@ def main():  # noqa: C901, PLR0912, PLR0915
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-bgzf", action="store_true",
                     help="also time the e2e pass with BGZF-compressed host buffers inflated on the device "
-                         "(ugvc_submit_bgzf; adds an e2e_bgzf object, off by default)")
+                         "(ugvc_submit_bgzf; adds an e2e_bgzf object; on by default at N=1)")
+    ap.add_argument("--no-e2e-bgzf", action="store_true")
+    ap.add_argument("--no-e2e-file", action="store_true",
+                    help="skip the file-to-file leg (BASELINE configs[1] through `ugvc filter_variants_pipeline`, N=1 only)")
+    ap.add_argument("--e2e-file-records", type=int, default=5_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_e2e and not args.no_e2e_bgzf:
+        args.e2e_bgzf = True
     claim_stdout()
     if args.warmup < 3:  # noqa: PLR2004
         args.warmup = 3
@@ -468,7 +474,7 @@ def main():  # noqa: C901, PLR0912, PLR0915
     # dram__bytes_write.sum of one launch and the records that launch parsed)
     traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     ncu_traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-    stage_kernel = {"k1_field_parse": "k1_fast", "k3_inference": "k3_heap", "k2_feature_assembly": "k2_features",
+    stage_kernel = {"k1_field_parse": "k1_tok", "k3_inference": "k3_heap", "k2_feature_assembly": "k2_features",
                     "k0_line_index": "k0_index"}
 
     def traffic_of(stage):
@@ -658,6 +664,33 @@ def main():  # noqa: C901, PLR0912, PLR0915
         cpu["filter_parity_on_sample"] = bool(np.array_equal(want_low, got_low))
         cpu["max_abs_prob_diff_on_sample"] = float(np.abs(res["probs"] - tmp_p[:n_s].cpu().numpy()).max())
 
+    # ---- file to file through the drop-in CLI (BASELINE.md section 4's clock: .vcf.gz in -> .vcf.gz + .tbi out), N=1:
+    # BASELINE configs[1] (5 M records, logistic regression) in a child process that writes the input, runs
+    # filter_variants_pipeline.run twice in-process and once as a fresh `python ugvc ...`, and checks the output
+    e2e_file = None
+    if rank == 0 and world == 1 and not args.no_e2e and not args.no_e2e_file:
+        import subprocess
+        import tempfile
+        del d_text
+        torch.cuda.empty_cache()
+        with tempfile.TemporaryDirectory(prefix="bench_cfg2_") as work:
+            t0 = time.perf_counter()
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "run_cfg2_cli.py"), "--records",
+                                str(args.e2e_file_records), "--runs", "2", "--workdir", work], capture_output=True, text=True,
+                               check=False)
+            try:
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                ck = d.get("checks", {})
+                e2e_file = {"value": d["variants_per_s_file_to_file"], "unit": "variants/s", "records": d["records"],
+                            "workload": d["config"], "wall_s": d["cli_wall_s"], "wall_s_runs": d["cli_wall_s_runs"],
+                            "fresh_process_wall_s": d.get("cli_process_wall_s"),
+                            "fresh_process_variants_per_s": d.get("variants_per_s_process"),
+                            "input_file_bytes": d["input_file_bytes"], "output_file_bytes": d["output_file_bytes"],
+                            "checks_ok": bool(ck) and "error" not in ck and all(v for k, v in ck.items() if isinstance(v, bool)),
+                            "checks": ck, "timing_note": d.get("timing_note"), "leg_seconds": time.perf_counter() - t0}
+            except Exception as e:  # noqa: BLE001
+                e2e_file = {"error": f"{type(e).__name__}: {e}", "stderr_tail": r.stderr[-600:]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "variants/s", "n_gpus": world, "steps": args.steps,
@@ -673,6 +706,7 @@ def main():  # noqa: C901, PLR0912, PLR0915
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity,
             **({"e2e_bgzf": e2e_bgzf} if e2e_bgzf is not None else {}),
+            **({"e2e_file": e2e_file} if e2e_file is not None else {}),
             "counts_last_steps": {"n_records": counts_total[0], "n_low_score": counts_total[1],
                                   "n_pass": counts_total[2], "n_cg": counts_total[3]},
         }

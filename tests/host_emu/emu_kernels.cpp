@@ -13,13 +13,11 @@
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 alignas(16) uint8_t k1_smem[64 * 1024];
 alignas(16) uint8_t smem3[8 * 1024 * 1024];  // K3: feature tile + the whole forest
-alignas(16) uint8_t kf_smem_emu[128 * 1024];  // K1 tile kernel (queue form)
-alignas(16) uint8_t kt_smem_emu[128 * 1024];  // K1 tile kernel (token form)
+alignas(16) uint8_t kt_smem_emu[128 * 1024];  // K1 tile kernel
 
 #include "../../variantcalling_b200/csrc/kernels.cu"
 
 static_assert(K1_SMEM_BYTES <= sizeof(k1_smem), "k1_smem too small");
-static_assert(KF_SMEM_BYTES <= sizeof(kf_smem_emu), "kf_smem_emu too small");
 static_assert(KT_SMEM_BYTES <= sizeof(kt_smem_emu), "kt_smem_emu too small");
 
 static void one_thread_grid() {
@@ -66,33 +64,24 @@ void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_t
 #endif
 }
 
-// both K1 tiers: the tile kernel's phases run one after the other in the single emulated thread (every phase is a
-// thread-strided loop), then the generic parser takes the slow list.  UGVC_EMU_G=<g> forces g walker lanes per
-// record so that the re-synchronisation on ';' is exercised too.
+// both K1 tiers: the tile kernel emulates all 512 threads of its CTA phase by phase (KT_FOR_THREADS), then the generic
+// parser takes the slow list.  UGVC_EMU_WCAP=<n> caps the records per window (several windows per tile).
 void launch_k1_fast(const DevPlan& plan, const DevFast& fast, const DevSchedule& sched, const uint8_t* d_text, size_t n_bytes,
                     uint32_t* scratch, int64_t* line_start, size_t cap_records, int64_t* d_n_records, uint32_t* raw,
                     size_t row_stride, ugvc_recinfo* recinfo, uint32_t* slow_list, unsigned long long* d_err,
                     long long* d_counts, int, cudaStream_t) {
-    const size_t n_tiles = (n_bytes + KF_TILE - 1) / KF_TILE;
+    const size_t n_tiles = (n_bytes + KT_TILE - 1) / KT_TILE;
     memset(scratch, 0, 8 + n_tiles * sizeof(unsigned long long));
     if (n_tiles == 0) {
         *d_n_records = 0;
         line_start[0] = 0;
         return;
     }
-    const char* g = getenv("UGVC_EMU_G");
-    ugvc_emu_force_g = g ? atoi(g) : 0;
     one_thread_grid();
-    // the token form emulates all 512 threads of its CTA phase by phase (KT_FOR_THREADS); UGVC_K1_TILE_KERNEL=fast: the queue form
-    const char* which = getenv("UGVC_K1_TILE_KERNEL");
     uint32_t wcap = kt_window_records(plan.h.n_slots);
-    if (const char* w = getenv("UGVC_EMU_WCAP")) wcap = (uint32_t)atoi(w) < wcap ? (uint32_t)atoi(w) : wcap;  // tests: small windows
-    if (wcap >= 16u && !(which && which[0] == 'f'))
-        k1_tok(plan, fast, d_text, n_bytes, reinterpret_cast<unsigned long long*>(scratch) + 1, scratch, scratch + 1, n_tiles,
-               line_start, cap_records, d_n_records, raw, row_stride, recinfo, slow_list, d_err, d_counts, wcap);
-    else
-        k1_fast(plan, fast, d_text, n_bytes, reinterpret_cast<unsigned long long*>(scratch) + 1, scratch, scratch + 1, n_tiles,
-                line_start, cap_records, d_n_records, raw, row_stride, recinfo, slow_list, d_err, d_counts);
+    if (const char* w = getenv("UGVC_EMU_WCAP")) wcap = (uint32_t)atoi(w) < wcap ? (uint32_t)atoi(w) : wcap;
+    k1_tok(plan, fast, d_text, n_bytes, reinterpret_cast<unsigned long long*>(scratch) + 1, scratch, scratch + 1, n_tiles,
+           line_start, cap_records, d_n_records, raw, row_stride, recinfo, slow_list, d_err, d_counts, wcap);
     one_thread_grid();
     k1_parse(plan, sched, d_text, line_start, d_n_records, raw, row_stride, recinfo, d_err, d_counts, slow_list, scratch + 1);
 }

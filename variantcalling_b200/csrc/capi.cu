@@ -81,7 +81,7 @@ struct ugvc_ctx {
 #endif
     DevSchedule sched{};           // learned key order (empty: generic path only)
     SchedEntry* d_sched = nullptr;
-    DevFast fast{};                // key table / FORMAT column / slot kinds of the tile kernel (k1_fast)
+    DevFast fast{};                // key table / FORMAT column / slot kinds of the tile kernel (k1_tok)
     FastKey* d_fast_keys = nullptr;
     uint8_t* d_fast_htab = nullptr;
     uint8_t* d_slot_kind = nullptr;
@@ -210,7 +210,7 @@ static size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
 
 static int find_host_tag(const ugvc_ctx* ctx, const std::string& name);
 
-// Tables of the tile kernel (k1_fast): every INFO key it may meet -- the plan's tags declared in ##INFO
+// Tables of the tile kernel (k1_tok): every INFO key it may meet -- the plan's tags declared in ##INFO
 // plus the keys seen in the data (`info_keys`, "KEY;KEY!;..." as for the key order; '!' marks a key that
 // came without a value) -- the usual FORMAT column, the kind bits of every slot, the fixed-column slots.
 static int build_fast(ugvc_ctx* ctx, const std::string& info_keys, const std::string& format_keys) {

@@ -775,7 +775,6 @@ __device__ __noinline__ Cur decode_sched(RawOut o, unsigned long long meta, Cur 
 #undef K1_KERNEL_NAME
 #endif
 
-#include "k1_fast.inc"
 #include "k1_tok.inc"
 
 size_t k1_smem_bytes(const DevPlan&) { return (size_t)K1_SMEM_BYTES; }
@@ -829,34 +828,29 @@ void launch_k1(const DevPlan& plan, const DevSchedule& sched, const uint8_t* d_t
 #endif
 }
 
-// K1, both tiers: the tile kernel (line index + parse of the usual records) and the generic parser over
+// K1, both tiers: the tile kernel (line index + parse of the usual records, k1_tok.inc) and the generic parser over
 // the records it put on the slow list.  scratch: [0] tile ticket, [1] slow-record count, then one
 // 64-bit look-back state word per tile.
+__global__ void k1_tile_empty(int64_t* __restrict__ line_start, int64_t* __restrict__ n_records) {
+    *n_records = 0;
+    line_start[0] = 0;
+}
 void launch_k1_fast(const DevPlan& plan, const DevFast& fast, const DevSchedule& sched, const uint8_t* d_text, size_t n_bytes,
                     uint32_t* scratch, int64_t* line_start, size_t cap_records, int64_t* d_n_records, uint32_t* raw,
                     size_t row_stride, ugvc_recinfo* recinfo, uint32_t* slow_list, unsigned long long* d_err,
                     long long* d_counts, int sm_count, cudaStream_t st) {
-    const size_t n_tiles = (n_bytes + KF_TILE - 1) / KF_TILE;
+    const size_t n_tiles = (n_bytes + KT_TILE - 1) / KT_TILE;
     cudaMemsetAsync(scratch, 0, 8 + n_tiles * sizeof(unsigned long long), st);
     if (n_tiles == 0) {
-        k1_fast_empty<<<1, 1, 0, st>>>(line_start, d_n_records);
+        k1_tile_empty<<<1, 1, 0, st>>>(line_start, d_n_records);
         return;
     }
-    const size_t blocks = n_tiles < (size_t)sm_count * KF_MIN_CTAS ? n_tiles : (size_t)sm_count * KF_MIN_CTAS;
-    // the token form (k1_tok) unless the plan has so many slots that a window would hold under sixteen records;
-    // UGVC_K1_TILE_KERNEL=fast selects the queue form (differential tests, profiling)
-    static const char* which = getenv("UGVC_K1_TILE_KERNEL");
-    const uint32_t wcap = kt_window_records(plan.h.n_slots);
-    if (wcap >= 16u && !(which && which[0] == 'f'))
-        k1_tok<<<(unsigned)blocks, KT_TPB, KT_SMEM_BYTES, st>>>(plan, fast, d_text, n_bytes,
-                                                                reinterpret_cast<unsigned long long*>(scratch) + 1, scratch,
-                                                                scratch + 1, n_tiles, line_start, cap_records, d_n_records, raw,
-                                                                row_stride, recinfo, slow_list, d_err, d_counts, wcap);
-    else
-        k1_fast<<<(unsigned)blocks, KF_TPB, KF_SMEM_BYTES, st>>>(plan, fast, d_text, n_bytes,
-                                                                 reinterpret_cast<unsigned long long*>(scratch) + 1, scratch,
-                                                                 scratch + 1, n_tiles, line_start, cap_records, d_n_records, raw,
-                                                                 row_stride, recinfo, slow_list, d_err, d_counts);
+    const size_t blocks = n_tiles < (size_t)sm_count * 2 ? n_tiles : (size_t)sm_count * 2;  // two resident CTAs per SM
+    const uint32_t wcap = kt_window_records(plan.h.n_slots);  // >= 24 for any plan (at most 255 slots)
+    k1_tok<<<(unsigned)blocks, KT_TPB, KT_SMEM_BYTES, st>>>(plan, fast, d_text, n_bytes,
+                                                            reinterpret_cast<unsigned long long*>(scratch) + 1, scratch, scratch + 1,
+                                                            n_tiles, line_start, cap_records, d_n_records, raw, row_stride, recinfo,
+                                                            slow_list, d_err, d_counts, wcap);
     // the slow tier: usually an empty list (the CTAs leave at once)
     k1_parse<<<sm_count * 2, K1_TPB, k1_smem_bytes(plan), st>>>(plan, sched, d_text, line_start, d_n_records, raw, row_stride,
                                                                 recinfo, d_err, d_counts, slow_list, scratch + 1);
@@ -1653,8 +1647,6 @@ void launch_k3(const DevPlan& plan, const float* feats, size_t row_stride, const
 cudaError_t kernels_configure(const DevPlan& plan) {
     cudaError_t e = cudaFuncSetAttribute(k1_parse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)k1_smem_bytes(plan));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k1_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k1_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT_SMEM_BYTES);
     if (e != cudaSuccess) return e;

@@ -71,7 +71,7 @@ struct DevSchedule {
 };
 
 
-// ---- K1 fast tier (k1_fast.inc) -----------------------------------------------------------
+// ---- K1 fast tier (k1_tok.inc) ------------------------------------------------------------
 // The tile kernel identifies INFO keys through a hash table of every key it may meet: the plan's
 // tags declared in ##INFO plus the keys ugvc_set_key_order() saw in the data (keys the plan does
 // not need decode to nothing).  A record that carries anything else -- an unknown key, a literal
