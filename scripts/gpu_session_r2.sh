@@ -10,7 +10,7 @@ bash scripts/gpu_probe.sh > /dev/null 2>&1; cp gpurun_out/box.txt "$out/box.txt"
 if [ "${SKIP_TESTS:-0}" != 1 ]; then
   timeout 900 python -m pytest tests -q -m gpu --maxfail=6 > "$out/tests.log" 2>&1; tail -3 "$out/tests.log"
 fi
-timeout 500 python bench.py ${BENCH_ARGS:-} > "$out/bench_n1.json" 2> "$out/bench_n1.err"; tail -c 1500 "$out/bench_n1.json"; echo
+timeout 800 python bench.py ${BENCH_ARGS:-} > "$out/bench_n1.json" 2> "$out/bench_n1.err"; tail -c 1500 "$out/bench_n1.json"; echo
 if [ "${SKIP_LEGACY:-0}" != 1 ]; then
   UGVC_K1_LEGACY=1 timeout 300 python bench.py --no-e2e --no-cpu-baseline --steps 3 > "$out/bench_legacy.json" 2> "$out/bench_legacy.err"
   python - <<PY
