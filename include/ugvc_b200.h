@@ -333,6 +333,41 @@ int ugvc_conc_classify(ugvc_conc* h, int64_t n, const int8_t* gt_ultima, const i
 int ugvc_conc_curve(ugvc_conc* h, int group, double* precision, double* recall, double* thresholds,
                     size_t capacity);
 
+/* ---- --treat_multiallelics on the device -------------
+ * Replaces, per contig, the frame surgery of training_prep.process_multiallelic_spandel
+ * (ugbio_filtering/training_prep.py:226-287: select_overlapping_variants multiallelics.py:13-62,
+ * split_multiallelic_variants :65-127, split_multiallelic_variants_with_spandel spandel.py:11-63,
+ * extract_allele_subset_from_multiallelic(_spanning_deletion) multiallelics.py:130-177 / spandel.py:66-128,
+ * classify_hmer_indel_relative :385-465, cleanup_multiallelics :503-559) and the merge of
+ * variant_filtering_utils.combine_multiallelic_spandel / merge_and_assign_pls (:309-408).
+ *   ugvc_ma_set_rules  per-tag rules derived from the VCF header by the host (variantcalling_b200/multiallelics.py:
+ *                      rules_blob): how the values of every loaded per-allele tag are sub-sampled
+ *   ugvc_ma_build      host text of one contig + line_start / recinfo of the index pass (ugvc_filter_batch with the
+ *                      model-less plan) + the contig's reference sequence -> groups, split rows, scored text.
+ *                      out[0..6] = n_singles, n_cluster_records, n_kept_records, n_split_rows, kept_bytes,
+ *                      rows_bytes, entries of the widest two-row group's genotype vector.
+ *                      UGVC_E_DATA: the reference raises on a group (ugvc_ma_data_error: group index in processing
+ *                      order -- multi-allelic singles first, then cluster records -- and the reason code:
+ *                      1 AssertionError (GT without the selected alleles), 2 / 3 RuntimeError (Number=G / Number=n tag),
+ *                      4 RuntimeError ('*' without its deletion), 5 ValueError (flow key of a non-ACGT sequence),
+ *                      6 IndexError, 7 TypeError, 8 ValueError (not an integer), 9 limits, 10 IndexError (2-class merge))
+ *   ugvc_ma_fetch      the text of the scored pass (untouched lines in input order, then the split rows: singles,
+ *                      then clusters -- the row order of the reference's frame) and the group table
+ *   ugvc_ma_merge      fp64 class likelihoods of the scored pass (row-major n_kept + n_split_rows by n_classes) ->
+ *                      out[n_records][width] in input record order, zero padded, width = max(n_classes, out[6]) */
+typedef struct ugvc_ma ugvc_ma;
+int ugvc_ma_create(int device, ugvc_ma** out);
+void ugvc_ma_free(ugvc_ma* h);
+const char* ugvc_ma_last_error(const ugvc_ma* h);
+long long ugvc_ma_launch_count(const ugvc_ma* h);
+int ugvc_ma_set_rules(ugvc_ma* h, const void* blob, size_t n_bytes);
+int ugvc_ma_build(ugvc_ma* h, const uint8_t* text, size_t n_bytes, const int64_t* line_start, const ugvc_recinfo* recinfo,
+                  int64_t n_records, const uint8_t* ref_seq, size_t ref_len, int64_t out[8]);
+int ugvc_ma_data_error(const ugvc_ma* h, int64_t* group, int32_t* code);
+int ugvc_ma_fetch(ugvc_ma* h, uint8_t* out_text, size_t capacity, int32_t* out_origin, uint8_t* out_n_rows,
+                  uint8_t* out_n_alleles, size_t capacity_groups);
+int ugvc_ma_merge(ugvc_ma* h, const double* lik, int64_t n_rows, int n_classes, double* out, int width);
+
 /* ---- test hook ------------------------------------------------------------ */
 /* K1's numeric-literal parser (csrc/numparse.h) compiled for the host: parses one token of
  * `text` (NUL-terminated); returns 0 ok / 1 missing (".") / 2 not exactly parseable. */

@@ -1,0 +1,233 @@
+"""GPU: the --treat_multiallelics kernels (csrc/multiallelic.cu, C ABI ugvc_ma_*) against the oracle and against the
+Python model they were written from (variantcalling_b200.multiallelics.SplitPlan).
+
+ * split rows read back through the oracle loader + the fitted transformer give the features of the oracle's split
+   frame (which is pinned cell by cell to frames produced by the reference's own functions,
+   tests/test_multiallelics_cpu.py), the overlap sets equal the reference row loop's, the merged likelihoods equal
+   combine_multiallelic_spandel's;
+ * row for row the device text equals the model's (QD is spelled differently: 19 exact digits of the same double);
+ * mutated records (missing / malformed PL, GT, DP, X_IL, VARIANT_TYPE, symbolic and '*' alleles, records next to the
+   contig start, INFO keys that are FORMAT keys too, extra samples ...) end the same way on both sides: same text,
+   or the same exception type -- the reference's error contract.
+The file also runs on the host emulation of the kernel sources (tests/test_host_emu_cpu.py)."""
+import random
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import multiallelic_ref as MR
+from oracle import ref_pipeline as R
+from oracle.vcf_reader import OracleVariantFile
+from tests import util
+from tests.test_multiallelics_cpu import contig_text, cpu_index
+from variantcalling_b200 import multiallelics as PM
+from variantcalling_b200.vcf_header import VcfHeader
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def case():
+    ds, tr, _model, _ = util.make_multiallelic_case(12, "lr")
+    hdr = VcfHeader(ds["header_text"])
+    return ds, tr, hdr, hdr.loader_columns(ds["customs"])
+
+
+def norm_qd(line: bytes) -> bytes:
+    def f(m):
+        v = m.group(1)
+        try:
+            return b"QD=" + (v if v in (b".", b"") else repr(float(v)).encode())
+        except ValueError:
+            return b"QD=" + v
+    return re.sub(rb"QD=([^;\t]*)", f, line)
+
+
+def test_split_rows_and_merge_match_the_oracle(case, gpu_ctx):
+    ds, tr, hdr, cols = case
+    rng = np.random.default_rng(12)
+    plan = None
+    for contig in ("chrM1", "chrM2"):
+        df = R.get_vcf_df(ds["vf"], contig, ds["customs"])
+        want_split = MR.process_multiallelic_spandel(df, ds["ref"][contig], ds["vf"].header)
+        text = contig_text(ds, contig)
+        ls, ri = cpu_index(text)
+        plan = PM.make_split_plan(hdr, cols, ds["ref"][contig], 0, reuse=plan)  # the handle carries over, as in the tool
+        assert isinstance(plan, PM.DeviceSplitPlan)
+        new_text = plan.build(np.frombuffer(text, dtype=np.uint8), ls, ri).tobytes()
+        assert plan.launch_count() > 0
+        assert sorted(int(o) for o in plan.origins) == sorted(sum(MR.overlapping_sets(df), []))
+        got_df = R.get_vcf_df(OracleVariantFile(ds["header_text"].encode() + new_text), contig, ds["customs"])
+        assert got_df.shape[0] == want_split.shape[0]
+        with pd.option_context("future.infer_string", False):
+            want_x = tr.transform(R.harness_float_columns(want_split)).to_numpy(dtype=np.float64)
+            got_x = tr.transform(R.harness_float_columns(got_df)).to_numpy(dtype=np.float64)
+        bad = np.argwhere(want_x.astype(np.float32) != got_x.astype(np.float32))
+        assert bad.size == 0, (bad[:5], want_x[tuple(bad[0])], got_x[tuple(bad[0])], new_text.split(b"\n")[bad[0][0]])
+        # QD as the reference's frame holds it: the text of a split row is the same double, not only the same float32
+        n_kept = int(plan.kept.sum())
+        want_qd = want_split["qd"].to_numpy(dtype=np.float64)[n_kept:]
+        texts = [re.search(rb"QD=([^;\t]*)", ln).group(1) for ln in new_text.split(b"\n")[n_kept:-1]]
+        got_qd = np.array([np.nan if t == b"." else float(t) for t in texts])
+        assert len(texts) == int(plan.n_rows.sum()) and np.array_equal(want_qd, got_qd, equal_nan=True)
+        scores = rng.dirichlet(np.ones(3), size=want_split.shape[0])
+        original = df.copy()
+        src = [x in original.index for x in want_split.index]
+        dst = [x in want_split.index for x in original.index]
+        original["ml_lik"] = pd.Series([list(x) for x in scores[src, :]], index=original.loc[dst].index)
+        merged = MR.combine_multiallelic_spandel(want_split, original, scores)
+        lik = plan.merge(scores)
+        for i, want in enumerate(merged["ml_lik"]):
+            want = np.asarray(want, dtype=np.float64)
+            assert np.array_equal(lik[i, :want.size], want) and not lik[i, want.size:].any(), (i, lik[i], want)
+    plan.close()
+
+
+def test_rows_equal_the_python_model_line_for_line(case, gpu_ctx):
+    ds, _tr, hdr, cols = case
+    for contig in ("chrM1", "chrM2"):
+        text = np.frombuffer(contig_text(ds, contig), dtype=np.uint8)
+        ls, ri = cpu_index(text.tobytes())
+        host = PM.SplitPlan(hdr, cols, ds["ref"][contig])
+        want = host.build(text, ls, ri).tobytes().split(b"\n")
+        dev = PM.DeviceSplitPlan(hdr, cols, ds["ref"][contig])
+        got = dev.build(text, ls, ri).tobytes().split(b"\n")
+        assert [g.origin for g in host.groups] == [int(o) for o in dev.origins]
+        assert [len(g.rows) for g in host.groups] == [int(r) for r in dev.n_rows]
+        assert len(want) == len(got)
+        for i, (a, b) in enumerate(zip(want, got)):
+            assert norm_qd(a) == norm_qd(b), (contig, i, a, b)
+        lik = np.random.default_rng(3).dirichlet(np.ones(3), size=len(want) - 1)
+        assert np.array_equal(host.merge(lik), dev.merge(lik))
+        with pytest.raises(IndexError):
+            dev.merge(lik[:, :2].copy())  # a 2-class model has no hom-alt likelihood to spread
+        with pytest.raises(ValueError, match="unexpected number of rows"):
+            dev.merge(lik[:-1])
+        dev.close()
+
+
+def _mutate(rng, line: str) -> str:  # noqa: PLR0912, PLR0915
+    c = line.split("\t")
+    info, fmt, smp, alts = c[7].split(";"), c[8].split(":"), c[9].split(":"), c[4].split(",")
+
+    def drop(tag):
+        return [kv for kv in info if kv.split("=")[0] != tag]
+
+    def swap(tag, choices):
+        return [kv if not kv.startswith(tag + "=") else tag + "=" + rng.choice(choices) for kv in info]
+
+    m = rng.randrange(26)
+    if m == 0 and "PL" in fmt:
+        pl = smp[fmt.index("PL")].split(",")
+        pl[rng.randrange(len(pl))] = "."
+        smp[fmt.index("PL")] = ",".join(pl)
+    elif m == 1 and "PL" in fmt:
+        i = fmt.index("PL")
+        del fmt[i], smp[i]
+    elif m == 2:
+        smp[0] = rng.choice(["0|1", "./.", ".", "1", "1|2", "0/1/2", "2/1", "x/1", "1/1", ""])
+    elif m == 3:
+        c[3] = c[3].lower()
+        alts = [a.lower() if rng.random() < 0.5 else a for a in alts]  # noqa: PLR2004
+    elif m == 4 and "DP" in fmt:
+        smp[fmt.index("DP")] = rng.choice([".", "0", "", "7", "x"])
+    elif m == 5:
+        info = drop("X_IL")
+    elif m == 6:
+        info = drop("VARIANT_TYPE") + rng.choice([[], ["VARIANT_TYPE"], ["VARIANT_TYPE=snp"], ["VARIANT_TYPE=h-indel"],
+                                                   ["VARIANT_TYPE=non-h-indel"], ["VARIANT_TYPE=other"], ["VARIANT_TYPE="]])
+    elif m == 7:
+        info = drop("QD")
+    elif m == 8 and "GQ" in fmt:
+        i = fmt.index("GQ")
+        del fmt[i], smp[i]
+    elif m == 9:
+        c += [":".join(smp), "./."]
+    elif m == 10 and "AD" in fmt:
+        ad = smp[fmt.index("AD")].split(",")
+        smp[fmt.index("AD")] = ",".join(ad[:rng.randrange(1, len(ad) + 1)])
+    elif m == 11:
+        alts[rng.randrange(len(alts))] = rng.choice(["<DEL>", "<NON_REF>", "*", "N", "ANT", "a*"])
+    elif m == 12:
+        info = []
+    elif m == 13 and len(alts) > 1:
+        alts[1] = alts[0]
+    elif m == 14:
+        info.insert(rng.randrange(len(info) + 1), rng.choice(["AD=1,2,3", "GQ=5", "PL=1,2,3", "gt=0/1", "DP"]))
+    elif m == 15:
+        smp = smp[:rng.randrange(0, len(smp))] or [smp[0]]
+    elif m == 16:
+        alts = [rng.choice([".", "*"])]
+    elif m == 17:
+        extra = ["C", "G", "TT", "GA", "*"]
+        rng.shuffle(extra)
+        alts = alts + extra[:rng.randrange(1, 4)]
+        if "PL" in fmt and rng.random() < 0.8:  # noqa: PLR2004
+            n = len(alts) + 1
+            smp[fmt.index("PL")] = ",".join(str(rng.randrange(0, 500)) for _ in range(n * (n + 1) // 2))
+    elif m == 18:
+        info = drop("X_HIL")
+    elif m == 19:
+        info = swap("X_IL", [".", "", "3", "x", ".,2"])
+    elif m == 20:
+        info = swap("DP", [".", "0", "-3", "12"])
+        if "DP" in fmt and rng.random() < 0.7:  # noqa: PLR2004
+            i = fmt.index("DP")
+            del fmt[i], smp[i]
+    elif m == 21:
+        info = swap("AC", ["1"])
+    elif m == 22:
+        info = swap("X_HIL", [".", "0", "5", ""])
+    elif m == 23:
+        info = [""] + info + [""]
+    elif m == 24 and "PL" in fmt:
+        pl = smp[fmt.index("PL")].split(",")
+        smp[fmt.index("PL")] = ",".join(pl[:rng.randrange(1, len(pl))])
+    elif m == 25:
+        c[3] = c[3] + rng.choice(["N", "n", "R"])
+    c[4], c[7], c[8], c[9] = ",".join(alts), (";".join(info) if info else "."), ":".join(fmt), ":".join(smp)
+    return "\t".join(c)
+
+
+def _outcome(plan, text, ls, ri, seed):
+    try:
+        out = plan.build(np.frombuffer(text, dtype=np.uint8), ls, ri).tobytes()
+        lik = np.random.default_rng(seed).dirichlet(np.ones(3), size=out.count(b"\n"))
+        return "ok", [norm_qd(ln) for ln in out.split(b"\n")], plan.merge(lik)
+    except Exception as e:  # noqa: BLE001
+        return type(e).__name__, None, None
+
+
+def test_mutated_records_end_the_same_way_as_in_the_model(case, gpu_ctx):
+    ds, _tr, hdr, cols = case
+    ends = {}
+    dev = None
+    for it in range(120):
+        rng = random.Random(7000 + it)
+        contig = rng.choice(["chrM1", "chrM2"])
+        lines = [ln for ln in ds["lines"] if ln.split("\t", 1)[0] == contig]
+        a = rng.randrange(0, max(1, len(lines) - 60))
+        lines = lines[a:a + rng.randrange(20, 60)]
+        if rng.random() < 0.3:  # noqa: PLR2004  (records next to the contig start: the window slice goes negative)
+            shift = int(lines[0].split("\t")[1]) - rng.randrange(1, 25)
+            lines = ["\t".join([c[0], str(int(c[1]) - shift)] + c[2:]) for c in (ln.split("\t") for ln in lines)]
+        multi = [i for i, ln in enumerate(lines) if "," in ln.split("\t")[4] or len(ln.split("\t")[3]) > 1]
+        for _ in range(rng.randrange(0, 4)):
+            i = rng.choice(multi) if multi and rng.random() < 0.85 else rng.randrange(len(lines))  # noqa: PLR2004
+            lines[i] = _mutate(rng, lines[i])
+        text = ("\n".join(lines) + "\n").encode()
+        try:
+            ls, ri = cpu_index(text)
+        except ValueError:
+            continue
+        want = _outcome(PM.SplitPlan(hdr, cols, ds["ref"][contig]), text, ls, ri, it)
+        dev = PM.make_split_plan(hdr, cols, ds["ref"][contig], 0, reuse=dev)
+        got = _outcome(dev, text, ls, ri, it)
+        assert want[0] == got[0], (it, want[0], got[0], text[:300])
+        ends[want[0]] = ends.get(want[0], 0) + 1
+        if want[0] == "ok":
+            assert want[1] == got[1], (it, [(x, y) for x, y in zip(want[1], got[1]) if x != y][:1])
+            assert np.array_equal(want[2], got[2]), it
+    assert ends.get("ok", 0) > 40 and len(ends) >= 5, ends  # noqa: PLR2004  (the reference's failure types all occur)

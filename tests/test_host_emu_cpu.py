@@ -6,7 +6,7 @@ memory on the heap -- into tests/host_emu/_build/libugvc_emu.so.  This test poin
 that library (UGVC_LIB_PATH, the developer override of variantcalling_b200/lib.py) and runs the
 `gpu`-marked parity files there, so the driver's CPU check already compares the code the GPU will
 execute with the oracle: features bit-identical, FILTER identical, CLI output line for line, the
-inputs the reference raises on, --treat_multiallelics, the fuzzed records.
+inputs the reference raises on, --treat_multiallelics (its kernels, csrc/multiallelic.cu, included), the fuzzed records.
 
 Test infrastructure only: the package never loads the emulated library, and
 tests/test_capi_cpu.py::test_no_cuda_device_fails_loudly keeps asserting that the product library
@@ -22,7 +22,8 @@ EMU_DIR = os.path.join(ROOT, "tests", "host_emu")
 EMU_LIB = os.path.join(EMU_DIR, "_build", "libugvc_emu.so")
 
 FILES = ["tests/test_gpu_parity.py", "tests/test_gpu_edges.py", "tests/test_gpu_fuzz.py", "tests/test_gpu_cnv.py",
-         "tests/test_gpu_cli.py", "tests/test_gpu_multiallelics.py", "tests/test_gpu_x_model_apply.py", "tests/test_gpu_x_deepvariant.py", "tests/test_gpu_x_bgzf.py", "tests/test_gpu_y_tiletok.py"]
+         "tests/test_gpu_cli.py", "tests/test_gpu_multiallelics.py", "tests/test_gpu_x_model_apply.py", "tests/test_gpu_x_deepvariant.py", "tests/test_gpu_x_bgzf.py", "tests/test_gpu_y_tiletok.py",
+         "tests/test_gpu_z_multiallelic_device.py"]
 NEED_THE_DEVICE_GENERATOR = ["tests/test_gpu_edges.py::test_device_generator_text_parity",
                              "tests/test_gpu_parity.py::test_full_size_properties_batching_invariance"]
 

@@ -534,6 +534,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
             return text, bgzf_io.count_lines(text, args.io_threads)
 
         in_pool, out_pool = _PinnedPool(3), _PinnedPool(3)  # two device calls in flight + the reader / the writer
+        split_plans = [None]  # --treat_multiallelics: the device split plan, carried from contig to contig
         dev_ms = np.zeros(5)
 
         def host_contig(contig: str, loaded):
@@ -560,8 +561,9 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                     idx_ctx.reserve(idx_reserved[0], idx_reserved[1], 1)
                 idx = idx_ctx.filter_batch(text, args.decision_threshold)
                 logger.info("Processing multiallelics -> pre-classifier")
-                sp = multiallelics.SplitPlan(header, header.loader_columns(args.custom_annotations),
-                                             multiallelics.read_fasta_contig(args.ref_fasta, contig))
+                sp = split_plans[0] = multiallelics.make_split_plan(
+                    header, header.loader_columns(args.custom_annotations),
+                    multiallelics.read_fasta_contig(args.ref_fasta, contig), device, reuse=split_plans[0])
                 scored_text = sp.build(text, idx["line_start"], idx["recinfo"])
                 n_scored = int(np.count_nonzero(scored_text == 10))  # noqa: PLR2004
                 need = (scored_text.size + 4096, n_scored + 128)

@@ -97,6 +97,15 @@ SIGNATURES = {
     "ugvc_conc_run": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "ugvc_conc_classify": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "ugvc_conc_curve": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz]),
+    "ugvc_ma_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "ugvc_ma_free": (None, [_vp]),
+    "ugvc_ma_last_error": (C.c_char_p, [_vp]),
+    "ugvc_ma_launch_count": (C.c_longlong, [_vp]),
+    "ugvc_ma_set_rules": (C.c_int, [_vp, _vp, _sz]),
+    "ugvc_ma_build": (C.c_int, [_vp, _vp, _sz, _vp, _vp, C.c_int64, _vp, _sz, _i64p]),
+    "ugvc_ma_data_error": (C.c_int, [_vp, _i64p, C.POINTER(C.c_int32)]),
+    "ugvc_ma_fetch": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp, _sz]),
+    "ugvc_ma_merge": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
     "ugvc_tbi_summary": (C.c_int, [_vp, C.c_size_t, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ugvc_test_deflate_block": (C.c_int64, [_vp, C.c_uint32, _vp]),
     "ugvc_test_deflate_block_lanes": (C.c_int64, [_vp, C.c_uint32, _vp]),

@@ -19,7 +19,9 @@ as ordinary records:
   scored pass (K0..K3)          ->  fp64 class likelihoods of every row of that text
   SplitPlan.merge()             ->  N x W likelihood matrix in input record order
 
-Only the records in groups (~1 %) are touched by Python; everything else is array work.
+``DeviceSplitPlan`` runs find_overlaps / build / merge as CUDA kernels (csrc/multiallelic.cu, C ABI ``ugvc_ma_*``) and is
+what the tool uses; ``SplitPlan`` is the same algorithm in Python -- the model the kernels were written from, kept for
+differential tests and as ``UGVC_MA_HOST=1`` (A/B), like ``UGVC_K1_LEGACY`` for the generic parser.
 The reference's error behaviour is kept: no multi-allelic site on a
 contig -> ValueError, no deletion cluster -> KeyError('spanning_deletion'), a called genotype
 without the selected alleles -> AssertionError, per-genotype (Number=G) tags other than PL ->
@@ -27,8 +29,10 @@ RuntimeError, a 2-class model -> IndexError.
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 import re
+import struct
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -455,7 +459,7 @@ class SplitPlan:
 
         def alleles_of(i: int) -> tuple:
             c = bytes(view[int(line_start[i]):int(line_start[i + 1])]).split(b"\t", 5)
-            return (c[3],) + tuple(c[4].split(b","))
+            return (c[3],) + (() if c[4] == b"." else tuple(c[4].split(b",")))
 
         del_len = np.zeros(n, dtype=np.int64)
         for i in np.flatnonzero(ref_len > 1):  # only a REF longer than one base can be a deletion
@@ -522,6 +526,183 @@ class SplitPlan:
             row[where] = vals
             out[g.origin] = row
         return out
+
+
+# ------------------------------------------------------------------ the device form (csrc/multiallelic.cu)
+MA_KEEP, MA_SUB_A, MA_SUB_R, MA_ERR_G, MA_ERR_NUM, MA_SPECIAL = 0, 1, 2, 3, 4, 5
+_SPECIAL_INFO = ("x_ic", "x_il", "x_hil", "x_hin")
+
+
+def rules_blob(plan: SplitPlan) -> bytes:
+    """The per-tag rules of ``SplitPlan._rewrite`` / ``convert`` as the flat table ``ugvc_ma_set_rules`` takes: for every
+    INFO / FORMAT tag of the header (lower-cased, first spelling wins, as in ``plan.rule``) what happens to its
+    value in a split row -- kept, the pair's elements of a Number=A / Number=R list, an error for Number=G /
+    Number=n, or replaced by a derived value (X_IC / X_IL / X_HIL / X_HIN when the loader keeps the column)."""
+    header = plan.header
+
+    def table(is_format: bool, tags) -> list:
+        out, seen = [], set()
+        for tag in tags:
+            col = tag.lower()
+            if col in seen:
+                continue
+            seen.add(col)
+            action, number = MA_KEEP, 0
+            if not is_format and col in _SPECIAL_INFO and col in plan.loaded:
+                action = MA_SPECIAL + _SPECIAL_INFO.index(col)
+            elif col in plan.loaded and col not in plan.SPECIAL:
+                rule = plan.rule.get((is_format, col))
+                if rule == "A":
+                    action = MA_SUB_A
+                elif rule == "R":
+                    action = MA_SUB_R
+                elif rule == "G":
+                    action = MA_ERR_G
+                elif rule is not None and rule != ".":
+                    action, number = MA_ERR_NUM, int(rule) & 0xFFFF
+            name = col.encode()
+            if action != MA_KEEP and len(name) <= 32:  # noqa: PLR2004
+                out.append(struct.pack("<32sBBH", name, len(name), action, number))
+        return out
+
+    info, fmt = table(False, header.info), table(True, header.formats)
+    flags = (1 if "QD" in header.info else 0) | (2 if "GQ" in header.formats else 0)
+    spell = []
+    for k, col in enumerate(_SPECIAL_INFO):
+        if col in plan.loaded:
+            flags |= 1 << (4 + k)
+        spell.append(plan.header_tag(col).encode()[:32])
+    head = struct.pack("<IIII", 0x4D41524C, len(info), len(fmt), flags)
+    head += b"".join(struct.pack("<32s", t) for t in spell) + bytes(len(t) for t in spell)
+    return head + b"".join(info) + b"".join(fmt)
+
+
+_MA_ERRORS = {
+    1: (AssertionError, "One of the alleles should be present in the GT"),
+    2: (RuntimeError, "Special treatment is required for 'G' fields, not supported by this function"),
+    3: (RuntimeError, "Number of a per-allele tag is not supported"),
+    4: (RuntimeError, "Can't deal with spanning deletion allele without the spandel"),
+    5: (ValueError, "Input contains non ACGTacgt characters"),
+    6: (IndexError, "list index out of range"),
+    7: (TypeError, "'NoneType' object is not subscriptable"),
+    8: (ValueError, "invalid literal for int() with base 10"),
+    9: (RuntimeError, "a record beyond the limits of the device split (more than 32 alleles, or a malformed line)"),
+    10: (IndexError, "list index out of range"),
+}
+
+
+class DeviceSplitPlan:
+    """``SplitPlan`` on the device: same constructor, ``build`` and ``merge``; owns a ``ugvc_ma`` handle."""
+
+    def __init__(self, header, loaded_columns: dict, ref_seq: str, device: int = 0):
+        from variantcalling_b200 import lib
+
+        self._lib = lib.load_library()
+        self._UgvcError = lib.UgvcError
+        self.host = SplitPlan(header, loaded_columns, "")  # the rule tables only (its build / merge are not used)
+        self.set_reference(ref_seq)
+        h = C.c_void_p()
+        rc = self._lib.ugvc_ma_create(device, C.byref(h))
+        if rc != 0:
+            raise lib.UgvcError(rc, "ugvc_ma_create failed (no CUDA device?)")
+        self.h = h
+        blob = rules_blob(self.host)
+        self._check(self._lib.ugvc_ma_set_rules(self.h, blob, len(blob)))
+        self.kept: np.ndarray | None = None
+        self.origins = np.zeros(0, dtype=np.int32)   # record of every group, in processing order
+        self.n_rows = np.zeros(0, dtype=np.uint8)
+        self.group_alleles = np.zeros(0, dtype=np.uint8)
+        self.stats = np.zeros(8, dtype=np.int64)
+
+    def set_reference(self, ref_seq):
+        """The next contig's sequence (the handle and its device buffers are reused from contig to contig)."""
+        self.ref = np.frombuffer(ref_seq.encode() if isinstance(ref_seq, str) else bytes(ref_seq), dtype=np.uint8)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.ugvc_ma_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001, S110
+            pass
+
+    def launch_count(self) -> int:
+        return int(self._lib.ugvc_ma_launch_count(self.h))
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise self._UgvcError(rc, self._lib.ugvc_ma_last_error(self.h).decode())
+
+    def build(self, text: np.ndarray, line_start: np.ndarray, recinfo: np.ndarray) -> np.ndarray:
+        """-> the text of the scored pass (``SplitPlan.build``).  The reference's failures keep their types."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        line_start = np.ascontiguousarray(line_start, dtype=np.int64)
+        recinfo = np.ascontiguousarray(recinfo)
+        n = int(recinfo.size)
+        rc = self._lib.ugvc_ma_build(self.h, text.ctypes.data, text.size, line_start.ctypes.data, recinfo.ctypes.data, n,
+                                     self.ref.ctypes.data if self.ref.size else None, self.ref.size,
+                                     self.stats.ctypes.data_as(C.POINTER(C.c_int64)))
+        n_singles, n_cluster = int(self.stats[0]), int(self.stats[1])
+        if rc not in (0, -4):
+            self._check(rc)
+        err_group, err_code = -1, 0
+        if rc == -4:  # noqa: PLR2004  (UGVC_E_DATA)
+            g, c = C.c_int64(), C.c_int32()
+            self._lib.ugvc_ma_data_error(self.h, C.byref(g), C.byref(c))
+            err_group, err_code = g.value, c.value
+        # the order in which the reference meets its failures (training_prep.py:255-287)
+        if n_singles == 0:
+            raise ValueError("No objects to concatenate")  # pd.concat([]) in training_prep.py:261
+        if 0 <= err_group < n_singles:
+            self._raise(err_code)
+        if n_cluster == 0:
+            raise KeyError("spanning_deletion")  # variant_filtering_utils.py:339 on a frame without the column
+        if err_group >= 0:
+            self._raise(err_code)
+        n_groups = n_singles + n_cluster
+        out = np.empty(int(self.stats[4] + self.stats[5]), dtype=np.uint8)
+        self.origins = np.empty(n_groups, dtype=np.int32)
+        self.n_rows = np.empty(n_groups, dtype=np.uint8)
+        self.group_alleles = np.empty(n_groups, dtype=np.uint8)
+        self._check(self._lib.ugvc_ma_fetch(self.h, out.ctypes.data, out.size, self.origins.ctypes.data, self.n_rows.ctypes.data,
+                                            self.group_alleles.ctypes.data, n_groups))
+        kept = np.ones(n, dtype=bool)
+        kept[self.origins] = False
+        self.kept = kept
+        return out
+
+    @staticmethod
+    def _raise(code: int):
+        exc, msg = _MA_ERRORS.get(code, (RuntimeError, f"device split failed with code {code}"))
+        raise exc(msg)
+
+    def merge(self, lik: np.ndarray) -> np.ndarray:
+        """``SplitPlan.merge``: (n_kept + n_split, K) likelihoods -> (N, W) in input record order."""
+        lik = np.ascontiguousarray(lik, dtype=np.float64)
+        n_rows, k = lik.shape
+        if n_rows != int(self.stats[2] + self.stats[3]):
+            raise ValueError("scored pass returned an unexpected number of rows")
+        width = max(k, int(self.stats[6]))
+        out = np.empty((int(self.kept.size), width), dtype=np.float64)
+        rc = self._lib.ugvc_ma_merge(self.h, lik.ctypes.data, n_rows, k, out.ctypes.data, width)
+        if rc == -4:  # noqa: PLR2004
+            raise IndexError("list index out of range")  # a 2-class model has no hom-alt likelihood to spread
+        self._check(rc)
+        return out
+
+
+def make_split_plan(header, loaded_columns: dict, ref_seq: str, device: int = 0, reuse=None):
+    """The tool's split plan: the device form (``reuse``: the plan of the previous contig, whose handle and buffers
+    carry over), or the Python model of it with UGVC_MA_HOST=1 (A/B, like UGVC_K1_LEGACY)."""
+    if os.environ.get("UGVC_MA_HOST", "0") not in ("", "0"):
+        return SplitPlan(header, loaded_columns, ref_seq)
+    if isinstance(reuse, DeviceSplitPlan) and reuse.h:
+        reuse.set_reference(ref_seq)
+        return reuse
+    return DeviceSplitPlan(header, loaded_columns, ref_seq, device)
 
 
 def score_math(lik: np.ndarray, threshold: float):
