@@ -135,11 +135,16 @@ def query(vcf_path: str, index: TabixIndex, name: str, beg: int, end: int) -> li
         for line in read_virtual(raw, cache, cb, ce).split(b"\n"):
             if not line or line.startswith(b"#"):
                 continue
-            cols = line.split(b"\t", 5)
+            cols = line.split(b"\t", 8)
             if cols[0].decode() != name:
                 continue
             pos0 = int(cols[1]) - 1
             rec_end = pos0 + max(1, len(cols[3]))
+            # htslib: a record ends at INFO/END when the tag is there and beyond POS (rlen = END - pos)
+            for kv in (cols[7].split(b";") if len(cols) > 7 else []):  # noqa: PLR2004
+                if kv.startswith(b"END=") and kv[4:].isdigit():
+                    rec_end = int(kv[4:]) if int(kv[4:]) > pos0 else rec_end
+                    break
             if pos0 < end and rec_end > beg and (cols[1], line) not in seen:
                 seen.add((cols[1], line))
                 hits.append((pos0, line))

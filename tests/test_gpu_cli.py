@@ -216,3 +216,48 @@ def test_cli_device_groups_cut_contigs_at_index_entries(job):
     # the pieces really were pieces: the linear index of the input offers cut points inside chr1
     _, lin = bgzf_io.read_tbi(job["vcf"] + ".tbi", linear=True)
     assert lin["chr1"].size > 4
+
+
+def test_index_ends_records_at_info_end(job):
+    """A header that declares INFO/END (gVCF blocks, symbolic alleles): htslib's tabix -- what `bcftools index -t`
+    writes for the reference, filter_variants_pipeline.py:231 -- ends such a record at END, so a region query that
+    overlaps only its tail finds it.  Read back with the independent spec reader of oracle/tabix_ref.py."""
+    from oracle import tabix_ref as TR
+
+    ds = job["ds"]
+    header = [ln for ln in ds["header"] if not ln.startswith("#CHROM")]
+    header += ['##INFO=<ID=END,Number=1,Type=Integer,Description="Stop position of the interval">', ds["header"][-1]]
+    lines = list(ds["lines"])
+    long_ones = {}
+    for i in range(50, 6000, 1100):
+        c = lines[i].split("\t")
+        if c[0] != "chr1":
+            continue
+        end = int(c[1]) + 150_000 + i
+        c[7] += f";END={end}"
+        lines[i] = "\t".join(c)
+        long_ones[i] = (int(c[1]), end)
+    k = 75  # an END that is not beyond POS is ignored
+    c = lines[k].split("\t")
+    c[7] = "END=1;" + c[7]
+    lines[k] = "\t".join(c)
+    assert len(long_ones) >= 4  # noqa: PLR2004
+    vcf, out = str(job["dir"] / "in_end.vcf.gz"), str(job["dir"] / "out_end.vcf.gz")
+    bgzf_io.write_vcf_gz(vcf, header, lines)
+    argv = ["--input_file", vcf, "--model_file", job["model"], "--output_file", out]
+    for cu in ds["customs"]:
+        argv += ["--custom_annotations", cu]
+    fvp.run(argv)
+    vf = OracleVariantFile(("\n".join(header) + "\n" + "\n".join(lines) + "\n").encode())
+    exp = R.filter_variants(vf, job["model_obj"], job["tr"], custom_annotations=ds["customs"])
+    _, recs = read_out(out)
+    assert recs == exp["lines"]
+    idx = TR.TabixIndex(out + ".tbi")
+    for i, (pos, end) in long_ones.items():
+        tail = TR.query(out, idx, "chr1", end - 10, end - 5)  # overlaps nothing but the tail of record i
+        assert any(ln.split(b"\t")[1] == str(pos).encode() and f"END={end}".encode() in ln for ln in tail), (i, pos, end)
+        assert not TR.query(out, idx, "chr1", end, end + 1) or all(
+            int(ln.split(b"\t")[1]) - 1 < end + 1 for ln in TR.query(out, idx, "chr1", end, end + 1))
+    # the record with END=1 keeps its REF-length end
+    p75 = int(lines[k].split("\t")[1])
+    assert any(int(ln.split(b"\t")[1]) == p75 for ln in TR.query(out, idx, "chr1", p75 - 1, p75))

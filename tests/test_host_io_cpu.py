@@ -198,3 +198,37 @@ def test_count_lines_equals_numpy():
             assert bgzf_io.count_lines(a, threads) == int(np.count_nonzero(a == 10))
     assert bgzf_io.count_lines(np.frombuffer(b"a\nb\n\n", dtype=np.uint8)) == 3
     assert bgzf_io.count_lines(np.arange(100, dtype=np.uint8)[::2]) == 1  # non-contiguous views are copied first
+
+
+def test_info_end_positions_follow_htslib():
+    """The index end of a record is INFO/END when the tag is there and beyond POS (htslib's rlen for VCF), found in
+    the INFO column only."""
+    from variantcalling_b200.filter_variants_pipeline import info_end_positions
+    from variantcalling_b200.lib import RECINFO_DTYPE
+
+    lines = [
+        "chr1\t100\t.\tA\t<DEL>\t50\t.\tSVTYPE=DEL;END=5000;DP=3\tGT\t0/1",
+        "chr1\t200\tEND=9\tA\tC\t50\t.\tDP=3\tGT\t0/1",                      # not in INFO
+        "chr1\t300\t.\tA\t<NON_REF>\t.\t.\tEND=450\tGT\t0/0",
+        "chr1\t400\t.\tAT\tA\t50\tPASS\tDP=1;XEND=7;END=350;END=9999\tGT:END=1\t0/1:5",  # END before POS: ignored by htslib
+        "chr1\t500\t.\tA\tC\t50\t.\tDP=3;END=\tGT\t0/1",                      # no digits
+        "chr1\t600\t.\tA\tC\t50\t.\tDP=3;END=700",                             # no FORMAT column
+    ]
+    text = np.frombuffer(("\n".join(lines) + "\n").encode(), dtype=np.uint8)
+    n = len(lines)
+    ls = np.zeros(n + 1, dtype=np.int64)
+    ri = np.zeros(n, dtype=RECINFO_DTYPE)
+    at = 0
+    for i, ln in enumerate(lines):
+        c = ln.split("\t")
+        ls[i] = at
+        ri["pos"][i] = int(c[1])
+        ri["info_off"][i] = sum(len(x) + 1 for x in c[:7])
+        ri["format_off"][i] = sum(len(x) + 1 for x in c[:8])
+        at += len(ln) + 1
+    ls[n] = at
+    got = info_end_positions(text, ls, ri, n)
+    assert got.tolist() == [5000, 0, 450, 350, 0, 700]
+    beg = ri["pos"].astype(np.int64) - 1
+    end = np.where(got > beg, got, beg + 1)
+    assert end.tolist() == [5000, 200, 450, 400, 500, 700]

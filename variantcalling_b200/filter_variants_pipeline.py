@@ -97,6 +97,33 @@ def _blacklist_positions(blacklists, contig: str) -> list[tuple[str, np.ndarray]
     return out
 
 
+
+def info_end_positions(text: np.ndarray, line_start: np.ndarray, recinfo: np.ndarray, n: int) -> np.ndarray:
+    """INFO/END of every record (0 where there is none): htslib's tabix for VCF ends a record at END when the tag
+    is present and lies beyond POS -- gVCF blocks, symbolic <DEL> / <CNV> alleles -- so that region queries that
+    overlap only the tail of a long record find it (`bcftools index -t`, filter_variants_pipeline.py:231)."""
+    out = np.zeros(n, dtype=np.int64)
+    if text.size < 6:  # noqa: PLR2004
+        return out
+    hit = np.flatnonzero((text[1:-4] == 69) & (text[2:-3] == 78) & (text[3:-2] == 68) & (text[4:-1] == 61)  # noqa: PLR2004
+                         & ((text[:-5] == 9) | (text[:-5] == 59))) + 1  # noqa: PLR2004  "END=" behind a tab or ';'
+    if hit.size == 0:
+        return out
+    rec = np.searchsorted(line_start[:n + 1], hit, side="right") - 1
+    ok = (rec >= 0) & (rec < n)
+    hit, rec = hit[ok], rec[ok]
+    ls = line_start[rec]
+    inside = (hit >= ls + recinfo["info_off"][rec]) & (hit < ls + recinfo["format_off"][rec])  # the INFO column only
+    for h, r in zip(hit[inside], rec[inside]):
+        p, v = int(h) + 4, 0
+        while p < text.size and 48 <= text[p] <= 57:  # noqa: PLR2004
+            v = v * 10 + int(text[p]) - 48
+            p += 1
+        if p > h + 4 and text[p] in (9, 10, 59) and out[r] == 0:  # noqa: PLR2004  (the first END of a line counts)
+            out[r] = v
+    return out
+
+
 class _Splicer:
     """Output side: splice + BGZF append + bookkeeping for the tabix index."""
 
@@ -108,6 +135,7 @@ class _Splicer:
         # tabix sections are built contig by contig on the writer thread (single-process runs), beside the GPU passes
         self.sections: list[bytes] = []
         self._cur: list[tuple] = []
+        self.index_info_end = False  # the header declares INFO/END: records end there in the index (htslib's rule)
         self.keep_arrays = False  # multi-rank runs: rank 0 shifts the virtual offsets, so the arrays travel instead
         self.L = lib.load_library()
         self.seconds = {"splice": 0.0, "deflate": 0.0}
@@ -163,7 +191,11 @@ class _Splicer:
         ri = res["recinfo"]
         beg = ri["pos"].astype(np.int64) - 1
         self._check_writer()
-        self._queue.put((contig, out[:nb], n, beg, beg + np.maximum(1, (ri["flags"] >> 8).astype(np.int64)), out_ls))
+        end = beg + np.maximum(1, (ri["flags"] >> 8).astype(np.int64))
+        if self.index_info_end:
+            info_end = info_end_positions(text, res["line_start"], ri, n)
+            end = np.where(info_end > beg, info_end, end)  # htslib ignores an END that is not beyond POS
+        self._queue.put((contig, out[:nb], n, beg, end, out_ls))
 
     def write_device_batch(self, contigs: list[str], bounds: np.ndarray, res: dict, release=None):
         """Records edited and BGZF-compressed on the device (lib.Context.filter_bgzf): only file and index work is left.
@@ -516,7 +548,11 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
 
         # compressed bytes both ways: the contig's BGZF blocks go to the device as they are, come back filtered, edited
         # and compressed again (ugvc_filter_bgzf); what that path does not cover keeps the host readers / writers
-        device_io = bool(with_model and not split_sites and not recal and blacklists is None and not args.host_io)
+        # (a header that declares INFO/END keeps the host writer: the index then ends records at END, which the device
+        # writer's recinfo does not carry)
+        out.index_info_end = "END" in header.info
+        device_io = bool(with_model and not split_sites and not recal and blacklists is None and not args.host_io
+                         and not out.index_info_end)
         file_flags = (lib.FILE_OVERWRITE_QUAL if args.overwrite_qual_tag else 0) | \
                      (lib.FILE_BLACKLIST_CG if args.blacklist_cg_insertions else 0)
 
