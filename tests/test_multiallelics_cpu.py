@@ -176,3 +176,36 @@ def test_find_overlaps_equals_the_row_loop_on_random_layouts():
         singles, clusters = PM.find_overlaps(pos, np.array([len(a) for a in alleles]), del_len,
                                              np.array(["*" in a for a in alleles]))
         assert sorted([[m] for m in singles] + clusters) == want
+
+
+def test_device_rule_table_follows_the_header():
+    """rules_blob (what ugvc_ma_set_rules takes): per-allele tags of the loaded columns are sub-sampled by their Number,
+    the derived tags are replaced, everything else travels as it is (SplitPlan.convert / vcftools.py:687-778)."""
+    import struct
+
+    from tests import util
+    from variantcalling_b200 import multiallelics as PM
+    from variantcalling_b200.vcf_header import VcfHeader
+
+    ds = util.make_dataset(n_records=50, n_custom=2, seed=3)
+    extra = ['##INFO=<ID=GLS,Number=G,Type=Float,Description="x">', '##INFO=<ID=PAIR,Number=2,Type=Integer,Description="x">',
+             '##FORMAT=<ID=GP,Number=G,Type=Float,Description="x">']
+    hdr = VcfHeader("\n".join(ds["header"][:-1] + extra + ds["header"][-1:]) + "\n")
+    cols = dict(hdr.loader_columns(ds["customs"]), gls="GLS", pair="PAIR", gp="GP")
+    blob = PM.rules_blob(PM.SplitPlan(hdr, cols, ""))
+    magic, n_info, n_fmt, flags = struct.unpack_from("<IIII", blob, 0)
+    assert magic == 0x4D41524C and len(blob) == 148 + 36 * (n_info + n_fmt)  # noqa: PLR2004
+    rules = {}
+    for i in range(n_info + n_fmt):
+        name, ln, action, number = struct.unpack_from("<32sBBH", blob, 148 + 36 * i)
+        rules[(i >= n_info, name[:ln].decode())] = (action, number)
+    assert rules[(False, "ac")][0] == PM.MA_SUB_A and rules[(False, "mq0c")][0] == PM.MA_SUB_R
+    assert rules[(True, "ad")][0] == PM.MA_SUB_R
+    assert (False, "hapcomp") not in rules and (False, "dp") not in rules  # Number=A overridden to 1; scalars are kept
+    assert (True, "pl") not in rules and (True, "gt") not in rules          # handled by the split itself
+    assert rules[(False, "gls")][0] == PM.MA_ERR_G and rules[(True, "gp")][0] == PM.MA_ERR_G
+    assert rules[(False, "pair")] == (PM.MA_ERR_NUM, 2)
+    assert [rules[(False, c)][0] for c in ("x_ic", "x_il", "x_hil", "x_hin")] == [PM.MA_SPECIAL + k for k in range(4)]
+    assert flags & 1 and flags & 2 and (flags >> 4) & 0xF == 0xF  # noqa: PLR2004  QD / GQ in the header, the four derived tags loaded
+    spell = [blob[16 + 32 * k: 16 + 32 * k + blob[144 + k]].decode() for k in range(4)]
+    assert spell == ["X_IC", "X_IL", "X_HIL", "X_HIN"]
