@@ -95,6 +95,20 @@ struct MaGroup {
 #else
 #define MA_LAUNCH(kern, grid, block, st, ...) kern<<<grid, block, 0, st>>>(__VA_ARGS__)
 #endif
+// the row kernels give a warp to every group: the lanes stage the group's line(s) in shared memory (the builder scans
+// a line many times, byte by byte: from global memory every step waits for L2), lane 0 runs the builder on the copy
+#ifdef UGVC_HOST_EMU
+#define MA_LANES 1u
+#define MA_LANE 0u
+#define MA_WARP_SYNC() ((void)0)
+#else
+#define MA_LANES 32u
+#define MA_LANE (threadIdx.x & 31u)
+#define MA_WARP_SYNC() __syncwarp()
+#endif
+#define MA_ROW_WARPS 4u
+#define MA_STAGE_BYTES 4096u   // per line; a longer line is read where it lies
+#define MA_RULES_SMEM 96u
 #define MA_TID ((int64_t)blockIdx.x * blockDim.x + threadIdx.x)
 #define MA_NTHREADS ((int64_t)gridDim.x * blockDim.x)
 
@@ -268,6 +282,7 @@ __device__ inline void ma_put_double(MaSink& s, double v) {
 // one record
 // ---------------------------------------------------------------------------------------------------
 struct MaRec {
+    const uint8_t* t;  // the pointer through which this record's absolute text offsets are read (the text, or a staged copy of the line)
     MaSpan col[10];
     uint32_t n_cols;   // columns on the line
     uint32_t rest_b;   // the tab in front of column 10 (cols[10:] travel verbatim), line end when there is none
@@ -280,6 +295,7 @@ struct MaRec {
 
 // the columns and alleles of the line [ls, le): le is the position of its newline
 __device__ inline int ma_parse_rec(const uint8_t* t, uint32_t ls, uint32_t le, MaRec* r) {
+    r->t = t;
     r->le = le;
     uint32_t b = ls, c = 0;
     r->rest_b = le;
@@ -519,11 +535,12 @@ __device__ inline int ma_classify_hmer(const uint8_t* t, const MaRec& r, int pa,
         // the deletion itself: its REF and first ALT placed where the deletion starts; the second of what is kept
         int kept = 0;
         const int rel = (int)(head->pos - (r.pos - 20));
+        const uint8_t* th = head->t;
         for (int c = 0; c < 2 && c < head->n_alleles; ++c) {
             const MaSpan a = head->al[c];
-            if (ma_symbolic(t, a)) continue;
+            if (ma_symbolic(th, a)) continue;
             if (kept == 1) {
-                if (nh < 2) haps[nh] = ma_place(win, wl, rel, (int)head->al[0].len(), t + a.b, (int)a.len());
+                if (nh < 2) haps[nh] = ma_place(win, wl, rel, (int)head->al[0].len(), th + a.b, (int)a.len());
                 ++nh;
             }
             ++kept;
@@ -596,8 +613,9 @@ __device__ inline int ma_convert(MaSink& s, const uint8_t* t, MaSpan v, unsigned
 // pa < 0: the record as it is (a biallelic deletion heading a cluster)
 // check: also walk the conversions in the reference's order first, so that a record with several defects fails with
 // the error the reference meets first (the planning pass; the writing pass only sees rows that passed)
-__device__ int ma_row(MaSink& s, const uint8_t* t, const MaRules& R, const MaRec& r, int pa, int pb, const MaRec* head,
+__device__ int ma_row(MaSink& s, const MaRules& R, const MaRec& r, int pa, int pb, const MaRec* head,
                       const uint8_t* ref, long long ref_len, bool check) {
+    const uint8_t* t = r.t;
     const bool as_is = pa < 0;
     int rc;
     MaSpan plv;
@@ -617,18 +635,19 @@ __device__ int ma_row(MaSink& s, const uint8_t* t, const MaRules& R, const MaRec
         if (!indel) {
             x_ic = "NA";
         } else if (star) {
+            const uint8_t* th = head->t;
             MaSpan v, el;
-            if (!ma_info_value(t, *head, "X_IL", &v)) return MA_E_TYPE;
-            ma_elem(t, v, ',', 0, &el);
+            if (!ma_info_value(th, *head, "X_IL", &v)) return MA_E_TYPE;
+            ma_elem(th, v, ',', 0, &el);
             // every element is converted (int_tuple), the first one is used
             MaSpan e2;
-            for (uint32_t i = 0; ma_elem(t, v, ',', i, &e2); ++i) {
+            for (uint32_t i = 0; ma_elem(th, v, ',', i, &e2); ++i) {
                 long long x;
-                if (!ma_is_missing(t, e2) && ma_int(t, e2, &x) != MA_OK) return MA_E_VALUE;
+                if (!ma_is_missing(th, e2) && ma_int(th, e2, &x) != MA_OK) return MA_E_VALUE;
             }
             x_ic = "del";
-            il_none = ma_is_missing(t, el);
-            if (!il_none) ma_int(t, el, &il);
+            il_none = ma_is_missing(th, el);
+            if (!il_none) ma_int(th, el, &il);
         } else if (a0.len() > a1.len()) {
             x_ic = "del";
             il_none = false;
@@ -1161,10 +1180,13 @@ __device__ inline uint8_t ma_first_like(const uint8_t* t, const MaRec& r, int a)
         if (ma_eq_span(t, r.al[i], r.al[a])) return (uint8_t)i;
     return (uint8_t)a;
 }
-__device__ int ma_plan_group(const uint8_t* t, const int64_t* line_start, MaGroup& G, MaRec* r, MaRec* head, bool* use_head) {
+// tr / th: the pointers through which the record's and the spanning deletion's line are read (ma_stage)
+__device__ int ma_plan_group(const uint8_t* tr, const uint8_t* th, const int64_t* line_start, MaGroup& G, MaRec* r, MaRec* head,
+                             bool* use_head) {
+    const uint8_t* t = tr;
     int rc;
     *use_head = false;
-    if ((rc = ma_parse_rec(t, (uint32_t)line_start[G.origin], (uint32_t)line_start[G.origin + 1] - 1u, r)) != MA_OK) return rc;
+    if ((rc = ma_parse_rec(tr, (uint32_t)line_start[G.origin], (uint32_t)line_start[G.origin + 1] - 1u, r)) != MA_OK) return rc;
     if (r->n_alleles > MA_MAX_ALLELES) return MA_E_LIMIT;
     G.n_alleles = (uint8_t)r->n_alleles;
     if (G.kind == 0xFFu) G.kind = r->n_alleles == 2 ? MA_KIND_AS_IS : MA_KIND_PLAIN;
@@ -1173,7 +1195,7 @@ __device__ int ma_plan_group(const uint8_t* t, const int64_t* line_start, MaGrou
         return MA_OK;
     }
     if (G.kind == MA_KIND_SPANNED) {
-        if ((rc = ma_parse_rec(t, (uint32_t)line_start[G.head], (uint32_t)line_start[G.head + 1] - 1u, head)) != MA_OK) return rc;
+        if ((rc = ma_parse_rec(th, (uint32_t)line_start[G.head], (uint32_t)line_start[G.head + 1] - 1u, head)) != MA_OK) return rc;
         if (head->n_alleles > MA_MAX_ALLELES) return MA_E_LIMIT;
         *use_head = true;
     }
@@ -1230,61 +1252,135 @@ __device__ int ma_plan_group(const uint8_t* t, const int64_t* line_start, MaGrou
     }
     return MA_OK;
 }
-__global__ void ma_plan_rows(const uint8_t* __restrict__ t, const int64_t* __restrict__ line_start, MaRules R,
-                             const uint8_t* __restrict__ ref, int64_t ref_len, MaGroup* __restrict__ groups,
+// the line [ls, le] (its newline included) -> buf; returns the pointer through which the line's absolute text offsets
+// reach the copy (buf - ls: only ever dereferenced at offsets inside the line), or t when the line does not fit
+__device__ inline const uint8_t* ma_stage(const uint8_t* t, uint32_t ls, uint32_t le, uint8_t* buf) {
+    const uint32_t len = le + 1u - ls;
+    if (len > MA_STAGE_BYTES) return t;
+    for (uint32_t b = MA_LANE; b < len; b += MA_LANES) buf[b] = t[ls + b];
+    return buf - ls;
+}
+struct MaRowShared {
+    uint8_t line[MA_ROW_WARPS][2][MA_STAGE_BYTES];
+    MaRule rules[MA_RULES_SMEM];
+};
+// the rule table in shared memory when it fits (every INFO / FORMAT key of a row is looked up in it)
+__device__ inline MaRules ma_stage_rules(const MaRules& R, MaRule* buf) {
+    MaRules out = R;
+    const uint32_t n = R.h.n_info + R.h.n_fmt;
+    if (n <= MA_RULES_SMEM) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(R.info);  // (the two tables are one array: info, then fmt)
+        uint32_t* dst = reinterpret_cast<uint32_t*>(buf);
+        for (uint32_t i = threadIdx.x; i < n * (uint32_t)(sizeof(MaRule) / 4u); i += blockDim.x) dst[i] = src[i];
+        out.info = buf;
+        out.fmt = buf + R.h.n_info;
+    }
+    __syncthreads();
+    return out;
+}
+__global__ void __launch_bounds__(MA_ROW_WARPS * 32) ma_plan_rows(const uint8_t* __restrict__ t, const int64_t* __restrict__ line_start,
+                             MaRules Rg, const uint8_t* __restrict__ ref, int64_t ref_len, MaGroup* __restrict__ groups,
                              int64_t n_groups, unsigned long long* err, int* width_groups) {
-    for (int64_t g = MA_TID; g < n_groups; g += MA_NTHREADS) {
+    __shared__ __align__(16) MaRowShared sh;
+    const MaRules R = ma_stage_rules(Rg, sh.rules);
+    const uint32_t warp = threadIdx.x / MA_LANES;
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x / MA_LANES);
+    for (int64_t g = (int64_t)blockIdx.x * (blockDim.x / MA_LANES) + warp; g < n_groups; g += n_warps) {
         MaGroup G = groups[g];
-        MaRec r, head;
-        bool use_head;
-        int rc = ma_plan_group(t, line_start, G, &r, &head, &use_head);
-        for (int k = 0; rc == MA_OK && k < G.n_rows; ++k) {
-            MaSink s{nullptr, 0};
-            if (G.kind == MA_KIND_AS_IS) rc = ma_row(s, t, R, r, -1, -1, nullptr, ref, ref_len, true);
-            else rc = ma_row(s, t, R, r, G.pair[2 * k], G.pair[2 * k + 1], use_head ? &head : nullptr, ref, ref_len, true);
-            G.size[k] = s.n;
+        const uint8_t* tr = ma_stage(t, (uint32_t)line_start[G.origin], (uint32_t)line_start[G.origin + 1] - 1u, sh.line[warp][0]);
+        const uint8_t* th = G.head >= 0 ? ma_stage(t, (uint32_t)line_start[G.head], (uint32_t)line_start[G.head + 1] - 1u, sh.line[warp][1]) : t;
+        MA_WARP_SYNC();
+        if (MA_LANE == 0u) {
+            MaRec r, head;
+            bool use_head;
+            int rc = ma_plan_group(tr, th, line_start, G, &r, &head, &use_head);
+            for (int k = 0; rc == MA_OK && k < G.n_rows; ++k) {
+                MaSink s{nullptr, 0};
+                if (G.kind == MA_KIND_AS_IS) rc = ma_row(s, R, r, -1, -1, nullptr, ref, ref_len, true);
+                else rc = ma_row(s, R, r, G.pair[2 * k], G.pair[2 * k + 1], use_head ? &head : nullptr, ref, ref_len, true);
+                G.size[k] = s.n;
+            }
+            if (rc != MA_OK) {
+                G.err = (uint8_t)rc;
+                G.n_rows = 0;
+                atomicMin(err, ((unsigned long long)g << 8) | (unsigned long long)rc);
+            } else if (G.n_rows == 2) {
+                atomicMax(width_groups, (int)G.n_alleles * ((int)G.n_alleles + 1) / 2);
+            }
+            groups[g] = G;
         }
-        if (rc != MA_OK) {
-            G.err = (uint8_t)rc;
-            G.n_rows = 0;
-            atomicMin(err, ((unsigned long long)g << 8) | (unsigned long long)rc);
-        } else if (G.n_rows == 2) {
-            atomicMax(width_groups, (int)G.n_alleles * ((int)G.n_alleles + 1) / 2);
-        }
-        groups[g] = G;
+        MA_WARP_SYNC();  // the buffers are free for the warp's next group
     }
 }
-// row offsets in group order (one thread: about 1 % of the records are groups)
-__global__ void ma_row_offsets(MaGroup* groups, int64_t n_groups, int64_t* totals) {
+// row offsets in group order: three-phase scan over chunks of MA_CHUNK groups of {bytes, rows}
+__global__ void ma_rowoff_agg(const MaGroup* __restrict__ groups, int64_t n_groups, int64_t* __restrict__ agg2) {
+    const int64_t n_chunks = (n_groups + MA_CHUNK - 1) / MA_CHUNK;
+    for (int64_t c = MA_TID; c < n_chunks; c += MA_NTHREADS) {
+        int64_t bytes = 0, rows = 0;
+        const int64_t e = (c + 1) * MA_CHUNK < n_groups ? (c + 1) * MA_CHUNK : n_groups;
+        for (int64_t g = c * MA_CHUNK; g < e; ++g) {
+            const int nr = groups[g].n_rows;
+            rows += nr;
+            for (int k = 0; k < nr; ++k) bytes += groups[g].size[k];
+        }
+        agg2[2 * c] = bytes;
+        agg2[2 * c + 1] = rows;
+    }
+}
+__global__ void ma_spine_sum2(int64_t* agg2, int64_t n_chunks, int64_t* totals) {
     if (MA_TID != 0) return;
-    int64_t off = 0;
-    int32_t row = 0;
-    for (int64_t g = 0; g < n_groups; ++g) {
-        groups[g].row0 = row;
-        for (int k = 0; k < groups[g].n_rows; ++k) {
-            groups[g].row_off[k] = off;
-            off += groups[g].size[k];
-        }
-        row += groups[g].n_rows;
+    int64_t bytes = 0, rows = 0;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int64_t b = agg2[2 * c], r = agg2[2 * c + 1];
+        agg2[2 * c] = bytes;
+        agg2[2 * c + 1] = rows;
+        bytes += b;
+        rows += r;
     }
-    totals[4] = off;
-    totals[5] = row;
+    totals[4] = bytes;
+    totals[5] = rows;
 }
-__global__ void ma_write_rows(const uint8_t* __restrict__ t, const int64_t* __restrict__ line_start, MaRules R,
-                              const uint8_t* __restrict__ ref, int64_t ref_len, const MaGroup* __restrict__ groups,
-                              int64_t n_groups, uint8_t* __restrict__ out) {
-    for (int64_t g = MA_TID; g < n_groups; g += MA_NTHREADS) {
-        MaGroup G = groups[g];
-        if (G.n_rows == 0) continue;
-        MaRec r, head;
-        ma_parse_rec(t, (uint32_t)line_start[G.origin], (uint32_t)line_start[G.origin + 1] - 1u, &r);
-        const bool use_head = G.kind == MA_KIND_SPANNED;
-        if (use_head) ma_parse_rec(t, (uint32_t)line_start[G.head], (uint32_t)line_start[G.head + 1] - 1u, &head);
-        for (int k = 0; k < G.n_rows; ++k) {
-            MaSink s{out + G.row_off[k], 0};
-            if (G.kind == MA_KIND_AS_IS) ma_row(s, t, R, r, -1, -1, nullptr, ref, ref_len, false);
-            else ma_row(s, t, R, r, G.pair[2 * k], G.pair[2 * k + 1], use_head ? &head : nullptr, ref, ref_len, false);
+__global__ void ma_rowoff_apply(MaGroup* __restrict__ groups, int64_t n_groups, const int64_t* __restrict__ agg2) {
+    const int64_t n_chunks = (n_groups + MA_CHUNK - 1) / MA_CHUNK;
+    for (int64_t c = MA_TID; c < n_chunks; c += MA_NTHREADS) {
+        int64_t off = agg2[2 * c], row = agg2[2 * c + 1];
+        const int64_t e = (c + 1) * MA_CHUNK < n_groups ? (c + 1) * MA_CHUNK : n_groups;
+        for (int64_t g = c * MA_CHUNK; g < e; ++g) {
+            const int nr = groups[g].n_rows;
+            groups[g].row0 = (int32_t)row;
+            for (int k = 0; k < nr; ++k) {
+                groups[g].row_off[k] = off;
+                off += groups[g].size[k];
+            }
+            row += nr;
         }
+    }
+}
+__global__ void __launch_bounds__(MA_ROW_WARPS * 32) ma_write_rows(const uint8_t* __restrict__ t, const int64_t* __restrict__ line_start,
+                              MaRules Rg, const uint8_t* __restrict__ ref, int64_t ref_len, const MaGroup* __restrict__ groups,
+                              int64_t n_groups, uint8_t* __restrict__ out) {
+    __shared__ __align__(16) MaRowShared sh;
+    const MaRules R = ma_stage_rules(Rg, sh.rules);
+    const uint32_t warp = threadIdx.x / MA_LANES;
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x / MA_LANES);
+    for (int64_t g = (int64_t)blockIdx.x * (blockDim.x / MA_LANES) + warp; g < n_groups; g += n_warps) {
+        const MaGroup G = groups[g];
+        if (G.n_rows == 0) continue;  // (warp-uniform)
+        const uint8_t* tr = ma_stage(t, (uint32_t)line_start[G.origin], (uint32_t)line_start[G.origin + 1] - 1u, sh.line[warp][0]);
+        const bool use_head = G.kind == MA_KIND_SPANNED;
+        const uint8_t* th = use_head ? ma_stage(t, (uint32_t)line_start[G.head], (uint32_t)line_start[G.head + 1] - 1u, sh.line[warp][1]) : t;
+        MA_WARP_SYNC();
+        if (MA_LANE == 0u) {
+            MaRec r, head;
+            ma_parse_rec(tr, (uint32_t)line_start[G.origin], (uint32_t)line_start[G.origin + 1] - 1u, &r);
+            if (use_head) ma_parse_rec(th, (uint32_t)line_start[G.head], (uint32_t)line_start[G.head + 1] - 1u, &head);
+            for (int k = 0; k < G.n_rows; ++k) {
+                MaSink s{out + G.row_off[k], 0};
+                if (G.kind == MA_KIND_AS_IS) ma_row(s, R, r, -1, -1, nullptr, ref, ref_len, false);
+                else ma_row(s, R, r, G.pair[2 * k], G.pair[2 * k + 1], use_head ? &head : nullptr, ref, ref_len, false);
+            }
+        }
+        MA_WARP_SYNC();
     }
 }
 // the untouched lines in input order: a CTA per chunk of records, its threads on consecutive bytes of a line
@@ -1527,13 +1623,23 @@ extern "C" int ugvc_ma_build(ugvc_ma* h, const uint8_t* text, size_t n_bytes, co
     }
     MA_LAUNCH(ma_groups_apply, grid_chunk, 64, st, n, h->d_line_start, h->d_owner, h->d_flags, h->d_recinfo, h->d_agg4, h->d_scalars,
               h->d_groups, h->d_kept_off, h->d_rec_row);
-    const int grid_grp = (int)((h->n_groups + 63) / 64 < (int64_t)h->sm_count * 8 ? (h->n_groups + 63) / 64 : (int64_t)h->sm_count * 8);
+    // a warp per group
+    const int64_t grp_ctas = (h->n_groups + MA_ROW_WARPS - 1) / MA_ROW_WARPS;
+    const int grid_grp = (int)(grp_ctas < (int64_t)h->sm_count * 16 ? grp_ctas : (int64_t)h->sm_count * 16);
+    const int row_tpb = (int)(MA_ROW_WARPS * MA_LANES);
+    const int64_t grp_chunks = (h->n_groups + MA_CHUNK - 1) / MA_CHUNK;
+    const int grid_gchunk = (int)((grp_chunks + 63) / 64 > 0 ? (grp_chunks + 63) / 64 : 1);
     if (h->n_groups) {
-        MA_LAUNCH(ma_plan_rows, grid_grp, 64, st, h->d_text, h->d_line_start, h->rules, h->d_ref, (int64_t)ref_len, h->d_groups, h->n_groups,
+        MA_LAUNCH(ma_plan_rows, grid_grp, row_tpb, st, h->d_text, h->d_line_start, h->rules, h->d_ref, (int64_t)ref_len, h->d_groups, h->n_groups,
                   d_err, d_width);
+        MA_LAUNCH(ma_rowoff_agg, grid_gchunk, 64, st, h->d_groups, h->n_groups, h->d_agg4);
+        h->launches += 2;
+    }
+    MA_LAUNCH(ma_spine_sum2, 1, 1, st, h->d_agg4, grp_chunks, h->d_scalars);
+    if (h->n_groups) {
+        MA_LAUNCH(ma_rowoff_apply, grid_gchunk, 64, st, h->d_groups, h->n_groups, h->d_agg4);
         h->launches += 1;
     }
-    MA_LAUNCH(ma_row_offsets, 1, 1, st, h->d_groups, h->n_groups, h->d_scalars);
     h->launches += 2;
     MA_CU(cudaMemcpyAsync(totals, h->d_scalars, sizeof(totals), cudaMemcpyDeviceToHost, st));
     MA_CU(cudaStreamSynchronize(st));
@@ -1554,9 +1660,10 @@ extern "C" int ugvc_ma_build(ugvc_ma* h, const uint8_t* text, size_t n_bytes, co
         MA_CU(ma_grow(&h->d_out, &c, (size_t)(h->kept_bytes + h->rows_bytes) + 64, (size_t)h->kept_bytes / 16));
         h->cap_out = c;
     }
-    MA_LAUNCH(ma_copy_kept, grid_chunk > 0 ? grid_chunk * 4 : 1, 128, st, h->d_text, h->d_line_start, h->d_kept_off, n, h->d_out);
+    const int grid_copy = (int)(n_chunks < (int64_t)h->sm_count * 16 ? n_chunks : (int64_t)h->sm_count * 16);  // a CTA per chunk of records
+    MA_LAUNCH(ma_copy_kept, grid_copy, 128, st, h->d_text, h->d_line_start, h->d_kept_off, n, h->d_out);
     if (h->n_groups) {
-        MA_LAUNCH(ma_write_rows, grid_grp, 64, st, h->d_text, h->d_line_start, h->rules, h->d_ref, (int64_t)ref_len, h->d_groups, h->n_groups,
+        MA_LAUNCH(ma_write_rows, grid_grp, row_tpb, st, h->d_text, h->d_line_start, h->rules, h->d_ref, (int64_t)ref_len, h->d_groups, h->n_groups,
                   h->d_out + h->kept_bytes);
         h->launches += 1;
     }
