@@ -12,16 +12,16 @@
 //   ma_owner_*        chunked max-scan of the head index: every '*' record joins the cluster of the head before it
 //   ma_groups_*       multi-allelic singles and flushed clusters -> the group list (singles ascending, then the
 //                     cluster records ascending: the row order of the reference's frame), kept-line offsets
-//   ma_plan_rows      one thread per group: allele pairs to genotype (strongest ALT by its hom-alt PL, '*' weakest),
+//   ma_plan_rows      one warp per group (lines staged in shared memory, lane 0 runs the builder): allele pairs to genotype (strongest ALT by its hom-alt PL, '*' weakest),
 //                     row sizes, the allele indices the merge needs
-//   ma_write_rows     one thread per group: the rows as VCF lines -- per-allele INFO / FORMAT values sub-sampled by
+//   ma_write_rows     one warp per group: the rows as VCF lines -- per-allele INFO / FORMAT values sub-sampled by
 //                     the header's Number, GT / PL of the pair, X_IC / X_IL, X_HIL / X_HIN from the flow-space keys of
 //                     the two haplotypes in the +-20 bp reference window, VARIANT_TYPE / QUAL / GQ / QD recomputed
 //   ma_copy_kept      the untouched lines, compacted in input order in front of the rows
 //   ma_merge          one thread per record: likelihoods of the scored pass -> N x W matrix in input record order
 //
 // The rows are TEXT on purpose: the scored pass then runs the ordinary K1..K3 kernels on them, so the split rows
-// get the features any record gets.  Every kernel is a grid-stride loop without shared memory, so the host
+// get the features any record gets.  Every kernel is a grid-stride loop (shared memory only stages copies), so the host
 // emulation (tests/host_emu) runs the same source with one emulated thread.  Scans are three-phase over chunks of
 // 256 records (chunk aggregate, one-thread spine over the aggregates, chunk rescan): the branch touches about 1 % of
 // the records and 16 bytes of state per record, far below the cost of the scored pass.
