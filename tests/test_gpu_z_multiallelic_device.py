@@ -231,3 +231,31 @@ def test_mutated_records_end_the_same_way_as_in_the_model(case, gpu_ctx):
             assert want[1] == got[1], (it, [(x, y) for x, y in zip(want[1], got[1]) if x != y][:1])
             assert np.array_equal(want[2], got[2]), it
     assert ends.get("ok", 0) > 40 and len(ends) >= 5, ends  # noqa: PLR2004  (the reference's failure types all occur)
+
+
+def test_lines_longer_than_the_staging_buffer(case, gpu_ctx):
+    """The row kernels stage a group's line in 4 KiB of shared memory; a longer line (a long ID, a padded annotation)
+    is read where it lies.  Same rows either way."""
+    ds, _tr, hdr, cols = case
+    contig = "chrM1"
+    lines = [ln for ln in ds["lines"] if ln.split("\t", 1)[0] == contig][:400]
+    rng = random.Random(5)
+    grown = 0
+    for i, ln in enumerate(lines):
+        c = ln.split("\t")
+        if ("," in c[4] or len(c[3]) > 1) and rng.random() < 0.5:  # noqa: PLR2004  (records that end up in groups)
+            c[2] = "rs" + "7" * rng.choice([3000, 4090, 4096, 5000, 9000])
+            if rng.random() < 0.5:  # noqa: PLR2004
+                c[7] += ";PAD=" + "x" * 4200
+            lines[i] = "\t".join(c)
+            grown += 1
+    assert grown > 20  # noqa: PLR2004
+    text = np.frombuffer(("\n".join(lines) + "\n").encode(), dtype=np.uint8)
+    ls, ri = cpu_index(text.tobytes())
+    host = PM.SplitPlan(hdr, cols, ds["ref"][contig])
+    want = [norm_qd(x) for x in host.build(text, ls, ri).tobytes().split(b"\n")]
+    dev = PM.DeviceSplitPlan(hdr, cols, ds["ref"][contig])
+    got = [norm_qd(x) for x in dev.build(text, ls, ri).tobytes().split(b"\n")]
+    assert want == got
+    assert max(len(x) for x in got) > 8000  # noqa: PLR2004
+    dev.close()
