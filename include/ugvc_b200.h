@@ -354,7 +354,8 @@ int ugvc_conc_curve(ugvc_conc* h, int group, double* precision, double* recall, 
  *   ugvc_ma_fetch      the text of the scored pass (untouched lines in input order, then the split rows: singles,
  *                      then clusters -- the row order of the reference's frame) and the group table
  *   ugvc_ma_merge      fp64 class likelihoods of the scored pass (row-major n_kept + n_split_rows by n_classes) ->
- *                      out[n_records][width] in input record order, zero padded, width = max(n_classes, out[6]) */
+ *                      out[n_records][width] in input record order, zero padded, width = max(n_classes, out[6])
+ * One handle per GPU and host thread (not thread-safe per handle); it keeps its device buffers from contig to contig. */
 typedef struct ugvc_ma ugvc_ma;
 int ugvc_ma_create(int device, ugvc_ma** out);
 void ugvc_ma_free(ugvc_ma* h);

@@ -1479,8 +1479,14 @@ static cudaError_t ma_grow(T** p, size_t* cap, size_t need, size_t slack) {
     if (*p && *cap >= need) return cudaSuccess;
     if (*p) cudaFree(*p);
     *p = nullptr;
+    *cap = 0;
+    const cudaError_t e = cudaMalloc(p, (need + slack) * sizeof(T));
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return e;
+    }
     *cap = need + slack;
-    return cudaMalloc(p, *cap * sizeof(T));
+    return cudaSuccess;
 }
 
 extern "C" int ugvc_ma_create(int device, ugvc_ma** out) {
@@ -1527,6 +1533,7 @@ extern "C" int ugvc_ma_set_rules(ugvc_ma* h, const void* blob, size_t n_bytes) {
     for (size_t i = 0; i < n_rules; ++i)
         if (src[i].len == 0 || src[i].len > 32 || src[i].action > MA_SPECIAL + 3) return ma_fail(h, UGVC_E_PLAN, "bad rule");
     MA_CU(cudaSetDevice(h->device));
+    h->has_rules = false;  // (until the new table is in place)
     cudaFree(h->d_rules);
     h->d_rules = nullptr;
     MA_CU(cudaMalloc(&h->d_rules, (n_rules ? n_rules : 1) * sizeof(MaRule)));

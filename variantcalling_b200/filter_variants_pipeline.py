@@ -114,13 +114,23 @@ def info_end_positions(text: np.ndarray, line_start: np.ndarray, recinfo: np.nda
     hit, rec = hit[ok], rec[ok]
     ls = line_start[rec]
     inside = (hit >= ls + recinfo["info_off"][rec]) & (hit < ls + recinfo["format_off"][rec])  # the INFO column only
-    for h, r in zip(hit[inside], rec[inside]):
-        p, v = int(h) + 4, 0
-        while p < text.size and 48 <= text[p] <= 57:  # noqa: PLR2004
-            v = v * 10 + int(text[p]) - 48
-            p += 1
-        if p > h + 4 and text[p] in (9, 10, 59) and out[r] == 0:  # noqa: PLR2004  (the first END of a line counts)
-            out[r] = v
+    hit, rec = hit[inside], rec[inside]
+    if hit.size == 0:
+        return out
+    first = np.concatenate(([True], rec[1:] != rec[:-1]))  # the first END of a line counts
+    hit, rec = hit[first], rec[first]
+    p, last = hit + 4, text.size - 1
+    value = np.zeros(hit.size, dtype=np.int64)
+    n_digits = np.zeros(hit.size, dtype=np.int64)
+    alive = np.ones(hit.size, dtype=bool)
+    for k in range(11):  # POS / END are int32 in htslib: ten digits at most
+        c = text[np.minimum(p + k, last)].astype(np.int64)
+        alive &= (c >= 48) & (c <= 57) & (p + k <= last)  # noqa: PLR2004
+        value = np.where(alive, value * 10 + (c - 48), value)
+        n_digits += alive
+    stop = text[np.minimum(p + n_digits, last)]
+    ok = (n_digits > 0) & (n_digits <= 10) & ((stop == 9) | (stop == 10) | (stop == 59))  # noqa: PLR2004
+    out[rec[ok]] = value[ok]
     return out
 
 
