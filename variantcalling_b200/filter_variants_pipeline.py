@@ -868,6 +868,8 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
         ctx.close()
         if idx_ctx is not None:
             idx_ctx.close()
+        if split_plans[0] is not None and hasattr(split_plans[0], "close"):
+            split_plans[0].close()
         logger.info(
             f"{totals['n_records']} records written: {totals['n_low_score']} LOW_SCORE, "
             f"{totals['n_records'] - totals['n_low_score']} not LOW_SCORE, {totals['n_blacklisted']} blacklisted")
