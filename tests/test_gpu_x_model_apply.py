@@ -77,3 +77,49 @@ def test_c_abi_contract(gpu_ctx, data):
     with pytest.raises(lib.UgvcDataError):
         gpu_ctx.predict_features(bad)
     assert gpu_ctx.last_data_error()[:2] == (3, 5)
+
+
+def test_featuremap_predict_record_with_xgb(data, tmp_path):
+    """featuremap_xgb_prediction.predict_record_with_xgb (:295-321): columns picked by the booster's feature names, object
+    columns label-encoded per call (sorted distinct strings), nulls -> 0, probability of class 1 -- against the
+    restated xgboost predictor on the frame prepared the reference's way (sklearn's LabelEncoder itself)."""
+    import json
+
+    from sklearn.preprocessing import LabelEncoder
+
+    rng = np.random.default_rng(8)
+    n = 3000
+    with pd.option_context("future.infer_string", False):  # harness: object columns, as the reference's pandas builds them
+        frame = pd.DataFrame({
+            "x_qual_mean": rng.normal(30, 5, n), "alt_reads": rng.integers(1, 40, n),
+            "ref_allele": rng.choice(list("ACGT"), n).astype(object),  # object columns, as the reference's pandas builds them
+            "alt_allele": rng.choice(["A", "C", "G", "T", "AT", "10", "9"], n).astype(object), "is_cycle_skip": rng.random(n) < 0.3,
+            "vaf": rng.random(n), "unused": rng.normal(size=n), "st_mixed": rng.integers(0, 5, n).astype(float),
+        })
+    frame.loc[rng.random(n) < 0.1, "vaf"] = np.nan
+    frame.loc[rng.random(n) < 0.05, "st_mixed"] = np.nan
+    features = ["alt_reads", "x_qual_mean", "alt_allele", "ref_allele", "is_cycle_skip", "vaf", "st_mixed"]
+    ref = frame[features].copy()           # the reference's preparation, with sklearn's own encoder
+    for col in ref.select_dtypes(include=["object", "category"]).columns:
+        ref.loc[:, col] = LabelEncoder().fit_transform(ref[col].astype(str))
+    ref = ref.fillna(0).infer_objects(copy=False)
+    x = ref.to_numpy(dtype=np.float32)
+    y = (x[:, 0] + 3 * x[:, 2] - 10 * x[:, 5] + rng.normal(0, 2, n) > 12).astype(int)
+    doc = XP.sklearn_gb_to_xgb_json(util.fit_model("gb_small", x.astype(np.float64), y))
+    doc["learner"]["feature_names"] = features
+    want = XP.predict_proba(doc, x)[:, 1]
+    path = str(tmp_path / "model.json")
+    with open(path, "w") as fh:
+        json.dump(doc, fh)
+    got = MA.predict_record_with_xgb(frame, path)
+    assert got.dtype == np.float32 and got.shape == (n,)
+    np.testing.assert_allclose(got, want, atol=2e-6, rtol=0)
+    assert np.array_equal(MA.predict_record_with_xgb(frame.iloc[:0], doc), np.zeros(0, dtype=np.float32))
+    sub = frame.iloc[:50]                  # the codes depend on the frame: a subset is encoded on its own strings
+    ref_sub = sub[features].copy()
+    for col in ref_sub.select_dtypes(include=["object", "category"]).columns:
+        ref_sub.loc[:, col] = LabelEncoder().fit_transform(ref_sub[col].astype(str))
+    want_sub = XP.predict_proba(doc, ref_sub.fillna(0).infer_objects(copy=False).to_numpy(dtype=np.float32))[:, 1]
+    np.testing.assert_allclose(MA.predict_record_with_xgb(sub, doc), want_sub, atol=2e-6, rtol=0)
+    with pytest.raises(ValueError, match="feature_names"):
+        MA.predict_record_with_xgb(frame, {"learner": {k: v for k, v in doc["learner"].items() if k != "feature_names"}})

@@ -8,9 +8,14 @@ and :class:`GpuClassifier` gives the same step to the other model-apply tools th
 an xgboost / sklearn classifier).  Supported models: what ``model_compiler`` lowers (sklearn
 LogisticRegression / GradientBoostingClassifier / RandomForestClassifier, xgboost JSON or Booster).
 Probabilities come back in the trainer's precision (fp64 for sklearn, fp32 values for xgboost).
+``predict_record_with_xgb`` is the model step of the featuremap tool
+(``ugbio_featuremap/featuremap_xgb_prediction.py:258-262,295-321``) with the same signature: the frame its
+``df_vcf_manual_aggregation`` built, the model file, the probability of class 1 back.
 There is no CPU path.
 """
 from __future__ import annotations
+
+import json
 
 import numpy as np
 import pandas as pd
@@ -87,3 +92,50 @@ def apply_model(input_df: pd.DataFrame, model, transformer, classifier: GpuClass
         if own:
             clf.close()
     return predictions, probabilities
+
+
+# ------------------------------------------------------------------ featuremap_xgb_prediction.py:258-262,295-321
+def set_categorial_columns(df: pd.DataFrame) -> None:
+    """In place, like the reference's helper: every object / category column becomes the rank of ``str(value)`` among
+    the sorted distinct strings of THIS frame (``LabelEncoder().fit_transform(df[col].astype(str))``)."""
+    for col in df.select_dtypes(include=["object", "category", "string"]).columns:
+        _, codes = np.unique(df[col].astype(str).to_numpy(dtype=object).astype(str), return_inverse=True)
+        df[col] = codes.astype(np.int64)
+
+
+def load_xgb_document(xgb_model) -> dict:
+    """The model file of ``XGBClassifier.load_model`` (JSON or UBJSON), a parsed document, or raw bytes of either."""
+    if isinstance(xgb_model, dict):
+        return xgb_model
+    raw = xgb_model
+    if isinstance(xgb_model, str):
+        with open(xgb_model, "rb") as fh:
+            raw = fh.read()
+    try:
+        return json.loads(raw)
+    except (UnicodeDecodeError, json.JSONDecodeError):
+        from variantcalling_b200 import ubjson
+
+        return ubjson.loads(bytes(raw))
+
+
+def predict_record_with_xgb(df_variants: pd.DataFrame, xgb_model, classifier: GpuClassifier | None = None) -> np.ndarray:
+    """-> probability of class "1" for every row (the reference's ``df_probabilities["1"].to_numpy()``).
+    Columns = the booster's ``feature_names``; object columns label-encoded per call, nulls filled with 0; then K3."""
+    doc = load_xgb_document(xgb_model)
+    features = doc["learner"].get("feature_names") or []
+    if not features:
+        raise ValueError("the model document carries no feature_names (it was not trained on a data frame)")
+    x = df_variants[list(features)].copy()
+    set_categorial_columns(x)
+    x = x.fillna(0)
+    own = classifier is None
+    clf = classifier or GpuClassifier(doc, n_features=len(features), max_rows=min(MAX_CHUNK_SIZE, max(1, x.shape[0])))
+    try:
+        if x.shape[0] == 0:
+            return np.zeros(0, dtype=np.float32)
+        probabilities = clf.predict_proba(x.to_numpy(dtype=np.float32))
+    finally:
+        if own:
+            clf.close()
+    return probabilities[:, 1].astype(np.float32)  # xgboost's probabilities are fp32 values
