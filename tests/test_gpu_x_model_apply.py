@@ -80,7 +80,7 @@ def test_c_abi_contract(gpu_ctx, data):
 
 
 def test_featuremap_predict_record_with_xgb(data, tmp_path):
-    """featuremap_xgb_prediction.predict_record_with_xgb (:295-321): columns picked by the booster's feature names, object
+    """featuremap_xgb_prediction.predict_record_with_xgb (:301-323): columns picked by the booster's feature names, object
     columns label-encoded per call (sorted distinct strings), nulls -> 0, probability of class 1 -- against the
     restated xgboost predictor on the frame prepared the reference's way (sklearn's LabelEncoder itself)."""
     import json

@@ -9,7 +9,7 @@ an xgboost / sklearn classifier).  Supported models: what ``model_compiler`` low
 LogisticRegression / GradientBoostingClassifier / RandomForestClassifier, xgboost JSON or Booster).
 Probabilities come back in the trainer's precision (fp64 for sklearn, fp32 values for xgboost).
 ``predict_record_with_xgb`` is the model step of the featuremap tool
-(``ugbio_featuremap/featuremap_xgb_prediction.py:258-262,295-321``) with the same signature: the frame its
+(``ugbio_featuremap/featuremap_xgb_prediction.py:258-262,301-323``) with the same signature: the frame its
 ``df_vcf_manual_aggregation`` built, the model file, the probability of class 1 back.
 There is no CPU path.
 """
@@ -94,7 +94,7 @@ def apply_model(input_df: pd.DataFrame, model, transformer, classifier: GpuClass
     return predictions, probabilities
 
 
-# ------------------------------------------------------------------ featuremap_xgb_prediction.py:258-262,295-321
+# ------------------------------------------------------------------ featuremap_xgb_prediction.py:258-262,301-323
 def set_categorial_columns(df: pd.DataFrame) -> None:
     """In place, like the reference's helper: every object / category column becomes the rank of ``str(value)`` among
     the sorted distinct strings of THIS frame (``LabelEncoder().fit_transform(df[col].astype(str))``)."""
