@@ -609,7 +609,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                 logger.info("Processing multiallelics -> pre-classifier")
                 sp = split_plans[0] = multiallelics.make_split_plan(
                     header, header.loader_columns(args.custom_annotations),
-                    multiallelics.read_fasta_contig(args.ref_fasta, contig), device, reuse=split_plans[0])
+                    multiallelics.read_fasta_contig(args.ref_fasta, contig, as_bytes=True), device, reuse=split_plans[0])
                 scored_text = sp.build(text, idx["line_start"], idx["recinfo"])
                 n_scored = int(np.count_nonzero(scored_text == 10))  # noqa: PLR2004
                 need = (scored_text.size + 4096, n_scored + 128)

@@ -44,8 +44,9 @@ _NOT_REF_CHARS = re.compile(r"[^.ATCG]")
 
 
 # ------------------------------------------------------------------ FASTA
-def read_fasta_contig(path: str, contig: str) -> str:
-    """Sequence of one contig (via ``path.fai`` when present, else a linear scan)."""
+def read_fasta_contig(path: str, contig: str, *, as_bytes: bool = False):
+    """Sequence of one contig (via ``path.fai`` when present, else a linear scan): a ``str``, or with ``as_bytes``
+    the raw bytes (what the device plan uploads; no decode / encode round trip of a 250 MB chromosome)."""
     fai = path + ".fai"
     if os.path.exists(fai):
         with open(fai) as fh:
@@ -57,20 +58,22 @@ def read_fasta_contig(path: str, contig: str) -> str:
                     with open(path, "rb") as fa:
                         fa.seek(offset)
                         raw = fa.read(length + n_lines * (width - bases))
-                    return raw.replace(b"\n", b"").replace(b"\r", b"")[:length].decode()
+                    seq = raw.replace(b"\n", b"").replace(b"\r", b"")[:length]
+                    return seq if as_bytes else seq.decode()
         raise KeyError(contig)
     seq, on = [], False
-    with open(path) as fa:
+    with open(path, "rb") as fa:
         for ln in fa:
-            if ln.startswith(">"):
+            if ln.startswith(b">"):
                 if on:
                     break
-                on = ln[1:].split()[0] == contig
+                on = ln[1:].split()[0].decode() == contig if ln[1:].split() else False
             elif on:
                 seq.append(ln.strip())
     if not on and not seq:
         raise KeyError(contig)
-    return "".join(seq)
+    out = b"".join(seq)
+    return out if as_bytes else out.decode()
 
 
 # ------------------------------------------------------------------ genotype / PL index arithmetic
@@ -615,8 +618,12 @@ class DeviceSplitPlan:
         self.stats = np.zeros(8, dtype=np.int64)
 
     def set_reference(self, ref_seq):
-        """The next contig's sequence (the handle and its device buffers are reused from contig to contig)."""
-        self.ref = np.frombuffer(ref_seq.encode() if isinstance(ref_seq, str) else bytes(ref_seq), dtype=np.uint8)
+        """The next contig's sequence: str, bytes or a uint8 array (the handle and its device buffers are reused from
+        contig to contig)."""
+        if isinstance(ref_seq, np.ndarray):
+            self.ref = np.ascontiguousarray(ref_seq, dtype=np.uint8)
+        else:
+            self.ref = np.frombuffer(ref_seq.encode() if isinstance(ref_seq, str) else ref_seq, dtype=np.uint8)
 
     def close(self):
         if getattr(self, "h", None):
@@ -698,7 +705,7 @@ def make_split_plan(header, loaded_columns: dict, ref_seq: str, device: int = 0,
     """The tool's split plan: the device form (``reuse``: the plan of the previous contig, whose handle and buffers
     carry over), or the Python model of it with UGVC_MA_HOST=1 (A/B, like UGVC_K1_LEGACY)."""
     if os.environ.get("UGVC_MA_HOST", "0") not in ("", "0"):
-        return SplitPlan(header, loaded_columns, ref_seq)
+        return SplitPlan(header, loaded_columns, ref_seq if isinstance(ref_seq, str) else bytes(ref_seq).decode())
     if isinstance(reuse, DeviceSplitPlan) and reuse.h:
         reuse.set_reference(ref_seq)
         return reuse
