@@ -209,3 +209,34 @@ def test_device_rule_table_follows_the_header():
     assert flags & 1 and flags & 2 and (flags >> 4) & 0xF == 0xF  # noqa: PLR2004  QD / GQ in the header, the four derived tags loaded
     spell = [blob[16 + 32 * k: 16 + 32 * k + blob[144 + k]].decode() for k in range(4)]
     assert spell == ["X_IC", "X_IL", "X_HIL", "X_HIN"]
+
+
+def test_fasta_reader_with_and_without_index(tmp_path):
+    """read_fasta_contig: the .fai route (offset / line-width arithmetic of a samtools index) and the linear scan give
+    the same sequence, as str and as bytes."""
+    from tests import multiallelic_data as MD
+    from variantcalling_b200 import multiallelics as PM
+
+    ref = MD.make_reference(4)
+    ref["tiny"] = "ACGTN"
+    path = str(tmp_path / "ref.fa")
+    with open(path, "w") as fh:
+        fh.write(MD.fasta_text(ref, width=70))
+    for name, seq in ref.items():
+        assert PM.read_fasta_contig(path, name) == seq
+        assert PM.read_fasta_contig(path, name, as_bytes=True) == seq.encode()
+    with pytest.raises(KeyError):
+        PM.read_fasta_contig(path, "chrNOPE")
+    # samtools faidx columns: name, length, offset of the first base, bases per line, bytes per line
+    fai, at = [], 0
+    for name, seq in ref.items():
+        at += len(name) + 2
+        fai.append(f"{name}\t{len(seq)}\t{at}\t70\t71")
+        at += len(seq) + (len(seq) + 69) // 70
+    with open(path + ".fai", "w") as fh:
+        fh.write("\n".join(fai) + "\n")
+    for name, seq in ref.items():
+        assert PM.read_fasta_contig(path, name) == seq
+        assert PM.read_fasta_contig(path, name, as_bytes=True) == seq.encode()
+    with pytest.raises(KeyError):
+        PM.read_fasta_contig(path, "chrNOPE")
