@@ -259,3 +259,49 @@ def test_lines_longer_than_the_staging_buffer(case, gpu_ctx):
     assert want == got
     assert max(len(x) for x in got) > 8000  # noqa: PLR2004
     dev.close()
+
+
+def test_overlap_scan_on_random_layouts(case, gpu_ctx):
+    """The chunked scans of the overlap detection against the model's find_overlaps (itself checked against the
+    reference's row loop in tests/test_multiallelics_cpu.py) on random layouts: deletions spanning deletions, '*' rows
+    before any deletion, clusters left open at the end, contigs longer than one scan chunk."""
+    ds, _tr, hdr, cols = case
+    rng = np.random.default_rng(17)
+    dev = None
+    seen = set()
+    for it in range(160):
+        n = int(rng.integers(1, 40)) if it % 8 else int(rng.integers(600, 1500))  # some layouts span several chunks of 256
+        pos = np.sort(rng.integers(30, 60 + 3 * n, size=n))
+        lines = []
+        for i in range(n):
+            kind = rng.random()
+            ref = "A" * int(rng.integers(1, 6)) if kind < 0.4 else "A"
+            alts = ["C"]
+            if kind < 0.4 and rng.random() < 0.8:
+                alts = ["A" * int(rng.integers(1, len(ref) + 1))]
+            if rng.random() < 0.3:
+                alts.append("*")
+            if rng.random() < 0.3:
+                alts.append("AT")
+            n_all = len(alts) + 1
+            pl = ",".join(str(int(v)) for v in rng.integers(0, 200, size=n_all * (n_all + 1) // 2))
+            gt = f"{int(rng.integers(0, n_all))}/{int(rng.integers(1, n_all))}"
+            lines.append(f"chrM1\t{pos[i]}\t.\t{ref}\t{','.join(alts)}\t50\t.\tDP=20;VARIANT_TYPE=snp;X_HIL=0;X_IL=1\tGT:PL\t{gt}:{pl}")
+        text = ("\n".join(lines) + "\n").encode()
+        ls, ri = cpu_index(text)
+        ref_seq = "ACGT" * 2000
+        host = PM.SplitPlan(hdr, cols, ref_seq)
+        try:
+            host.build(np.frombuffer(text, dtype=np.uint8), ls, ri)
+            want = ("ok", [g.origin for g in host.groups], [len(g.rows) for g in host.groups])
+        except Exception as e:  # noqa: BLE001
+            want = (type(e).__name__, None, None)
+        dev = PM.make_split_plan(hdr, cols, ref_seq, 0, reuse=dev)
+        try:
+            dev.build(np.frombuffer(text, dtype=np.uint8), ls, ri)
+            got = ("ok", [int(o) for o in dev.origins], [int(r) for r in dev.n_rows])
+        except Exception as e:  # noqa: BLE001
+            got = (type(e).__name__, None, None)
+        assert want == got, (it, want[0], got[0])
+        seen.add(want[0])
+    assert {"ok", "ValueError", "KeyError"} <= seen, seen
