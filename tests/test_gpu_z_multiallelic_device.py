@@ -305,3 +305,108 @@ def test_overlap_scan_on_random_layouts(case, gpu_ctx):
         assert want == got, (it, want[0], got[0])
         seen.add(want[0])
     assert {"ok", "ValueError", "KeyError"} <= seen, seen
+
+
+# ---------------------------------------------------------------- the reference's own unit-test tables, through the kernels
+def _kat_line(pos, alleles, gt, hom, extra_info=""):
+    """One record: `hom` = hom-alt PL per ALT (sets the allele order), every other PL entry 500 (300 for 0/0)."""
+    n = len(alleles)
+    pl = [500] * (n * (n + 1) // 2)
+    pl[0] = 300
+    for i, v in enumerate(hom, start=1):
+        pl[i * (i + 1) // 2 + i] = v
+    info = "DP=20;QD=1.00;VARIANT_TYPE=snp;X_HIL=0;X_HIN=.;X_IC=NA;X_IL=." + extra_info
+    return f"chrM1\t{pos}\t.\t{alleles[0]}\t{','.join(alleles[1:])}\t50\t.\t{info}\tGT:DP:GQ:PL\t{gt}:20:10:{','.join(map(str, pl))}"
+
+
+_KAT_FILLERS = [_kat_line(100, ("A", "C", "G"), "1/2", (10, 20)),                      # a plain multi-allelic single
+                _kat_line(200, ("GAT", "G"), "0/1", (10,)).replace("X_IL=.", "X_IL=2"),  # a deletion ...
+                _kat_line(201, ("A", "C", "*"), "1/2", (10, 20)),                       # ... and the row it spans
+                _kat_line(300, ("A", "C"), "0/1", (10,))]  # a later record closes the cluster (the reference never flushes the last one)
+
+
+def _kat_rows(dev_plan, lines, ref_seq, pos):
+    text = ("\n".join(sorted(lines, key=lambda ln: int(ln.split("\t")[1]))) + "\n").encode()
+    ls, ri = cpu_index(text)
+    dev_plan.set_reference(ref_seq)
+    out = dev_plan.build(np.frombuffer(text, dtype=np.uint8), ls, ri).tobytes().decode().split("\n")[:-1]
+    rows = [ln.split("\t") for ln in out[int(dev_plan.kept.sum()):]]
+    rows = [r for r in rows if int(r[1]) == pos]
+    return [dict(alleles=(r[3], r[4]), info=dict(kv.split("=", 1) for kv in r[7].split(";")), gt=r[9].split(":")[0],
+                 pl=tuple(int(v) for v in r[9].split(":")[3].split(","))) for r in rows]
+
+
+def test_reference_unit_test_tables_through_the_kernels(case, gpu_ctx):
+    """ugbio_filtering tests/unit/test_multiallelics.py:14-120: the in-code tables of select_overlapping_variants,
+    encode_gt_for_allele_subset, select_pl_for_allele_subset, indel_classify_subset (with and without the spanning
+    deletion) and classify_hmer_indel_relative, each reached through a record whose PLs select the table's allele pair."""
+    from tests.test_multiallelics_cpu import (REF_KAT_HMER, REF_KAT_HMER_REF, REF_KAT_INDEL_CLASS, REF_KAT_INDEL_CLASS_SPANDEL,
+                                              REF_KAT_OVERLAP)
+
+    _ds, _tr, hdr, cols = case
+    ref_seq = REF_KAT_HMER_REF + "ACGT" * 100
+    dev = PM.DeviceSplitPlan(hdr, cols, ref_seq)
+
+    def order_for(pair, n):
+        """(gt, hom-alt PLs) that make `pair` the first row (0, k) or the second row (a, b) of the split."""
+        hom = [400] * (n - 1)
+        if pair[0] == 0:
+            hom[pair[1] - 1] = 5
+            return f"0/{pair[1]}", hom
+        hom[pair[0] - 1], hom[pair[1] - 1] = 5, 10
+        return f"{pair[0]}/{pair[1]}", hom
+
+    # select_overlapping_variants: the table's records, one '*' cluster and one multi-allelic single
+    lines = []
+    for al, p in zip(REF_KAT_OVERLAP["alleles"], REF_KAT_OVERLAP["positions"]):
+        n = len(al)
+        x_il = f"X_IL={max(1, len(al[0]) - 1)}"
+        lines.append(_kat_line(p, tuple(al), "0/1", [10 * (i + 1) for i in range(n - 1)]).replace("X_IL=.", x_il))
+    text = ("\n".join(lines) + "\n").encode()
+    ls, ri = cpu_index(text)
+    dev.build(np.frombuffer(text, dtype=np.uint8), ls, ri)
+    n_singles = int(dev.stats[0])
+    assert [[int(o)] for o in dev.origins[:n_singles]] + [[int(o) for o in dev.origins[n_singles:]]] == REF_KAT_OVERLAP["expected"]
+
+    # encode_gt_for_allele_subset / select_pl_for_allele_subset (the reachable rows of the tables)
+    rows = _kat_rows(dev, _KAT_FILLERS + [_kat_line(22, ("A", "C", "G"), "0/1", (20, 60))], ref_seq, 22)
+    assert [r["gt"] for r in rows] == ["0/1", "0/0"]                      # (0, 1) over (1, 2) -> (0, 0)
+    rows = _kat_rows(dev, _KAT_FILLERS + [_kat_line(22, ("A", "C", "G"), "1/1", (20, 60))], ref_seq, 22)
+    assert rows[1]["gt"] == "0/0"                                          # (1, 1) over (1, 2) -> (0, 0)
+    rows = _kat_rows(dev, _KAT_FILLERS + [_kat_line(22, ("A", "C", "G"), "1/2", (20, 60))], ref_seq, 22)
+    assert rows[1]["gt"] == "0/1"                                          # (1, 2) over (1, 2) -> (0, 1)
+    line = _kat_line(22, ("A", "C", "G"), "1/2", (20, 60)).rsplit(":", 1)[0] + ":0,10,20,40,50,60"
+    rows = _kat_rows(dev, _KAT_FILLERS + [line], ref_seq, 22)
+    assert rows[1]["pl"] == (0, 30, 40)                                    # (0,10,20,40,50,60) over (1, 2)
+    line = _kat_line(22, ("A", "C", "G", "T"), "0/3", (20, 60, 140)).rsplit(":", 1)[0] + ":0,10,20,40,50,60,100,120,130,140"
+    rows = _kat_rows(dev, _KAT_FILLERS + [line], ref_seq, 22)
+    assert rows[0]["alleles"] == ("A", "T") and rows[0]["pl"] == (0, 100, 140)   # ... over (0, 3)
+
+    # indel_classify_subset
+    for alleles, pair, (ic, il) in REF_KAT_INDEL_CLASS:
+        gt, hom = order_for(pair, len(alleles))
+        rows = _kat_rows(dev, _KAT_FILLERS + [_kat_line(22, alleles, gt, hom)], ref_seq, 22)
+        r = rows[0 if pair[0] == 0 else 1]
+        assert r["alleles"] == (alleles[pair[0]], alleles[pair[1]])
+        assert (r["info"]["X_IC"], r["info"]["X_IL"]) == (ic[0], "." if il[0] is None else str(il[0])), (alleles, pair, r["info"])
+    # ... with the spanning deletion: x_il = (4, 5) on the deletion's line
+    head = _kat_line(21, ("GA", "G"), "0/1", (10,)).replace("X_IL=.", "X_IL=4,5")
+    for alleles, pair, (ic, il) in REF_KAT_INDEL_CLASS_SPANDEL:
+        if pair == (0, 2):
+            continue  # (REF, '*') is never a row: '*' is forced to be the weakest allele (spandel.py:11-63)
+        gt, hom = order_for((0, 1) if pair[0] == 0 else (1, 2), len(alleles))
+        rows = _kat_rows(dev, [_KAT_FILLERS[0], head, _kat_line(22, alleles, "0/1" if pair[0] == 0 else "1/1", hom)], ref_seq, 22)
+        r = rows[0 if pair[0] == 0 else 1]
+        want_alt = alleles[pair[1]] if alleles[pair[1]] != "*" else "*" * (len(alleles[pair[0]]) + 1)
+        assert r["alleles"] == (alleles[pair[0]], want_alt)
+        assert (r["info"]["X_IC"], r["info"]["X_IL"]) == (ic[0], "." if il[0] is None else str(il[0])), (alleles, pair, r["info"])
+
+    # classify_hmer_indel_relative at position 22 of the table's reference (the biallelic first row of the table is no split)
+    for alleles, pair, (nuc, length) in REF_KAT_HMER[1:]:
+        star = "*" in alleles
+        gt, hom = order_for(pair, len(alleles))
+        others = [_KAT_FILLERS[0], head] if star else _KAT_FILLERS
+        rows = _kat_rows(dev, others + [_kat_line(22, alleles, "1/1" if star else gt, hom)], ref_seq, 22)
+        r = rows[1]
+        assert (r["info"]["X_HIN"], r["info"]["X_HIL"]) == (nuc, str(length)), (alleles, pair, r["info"])
+    dev.close()

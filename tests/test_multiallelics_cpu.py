@@ -240,3 +240,42 @@ def test_fasta_reader_with_and_without_index(tmp_path):
         assert PM.read_fasta_contig(path, name, as_bytes=True) == seq.encode()
     with pytest.raises(KeyError):
         PM.read_fasta_contig(path, "chrNOPE")
+
+
+# ---------------------------------------------------------------- the reference's own in-code known answers
+# ugbio_filtering tests/unit/test_multiallelics.py:14-120 (literal tables; shared with the device test)
+REF_KAT_OVERLAP = dict(alleles=[["A", "T"], ["A", "T", "C"], ["A", "TA"], ["C", "A"], ["TA", "T"], ["T", "*", "A"], ["TAA", "T"],
+                                ["A", "AAAT"]], positions=[10, 20, 30, 31, 40, 41, 60, 62], expected=[[1], [4, 5]])
+REF_KAT_INDEL_SUBSET = [(("A", "G", "C"), (0, 1), False), (("A", "AG", "C"), (0, 1), True), (("A", "AG", "AC"), (1, 2), False),
+                        (("A", "C", "AC"), (0, 2), True)]
+REF_KAT_INDEL_SUBSET_SPANDEL = [(("A", "*", "C"), (0, 1), True), (("A", "*", "C"), (0, 2), False), (("A", "AG", "*"), (1, 2), True)]
+REF_KAT_INDEL_CLASS = [(("A", "G", "C"), (0, 1), (("NA",), (None,))), (("A", "AG", "C"), (0, 1), (("ins",), (1,))),
+                       (("A", "AG", "AC"), (1, 2), (("NA",), (None,))), (("A", "C", "AC"), (0, 2), (("ins",), (1,))),
+                       (("A", "AC", "C"), (1, 2), (("del",), (1,)))]
+REF_KAT_INDEL_CLASS_SPANDEL = [(("A", "G", "*"), (0, 1), (("NA",), (None,))), (("A", "AG", "*"), (0, 1), (("ins",), (1,))),
+                               (("A", "C", "*"), (0, 2), (("del",), (4,))), (("A", "AC", "*"), (1, 2), (("del",), (4,)))]  # spandel x_il = (4, 5)
+REF_KAT_HMER_REF = "A" * 20 + "G" + "ACCGCT" + "A" * 20
+REF_KAT_HMER_SPANDEL = dict(alleles=("GA", "G"), pos=21)
+REF_KAT_HMER = [(("A", "C"), (0, 1), (".", 0)), (("A", "C", "CA"), (1, 2), (".", 0)), (("A", "C", "CC"), (1, 2), ("C", 4)),
+                (("A", "CC", "C"), (1, 2), ("C", 4)), (("A", "C", "*"), (1, 2), ("C", 3))]  # all at pos 22
+
+
+def test_oracle_reproduces_the_reference_unit_test_tables():
+    df = pd.DataFrame({"alleles": REF_KAT_OVERLAP["alleles"], "pos": REF_KAT_OVERLAP["positions"]})
+    assert MR.overlapping_sets(df) == REF_KAT_OVERLAP["expected"]
+    for gt, pair, want in [((0, 1), (1, 2), (0, 0)), ((1, 1), (1, 2), (0, 0)), ((2, 2), (1, 2), (1, 1)), ((1, 2), (1, 2), (0, 1))]:
+        assert MR.gt_subset(gt, pair) == want
+    for pl, pair, want in [((0, 10, 20), (0, 1), (0, 10, 20)), ((0, 10, 20, 40, 50, 60), (1, 2), (0, 30, 40)),
+                           ((0, 10, 20, 40, 50, 60, 100, 120, 130, 140), (0, 3), (0, 100, 140))]:
+        assert MR.pl_subset(pl, pair) == want
+    for alleles, pair, want in REF_KAT_INDEL_SUBSET:
+        assert MR.indel_subset(alleles, pair) == want
+    for alleles, pair, want in REF_KAT_INDEL_SUBSET_SPANDEL:
+        assert MR.indel_subset(alleles, pair, spandel=pd.Series([0])) == want
+    for alleles, pair, want in REF_KAT_INDEL_CLASS:
+        assert MR.indel_class_subset(alleles, pair) == want
+    for alleles, pair, want in REF_KAT_INDEL_CLASS_SPANDEL:
+        assert MR.indel_class_subset(alleles, pair, spandel=pd.Series({"x_il": (4, 5)})) == want
+    for alleles, pair, want in REF_KAT_HMER:
+        got = MR.hmer_indel_relative(alleles, pair, REF_KAT_HMER_REF, 22, spandel=pd.Series(REF_KAT_HMER_SPANDEL))
+        assert got == want, (alleles, pair, got, want)
