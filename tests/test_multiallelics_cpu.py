@@ -279,3 +279,16 @@ def test_oracle_reproduces_the_reference_unit_test_tables():
     for alleles, pair, want in REF_KAT_HMER:
         got = MR.hmer_indel_relative(alleles, pair, REF_KAT_HMER_REF, 22, spandel=pd.Series(REF_KAT_HMER_SPANDEL))
         assert got == want, (alleles, pair, got, want)
+
+
+def test_oracle_flow_key_known_answers():
+    # ugbio_core tests/unit/flow_format/test_flow_based_read.py:62-92 (generate_key_from_sequence, flow order ACGT)
+    assert MR.flow_key("AAGGTTCC", "ACGT").tolist() == [2, 0, 2, 2, 0, 2]
+    assert MR.flow_key("", "ACGT").tolist() == []
+    with pytest.raises(ValueError):
+        MR.flow_key("AAGGTTCCNN", "ACGT")
+    # the product's Python model of the kernels spells the same keys in the TGCA order the branch uses
+    from variantcalling_b200 import multiallelics as PM
+
+    for seq in ("AAGGTTCC", "T", "ACGTTTGCA", "GGGG"):
+        assert PM._flow_key(seq) == MR.flow_key(seq, "TGCA").tolist()  # noqa: SLF001
