@@ -89,3 +89,32 @@ def test_cli_on_a_deepvariant_file(dv, tmp_path):
     text = gzip.open(out).read().decode().split("\n")[:-1]
     assert [ln for ln in text if ln.startswith("#")] == exp["header"]
     assert [ln for ln in text if not ln.startswith("#")] == exp["lines"]
+
+
+@pytest.mark.parametrize("flavour,key", [(VcfType.DEEP_VARIANT, "features_deep_variant"), (VcfType.JOINT, "features_joint")])
+def test_flavours_against_the_reference_transformers_own_output(gpu_ctx, flavour, key):
+    """Device features bit-identical to what the REFERENCE's get_transformer(flavour).fit_transform produced on the same
+    records (tests/golden/transformer_flavours.npz, scripts/make_golden_flavours.py)."""
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "transformer_flavours.npz"))
+    text, customs = bytes(z["vcf_text"]), [str(c) for c in z["customs"]]
+    at = text.index(b"#CHROM")
+    at = text.index(b"\n", at) + 1
+    header_text, records = text[:at].decode(), text[at:]
+    df = R.harness_float_columns(R.get_vcf_df(OracleVariantFile(text), None, customs))
+    tr = T.get_transformer(flavour, [c.lower() for c in customs])
+    with pd.option_context("future.infer_string", False):
+        x = tr.fit_transform(df).to_numpy(dtype=np.float64)
+    labels = (np.arange(x.shape[0]) % 3 == 0).astype(int)
+    plan = MC.compile_plan(VcfHeader(header_text), tr, util.fit_model("lr", x, labels), customs)
+    gpu_ctx.load_plan(plan.blob)
+    gpu_ctx.reserve(len(records) + 1024, x.shape[0] + 16, 1)
+    for mode in ("generic", "learned"):
+        gpu_ctx.set_key_order(*(lib.learn_key_order(records) if mode == "learned" else ("", "")))
+        res = gpu_ctx.filter_batch(records, 30.0)
+        feats = gpu_ctx.debug_features(res["n_records"]).T
+        want = z[key].astype(np.float32)
+        assert feats.shape == want.shape
+        bad = np.argwhere(feats != want)
+        assert bad.size == 0, f"[{mode}] first mismatch {bad[0]} ({plan.feature_names[bad[0][1]]})"

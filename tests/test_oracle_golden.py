@@ -213,3 +213,16 @@ def test_oracle_reader_scalar_versus_tuple_rule_known_answers():
     assert first.info["GAP_PERCENTAGE"] == 0.5 and isinstance(first.info["GAP_PERCENTAGE"], float)
     assert second.info["SVLEN"] == (100, 200) and second.info["CNV_SOURCE"] == ("cn.mops", "cnvpytor")
     assert second.info["GAP_PERCENTAGE"] == 1.0
+
+
+@pytest.mark.parametrize("flavour,key", [(VcfType.DEEP_VARIANT, "features_deep_variant"), (VcfType.JOINT, "features_joint")])
+def test_mirror_transformer_flavours_match_reference_golden(flavour, key):
+    """deep_variant / joint_callset: oracle loader + host mirror == the reference module's own fit_transform
+    (tests/golden/transformer_flavours.npz, scripts/make_golden_flavours.py; transformers.py:221-245,278)."""
+    z = np.load(os.path.join(GOLD, "transformer_flavours.npz"))
+    customs = [str(c) for c in z["customs"]]
+    df = R.harness_float_columns(R.get_vcf_df(OracleVariantFile(bytes(z["vcf_text"])), None, customs))
+    tr = T.get_transformer(flavour, [c.lower() for c in customs])
+    with pd.option_context("future.infer_string", False):
+        x = tr.fit_transform(df).to_numpy(dtype=np.float64)
+    assert x.shape == z[key].shape and np.array_equal(x, z[key], equal_nan=True)
