@@ -611,7 +611,9 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
                     header, header.loader_columns(args.custom_annotations),
                     multiallelics.read_fasta_contig(args.ref_fasta, contig, as_bytes=True), device, reuse=split_plans[0])
                 scored_text = sp.build(text, idx["line_start"], idx["recinfo"])
-                n_scored = int(np.count_nonzero(scored_text == 10))  # noqa: PLR2004
+                n_scored = getattr(sp, "n_scored_records", None)  # (the device plan counted them)
+                if n_scored is None:
+                    n_scored = int(np.count_nonzero(scored_text == 10))  # noqa: PLR2004
                 need = (scored_text.size + 4096, n_scored + 128)
                 if need[0] > reserved[0] or need[1] > reserved[1]:
                     reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))

@@ -639,6 +639,11 @@ class DeviceSplitPlan:
     def launch_count(self) -> int:
         return int(self._lib.ugvc_ma_launch_count(self.h))
 
+    @property
+    def n_scored_records(self) -> int:
+        """Lines of the text the last ``build`` returned (untouched records + split rows)."""
+        return int(self.stats[2] + self.stats[3])
+
     def _check(self, rc: int):
         if rc != 0:
             raise self._UgvcError(rc, self._lib.ugvc_ma_last_error(self.h).decode())
