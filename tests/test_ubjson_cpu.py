@@ -72,3 +72,24 @@ def test_binary_xgboost_document_lowers_like_the_json_one():
     as_json = MC.compile_plan_model_only(json.dumps(doc).encode(), x.shape[1])
     as_ubj = MC.compile_plan_model_only(enc(doc), x.shape[1])
     assert as_ubj.blob == as_json.blob and as_ubj.model_kind == MC.MODEL_XGB
+
+
+def test_model_files_of_either_flavour_load_as_the_same_document(tmp_path):
+    """model_apply.load_xgb_document: what XGBClassifier.load_model reads -- a .json or a .ubj file, raw bytes of either,
+    or the parsed document (the model step of the featuremap tool, featuremap_xgb_prediction.py:301-323)."""
+    import json
+
+    from variantcalling_b200 import model_apply as MA
+
+    doc = {"learner": {"feature_names": ["a", "b"], "objective": {"name": "binary:logistic"},
+                       "learner_model_param": {"base_score": "5E-1", "num_class": "0", "num_feature": "2"},
+                       "gradient_booster": {"name": "gbtree", "model": {"trees": [
+                           {"left_children": [1, -1, -1], "right_children": [2, -1, -1], "split_indices": [0, 0, 0],
+                            "split_conditions": [0.5, -0.25, 0.75], "default_left": [0, 0, 0]}], "tree_info": [0]}}}}
+    pj, pu = tmp_path / "m.json", tmp_path / "m.ubj"
+    pj.write_text(json.dumps(doc))
+    pu.write_bytes(enc(doc))
+    for source in (str(pj), str(pu), pj.read_bytes(), pu.read_bytes(), doc):
+        got = MA.load_xgb_document(source)
+        assert got["learner"]["feature_names"] == ["a", "b"]
+        assert [float(v) for v in got["learner"]["gradient_booster"]["model"]["trees"][0]["split_conditions"]] == [0.5, -0.25, 0.75]
