@@ -85,3 +85,40 @@ def test_two_rank_cli_run_equals_the_single_process_output(tmp_path):
     summary = [ln for ln in r1.stderr.splitlines() if "records written" in ln][0].split(" ", 2)[2]
     assert sum(summary in ln for ln in r2.stderr.splitlines()) == 2        # both ranks report the global counts
     assert "rank 0/2" in r2.stderr and "rank 1/2" in r2.stderr
+
+
+def test_two_rank_run_of_the_multiallelic_branch(tmp_path):
+    """--treat_multiallelics --recalibrate_genotype under two ranks: every rank builds its own device split plan for its
+    contigs (csrc/multiallelic.cu on the emulation); the assembled file equals the single-process output byte for byte."""
+    import gzip
+    import pickle
+
+    from tests import multiallelic_data as MD
+    from tests import util
+    from variantcalling_b200 import bgzf_io
+
+    build = subprocess.run(["make", "-C", EMU_DIR], capture_output=True, text=True, timeout=900)
+    assert build.returncode == 0, build.stderr[-3000:]
+    ds, tr, model, _split = util.make_multiallelic_case(21, "gb3")
+    vcf, fasta, mpath = str(tmp_path / "in.vcf.gz"), str(tmp_path / "ref.fa"), str(tmp_path / "m.pkl")
+    bgzf_io.write_vcf_gz(vcf, ds["header"], ds["lines"])
+    with open(fasta, "w") as fh:
+        fh.write(MD.fasta_text(ds["ref"]))
+    with open(mpath, "wb") as fh:
+        pickle.dump({"xgb": model, "transformer": tr}, fh)
+    tool = ["filter_variants_pipeline", "--input_file", vcf, "--model_file", mpath, "--treat_multiallelics", "--ref_fasta", fasta,
+            "--recalibrate_genotype", "--device", "0"]
+    for c in ds["customs"]:
+        tool += ["--custom_annotations", c]
+    env = dict(os.environ, UGVC_LIB_PATH=EMU_LIB)
+    env.pop("RANK", None), env.pop("WORLD_SIZE", None)
+    one, two = str(tmp_path / "one.vcf.gz"), str(tmp_path / "two.vcf.gz")
+    r1 = subprocess.run([sys.executable, "ugvc", *tool, "--output_file", one], cwd=ROOT, env=env, capture_output=True,
+                        text=True, timeout=900)
+    assert r1.returncode == 0, r1.stderr[-3000:]
+    r2 = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                         "--master-addr", "127.0.0.1", "--master-port", "29741", "ugvc/__main__.py", *tool,
+                         "--output_file", two], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r2.returncode == 0, r2.stderr[-4000:]
+    assert gzip.open(two).read() == gzip.open(one).read()
+    assert "Processing multiallelics" in r2.stderr
