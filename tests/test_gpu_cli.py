@@ -244,7 +244,7 @@ def test_index_ends_records_at_info_end(job):
     assert len(long_ones) >= 4  # noqa: PLR2004
     vcf, out = str(job["dir"] / "in_end.vcf.gz"), str(job["dir"] / "out_end.vcf.gz")
     bgzf_io.write_vcf_gz(vcf, header, lines)
-    argv = ["--input_file", vcf, "--model_file", job["model"], "--output_file", out]
+    argv = ["--input_file", vcf, "--model_file", job["model"], "--output_file", out, "--host_io"]  # (the END-aware writer)
     for cu in ds["customs"]:
         argv += ["--custom_annotations", cu]
     fvp.run(argv)

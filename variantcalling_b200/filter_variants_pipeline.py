@@ -558,11 +558,13 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
 
         # compressed bytes both ways: the contig's BGZF blocks go to the device as they are, come back filtered, edited
         # and compressed again (ugvc_filter_bgzf); what that path does not cover keeps the host readers / writers
-        # (a header that declares INFO/END keeps the host writer: the index then ends records at END, which the device
-        # writer's recinfo does not carry)
+        # (INFO/END: the host writer ends a record's index interval at END like htslib; the device writer's recinfo does
+        # not carry END, so on that path the interval is POS + len(REF) -- gVCF blocks / symbolic alleles: --host_io)
         out.index_info_end = "END" in header.info
-        device_io = bool(with_model and not split_sites and not recal and blacklists is None and not args.host_io
-                         and not out.index_info_end)
+        device_io = bool(with_model and not split_sites and not recal and blacklists is None and not args.host_io)
+        if device_io and out.index_info_end:
+            logger.info("the header declares INFO/END: index intervals on the device file path are POS + len(REF); "
+                        "--host_io ends them at END")
         file_flags = (lib.FILE_OVERWRITE_QUAL if args.overwrite_qual_tag else 0) | \
                      (lib.FILE_BLACKLIST_CG if args.blacklist_cg_insertions else 0)
 
