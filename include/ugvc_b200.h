@@ -247,6 +247,11 @@ int ugvc_bgzf_deflate_to_file(const char* path, const char* mode, const uint8_t*
                               uint32_t* out_block_csize, size_t block_capacity, size_t* out_n_blocks);
 /* Number of bytes equal to `byte` in data[0, n) (the record count of inflated VCF text), threaded. */
 int64_t ugvc_count_byte(const uint8_t* data, size_t n, int byte, int n_threads);
+/* INFO/END of every record of a batch (0 where there is none): the end of a record's tabix interval when it lies beyond
+ * POS, as htslib takes it for the index `bcftools index -t` writes (filter_variants_pipeline.py:231).  line_start /
+ * recinfo are the batch's outputs of ugvc_filter_batch.  Returns the number of records that carry the tag. */
+int64_t ugvc_info_end(const uint8_t* text, const int64_t* line_start, const ugvc_recinfo* recinfo, int64_t n_records,
+                      int64_t* out_end, int n_threads);
 /* Build the edited output text of a batch: for each record copy the original
  * line with FILTER rewritten (PASS removed / LOW_SCORE appended / empty -> PASS)
  * and TREE_SCORE (and optionally QUAL, BLACKLST) spliced in, exactly the rules of

@@ -664,6 +664,55 @@ extern "C" int64_t ugvc_count_byte(const uint8_t* data, size_t n, int byte, int 
     return total;
 }
 
+// INFO/END of every record (0 where the INFO column has no END=<digits> field): what htslib's tabix takes for the end of
+// a record's interval when the value lies beyond POS (gVCF blocks, symbolic alleles; bcftools index -t of the reference,
+// filter_variants_pipeline.py:231).  The first END field of a line counts; the column bounds come from recinfo.  Threaded.
+extern "C" int64_t ugvc_info_end(const uint8_t* text, const int64_t* line_start, const ugvc_recinfo* recinfo, int64_t n,
+                                 int64_t* out_end, int n_threads) {
+    if (n < 0 || (n && (!text || !line_start || !recinfo || !out_end))) return UGVC_E_ARG;
+    n_threads = clamp_threads(n_threads);
+    if ((int64_t)n_threads > n / 65536 + 1) n_threads = (int)(n / 65536 + 1);
+    std::vector<int64_t> part(n_threads, 0);
+    auto work = [&](int t) {
+        const int64_t lo = n * (int64_t)t / n_threads, hi = n * (int64_t)(t + 1) / n_threads;
+        int64_t found = 0;
+        for (int64_t i = lo; i < hi; ++i) {
+            out_end[i] = 0;
+            const uint8_t* p = text + line_start[i] + recinfo[i].info_off;
+            // format_off: one past the tab behind INFO, or line length + 1 when the line ends with the INFO column
+            const uint8_t* end = text + line_start[i] + recinfo[i].format_off - 1;
+            if (recinfo[i].format_off <= recinfo[i].info_off || end > text + line_start[i + 1]) continue;
+            while (p < end) {
+                const uint8_t* q = static_cast<const uint8_t*>(memchr(p, ';', (size_t)(end - p)));
+                if (!q) q = end;
+                if (q - p > 4 && p[0] == 'E' && p[1] == 'N' && p[2] == 'D' && p[3] == '=' && q - p <= 14) {
+                    int64_t v = 0;
+                    bool digits = true;
+                    for (const uint8_t* d = p + 4; d < q; ++d) {
+                        digits = digits && *d >= '0' && *d <= '9';
+                        v = v * 10 + (*d - '0');
+                    }
+                    if (digits) {
+                        out_end[i] = v;
+                        ++found;
+                    }
+                    break;  // the first END field of the line
+                }
+                if (q - p >= 4 && p[0] == 'E' && p[1] == 'N' && p[2] == 'D' && p[3] == '=') break;  // END= without a usable value
+                p = q + 1;
+            }
+        }
+        part[t] = found;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    int64_t total = 0;
+    for (int64_t c : part) total += c;
+    return total;
+}
+
 // The K1 numeric-literal parser compiled for the host (same header as the device code), so
 // the CPU tests can check it against strtod on millions of literals.
 extern "C" int ugvc_test_parse_float(const char* text, float* out_f32, double* out_f64, int* out_consumed) {

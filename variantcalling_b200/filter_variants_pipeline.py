@@ -98,39 +98,21 @@ def _blacklist_positions(blacklists, contig: str) -> list[tuple[str, np.ndarray]
 
 
 
-def info_end_positions(text: np.ndarray, line_start: np.ndarray, recinfo: np.ndarray, n: int) -> np.ndarray:
+def info_end_positions(text: np.ndarray, line_start: np.ndarray, recinfo: np.ndarray, n: int, n_threads: int = 0) -> np.ndarray:
     """INFO/END of every record (0 where there is none): htslib's tabix for VCF ends a record at END when the tag
     is present and lies beyond POS -- gVCF blocks, symbolic <DEL> / <CNV> alleles -- so that region queries that
-    overlap only the tail of a long record find it (`bcftools index -t`, filter_variants_pipeline.py:231)."""
+    overlap only the tail of a long record find it (`bcftools index -t`, filter_variants_pipeline.py:231).
+    One threaded pass over the INFO columns in C (csrc/hostio.cpp: ugvc_info_end)."""
     out = np.zeros(n, dtype=np.int64)
-    if text.size < 6:  # noqa: PLR2004
+    if n == 0:
         return out
-    hit = np.flatnonzero((text[1:-4] == 69) & (text[2:-3] == 78) & (text[3:-2] == 68) & (text[4:-1] == 61)  # noqa: PLR2004
-                         & ((text[:-5] == 9) | (text[:-5] == 59))) + 1  # noqa: PLR2004  "END=" behind a tab or ';'
-    if hit.size == 0:
-        return out
-    rec = np.searchsorted(line_start[:n + 1], hit, side="right") - 1
-    ok = (rec >= 0) & (rec < n)
-    hit, rec = hit[ok], rec[ok]
-    ls = line_start[rec]
-    inside = (hit >= ls + recinfo["info_off"][rec]) & (hit < ls + recinfo["format_off"][rec])  # the INFO column only
-    hit, rec = hit[inside], rec[inside]
-    if hit.size == 0:
-        return out
-    first = np.concatenate(([True], rec[1:] != rec[:-1]))  # the first END of a line counts
-    hit, rec = hit[first], rec[first]
-    p, last = hit + 4, text.size - 1
-    value = np.zeros(hit.size, dtype=np.int64)
-    n_digits = np.zeros(hit.size, dtype=np.int64)
-    alive = np.ones(hit.size, dtype=bool)
-    for k in range(11):  # POS / END are int32 in htslib: ten digits at most
-        c = text[np.minimum(p + k, last)].astype(np.int64)
-        alive &= (c >= 48) & (c <= 57) & (p + k <= last)  # noqa: PLR2004
-        value = np.where(alive, value * 10 + (c - 48), value)
-        n_digits += alive
-    stop = text[np.minimum(p + n_digits, last)]
-    ok = (n_digits > 0) & (n_digits <= 10) & ((stop == 9) | (stop == 10) | (stop == 59))  # noqa: PLR2004
-    out[rec[ok]] = value[ok]
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    line_start = np.ascontiguousarray(line_start, dtype=np.int64)
+    recinfo = np.ascontiguousarray(recinfo)
+    rc = lib.load_library().ugvc_info_end(text.ctypes.data, line_start.ctypes.data, recinfo.ctypes.data, n, out.ctypes.data,
+                                          n_threads)
+    if rc < 0:
+        raise OSError(f"ugvc_info_end failed (ugvc code {rc})")
     return out
 
 
@@ -203,7 +185,7 @@ class _Splicer:
         self._check_writer()
         end = beg + np.maximum(1, (ri["flags"] >> 8).astype(np.int64))
         if self.index_info_end:
-            info_end = info_end_positions(text, res["line_start"], ri, n)
+            info_end = info_end_positions(text, res["line_start"], ri, n, self.threads)
             end = np.where(info_end > beg, info_end, end)  # htslib ignores an END that is not beyond POS
         self._queue.put((contig, out[:nb], n, beg, end, out_ls))
 

@@ -83,6 +83,7 @@ SIGNATURES = {
     "ugvc_bgzf_deflate_to_file": (C.c_int, [C.c_char_p, C.c_char_p, _vp, _sz, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(C.c_uint64), _vp, _sz, C.POINTER(_sz)]),
     "ugvc_count_byte": (C.c_int64, [_vp, _sz, C.c_int, C.c_int]),
+    "ugvc_info_end": (C.c_int64, [_vp, _vp, _vp, C.c_int64, _vp, C.c_int]),
     "ugvc_splice_records": (C.c_int64, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp,
                                         _vp, C.c_int, _vp, _sz, _vp, C.c_int]),
     "ugvc_submit_bgzf": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_double]),
