@@ -383,13 +383,28 @@ def _split_batches(text: np.ndarray, limit: int):
     while b < n:
         e = min(n, b + limit)
         if e < n:
-            back = text[b:e][::-1]
-            k = int(np.argmax(back == 10))  # noqa: PLR2004
-            if back[k] == 10:  # noqa: PLR2004
-                e -= k
+            # the last newline of the window, looked for in growing tails (a line is a few hundred bytes: the first
+            # 64 KiB tail nearly always holds one -- no scan of the whole window)
+            cut, span = -1, 1 << 16
+            while cut < 0:
+                lo = max(b, e - span)
+                nl = np.flatnonzero(text[lo:e] == 10)  # noqa: PLR2004
+                if nl.size:
+                    cut = lo + int(nl[-1]) + 1
+                elif lo == b:
+                    break
+                span <<= 2
+            if cut > b:
+                e = cut
             else:  # no newline inside the window: extend to the end of this line
-                fwd = np.flatnonzero(text[e:] == 10)  # noqa: PLR2004
-                e = n if fwd.size == 0 else e + int(fwd[0]) + 1
+                at, step = e, 1 << 16
+                e = n
+                while at < n:
+                    nl = np.flatnonzero(text[at:at + step] == 10)  # noqa: PLR2004
+                    if nl.size:
+                        e = at + int(nl[0]) + 1
+                        break
+                    at += step
         yield b, e
         b = e
 
@@ -620,7 +635,7 @@ def run(argv: list[str]):  # noqa: C901, PLR0912, PLR0915
 
             ranges = list(_split_batches(text, batch_bytes))
             # records per batch (one scan of the text at most: a contig that fits one batch was counted on load)
-            n_in = [n_contig] if len(ranges) == 1 else [int(np.count_nonzero(text[b:e] == 10)) for b, e in ranges]  # noqa: PLR2004
+            n_in = [n_contig] if len(ranges) == 1 else [bgzf_io.count_lines(text[b:e], args.io_threads) for b, e in ranges]
             need = (max(e - b for b, e in ranges) + 4096, max(n_in) + 128)
             if need[0] > reserved[0] or need[1] > reserved[1]:
                 reserved = (max(need[0], reserved[0]), max(need[1], reserved[1]))
