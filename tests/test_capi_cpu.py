@@ -44,6 +44,13 @@ def test_no_cuda_device_fails_loudly():
     with pytest.raises(lib.UgvcError) as ei:
         lib.Context(0)
     assert "no CPU fallback" in str(ei.value)
+    # the --treat_multiallelics kernels and the model-apply step refuse the same way
+    from variantcalling_b200 import multiallelics
+    from variantcalling_b200.vcf_header import VcfHeader
+
+    hdr = VcfHeader("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+    with pytest.raises(lib.UgvcError):
+        multiallelics.DeviceSplitPlan(hdr, {}, "ACGT")
 
 
 def test_synth_header_host_call():
