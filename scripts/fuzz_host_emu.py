@@ -5,7 +5,7 @@ unknown INFO keys, permuted FORMAT columns, re-spelled and exotic numeric litera
 by feature in the generic and the learned-key-order mode.   python scripts/fuzz_host_emu.py 0 60"""
 import os, sys, warnings, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["UGVC_LIB_PATH"] = os.path.join(ROOT, "tests", "host_emu", "_build", "libugvc_emu.so")
+os.environ["UGVC_LIB_PATH"] = os.environ.get("UGVC_EMU_LIB") or os.path.join(ROOT, "tests", "host_emu", "_build", "libugvc_emu.so")
 sys.path.insert(0, ROOT); warnings.filterwarnings("ignore")
 import numpy as np, pandas as pd
 from oracle import ref_pipeline as R
